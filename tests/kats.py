@@ -1,0 +1,427 @@
+"""Known-answer tests transcribed from the reference's own test-suite
+(/root/reference/test/*.js).  Each function takes the store class to run on —
+the CPU oracle (tests/test_oracle_kats.py, pins the oracle) or the device store
+(tests/test_gpu_kats.py, marked gpu) — and asserts the values the reference's
+tests assert, so the same expectations gate both.  Citations give the reference
+test file and lines each case restates."""
+from __future__ import annotations
+
+import math
+
+from olap_in_memory_b200 import Cube, GenericDimension, TimeDimension
+
+NaN = math.nan
+
+
+def same(a, b):
+    """deepEqual with NaN == NaN."""
+    if isinstance(a, dict) and isinstance(b, dict):
+        return a.keys() == b.keys() and all(same(a[k], b[k]) for k in a)
+    if isinstance(a, (list, tuple)) and isinstance(b, (list, tuple)):
+        return len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+    if isinstance(a, (int, float)) and isinstance(b, (int, float)):
+        return (a != a and b != b) or a == b
+    return a == b
+
+
+def check(actual, expected):
+    assert same(actual, expected), f"\n  actual:   {actual}\n  expected: {expected}"
+
+
+def create_test_cube(store_cls, create_measures=True, fill=True):
+    """test/helpers/create-test-cube.js:3-58"""
+    period = GenericDimension("period", "season", ["summer", "winter"])
+    location = GenericDimension("location", "city", ["paris", "toledo", "tokyo"])
+    location.addAttribute("city", "country", {"paris": "france", "toledo": "spain", "tokyo": "japan"})
+    location.addAttribute("city", "continent", {"paris": "europe", "toledo": "europe", "tokyo": "asia"})
+    location.addAttribute("city", "citySize", {"paris": "big", "toledo": "small", "tokyo": "big"})
+    cube = Cube([location, period], store_cls)
+    if create_measures:
+        cube.createStoredMeasure("antennas", {"period": "sum", "location": "sum"}, "uint32")
+        cube.createStoredMeasure("routers", {"period": "sum", "location": "sum"}, "uint32")
+        cube.createComputedMeasure("router_by_antennas", "routers / antennas")
+    if fill:
+        cube.setNestedArray("antennas", [[1, 2], [4, 8], [16, 32]])
+        cube.setNestedArray("routers", [[3, 2], [4, 9], [16, 32]])
+    return cube
+
+
+# ------------------------------------------------------------ cube-drilling.js
+def kat_drillup_noop(S):  # cube-drilling.js:7-13
+    cube = create_test_cube(S)
+    assert cube.drillUp("location", "city") is cube
+
+
+def kat_drillup_cities_to_continents(S):  # cube-drilling.js:15-24
+    cube = create_test_cube(S)
+    check(cube.drillUp("location", "continent").getNestedArray("antennas"), [[5, 10], [16, 32]])
+
+
+def kat_drillup_incomplete(S):  # cube-drilling.js:26-69
+    cube = Cube([TimeDimension("time", "month", "2010-01", "2010-06")], S)
+    cube.createStoredMeasure("data_sum", {}, "float32", NaN)
+    cube.createStoredMeasure("data_avg", {"time": "average"}, "float32", NaN)
+    cube.hydrateFromSparseNestedObject("data_sum", {"2010-01": 1, "2010-03": 2})
+    cube.hydrateFromSparseNestedObject("data_avg", {"2010-01": 10, "2010-02": 0, "2010-03": 20})
+    new = cube.drillUp("time", "quarter")
+    check(new.getNestedObject("data_sum", True), {"2010-Q1": 3, "2010-Q2": NaN, "all": 3})
+    check(new.getNestedObject("data_avg", True), {"2010-Q1": 10, "2010-Q2": NaN, "all": 10})
+
+
+def kat_drilldown_noop(S):  # cube-drilling.js:73-83
+    cube = Cube([TimeDimension("time", "month", "2010-01", "2010-02")], S)
+    cube.createStoredMeasure("measure1", {"time": "sum"}, "float32")
+    cube.setNestedObject("measure1", {"2010-01": 100, "2010-02": 100})
+    assert cube.drillDown("time", "month") is cube
+
+
+def kat_drilldown_months_to_days_roundtrip(S):  # cube-drilling.js:85-105
+    cube = Cube([TimeDimension("time", "month", "2010-01", "2010-02")], S)
+    cube.createStoredMeasure("measure1", {"time": "sum"}, "uint32")
+    cube.createStoredMeasure("measure2", {"time": "average"}, "uint32")
+    cube.setNestedObject("measure1", {"2010-01": 100, "2010-02": 100})
+    cube.setNestedObject("measure2", {"2010-01": 100, "2010-02": 100})
+    new = cube.drillDown("time", "day")
+    assert new.storeSize == 59
+    check(new.drillUp("time", "month").getNestedObject("measure1"), cube.getNestedObject("measure1"))
+    check(new.drillUp("time", "month").getNestedObject("measure2"), cube.getNestedObject("measure2"))
+
+
+def kat_drilldown_month_week_roundtrip(S):  # cube-drilling.js:107-140
+    cube = Cube([TimeDimension("time", "month_week_mon", "2010-01-W1-mon", "2010-02-W1-mon")], S)
+    cube.createStoredMeasure("measure1", {"time": "sum"}, "uint32")
+    cube.createStoredMeasure("measure2", {"time": "average"}, "uint32")
+    cube.setNestedObject("measure1", {"2010-01-W1-mon": 100, "2010-02-W1-mon": 100})
+    cube.setNestedObject("measure2", {"2010-01-W1-mon": 100, "2010-02-W1-mon": 100})
+    new = cube.drillDown("time", "day")
+    check(new.drillUp("time", "month_week_mon").getNestedObject("measure1"), cube.getNestedObject("measure1"))
+    check(new.drillUp("time", "month_week_mon").getNestedObject("measure2"), cube.getNestedObject("measure2"))
+
+
+def kat_drilldown_quarter_to_month_incomplete(S):  # cube-drilling.js:142-189
+    cube = Cube([TimeDimension("time", "quarter", "2010-Q1", "2010-Q2")], S)
+    cube.createStoredMeasure("measure1", {"time": "sum"}, "float32", NaN)
+    cube.hydrateFromSparseNestedObject("measure1", {"2010-Q1": 90})
+    new = cube.drillDown("time", "month")
+    check(cube.getData("measure1"), [90, NaN])
+    check(new.drillUp("time", "quarter").getData("measure1"), [90, NaN])
+    check(new.getData("measure1"), [30, 30, 30, NaN, NaN, NaN])
+    check(list(new.getStatusMap("measure1").keys()), [0, 1, 2])
+
+
+# ----------------------------------------------------------- cube-dimension.js
+def _add_dimension_roundtrip(S, time_id, new_dimension):
+    cube = Cube([TimeDimension(time_id, "month", "2010-01", "2010-02")], S)
+    cube.createStoredMeasure("measure1", {"time": "sum"}, "float32", 0)
+    cube.createStoredMeasure("measure2", {"time": "average"}, "float32", 0)
+    cube.hydrateFromSparseNestedObject("measure1", {"2010-01": 100, "2010-02": 100})
+    cube.hydrateFromSparseNestedObject("measure2", {"2010-01": 100, "2010-02": 100})
+    new = cube.addDimension(new_dimension, {"measure1": "sum", "measure2": "average"})
+    for m in ("measure1", "measure2"):
+        check(new.removeDimension(new_dimension.id).getNestedObject(m), cube.getNestedObject(m))
+
+
+def kat_add_generic_dimension(S):  # cube-dimension.js:7-41
+    _add_dimension_roundtrip(S, "time", GenericDimension("location", "city", ["paris", "madrid", "berlin"]))
+
+
+def kat_add_time_dimension(S):  # cube-dimension.js:43-78
+    _add_dimension_roundtrip(S, "time1", TimeDimension("time2", "week_mon", "2010-W01-mon", "2010-W08-mon"))
+
+
+def kat_remove_dimension_all_aggregations(S):  # cube-dimension.js:81-145
+    period = GenericDimension("period", "season", ["summer", "winter"])
+    location = GenericDimension("location", "city", ["paris", "toledo", "tokyo"])
+    cube = Cube([location, period], S)
+    for agg in ("sum", "average", "highest", "lowest", "first", "last"):
+        cube.createStoredMeasure(f"antennas_{agg}", {"period": agg, "location": agg}, "float32", 0)
+        cube.setNestedArray(f"antennas_{agg}", [[1, 2], [4, 8], [16, 32]])
+    cube = cube.removeDimension("location")
+    check(cube.getNestedArray("antennas_sum"), [21, 42])
+    check(cube.getNestedArray("antennas_average"), [21 / 3, 42 / 3])
+    check(cube.getNestedArray("antennas_highest"), [16, 32])
+    check(cube.getNestedArray("antennas_lowest"), [1, 2])
+    check(cube.getNestedArray("antennas_first"), [1, 2])
+    check(cube.getNestedArray("antennas_last"), [16, 32])
+
+
+def kat_remove_dimension_empty(S):  # cube-dimension.js:147-171
+    cube = Cube(
+        [GenericDimension("location", "root", ["paris", "madrid", "berlin"]),
+         TimeDimension("time", "month", "2010-01", "2010-02")], S)
+    cube.createStoredMeasure("measure1", {}, "float32", 0)
+    zero = {"2010-01": 0, "2010-02": 0}
+    check(cube.getNestedObject("measure1"), {"paris": zero, "madrid": zero, "berlin": zero})
+    check(cube.removeDimension("location").getNestedObject("measure1"), zero)
+
+
+def kat_remove_dimension_sparse(S):  # cube-dimension.js:173-207
+    cube = Cube(
+        [GenericDimension("location", "root", ["paris", "madrid", "berlin"]),
+         TimeDimension("time", "month", "2010-01", "2010-02")], S)
+    cube.createStoredMeasure("measure1", {}, "float32", 0)
+    data = {
+        "paris": {"2010-01": 10, "2010-02": 0},
+        "madrid": {"2010-01": 0, "2010-02": 5},
+        "berlin": {"2010-01": 0, "2010-02": 10},
+    }
+    cube.hydrateFromSparseNestedObject("measure1", data)
+    check(cube.getNestedObject("measure1"), data)
+    check(cube.removeDimension("location").getNestedObject("measure1"), {"2010-01": 10, "2010-02": 15})
+
+
+def kat_reorder_2d(S):  # cube-dimension.js:217-227
+    cube = create_test_cube(S)
+    check(cube.reorderDimensions(["period", "location"]).getNestedArray("antennas"), [[1, 4, 16], [2, 8, 32]])
+
+
+def kat_reorder_3d(S):  # cube-dimension.js:229-278
+    cube = Cube(
+        [GenericDimension("dim1", "item", ["11", "12"]),
+         GenericDimension("dim2", "item", ["21", "22"]),
+         GenericDimension("dim3", "item", ["31", "32"])], S)
+    cube.createStoredMeasure("main")
+    cube.setData("main", [1, 2, 3, 4, 5, 6, 7, 8])
+    check(cube.reorderDimensions(["dim1", "dim2", "dim3"]).getNestedObject("main"),
+          {"11": {"21": {"31": 1, "32": 2}, "22": {"31": 3, "32": 4}},
+           "12": {"21": {"31": 5, "32": 6}, "22": {"31": 7, "32": 8}}})
+    check(cube.reorderDimensions(["dim1", "dim3", "dim2"]).getNestedObject("main"),
+          {"11": {"31": {"21": 1, "22": 3}, "32": {"21": 2, "22": 4}},
+           "12": {"31": {"21": 5, "22": 7}, "32": {"21": 6, "22": 8}}})
+    check(cube.reorderDimensions(["dim3", "dim2", "dim1"]).getNestedObject("main"),
+          {"31": {"21": {"11": 1, "12": 5}, "22": {"11": 3, "12": 7}},
+           "32": {"21": {"11": 2, "12": 6}, "22": {"11": 4, "12": 8}}})
+    check(cube.reorderDimensions(["dim3", "dim1", "dim2"]).getNestedObject("main"),
+          {"31": {"11": {"21": 1, "22": 3}, "12": {"21": 5, "22": 7}},
+           "32": {"11": {"21": 2, "22": 4}, "12": {"21": 6, "22": 8}}})
+
+
+# ----------------------------------------------------------- cube-filtering.js
+def kat_slice(S):  # cube-filtering.js:11-45
+    cube = create_test_cube(S)
+    paris = cube.slice("location", "city", "paris")
+    check(paris.getNestedArray("antennas"), [1, 2])
+    assert [d.id for d in paris.dimensions] == ["period"]
+    winter = cube.slice("period", "season", "winter")
+    check(winter.getNestedArray("antennas"), [2, 8, 32])
+    assert [d.id for d in winter.dimensions] == ["location"]
+    tol_win = cube.slice("period", "season", "winter").slice("location", "city", "toledo")
+    check(tol_win.getNestedArray("antennas"), 8)
+    assert len(tol_win.dimensions) == 0
+    empty = cube.slice("period", "all", "all").slice("location", "all", "all")
+    check(empty.getNestedArray("antennas"), 63)
+    assert len(empty.dimensions) == 0
+
+
+def kat_dice(S):  # cube-filtering.js:47-119
+    cube = create_test_cube(S)
+    assert cube.dice("location", "city", ["paris", "toledo", "tokyo"]) is cube
+    check(cube.dice("location", "city", ["paris", "toledo"]).getNestedArray("antennas"), [[1, 2], [4, 8]])
+    check(cube.dice("location", "city", ["toledo", "paris"]).getNestedArray("antennas"), [[1, 2], [4, 8]])
+    check(cube.dice("location", "continent", ["europe"]).getNestedArray("antennas"), [[1, 2], [4, 8]])
+    check(cube.dice("period", "season", ["winter"]).getNestedArray("antennas"), [[2], [8], [32]])
+    assert cube.dice("location", "city", ["nonexisting", "paris"]).storeSize == cube.storeSize / 3
+    assert cube.dice("location", "city", []).storeSize == 0
+    check(cube.dice("location", "city", ["toledo", "paris"], True).getNestedArray("antennas"), [[4, 8], [1, 2]])
+    try:
+        cube.dice("location", "continent", ["europe"], True)
+    except Exception:
+        pass
+    else:
+        raise AssertionError("reordering on a group attribute must throw")
+
+
+# ----------------------------------------------------------- cube-accessors.js
+def kat_accessors(S):  # cube-accessors.js:13-67
+    cube = create_test_cube(S)
+    assert cube.storeSize == 6
+    assert cube.byteLength == 48
+    check(cube.getData("antennas"), [1, 2, 4, 8, 16, 32])
+    check(cube.getNestedArray("antennas"), [[1, 2], [4, 8], [16, 32]])
+    check(cube.getNestedObject("antennas"),
+          {"paris": {"summer": 1, "winter": 2}, "toledo": {"summer": 4, "winter": 8},
+           "tokyo": {"summer": 16, "winter": 32}})
+    check(cube.getNestedObject("antennas", True),
+          {"paris": {"summer": 1, "winter": 2, "all": 3}, "toledo": {"summer": 4, "winter": 8, "all": 12},
+           "tokyo": {"summer": 16, "winter": 32, "all": 48}, "all": {"summer": 21, "winter": 42, "all": 63}})
+    zero_dim = Cube([], S)
+    zero_dim.createStoredMeasure("antennas")
+    zero_dim.setData("antennas", [32])
+    check(zero_dim.getNestedObject("antennas", True), 32)
+    check(cube.getData("router_by_antennas"), [3 / 1, 2 / 2, 4 / 4, 9 / 8, 16 / 16, 32 / 32])
+
+
+def kat_setters(S):  # cube-accessors.js:70-100
+    cube = create_test_cube(S, True, False)
+    cube.setData("antennas", [1, 2, 4, 8, 16, 32])
+    check(cube.getData("antennas"), [1, 2, 4, 8, 16, 32])
+    cube = create_test_cube(S, True, False)
+    cube.setNestedArray("antennas", [[1, 2], [4, 8], [16, 32]])
+    check(cube.getData("antennas"), [1, 2, 4, 8, 16, 32])
+    cube = create_test_cube(S, True, False)
+    cube.setNestedObject("antennas", {"paris": {"summer": 1, "winter": 2}, "toledo": {"summer": 4, "winter": 8},
+                                      "tokyo": {"summer": 16, "winter": 32}})
+    check(cube.getData("antennas"), [1, 2, 4, 8, 16, 32])
+    try:
+        cube.setData("antennas", [1, 2, 3])
+    except ValueError as e:
+        assert "value length is invalid: 6 !== 3" in str(e)  # in-memory.js:40-43
+    else:
+        raise AssertionError("setData with a wrong length must throw")
+
+
+def kat_hydrate_sparse(S):  # cube-accessors.js:102-144
+    def mk():
+        cube = Cube([GenericDimension("period", "season", ["summer", "winter"]),
+                     GenericDimension("location", "city", ["paris", "toledo", "tokyo"])], S)
+        cube.createStoredMeasure("antennas", {}, "float32", 0)
+        return cube
+
+    expected = {"summer": {"paris": 0, "toledo": 0, "tokyo": 0}, "winter": {"paris": 0, "toledo": 1, "tokyo": 0}}
+    cube = mk()
+    cube.hydrateFromSparseNestedObject("antennas", {"winter": {"toledo": 1}})
+    check(cube.getNestedObject("antennas"), expected)
+    cube = mk()
+    cube.hydrateFromSparseNestedObject("antennas", {"winter": {"toledo": 1, "losangeles": 2}})
+    check(cube.getNestedObject("antennas"), expected)
+    cube = create_test_cube(S)
+    cube.hydrateFromSparseNestedObject("antennas", {"toledo": {"summer": None}})
+    assert cube.getData("antennas")[2] == 0
+    assert cube.getStatusMap("antennas").get(2) is None
+    assert sorted(cube.getStatusMap("antennas").keys()) == [0, 1, 3, 4, 5]
+
+
+# ------------------------------------------------------------- cube-to-cube.js
+def kat_compose_nan_operators(S):  # cube-to-cube.js:346-382
+    cube1 = Cube([TimeDimension("time", "month", "2010-01", "2010-02")], S)
+    cube1.createStoredMeasure("antennas", {}, "float32", NaN)
+    cube1.setNestedArray("antennas", [1, 2])
+    cube2 = Cube([TimeDimension("time", "month", "2010-03", "2010-04")], S)
+    cube2.createStoredMeasure("routers", {}, "float32", NaN)
+    cube2.setNestedArray("routers", [3, 2])
+    new = cube1.compose(cube2, True)
+    new.createComputedMeasure("safe_sum", "antennas + routers")
+    new.createComputedMeasure("unsafe_sum", "antennas || routers")
+    assert new.dimensionIds == ["time"]
+    check(new.getData("antennas"), [1, 2, NaN, NaN])
+    check(new.getData("routers"), [NaN, NaN, 3, 2])
+    check(new.getData("safe_sum"), [NaN, NaN, NaN, NaN])
+    check(new.getData("unsafe_sum"), [1, 2, 3, 2])
+
+
+def kat_compose_different_roots(S):  # cube-to-cube.js:384-400
+    cube1 = Cube([TimeDimension("time", "month", "2010-01", "2010-04")], S)
+    cube1.createStoredMeasure("antennas", {}, "float32", NaN)
+    cube1.setNestedArray("antennas", [1, 2, 4, 8])
+    cube2 = Cube([TimeDimension("time", "quarter", "2010-Q1", "2010-Q3")], S)
+    cube2.createStoredMeasure("routers", {}, "float32", NaN)
+    cube2.setNestedArray("routers", [16, 32, 64])
+    new = cube1.compose(cube2, True)
+    assert new.dimensionIds == ["time"]
+    check(new.getData("antennas"), [7, 8, NaN])
+    check(new.getData("routers"), [16, 32, 64])
+
+
+def _big(S, dtype="uint32"):
+    cube = Cube([GenericDimension("period", "season", ["summer", "winter"]),
+                 GenericDimension("location", "city", ["paris", "toledo", "tokyo"])], S)
+    cube.createStoredMeasure("antennas", {}, dtype, 0)
+    return cube
+
+
+def kat_hydrate_from_cube(S):  # cube-to-cube.js:403-529
+    zero = {"paris": 0, "toledo": 0, "tokyo": 0}
+    # other cube lacks the measure (404-424)
+    cube = _big(S)
+    cube2 = Cube([GenericDimension("period", "season", ["winter"]),
+                  GenericDimension("location", "city", ["paris", "tokyo"])], S)
+    cube2.createStoredMeasure("otherMeasure", {}, "uint32", NaN)
+    cube.hydrateFromCube(cube2)
+    check(cube.getNestedObject("antennas"), {"summer": zero, "winter": zero})
+    # extra measures in the small cube (426-451)
+    cube = _big(S)
+    cube2 = Cube([GenericDimension("period", "season", ["winter"]),
+                  GenericDimension("location", "city", ["paris", "tokyo"])], S)
+    cube2.createStoredMeasure("antennas", {}, "uint32")
+    cube2.setNestedObject("antennas", {"winter": {"paris": 10, "tokyo": 20}})
+    cube2.createStoredMeasure("otherMeasure", {}, "uint32")
+    cube2.setNestedObject("otherMeasure", {"winter": {"paris": 30, "tokyo": 40}})
+    cube.hydrateFromCube(cube2)
+    check(cube.getNestedObject("antennas"), {"summer": zero, "winter": {"paris": 10, "toledo": 0, "tokyo": 20}})
+    # items that do not fit are dropped, order differs (476-503)
+    cube = _big(S)
+    cube2 = Cube([GenericDimension("period", "season", ["winter"]),
+                  GenericDimension("location", "city", ["tokyo", "losangeles", "paris"])], S)
+    cube2.createStoredMeasure("antennas", {}, "uint32", 0)
+    cube2.setNestedObject("antennas", {"winter": {"tokyo": 1, "losangeles": 2, "paris": 3}})
+    cube.hydrateFromCube(cube2)
+    check(cube.getNestedObject("antennas"), {"summer": zero, "winter": {"paris": 3, "toledo": 0, "tokyo": 1}})
+    # one extra dimension in the small cube is summed away (505-529)
+    cube = _big(S)
+    cube2 = Cube([GenericDimension("period", "season", ["winter"]),
+                  GenericDimension("something", "root", ["a", "b", "c"]),
+                  GenericDimension("location", "city", ["paris", "tokyo"])], S)
+    cube2.createStoredMeasure("antennas", {}, "uint32", 0)
+    cube2.setNestedObject("antennas", {"winter": {"a": {"paris": 1, "tokyo": 2}, "b": {"paris": 3, "tokyo": 4},
+                                                  "c": {"paris": 5, "tokyo": 6}}})
+    cube.hydrateFromCube(cube2)
+    check(cube.getNestedObject("antennas"), {"summer": zero, "winter": {"paris": 9, "toledo": 0, "tokyo": 12}})
+
+
+def kat_hydrate_missing_dimension_int_rounding(S):  # cube-to-cube.js:531-551  (32 -> 11,10,11)
+    cube = _big(S)
+    cube2 = Cube([GenericDimension("period", "season", ["winter"])], S)
+    cube2.createStoredMeasure("antennas", {}, "uint32", 0)
+    cube2.setNestedObject("antennas", {"winter": 32})
+    cube.hydrateFromCube(cube2)
+    check(cube.getNestedObject("antennas"),
+          {"summer": {"paris": 0, "toledo": 0, "tokyo": 0}, "winter": {"paris": 11, "toledo": 10, "tokyo": 11}})
+
+
+def kat_hydrate_drillup_needed(S):  # cube-to-cube.js:553-579
+    cube = Cube([TimeDimension("time", "quarter", "2010-Q1", "2010-Q3"),
+                 GenericDimension("location", "city", ["paris", "toledo", "tokyo"])], S)
+    cube.createStoredMeasure("antennas", {}, "uint32", 0)
+    cube2 = Cube([TimeDimension("time", "month", "2010-04", "2010-06"),
+                  GenericDimension("location", "city", ["toledo"])], S)
+    cube2.createStoredMeasure("antennas", {}, "uint32", 0)
+    cube2.setNestedObject("antennas", {"2010-04": {"toledo": 1}, "2010-05": {"toledo": 2}, "2010-06": {"toledo": 3}})
+    cube.hydrateFromCube(cube2)
+    zero = {"paris": 0, "toledo": 0, "tokyo": 0}
+    check(cube.getNestedObject("antennas"),
+          {"2010-Q1": zero, "2010-Q2": {"paris": 0, "toledo": 6, "tokyo": 0}, "2010-Q3": zero})
+
+
+def kat_hydrate_drilldown_needed(S):  # cube-to-cube.js:581-605  (100 -> 34,33,33)
+    cube = Cube([TimeDimension("time", "month", "2010-01", "2010-06"),
+                 GenericDimension("location", "city", ["paris", "toledo", "tokyo"])], S)
+    cube.createStoredMeasure("antennas", {}, "uint32", 0)
+    cube2 = Cube([TimeDimension("time", "quarter", "2010-Q2", "2010-Q2"),
+                  GenericDimension("location", "city", ["toledo"])], S)
+    cube2.createStoredMeasure("antennas", {}, "uint32", 0)
+    cube2.setNestedObject("antennas", {"2010-Q2": {"toledo": 100}})
+    cube.hydrateFromCube(cube2)
+    zero = {"paris": 0, "toledo": 0, "tokyo": 0}
+    check(cube.getNestedObject("antennas"),
+          {"2010-01": zero, "2010-02": zero, "2010-03": zero,
+           "2010-04": {"paris": 0, "toledo": 34, "tokyo": 0},
+           "2010-05": {"paris": 0, "toledo": 33, "tokyo": 0},
+           "2010-06": {"paris": 0, "toledo": 33, "tokyo": 0}})
+
+
+def kat_compose_intersection(S):  # cube-to-cube.js:6-48
+    period = GenericDimension("period", "season", ["summer", "winter"])
+    location = GenericDimension("location", "city", ["paris", "toledo", "tokyo"])
+    cube1 = Cube([location, period], S)
+    cube1.createStoredMeasure("antennas")
+    cube1.setNestedArray("antennas", [[1, 2], [4, 8], [16, 32]])
+    cube2 = Cube([location, period], S)
+    cube2.createStoredMeasure("routers")
+    cube2.setNestedArray("routers", [[3, 2], [4, 9], [16, 32]])
+    new = cube1.compose(cube2)
+    assert new.dimensionIds == ["location", "period"]
+    check(new.getNestedArray("routers"), [[3, 2], [4, 9], [16, 32]])
+    check(new.getNestedArray("antennas"), [[1, 2], [4, 8], [16, 32]])
+
+
+ALL_KATS = [v for k, v in sorted(globals().items()) if k.startswith("kat_")]
