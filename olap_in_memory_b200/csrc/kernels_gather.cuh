@@ -1,0 +1,229 @@
+// Output-driven gather kernels: dice (in-memory.js:213-263), reorder (178-211),
+// drillDown (336-430) and the scatter of load (139-176).
+//
+// All four are "re-index every cell through one small table per dimension".  The host
+// folds each dimension's map and the source stride into an int64 offset table
+//     tbl_d[new coordinate] = old coordinate * old stride
+// so the source offset of an output cell is a sum of D table reads.  Trailing
+// dimensions that are untouched and contiguous on both sides are merged into an inner
+// run of length I that is moved with 128-bit accesses.
+#pragma once
+#include "common.cuh"
+
+namespace olap {
+
+struct GatherMeasure {
+    const float* in;
+    float* out;
+    const uint8_t* st_in;
+    uint8_t* st_out;
+    const double* dist;  // drillDown distributions (nullable)
+    int64_t dist_len;
+    int nan_default;
+    int int_rounding;  // store type is int32/uint32 (in-memory.js:343)
+    int method_is_sum;
+};
+
+// one new-side dimension of a gather: either linear (offset = coord * stride) or a table
+struct GDim {
+    int64_t len = 1;
+    bool linear = true;
+    int64_t stride = 0;
+    std::vector<int64_t> tbl;
+    std::vector<int2> aux;  // drillDown only
+};
+
+enum GatherMode { G_COPY = 0, G_DOWN = 1 };
+
+struct GatherParams {
+    const GatherMeasure* meas;
+    int nd;                              // outer dimensions (tables)
+    uint32_t len[OLAP_MAX_DIMS];         // new length of each outer dimension
+    FastDiv div[OLAP_MAX_DIMS];
+    const int64_t* tbl[OLAP_MAX_DIMS];   // source offset contribution per new coordinate, or
+    int64_t lin[OLAP_MAX_DIMS];          // nullptr: the contribution is coordinate * lin[d]
+    const int2* aux[OLAP_MAX_DIMS];      // drillDown: {siblings, rank among siblings}; nullable
+    int64_t I;                           // inner run (elements), contiguous on both sides
+    uint32_t IV;                         // I / VEC
+    FastDiv div_iv;
+    int64_t n_vec;                       // rows * IV
+    int64_t rows;
+    int64_t new_size, old_size;          // for the distributions index formula
+    int* error_flag;                     // set to 1 + dist index when a distribution is missing
+};
+
+// in-memory.js:383-427 for one cell: `v` parent value, `n` siblings, `k` rank.
+__device__ __forceinline__ float down_value(const GatherMeasure& m, const GatherParams& p, float v, uint32_t n,
+                                            uint32_t k, int64_t new_idx, bool& ok) {
+    ok = false;
+    if (v == 0.0f || v != v) return default_of(m.nan_default);  // `if (!oldValue) continue`
+    double r;
+    if (m.dist) {
+        const int64_t added = p.new_size / p.old_size;
+        const int64_t shared = m.dist_len / added;
+        const int64_t di = (new_idx / (p.new_size / (shared > 0 ? shared : 1))) * added + (new_idx % added);
+        const double w = (di >= 0 && di < m.dist_len) ? m.dist[di] : __longlong_as_double(0x7ff8000000000000ll);
+        if (w != w) {
+            atomicCAS(p.error_flag, 0, (int)(di < 0x7ffffffe ? di + 1 : 0x7fffffff));
+            return default_of(m.nan_default);
+        }
+        r = (double)v * w;
+    } else if (m.method_is_sum) {
+        if (m.int_rounding) {
+            const double dn = (double)n;
+            const double base = floor((double)v / dn);
+            const double step = fmod((double)v, dn) / dn;
+            const bool last_is_same = floor((double)k * step) == floor(((double)k - 1.0) * step);
+            r = last_is_same ? base : base + 1.0;
+        } else {
+            r = (double)v / (double)n;
+        }
+    } else {
+        r = (double)v;
+    }
+    const float f = canon_store((float)r, m.nan_default);
+    ok = present_f(f, m.nan_default);
+    return f;
+}
+
+template <int MODE, int VEC, bool BIG>
+__global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ GatherParams p) {
+    constexpr int U = 2;  // independent vectors per thread
+    const GatherMeasure m = p.meas[blockIdx.y];
+    const int64_t base = (int64_t)blockIdx.x * (256 * U) + threadIdx.x;
+
+    int64_t src_off[U], dst_off[U];
+    uint32_t sib[U], rank[U];
+    bool live[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t t = base + u * 256;
+        live[u] = t < p.n_vec;
+        int64_t row;
+        uint32_t colv;
+        if (BIG) {
+            row = t / p.IV;
+            colv = (uint32_t)(t - row * p.IV);
+        } else {
+            const uint32_t r32 = p.div_iv.div((uint32_t)t);
+            colv = (uint32_t)t - r32 * p.IV;
+            row = r32;
+        }
+        int64_t off = (int64_t)colv * VEC;
+        dst_off[u] = row * p.I + off;
+        uint32_t n = 1, k = 0;
+        if (live[u]) {
+            if (BIG) {
+                int64_t rest = row;
+                for (int d = p.nd - 1; d >= 0; --d) {
+                    const int64_t q = rest / p.len[d];
+                    const uint32_t c = (uint32_t)(rest - q * p.len[d]);
+                    rest = q;
+                    off += p.tbl[d] ? p.tbl[d][c] : (int64_t)c * p.lin[d];
+                    if (MODE == G_DOWN && p.aux[d]) {
+                        const int2 a = p.aux[d][c];
+                        k += (uint32_t)a.y * n;  // ranks compose last-dimension-fastest
+                        n *= (uint32_t)a.x;
+                    }
+                }
+            } else {
+                uint32_t rest = (uint32_t)row;
+                for (int d = p.nd - 1; d >= 0; --d) {
+                    const uint32_t q = p.div[d].div(rest);
+                    const uint32_t c = rest - q * p.len[d];
+                    rest = q;
+                    off += p.tbl[d] ? p.tbl[d][c] : (int64_t)c * p.lin[d];
+                    if (MODE == G_DOWN && p.aux[d]) {
+                        const int2 a = p.aux[d][c];
+                        k += (uint32_t)a.y * n;
+                        n *= (uint32_t)a.x;
+                    }
+                }
+            }
+        }
+        src_off[u] = off;
+        sib[u] = n;
+        rank[u] = k;
+    }
+
+    float v[U][VEC];
+    uint32_t s[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        s[u] = 0;
+        if (!live[u]) continue;
+        if (VEC == 4) {
+            const float4 t = ld_stream4(m.in + src_off[u]);
+            v[u][0] = t.x; v[u][1 % VEC] = t.y; v[u][2 % VEC] = t.z; v[u][3 % VEC] = t.w;
+            if (m.st_in) s[u] = ld_stream_u32(m.st_in + src_off[u]);
+        } else {
+            v[u][0] = ld_stream1(m.in + src_off[u]);
+            if (m.st_in) s[u] = m.st_in[src_off[u]];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (!live[u]) continue;
+        if (MODE == G_DOWN) {
+            uint32_t so = 0;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                bool ok;
+                v[u][e] = down_value(m, p, v[u][e], sib[u], rank[u], dst_off[u] + e, ok);
+                const uint32_t sb = (s[u] >> (8 * e)) & 0xffu;
+                so |= (ok ? ((sb | OLAP_STATUS_INTERPOLATED) & 0xffu) : (uint32_t)OLAP_STATUS_UNSET) << (8 * e);
+            }
+            s[u] = so;
+        }
+        if (VEC == 4) {
+            st_stream4(m.out + dst_off[u], make_float4(v[u][0], v[u][1 % VEC], v[u][2 % VEC], v[u][3 % VEC]));
+            if (m.st_out) *reinterpret_cast<uint32_t*>(m.st_out + dst_off[u]) = s[u];
+        } else {
+            m.out[dst_off[u]] = v[u][0];
+            if (m.st_out) m.st_out[dst_off[u]] = (uint8_t)s[u];
+        }
+    }
+}
+
+// ---- load: input-driven scatter  dst[mine(his)] = src[his]  (in-memory.js:159-175).
+// Tables hold my offset contribution per his coordinate, or -1 when I lack the item
+// (then the cell is dropped).  His items are distinct, so the scatter is injective.
+struct ScatterParams {
+    const float* src;
+    float* dst;
+    const uint8_t* st_src;
+    uint8_t* st_dst;
+    int dst_nan_default;
+    int src_nan_default;
+    int nd;
+    int64_t len[OLAP_MAX_DIMS];
+    const int64_t* tbl[OLAP_MAX_DIMS];
+    int64_t n;
+};
+
+__global__ void __launch_bounds__(256) load_scatter_kernel(const __grid_constant__ ScatterParams p) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.n) return;
+    int64_t rest = t, off = 0;
+    bool drop = false;
+    for (int d = p.nd - 1; d >= 0; --d) {
+        const int64_t q = rest / p.len[d];
+        const int64_t c = rest - q * p.len[d];
+        rest = q;
+        const int64_t o = p.tbl[d][c];
+        drop |= o < 0;
+        off += o;
+    }
+    if (drop) return;
+    // otherStore.getValue(): unset cells read as HIS default; setValue() applies MY presence rule
+    const float v = p.src[t];
+    p.dst[off] = canon_store(v, p.dst_nan_default);
+    if (p.st_dst) {
+        const bool set = present_f(canon_store(v, p.dst_nan_default), p.dst_nan_default);
+        uint8_t s = set ? OLAP_STATUS_SET : OLAP_STATUS_UNSET;
+        if (p.st_src && set) s = p.st_src[t];  // "status flags are copied between cubes" README.md:704
+        p.st_dst[off] = s;
+    }
+}
+
+}  // namespace olap

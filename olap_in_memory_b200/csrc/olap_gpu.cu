@@ -1,0 +1,1101 @@
+// libolapgpu.so — C ABI (include/olap_gpu.h) over the sm_100a kernels.
+// Host logic here: argument validation with the reference's error texts, lowering of
+// the per-dimension int32 maps to CSR / offset tables, shape canonicalisation
+// ([O, C, I] view, merging of untouched axes), launch configuration.
+#include <math.h>
+#include <stdarg.h>
+
+#include <algorithm>
+#include <numeric>
+
+#include "common.cuh"
+#include "jit_eval.cuh"
+#include "kernels_drillup.cuh"
+#include "kernels_gather.cuh"
+#include "kernels_store.cuh"
+#include "kernels_tile.cuh"
+
+namespace olap {
+
+thread_local std::string g_error;
+Ctx g;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[2048];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define LAUNCHED() (++::olap::g_launches)
+
+int ensure_ctx() {
+    if (g.ready) {
+        // the calling thread may not have the device current yet
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cur != g.device) OLAP_CUDA(cudaSetDevice(g.device));
+        return OLAP_OK;
+    }
+    return olap_init(0);
+}
+
+static void begin_op() {
+    if (g.ev0) cudaEventRecord(g.ev0, g.stream);
+}
+static void end_op(const char* path) {
+    if (g.ev1) cudaEventRecord(g.ev1, g.stream);
+    g.timing_pending = true;
+    g.last_path = path;
+}
+
+int finish_op() {
+    OLAP_CUDA(cudaGetLastError());
+    if (!g.async) OLAP_CUDA(cudaStreamSynchronize(g.stream));
+    return OLAP_OK;
+}
+
+int dev_alloc(void** p, size_t bytes) {
+    *p = nullptr;
+    if (bytes == 0) bytes = 256;
+    cudaError_t e = cudaMallocAsync(p, bytes, g.stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? OLAP_E_NOMEM : OLAP_E_CUDA,
+                    "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return OLAP_OK;
+}
+int dev_free(void* p) {
+    if (p) OLAP_CUDA(cudaFreeAsync(p, g.stream));
+    return OLAP_OK;
+}
+
+static size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+int alloc_batch(int n, int64_t size, const int* types, const int* default_kinds, bool with_status,
+                bool shared_status, olap_store** out) {
+    const size_t vplane = pad256((size_t)size * sizeof(float));
+    const size_t splane = with_status ? pad256((size_t)size) : 0;
+    const int n_status = with_status ? (shared_status ? 1 : n) : 0;
+    const size_t bytes = vplane * n + splane * n_status;
+    Arena* arena = new Arena();
+    int rc = dev_alloc(&arena->base, bytes);
+    if (rc != OLAP_OK) { delete arena; return rc; }
+    arena->bytes = bytes;
+    arena->refs = n;
+    char* base = static_cast<char*>(arena->base);
+    for (int k = 0; k < n; ++k) {
+        olap_store* s = new olap_store();
+        s->size = size;
+        s->type = types[k];
+        s->default_kind = default_kinds[k];
+        s->values = reinterpret_cast<float*>(base + vplane * k);
+        s->status = with_status ? reinterpret_cast<uint8_t*>(base + vplane * n + splane * (shared_status ? 0 : k)) : nullptr;
+        s->arena = arena;
+        out[k] = s;
+    }
+    return OLAP_OK;
+}
+
+size_t TablePack::add(const void* data, size_t bytes) {
+    const size_t off = (host.size() + 15) & ~(size_t)15;
+    host.resize(off + bytes);
+    if (bytes) memcpy(host.data() + off, data, bytes);
+    return off;
+}
+
+int TablePack::upload() {
+    const size_t bytes = host.size();
+    OLAP_TRY(dev_alloc(&dev, bytes));
+    if (!bytes) return OLAP_OK;
+    if (g.pin_busy) {
+        OLAP_CUDA(cudaEventSynchronize(g.pin_free));
+        g.pin_busy = false;
+    }
+    if (g.pin_cap < bytes) {
+        if (g.pin) cudaFreeHost(g.pin);
+        g.pin = nullptr;
+        g.pin_cap = 0;
+        const size_t cap = std::max(bytes * 2, (size_t)1 << 20);
+        OLAP_CUDA(cudaHostAlloc((void**)&g.pin, cap, cudaHostAllocDefault));
+        g.pin_cap = cap;
+    }
+    memcpy(g.pin, host.data(), bytes);
+    OLAP_CUDA(cudaMemcpyAsync(dev, g.pin, bytes, cudaMemcpyHostToDevice, g.stream));
+    OLAP_CUDA(cudaEventRecord(g.pin_free, g.stream));
+    g.pin_busy = true;
+    return OLAP_OK;
+}
+
+int TablePack::release() {
+    int rc = dev_free(dev);
+    dev = nullptr;
+    return rc;
+}
+
+static int grid_for(int64_t n, int per_block) {
+    const int64_t want = ceil_div(n, per_block);
+    const int64_t cap = (int64_t)g.sm_count * 32;
+    return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+
+static bool mul_overflow(int64_t a, int64_t b, int64_t* out) { return __builtin_mul_overflow(a, b, out); }
+
+static int product(const int64_t* len, int nd, int64_t* out, const char* what) {
+    int64_t p = 1;
+    for (int d = 0; d < nd; ++d) {
+        if (len[d] < 0) return fail(OLAP_E_INVALID, "%s: negative dimension length", what);
+        if (mul_overflow(p, len[d], &p)) return fail(OLAP_E_INVALID, "%s: cube size overflows int64", what);
+    }
+    *out = p;
+    return OLAP_OK;
+}
+
+static int check_batch(olap_store* const* src, int n, const char* what, int64_t* size) {
+    if (!src || n < 1 || n > OLAP_MAX_MEASURES) return fail(OLAP_E_INVALID, "%s: 1..%d stores expected", what, OLAP_MAX_MEASURES);
+    for (int k = 0; k < n; ++k) {
+        if (!src[k]) return fail(OLAP_E_INVALID, "%s: null store", what);
+        if (src[k]->size != src[0]->size) return fail(OLAP_E_INVALID, "%s: stores of one call must have the same size", what);
+    }
+    *size = src[0]->size;
+    return OLAP_OK;
+}
+
+// Result stores of a transform: same type/default as their source, one arena.
+static int alloc_like(olap_store* const* src, int n, int64_t new_size, olap_store** out) {
+    int types[OLAP_MAX_MEASURES], defaults[OLAP_MAX_MEASURES];
+    bool with_status = true, shared = n > 1;
+    for (int k = 0; k < n; ++k) {
+        types[k] = src[k]->type;
+        defaults[k] = src[k]->default_kind;
+        with_status &= src[k]->status != nullptr;
+        shared &= src[k]->status == src[0]->status;
+    }
+    return alloc_batch(n, new_size, types, defaults, with_status, with_status && shared, out);
+}
+
+static int fill_default(olap_store* s) {
+    if (s->size == 0) return OLAP_OK;
+    fill_kernel<<<grid_for(s->size, kStoreThreads), kStoreThreads, 0, g.stream>>>(
+        s->values, s->status, s->size, s->default_kind ? __builtin_nanf("") : 0.0f, OLAP_STATUS_UNSET);
+    LAUNCHED();
+    return OLAP_OK;
+}
+
+// status planes that several stores share must be written by one of them only
+static const uint8_t* st_in_of(olap_store* const* src, int k) {
+    for (int q = 0; q < k; ++q)
+        if (src[q]->status == src[k]->status) return nullptr;
+    return src[k]->status;
+}
+static uint8_t* st_out_of(olap_store** out, int k) {
+    for (int q = 0; q < k; ++q)
+        if (out[q]->status == out[k]->status) return nullptr;
+    return out[k]->status;
+}
+
+// ---------------------------------------------------------------- drillUp
+struct Csr {
+    std::vector<int32_t> pstart, children;
+    bool contiguous = true;
+};
+
+static Csr build_csr(const int32_t* map, int64_t C, int64_t P) {
+    Csr c;
+    c.pstart.assign(P + 1, 0);
+    for (int64_t i = 0; i < C; ++i) c.pstart[map[i] + 1]++;
+    for (int64_t p = 0; p < P; ++p) c.pstart[p + 1] += c.pstart[p];
+    c.children.resize(C);
+    std::vector<int32_t> fill(c.pstart.begin(), c.pstart.end() - 1);
+    for (int64_t i = 0; i < C; ++i) c.children[fill[map[i]]++] = (int32_t)i;
+    for (int64_t i = 0; i < C; ++i)
+        if (c.children[i] != i) { c.contiguous = false; break; }
+    return c;
+}
+
+static uint32_t next_pow2(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static int launch_up_mid(const UpMeasure* d_meas, int n, const Csr& csr, const int32_t* d_pstart,
+                         const int32_t* d_children, int64_t O, int64_t C, int64_t P, int64_t I) {
+    const int VEC = (I % 4 == 0) ? 4 : 1;
+    const int64_t IV_total = I / VEC;
+    // chunk the inner run so that one row of output vectors fits 32-bit math
+    const int64_t max_row = ((int64_t)1 << 30);
+    int64_t chunk_iv = IV_total;
+    if (P * IV_total > max_row) chunk_iv = std::max<int64_t>(1, max_row / P);
+    for (int64_t iv0 = 0; iv0 < IV_total; iv0 += chunk_iv) {
+        const int64_t iv_n = std::min(chunk_iv, IV_total - iv0);
+        UpMidParams p{};
+        p.meas = d_meas;
+        p.pstart = d_pstart;
+        p.children = csr.contiguous ? nullptr : d_children;
+        p.O = O; p.C = (int32_t)C; p.P = (int32_t)P;
+        p.I = iv_n * VEC;
+        p.I_total = I;
+        p.in_row = C * I;
+        p.out_row = P * I;
+        p.i_base = iv0 * VEC;
+        p.IV = (uint32_t)iv_n;
+        p.div_iv = FastDiv((uint32_t)iv_n);
+        p.row_vecs = (uint32_t)(P * iv_n);
+        p.n_measures = n;
+        const uint32_t bx = std::min<uint32_t>(256, next_pow2(p.row_vecs));
+        const uint32_t by = 256 / bx;
+        p.blocks_per_row = (uint32_t)ceil_div(p.row_vecs, bx);
+        const int64_t gx = ceil_div(O, by) * p.blocks_per_row;
+        if (gx > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "drillUp: grid too large (%lld blocks)", (long long)gx);
+        dim3 grid((unsigned)gx, (unsigned)n), block(bx, by);
+        if (VEC == 4) drillup_mid_kernel<4><<<grid, block, 0, g.stream>>>(p);
+        else drillup_mid_kernel<1><<<grid, block, 0, g.stream>>>(p);
+        LAUNCHED();
+    }
+    return OLAP_OK;
+}
+
+}  // namespace olap
+
+using namespace olap;
+
+// =====================================================================================
+extern "C" {
+
+int olap_abi_version(void) { return OLAP_ABI_VERSION; }
+
+const char* olap_last_error(void) { return g_error.c_str(); }
+
+int olap_init(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(OLAP_E_CUDA, "no CUDA device available (%s); this store has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= count) return fail(OLAP_E_INVALID, "olap_init: device %d out of range [0, %d)", device, count);
+    if (g.ready && g.device == device) return OLAP_OK;
+    if (g.ready) return fail(OLAP_E_UNSUPPORTED, "olap_init: already bound to device %d (one device per process)", g.device);
+    OLAP_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    OLAP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(OLAP_E_UNSUPPORTED, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+    g.device = device;
+    g.sm_count = prop.multiProcessorCount;
+    OLAP_CUDA(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
+    g.stream = g.own_stream;
+    OLAP_CUDA(cudaEventCreate(&g.ev0));
+    OLAP_CUDA(cudaEventCreate(&g.ev1));
+    OLAP_CUDA(cudaEventCreateWithFlags(&g.pin_free, cudaEventDisableTiming));
+    cudaMemPool_t pool;
+    OLAP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;  // keep freed blocks cached: transforms allocate every call
+    OLAP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    g.ready = true;
+    return OLAP_OK;
+}
+
+int olap_set_stream(void* cuda_stream) {
+    OLAP_TRY(ensure_ctx());
+    OLAP_CUDA(cudaStreamSynchronize(g.stream));
+    g.stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : g.own_stream;
+    return OLAP_OK;
+}
+
+int olap_set_async(int enabled) {
+    g.async = enabled != 0;
+    return OLAP_OK;
+}
+
+int olap_sync(void) {
+    OLAP_TRY(ensure_ctx());
+    OLAP_CUDA(cudaStreamSynchronize(g.stream));
+    OLAP_CUDA(cudaGetLastError());
+    return OLAP_OK;
+}
+
+int olap_method_from_name(const char* name, int* method) {
+    static const char* names[] = {"sum", "average", "highest", "lowest", "first", "last", "product"};
+    if (name)
+        for (int k = 0; k < 7; ++k)
+            if (!strcmp(name, names[k])) { *method = k; return OLAP_OK; }
+    return fail(OLAP_E_INVALID, "Unsupported aggregation method: %s", name ? name : "undefined");
+}
+
+int64_t olap_kernel_launches(void) { return g_launches.load(); }
+
+double olap_last_op_ms(void) {
+    if (!g.ready) return 0.0;
+    if (g.timing_pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(g.ev1) == cudaSuccess && cudaEventElapsedTime(&ms, g.ev0, g.ev1) == cudaSuccess) g.last_ms = ms;
+        g.timing_pending = false;
+    }
+    return g.last_ms;
+}
+
+const char* olap_last_op_path(void) { return g.last_path; }
+
+// ---- pinned host buffers for the data boundary (so H2D/D2H run at PCIe speed) ----
+int olap_host_alloc(size_t bytes, void** out) {
+    OLAP_TRY(ensure_ctx());
+    OLAP_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return OLAP_OK;
+}
+int olap_host_free(void* p) {
+    if (p) OLAP_CUDA(cudaFreeHost(p));
+    return OLAP_OK;
+}
+
+// ---- life cycle -------------------------------------------------------------------
+static int check_type_default(int type, int default_kind) {
+    if (default_kind != OLAP_DEFAULT_ZERO && default_kind != OLAP_DEFAULT_NAN)
+        return fail(OLAP_E_INVALID, "Invalid default value, only NaN and 0 are supported");
+    if (type < OLAP_INT32 || type > OLAP_FLOAT64) return fail(OLAP_E_INVALID, "Invalid type");
+    return OLAP_OK;
+}
+
+int olap_store_create_batch(int n, int64_t size, const int* types, const int* default_kinds, int with_status,
+                            int shared_status, olap_store** out) {
+    if (n < 1 || n > OLAP_MAX_MEASURES || !out) return fail(OLAP_E_INVALID, "olap_store_create_batch: 1..%d stores expected", OLAP_MAX_MEASURES);
+    if (size < 0) return fail(OLAP_E_INVALID, "olap_store_create_batch: negative size");
+    for (int k = 0; k < n; ++k) OLAP_TRY(check_type_default(types[k], default_kinds[k]));
+    OLAP_TRY(ensure_ctx());
+    OLAP_TRY(alloc_batch(n, size, types, default_kinds, with_status != 0, shared_status != 0, out));
+    for (int k = 0; k < n; ++k) {
+        olap_store tmp = *out[k];
+        tmp.status = st_out_of(out, k);
+        OLAP_TRY(fill_default(&tmp));
+    }
+    return finish_op();
+}
+
+int olap_store_create(int64_t size, int type, int default_kind, int with_status, olap_store** out) {
+    return olap_store_create_batch(1, size, &type, &default_kind, with_status, 0, out);
+}
+
+int olap_store_destroy(olap_store* s) {
+    if (!s) return OLAP_OK;
+    Arena* a = s->arena;
+    delete s;
+    if (a && --a->refs == 0) {
+        if (g.ready) cudaFreeAsync(a->base, g.stream);
+        delete a;
+    }
+    return OLAP_OK;
+}
+
+int olap_store_clone(const olap_store* s, olap_store** out) {
+    if (!s || !out) return fail(OLAP_E_INVALID, "olap_store_clone: null argument");
+    OLAP_TRY(ensure_ctx());
+    OLAP_TRY(alloc_batch(1, s->size, &s->type, &s->default_kind, s->status != nullptr, false, out));
+    if (s->size) {
+        OLAP_CUDA(cudaMemcpyAsync((*out)->values, s->values, (size_t)s->size * 4, cudaMemcpyDeviceToDevice, g.stream));
+        if (s->status) OLAP_CUDA(cudaMemcpyAsync((*out)->status, s->status, (size_t)s->size, cudaMemcpyDeviceToDevice, g.stream));
+    }
+    return finish_op();
+}
+
+int64_t olap_store_size(const olap_store* s) { return s ? s->size : -1; }
+int64_t olap_store_byte_length(const olap_store* s) {
+    if (!s) return -1;
+    return s->size * (s->type == OLAP_FLOAT64 ? 8 : 4);
+}
+int olap_store_type(const olap_store* s) { return s ? s->type : -1; }
+int olap_store_default_kind(const olap_store* s) { return s ? s->default_kind : -1; }
+int olap_store_has_status(const olap_store* s) { return s && s->status ? 1 : 0; }
+void* olap_store_values_ptr(const olap_store* s) { return s ? s->values : nullptr; }
+void* olap_store_status_ptr(const olap_store* s) { return s ? s->status : nullptr; }
+
+// ---- data boundary ------------------------------------------------------------------
+static int check_len(const olap_store* s, int64_t n) {
+    if (!s) return fail(OLAP_E_INVALID, "null store");
+    if (s->size != n) return fail(OLAP_E_INVALID, "value length is invalid: %lld !== %lld", (long long)s->size, (long long)n);
+    return OLAP_OK;
+}
+
+int olap_store_upload_f32(olap_store* s, const float* host, int64_t n) {
+    OLAP_TRY(check_len(s, n));
+    OLAP_TRY(ensure_ctx());
+    if (n == 0) return OLAP_OK;
+    OLAP_CUDA(cudaMemcpyAsync(s->values, host, (size_t)n * 4, cudaMemcpyHostToDevice, g.stream));
+    canon_f32_kernel<<<grid_for(ceil_div(n, 4), kStoreThreads), kStoreThreads, 0, g.stream>>>(s->values, s->status, n, s->default_kind);
+    LAUNCHED();
+    return finish_op();
+}
+
+int olap_store_upload_f64(olap_store* s, const double* host, int64_t n) {
+    OLAP_TRY(check_len(s, n));
+    OLAP_TRY(ensure_ctx());
+    if (n == 0) return OLAP_OK;
+    void* tmp;
+    OLAP_TRY(dev_alloc(&tmp, (size_t)n * 8));
+    OLAP_CUDA(cudaMemcpyAsync(tmp, host, (size_t)n * 8, cudaMemcpyHostToDevice, g.stream));
+    from_f64_kernel<<<grid_for(n, kStoreThreads), kStoreThreads, 0, g.stream>>>((const double*)tmp, s->values, s->status, n, s->default_kind);
+    LAUNCHED();
+    OLAP_TRY(dev_free(tmp));
+    // the host buffer is borrowed for the call only
+    OLAP_CUDA(cudaStreamSynchronize(g.stream));
+    return finish_op();
+}
+
+int olap_store_download_f32(const olap_store* s, float* host, int64_t n) {
+    OLAP_TRY(check_len(s, n));
+    OLAP_TRY(ensure_ctx());
+    if (n == 0) return OLAP_OK;
+    OLAP_CUDA(cudaMemcpyAsync(host, s->values, (size_t)n * 4, cudaMemcpyDeviceToHost, g.stream));
+    OLAP_CUDA(cudaStreamSynchronize(g.stream));
+    return OLAP_OK;
+}
+
+int olap_store_download_f64(const olap_store* s, double* host, int64_t n) {
+    OLAP_TRY(check_len(s, n));
+    OLAP_TRY(ensure_ctx());
+    if (n == 0) return OLAP_OK;
+    void* tmp;
+    OLAP_TRY(dev_alloc(&tmp, (size_t)n * 8));
+    to_f64_kernel<<<grid_for(n, kStoreThreads), kStoreThreads, 0, g.stream>>>(s->values, (double*)tmp, n);
+    LAUNCHED();
+    OLAP_CUDA(cudaMemcpyAsync(host, tmp, (size_t)n * 8, cudaMemcpyDeviceToHost, g.stream));
+    OLAP_TRY(dev_free(tmp));
+    OLAP_CUDA(cudaStreamSynchronize(g.stream));
+    return OLAP_OK;
+}
+
+int olap_store_get_value(const olap_store* s, int64_t index, double* out) {
+    if (!s || !out) return fail(OLAP_E_INVALID, "olap_store_get_value: null argument");
+    OLAP_TRY(ensure_ctx());
+    if (index < 0 || index >= s->size) {  // Map.get(missing) ?? default
+        *out = s->default_kind ? NAN : 0.0;
+        return OLAP_OK;
+    }
+    float v;
+    OLAP_CUDA(cudaMemcpyAsync(&v, s->values + index, 4, cudaMemcpyDeviceToHost, g.stream));
+    OLAP_CUDA(cudaStreamSynchronize(g.stream));
+    *out = (double)v;
+    return OLAP_OK;
+}
+
+int olap_store_set_values(olap_store* s, const int64_t* indexes, const double* values, int64_t n) {
+    if (!s || (n && (!indexes || !values))) return fail(OLAP_E_INVALID, "olap_store_set_values: null argument");
+    OLAP_TRY(ensure_ctx());
+    if (n == 0) return OLAP_OK;
+    TablePack t;
+    const size_t oi = t.add(indexes, (size_t)n * 8);
+    const size_t ov = t.add(values, (size_t)n * 8);
+    OLAP_TRY(t.upload());
+    set_values_kernel<<<(unsigned)ceil_div(n, kStoreThreads), kStoreThreads, 0, g.stream>>>(
+        s->values, s->status, t.ptr<int64_t>(oi), t.ptr<double>(ov), n, s->size, s->default_kind);
+    LAUNCHED();
+    OLAP_TRY(t.release());
+    return finish_op();
+}
+
+int olap_store_set_value(olap_store* s, int64_t index, double value) { return olap_store_set_values(s, &index, &value, 1); }
+
+int olap_store_fill(olap_store* s, double value) {
+    if (!s) return fail(OLAP_E_INVALID, "olap_store_fill: null store");
+    OLAP_TRY(ensure_ctx());
+    if (s->size == 0) return OLAP_OK;
+    float v = (float)value;
+    const bool nan_default = s->default_kind != 0;
+    if (v != v) v = __builtin_nanf("");
+    if (!nan_default && v == 0.0f) v = 0.0f;
+    const bool set = nan_default ? (v == v) : (v != 0.0f);
+    fill_kernel<<<grid_for(s->size, kStoreThreads), kStoreThreads, 0, g.stream>>>(
+        s->values, s->status, s->size, v, set ? OLAP_STATUS_SET : OLAP_STATUS_UNSET);
+    LAUNCHED();
+    return finish_op();
+}
+
+static int total_and_count(const olap_store* s, double* sum, int64_t* count) {
+    OLAP_TRY(ensure_ctx());
+    *sum = 0.0;
+    *count = 0;
+    if (s->size == 0) return OLAP_OK;
+    const int blocks = grid_for(ceil_div(s->size, 4), kStoreThreads);
+    void* scratch;
+    const size_t bytes = (size_t)blocks * 16 + 64;
+    OLAP_TRY(dev_alloc(&scratch, bytes));
+    char* b = (char*)scratch;
+    double* psum = (double*)b;
+    unsigned long long* pcnt = (unsigned long long*)(b + (size_t)blocks * 8);
+    double* osum = (double*)(b + (size_t)blocks * 16);
+    unsigned long long* ocnt = (unsigned long long*)(b + (size_t)blocks * 16 + 8);
+    unsigned int* ticket = (unsigned int*)(b + (size_t)blocks * 16 + 16);
+    OLAP_CUDA(cudaMemsetAsync(ticket, 0, 4, g.stream));
+    total_kernel<<<blocks, kStoreThreads, 0, g.stream>>>(s->values, s->size, s->default_kind, psum, pcnt, ticket, osum, ocnt);
+    LAUNCHED();
+    struct { double s; unsigned long long c; } host;
+    OLAP_CUDA(cudaMemcpyAsync(&host, osum, 16, cudaMemcpyDeviceToHost, g.stream));
+    OLAP_TRY(dev_free(scratch));
+    OLAP_CUDA(cudaStreamSynchronize(g.stream));
+    *sum = host.s;
+    *count = (int64_t)host.c;
+    return OLAP_OK;
+}
+
+int olap_store_total(const olap_store* s, double* out) {
+    if (!s || !out) return fail(OLAP_E_INVALID, "olap_store_total: null argument");
+    int64_t c;
+    return total_and_count(s, out, &c);
+}
+
+int olap_store_count_present(const olap_store* s, int64_t* out) {
+    if (!s || !out) return fail(OLAP_E_INVALID, "olap_store_count_present: null argument");
+    double t;
+    return total_and_count(s, &t, out);
+}
+
+static int bytes_out(const olap_store* s, uint8_t* host, int64_t n, bool status) {
+    OLAP_TRY(check_len(s, n));
+    OLAP_TRY(ensure_ctx());
+    if (n == 0) return OLAP_OK;
+    if (status && s->status) {
+        OLAP_CUDA(cudaMemcpyAsync(host, s->status, (size_t)n, cudaMemcpyDeviceToHost, g.stream));
+        OLAP_CUDA(cudaStreamSynchronize(g.stream));
+        return OLAP_OK;
+    }
+    void* tmp;
+    OLAP_TRY(dev_alloc(&tmp, (size_t)n));
+    presence_kernel<<<grid_for(n, kStoreThreads), kStoreThreads, 0, g.stream>>>(
+        s->values, (uint8_t*)tmp, n, s->default_kind, status ? OLAP_STATUS_SET : 1, status ? OLAP_STATUS_UNSET : 0);
+    LAUNCHED();
+    OLAP_CUDA(cudaMemcpyAsync(host, tmp, (size_t)n, cudaMemcpyDeviceToHost, g.stream));
+    OLAP_TRY(dev_free(tmp));
+    OLAP_CUDA(cudaStreamSynchronize(g.stream));
+    return OLAP_OK;
+}
+
+int olap_store_presence(const olap_store* s, uint8_t* host, int64_t n) { return bytes_out(s, host, n, false); }
+int olap_store_status(const olap_store* s, uint8_t* host, int64_t n) { return bytes_out(s, host, n, true); }
+
+int olap_store_export_sparse(const olap_store* s, int64_t capacity, int64_t* keys, float* values, int64_t* count) {
+    if (!s || !count) return fail(OLAP_E_INVALID, "olap_store_export_sparse: null argument");
+    OLAP_TRY(ensure_ctx());
+    *count = 0;
+    if (s->size == 0) return OLAP_OK;
+    const int64_t nb = ceil_div(s->size, kCompactTile);
+    void* cnt;
+    OLAP_TRY(dev_alloc(&cnt, (size_t)(nb + 1) * 8));
+    unsigned long long* d_cnt = (unsigned long long*)cnt;
+    compact_count_kernel<<<(unsigned)nb, 256, 0, g.stream>>>(s->values, s->size, s->default_kind, d_cnt);
+    LAUNCHED();
+    compact_scan_kernel<<<1, 1024, 0, g.stream>>>(d_cnt, nb, d_cnt + nb);
+    LAUNCHED();
+    unsigned long long total = 0;
+    OLAP_CUDA(cudaMemcpyAsync(&total, d_cnt + nb, 8, cudaMemcpyDeviceToHost, g.stream));
+    OLAP_CUDA(cudaStreamSynchronize(g.stream));
+    *count = (int64_t)total;
+    int rc = OLAP_OK;
+    if (keys && values && total) {
+        if ((int64_t)total > capacity) {
+            rc = fail(OLAP_E_INVALID, "olap_store_export_sparse: capacity %lld < %llu set cells", (long long)capacity, total);
+        } else {
+            void *dk, *dv;
+            OLAP_TRY(dev_alloc(&dk, (size_t)total * 8));
+            OLAP_TRY(dev_alloc(&dv, (size_t)total * 4));
+            compact_write_kernel<<<(unsigned)nb, 256, 0, g.stream>>>(s->values, s->size, s->default_kind, d_cnt, (int64_t*)dk, (float*)dv);
+            LAUNCHED();
+            OLAP_CUDA(cudaMemcpyAsync(keys, dk, (size_t)total * 8, cudaMemcpyDeviceToHost, g.stream));
+            OLAP_CUDA(cudaMemcpyAsync(values, dv, (size_t)total * 4, cudaMemcpyDeviceToHost, g.stream));
+            OLAP_TRY(dev_free(dk));
+            OLAP_TRY(dev_free(dv));
+            OLAP_CUDA(cudaStreamSynchronize(g.stream));
+        }
+    }
+    OLAP_TRY(dev_free(cnt));
+    return rc;
+}
+
+int olap_store_import_sparse(olap_store* s, const int64_t* keys, const float* values, int64_t count) {
+    if (!s || (count && (!keys || !values))) return fail(OLAP_E_INVALID, "olap_store_import_sparse: null argument");
+    OLAP_TRY(ensure_ctx());
+    OLAP_TRY(fill_default(s));
+    if (count) {
+        TablePack t;
+        const size_t ok = t.add(keys, (size_t)count * 8);
+        const size_t ov = t.add(values, (size_t)count * 4);
+        OLAP_TRY(t.upload());
+        import_sparse_kernel<<<(unsigned)ceil_div(count, kStoreThreads), kStoreThreads, 0, g.stream>>>(
+            s->values, s->status, t.ptr<int64_t>(ok), t.ptr<float>(ov), count, s->size, s->default_kind);
+        LAUNCHED();
+        OLAP_TRY(t.release());
+    }
+    return finish_op();
+}
+
+// ---- drillUp --------------------------------------------------------------------------
+int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, const int64_t* old_len,
+                  const int64_t* new_len, const int32_t* const* maps, olap_store** out) {
+    int64_t size = 0, old_size = 0, new_size = 0;
+    OLAP_TRY(check_batch(src, n, "olap_drill_up", &size));
+    if (ndim < 0 || ndim > OLAP_MAX_DIMS) return fail(OLAP_E_INVALID, "olap_drill_up: at most %d dimensions", OLAP_MAX_DIMS);
+    if (!out || (ndim && (!old_len || !new_len || !maps))) return fail(OLAP_E_INVALID, "olap_drill_up: null argument");
+    OLAP_TRY(product(old_len, ndim, &old_size, "olap_drill_up"));
+    OLAP_TRY(product(new_len, ndim, &new_size, "olap_drill_up"));
+    if (old_size != size) return fail(OLAP_E_INVALID, "olap_drill_up: dimensions describe %lld cells, store has %lld", (long long)old_size, (long long)size);
+    for (int k = 0; k < n; ++k)
+        if (methods[k] < OLAP_SUM || methods[k] > OLAP_PRODUCT) return fail(OLAP_E_INVALID, "Unsupported aggregation method: %d", methods[k]);
+    std::vector<int> changed;
+    for (int d = 0; d < ndim; ++d) {
+        if (old_len[d] > 0x7fffffffLL || new_len[d] > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "olap_drill_up: dimension %d longer than 2^31-1", d);
+        bool identity = old_len[d] == new_len[d];
+        for (int64_t i = 0; i < old_len[d]; ++i) {
+            const int32_t m = maps[d][i];
+            if (m < 0 || m >= new_len[d]) return fail(OLAP_E_INVALID, "olap_drill_up: map of dimension %d sends item %lld to %d, outside [0, %lld)", d, (long long)i, m, (long long)new_len[d]);
+            identity &= m == i;
+        }
+        if (!identity) changed.push_back(d);
+    }
+    OLAP_TRY(ensure_ctx());
+    OLAP_TRY(alloc_like(src, n, new_size, out));
+    begin_op();
+    const char* path = "drillup/empty";
+    if (new_size == 0) {
+        // nothing to compute
+    } else if (old_size == 0) {
+        for (int k = 0; k < n; ++k) { olap_store t = *out[k]; t.status = st_out_of(out, k); OLAP_TRY(fill_default(&t)); }
+    } else {
+        std::vector<UpMeasure> meas(n);
+        for (int k = 0; k < n; ++k)
+            meas[k] = UpMeasure{src[k]->values, out[k]->values, out[k]->status ? st_in_of(src, k) : nullptr,
+                                st_in_of(src, k) ? st_out_of(out, k) : nullptr, methods[k], src[k]->default_kind};
+        TablePack t;
+        const size_t o_meas = t.add(meas.data(), sizeof(UpMeasure) * n);
+        if (changed.size() <= 1) {
+            // view the cube as [O, C, I] around the changed dimension (or the last one for a plain copy)
+            const int d = changed.empty() ? std::max(0, ndim - 1) : changed[0];
+            int64_t O = 1, I = 1;
+            for (int q = 0; q < d; ++q) O *= old_len[q];
+            for (int q = d + 1; q < ndim; ++q) I *= old_len[q];
+            const int64_t C = ndim ? old_len[d] : 1, P = ndim ? new_len[d] : 1;
+            static const int32_t zero = 0;
+            const Csr csr = build_csr(ndim ? maps[d] : &zero, C, P);
+            const size_t o_ps = t.add(csr.pstart.data(), csr.pstart.size() * 4);
+            const size_t o_ch = t.add(csr.children.data(), csr.children.size() * 4);
+            OLAP_TRY(t.upload());
+            TileDecision tile = tile_plan(O, C, P, I, n);
+            if (tile.use) {
+                path = "drillup/tile";
+                OLAP_TRY(launch_up_tile(t.ptr<UpMeasure>(o_meas), n, csr.contiguous, t.ptr<int32_t>(o_ps), t.ptr<int32_t>(o_ch), O, C, P, I, tile));
+            } else {
+                path = (I % 4 == 0) ? "drillup/mid-vec4" : "drillup/mid-scalar";
+                OLAP_TRY(launch_up_mid(t.ptr<UpMeasure>(o_meas), n, csr, t.ptr<int32_t>(o_ps), t.ptr<int32_t>(o_ch), O, C, P, I));
+            }
+        } else {
+            path = "drillup/generic";
+            UpGenParams p{};
+            p.nd = ndim;
+            p.n_out = new_size;
+            std::vector<size_t> o_ps(ndim), o_ch(ndim);
+            int64_t stride = 1;
+            for (int d = ndim - 1; d >= 0; --d) {
+                p.new_len[d] = new_len[d];
+                p.old_stride[d] = stride;
+                stride *= old_len[d];
+                const Csr csr = build_csr(maps[d], old_len[d], new_len[d]);
+                o_ps[d] = t.add(csr.pstart.data(), csr.pstart.size() * 4);
+                o_ch[d] = t.add(csr.children.data(), csr.children.size() * 4);
+            }
+            OLAP_TRY(t.upload());
+            p.meas = t.ptr<UpMeasure>(o_meas);
+            for (int d = 0; d < ndim; ++d) { p.pstart[d] = t.ptr<int32_t>(o_ps[d]); p.children[d] = t.ptr<int32_t>(o_ch[d]); }
+            const int64_t gx = ceil_div(new_size, 256);
+            if (gx > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "olap_drill_up: grid too large");
+            drillup_generic_kernel<<<dim3((unsigned)gx, (unsigned)n), 256, 0, g.stream>>>(p);
+            LAUNCHED();
+        }
+        OLAP_TRY(t.release());
+    }
+    end_op(path);
+    return finish_op();
+}
+
+// ---- gather family ----------------------------------------------------------------------
+namespace {
+
+// Drop single-item dimensions (their constant offset goes to `const_off`) and merge
+// neighbours that stay adjacent and contiguous in the source.
+static void merge_dims(std::vector<GDim>& dims, int64_t* const_off) {
+    std::vector<GDim> out;
+    for (auto& d : dims) {
+        if (d.len == 1) {
+            if (!d.linear) *const_off += d.tbl[0];
+            continue;  // aux of a single item is {1 sibling, rank 0}: neutral
+        }
+        if (!out.empty() && out.back().linear && d.linear && out.back().stride == d.len * d.stride) {
+            out.back().len *= d.len;
+            out.back().stride = d.stride;
+        } else {
+            out.push_back(std::move(d));
+        }
+    }
+    dims.swap(out);
+}
+
+static int run_gather(int mode, olap_store* const* src, int n, std::vector<GDim>& dims, int64_t new_size, int64_t old_size,
+                      const std::vector<GatherMeasure>& meas_in, int* d_error, const char** path) {
+    int64_t const_off = 0;
+    merge_dims(dims, &const_off);
+    int64_t I = 1;
+    if (!dims.empty() && dims.back().linear && dims.back().stride == 1 && dims.back().aux.empty()) {
+        I = dims.back().len;
+        dims.pop_back();
+    }
+    if ((int)dims.size() > OLAP_MAX_DIMS) return fail(OLAP_E_UNSUPPORTED, "too many dimensions");
+    int VEC = (I % 4 == 0) ? 4 : 1;
+    // every offset must keep 16-byte alignment for the 128-bit path
+    if (VEC == 4) {
+        if (const_off % 4) VEC = 1;
+        for (auto& d : dims) {
+            if (d.linear) { if (d.stride % 4) VEC = 1; }
+            else for (int64_t v : d.tbl) if (v % 4) { VEC = 1; break; }
+        }
+    }
+    GatherParams p{};
+    TablePack t;
+    std::vector<GatherMeasure> meas = meas_in;
+    for (auto& m : meas) { m.in += const_off; if (m.st_in) m.st_in += const_off; }
+    const size_t o_meas = t.add(meas.data(), sizeof(GatherMeasure) * n);
+    std::vector<size_t> o_tbl(dims.size(), 0), o_aux(dims.size(), 0);
+    int64_t rows = 1;
+    bool big = false;
+    for (size_t d = 0; d < dims.size(); ++d) {
+        if (dims[d].len > 0x7fffffffLL) {
+            if (!dims[d].linear) return fail(OLAP_E_UNSUPPORTED, "dimension longer than 2^31-1");
+            big = true;
+        }
+        if (!dims[d].linear) o_tbl[d] = t.add(dims[d].tbl.data(), dims[d].tbl.size() * 8);
+        if (!dims[d].aux.empty()) o_aux[d] = t.add(dims[d].aux.data(), dims[d].aux.size() * sizeof(int2));
+        rows *= dims[d].len;
+    }
+    OLAP_TRY(t.upload());
+    p.meas = t.ptr<GatherMeasure>(o_meas);
+    p.nd = (int)dims.size();
+    for (size_t d = 0; d < dims.size(); ++d) {
+        p.len[d] = (uint32_t)dims[d].len;
+        p.div[d] = FastDiv((uint32_t)dims[d].len);
+        p.tbl[d] = dims[d].linear ? nullptr : t.ptr<int64_t>(o_tbl[d]);
+        p.lin[d] = dims[d].stride;
+        p.aux[d] = dims[d].aux.empty() ? nullptr : t.ptr<int2>(o_aux[d]);
+    }
+    p.I = I;
+    const int64_t IV = I / VEC;
+    if (IV > 0x7fffffffLL) big = true;
+    p.IV = (uint32_t)IV;
+    p.div_iv = FastDiv((uint32_t)IV);
+    p.rows = rows;
+    p.n_vec = rows * IV;
+    if (p.n_vec >= ((int64_t)1 << 31) || rows >= ((int64_t)1 << 31)) big = true;
+    if (big && (IV > 0xffffffffLL)) return fail(OLAP_E_UNSUPPORTED, "inner run too long");
+    if (big) {
+        for (size_t d = 0; d < dims.size(); ++d)
+            if (dims[d].len > 0xffffffffLL) return fail(OLAP_E_UNSUPPORTED, "merged dimension longer than 2^32-1");
+        p.IV = (uint32_t)IV;
+    }
+    p.new_size = new_size;
+    p.old_size = old_size;
+    p.error_flag = d_error;
+    const int64_t gx = ceil_div(p.n_vec, 512);
+    if (gx > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "grid too large");
+    dim3 grid((unsigned)gx, (unsigned)n);
+#define OLAP_GATHER(M, V, B) gather_kernel<M, V, B><<<grid, 256, 0, g.stream>>>(p)
+    if (mode == G_COPY) {
+        if (VEC == 4) { if (big) OLAP_GATHER(G_COPY, 4, true); else OLAP_GATHER(G_COPY, 4, false); }
+        else { if (big) OLAP_GATHER(G_COPY, 1, true); else OLAP_GATHER(G_COPY, 1, false); }
+    } else {
+        if (VEC == 4) { if (big) OLAP_GATHER(G_DOWN, 4, true); else OLAP_GATHER(G_DOWN, 4, false); }
+        else { if (big) OLAP_GATHER(G_DOWN, 1, true); else OLAP_GATHER(G_DOWN, 1, false); }
+    }
+#undef OLAP_GATHER
+    LAUNCHED();
+    *path = VEC == 4 ? (big ? "gather/vec4-big" : "gather/vec4") : (big ? "gather/scalar-big" : "gather/scalar");
+    OLAP_TRY(t.release());
+    return OLAP_OK;
+}
+
+static std::vector<GatherMeasure> gather_measures(olap_store* const* src, olap_store** out, int n) {
+    std::vector<GatherMeasure> meas(n);
+    for (int k = 0; k < n; ++k) {
+        GatherMeasure m{};
+        m.in = src[k]->values;
+        m.out = out[k]->values;
+        m.st_in = out[k]->status ? st_in_of(src, k) : nullptr;
+        m.st_out = m.st_in ? st_out_of(out, k) : nullptr;
+        m.nan_default = src[k]->default_kind;
+        m.int_rounding = src[k]->type == OLAP_INT32 || src[k]->type == OLAP_UINT32;
+        m.method_is_sum = 1;
+        meas[k] = m;
+    }
+    return meas;
+}
+
+}  // namespace
+
+int olap_dice(olap_store* const* src, int n, int ndim, const int64_t* old_len, const int64_t* new_len,
+              const int32_t* const* keep, olap_store** out) {
+    int64_t size = 0, old_size = 0, new_size = 0;
+    OLAP_TRY(check_batch(src, n, "olap_dice", &size));
+    if (ndim < 0 || ndim > OLAP_MAX_DIMS) return fail(OLAP_E_INVALID, "olap_dice: at most %d dimensions", OLAP_MAX_DIMS);
+    if (!out || (ndim && (!old_len || !new_len || !keep))) return fail(OLAP_E_INVALID, "olap_dice: null argument");
+    OLAP_TRY(product(old_len, ndim, &old_size, "olap_dice"));
+    OLAP_TRY(product(new_len, ndim, &new_size, "olap_dice"));
+    if (old_size != size) return fail(OLAP_E_INVALID, "olap_dice: dimensions describe %lld cells, store has %lld", (long long)old_size, (long long)size);
+    std::vector<GDim> dims(ndim);
+    int64_t stride = 1;
+    for (int d = ndim - 1; d >= 0; --d) {
+        GDim& g_ = dims[d];
+        g_.len = new_len[d];
+        bool identity = new_len[d] == old_len[d];
+        for (int64_t j = 0; j < new_len[d]; ++j) {
+            const int32_t o = keep[d][j];
+            if (o < 0 || o >= old_len[d]) return fail(OLAP_E_INVALID, "olap_dice: dimension %d keeps item %d, outside [0, %lld)", d, o, (long long)old_len[d]);
+            identity &= o == j;
+        }
+        if (identity) { g_.linear = true; g_.stride = stride; }
+        else {
+            g_.linear = false;
+            g_.tbl.resize(new_len[d]);
+            for (int64_t j = 0; j < new_len[d]; ++j) g_.tbl[j] = (int64_t)keep[d][j] * stride;
+        }
+        stride *= old_len[d];
+    }
+    OLAP_TRY(ensure_ctx());
+    OLAP_TRY(alloc_like(src, n, new_size, out));
+    begin_op();
+    const char* path = "dice/empty";
+    if (new_size) {
+        auto meas = gather_measures(src, out, n);
+        OLAP_TRY(run_gather(G_COPY, src, n, dims, new_size, old_size, meas, nullptr, &path));
+    }
+    end_op(path);
+    return finish_op();
+}
+
+int olap_reorder(olap_store* const* src, int n, int ndim, const int64_t* old_len, const int32_t* new_to_old,
+                 olap_store** out) {
+    int64_t size = 0, old_size = 0;
+    OLAP_TRY(check_batch(src, n, "olap_reorder", &size));
+    if (ndim < 0 || ndim > OLAP_MAX_DIMS) return fail(OLAP_E_INVALID, "olap_reorder: at most %d dimensions", OLAP_MAX_DIMS);
+    if (!out || (ndim && (!old_len || !new_to_old))) return fail(OLAP_E_INVALID, "olap_reorder: null argument");
+    OLAP_TRY(product(old_len, ndim, &old_size, "olap_reorder"));
+    if (old_size != size) return fail(OLAP_E_INVALID, "olap_reorder: dimensions describe %lld cells, store has %lld", (long long)old_size, (long long)size);
+    std::vector<int64_t> old_stride(ndim);
+    int64_t stride = 1;
+    for (int d = ndim - 1; d >= 0; --d) { old_stride[d] = stride; stride *= old_len[d]; }
+    std::vector<bool> seen(ndim, false);
+    std::vector<GDim> dims(ndim);
+    for (int i = 0; i < ndim; ++i) {
+        const int o = new_to_old[i];
+        if (o < 0 || o >= ndim || seen[o]) return fail(OLAP_E_INVALID, "olap_reorder: new_to_old is not a permutation");
+        seen[o] = true;
+        dims[i].len = old_len[o];
+        dims[i].linear = true;
+        dims[i].stride = old_stride[o];
+    }
+    OLAP_TRY(ensure_ctx());
+    OLAP_TRY(alloc_like(src, n, size, out));
+    begin_op();
+    const char* path = "reorder/empty";
+    if (size) {
+        auto meas = gather_measures(src, out, n);
+        TransposePlan tp = transpose_plan(dims);
+        if (tp.use) {
+            path = "reorder/tile-transpose";
+            OLAP_TRY(launch_transpose(meas, n, tp));
+        } else {
+            OLAP_TRY(run_gather(G_COPY, src, n, dims, size, size, meas, nullptr, &path));
+        }
+    }
+    end_op(path);
+    return finish_op();
+}
+
+int olap_drill_down(olap_store* const* src, int n, const int* methods, int ndim, const int64_t* old_len,
+                    const int64_t* new_len, const int32_t* const* maps, const double* const* dist,
+                    const int64_t* dist_len, olap_store** out) {
+    int64_t size = 0, old_size = 0, new_size = 0;
+    OLAP_TRY(check_batch(src, n, "olap_drill_down", &size));
+    if (ndim < 0 || ndim > OLAP_MAX_DIMS) return fail(OLAP_E_INVALID, "olap_drill_down: at most %d dimensions", OLAP_MAX_DIMS);
+    if (!out || (ndim && (!old_len || !new_len || !maps))) return fail(OLAP_E_INVALID, "olap_drill_down: null argument");
+    OLAP_TRY(product(old_len, ndim, &old_size, "olap_drill_down"));
+    OLAP_TRY(product(new_len, ndim, &new_size, "olap_drill_down"));
+    if (old_size != size) return fail(OLAP_E_INVALID, "olap_drill_down: dimensions describe %lld cells, store has %lld", (long long)old_size, (long long)size);
+    std::vector<GDim> dims(ndim);
+    int64_t stride = 1;
+    for (int d = ndim - 1; d >= 0; --d) {
+        GDim& g_ = dims[d];
+        g_.len = new_len[d];
+        bool identity = new_len[d] == old_len[d];
+        for (int64_t j = 0; j < new_len[d]; ++j) {
+            const int32_t o = maps[d][j];
+            if (o < 0 || o >= old_len[d]) return fail(OLAP_E_INVALID, "olap_drill_down: map of dimension %d sends item %lld to %d, outside [0, %lld)", d, (long long)j, o, (long long)old_len[d]);
+            identity &= o == j;
+        }
+        if (identity) { g_.linear = true; g_.stride = stride; }
+        else {
+            g_.linear = false;
+            g_.tbl.resize(new_len[d]);
+            g_.aux.resize(new_len[d]);
+            std::vector<int32_t> count(old_len[d], 0);
+            for (int64_t j = 0; j < new_len[d]; ++j) {
+                g_.tbl[j] = (int64_t)maps[d][j] * stride;
+                g_.aux[j].y = count[maps[d][j]]++;  // rank among siblings, ascending new index
+            }
+            for (int64_t j = 0; j < new_len[d]; ++j) g_.aux[j].x = count[maps[d][j]];
+        }
+        stride *= old_len[d];
+    }
+    bool any_dist = false;
+    for (int k = 0; k < n; ++k) any_dist |= dist && dist[k];
+    if (any_dist && (old_size == 0 || new_size % old_size != 0)) return fail(OLAP_E_INVALID, "olap_drill_down: distributions need newSize to be a multiple of oldSize");
+    OLAP_TRY(ensure_ctx());
+    OLAP_TRY(alloc_like(src, n, new_size, out));
+    begin_op();
+    const char* path = "drilldown/empty";
+    int rc = OLAP_OK;
+    if (new_size && old_size == 0) {
+        for (int k = 0; k < n; ++k) { olap_store t = *out[k]; t.status = st_out_of(out, k); OLAP_TRY(fill_default(&t)); }
+    } else if (new_size) {
+        auto meas = gather_measures(src, out, n);
+        TablePack dpack;
+        std::vector<size_t> o_dist(n, 0);
+        if (any_dist) {
+            int zero = 0;
+            dpack.add(&zero, 4);  // error flag at offset 0
+            for (int k = 0; k < n; ++k)
+                if (dist[k]) o_dist[k] = dpack.add(dist[k], (size_t)dist_len[k] * 8);
+            OLAP_TRY(dpack.upload());
+        }
+        for (int k = 0; k < n; ++k) {
+            meas[k].method_is_sum = methods ? (methods[k] == OLAP_SUM) : 1;
+            if (any_dist && dist[k]) { meas[k].dist = dpack.ptr<double>(o_dist[k]); meas[k].dist_len = dist_len[k]; }
+        }
+        rc = run_gather(G_DOWN, src, n, dims, new_size, old_size, meas, any_dist ? dpack.ptr<int>(0) : nullptr, &path);
+        if (rc == OLAP_OK && any_dist) {
+            int flag = 0;
+            OLAP_CUDA(cudaMemcpyAsync(&flag, dpack.ptr<int>(0), 4, cudaMemcpyDeviceToHost, g.stream));
+            OLAP_CUDA(cudaStreamSynchronize(g.stream));
+            if (flag) rc = fail(OLAP_E_INVALID, "distribution missing for index %d", flag - 1);
+        }
+        if (any_dist) OLAP_TRY(dpack.release());
+    }
+    end_op(path);
+    if (rc != OLAP_OK) {
+        for (int k = 0; k < n; ++k) { olap_store_destroy(out[k]); out[k] = nullptr; }
+        return rc;
+    }
+    return finish_op();
+}
+
+int olap_load(olap_store* dst, const olap_store* src, int ndim, const int64_t* my_len, const int64_t* his_len,
+              const int32_t* const* his_to_mine) {
+    if (!dst || !src) return fail(OLAP_E_INVALID, "olap_load: null store");
+    if (ndim < 0 || ndim > OLAP_MAX_DIMS) return fail(OLAP_E_INVALID, "olap_load: at most %d dimensions", OLAP_MAX_DIMS);
+    int64_t my_size = 0, his_size = 0;
+    OLAP_TRY(product(my_len, ndim, &my_size, "olap_load"));
+    OLAP_TRY(product(his_len, ndim, &his_size, "olap_load"));
+    if (my_size != dst->size || his_size != src->size) return fail(OLAP_E_INVALID, "olap_load: dimensions do not match the stores");
+    OLAP_TRY(ensure_ctx());
+    begin_op();
+    if (his_size && my_size) {
+        ScatterParams p{};
+        TablePack t;
+        std::vector<size_t> offs(ndim);
+        int64_t stride = 1;
+        for (int d = ndim - 1; d >= 0; --d) {
+            std::vector<int64_t> tbl(his_len[d]);
+            for (int64_t j = 0; j < his_len[d]; ++j) {
+                const int32_t m = his_to_mine[d][j];
+                if (m >= my_len[d]) return fail(OLAP_E_INVALID, "olap_load: item index %d outside [0, %lld)", m, (long long)my_len[d]);
+                tbl[j] = m < 0 ? INT64_MIN / 32 : (int64_t)m * stride;
+            }
+            offs[d] = t.add(tbl.data(), tbl.size() * 8);
+            p.len[d] = his_len[d];
+            stride *= my_len[d];
+        }
+        OLAP_TRY(t.upload());
+        for (int d = 0; d < ndim; ++d) p.tbl[d] = t.ptr<int64_t>(offs[d]);
+        p.src = src->values; p.dst = dst->values;
+        p.st_src = src->status; p.st_dst = dst->status;
+        p.dst_nan_default = dst->default_kind; p.src_nan_default = src->default_kind;
+        p.nd = ndim; p.n = his_size;
+        const int64_t gx = ceil_div(his_size, 256);
+        if (gx > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "olap_load: grid too large");
+        load_scatter_kernel<<<(unsigned)gx, 256, 0, g.stream>>>(p);
+        LAUNCHED();
+        OLAP_TRY(t.release());
+    }
+    end_op("load/scatter");
+    return finish_op();
+}
+
+// ---- computed measures --------------------------------------------------------------------
+int olap_eval(const char* program, olap_store* const* inputs, int n_inputs, const double* totals, int n_totals,
+              double* out_host_f64, int out_type, int out_default_kind, olap_store** out_store) {
+    if (!program) return fail(OLAP_E_INVALID, "olap_eval: null program");
+    if (n_inputs < 0 || n_inputs > OLAP_MAX_MEASURES || n_totals < 0 || n_totals > OLAP_MAX_MEASURES) return fail(OLAP_E_INVALID, "olap_eval: too many inputs");
+    if ((out_host_f64 != nullptr) == (out_store != nullptr)) return fail(OLAP_E_INVALID, "olap_eval: exactly one of out_host_f64 / out_store");
+    if (n_inputs == 0) return fail(OLAP_E_INVALID, "olap_eval: a formula needs at least one stored measure to give the cube size");
+    int64_t size = 0;
+    OLAP_TRY(check_batch(inputs, n_inputs, "olap_eval", &size));
+    OLAP_TRY(ensure_ctx());
+    JitKernel* k = nullptr;
+    OLAP_TRY(jit_get(program, n_inputs, n_totals, &k));
+
+    float* out32 = nullptr;
+    uint8_t* st_out = nullptr;
+    double* out64 = nullptr;
+    olap_store* result = nullptr;
+    if (out_store) {
+        OLAP_TRY(check_type_default(out_type, out_default_kind));
+        bool with_status = true;
+        for (int q = 0; q < n_inputs; ++q) with_status &= inputs[q]->status != nullptr;
+        OLAP_TRY(alloc_batch(1, size, &out_type, &out_default_kind, with_status, false, &result));
+        out32 = result->values;
+        st_out = result->status;
+    } else if (size) {
+        void* tmp;
+        OLAP_TRY(dev_alloc(&tmp, (size_t)size * 8));
+        out64 = (double*)tmp;
+    }
+    begin_op();
+    if (size) {
+        std::vector<void*> args;
+        std::vector<const float*> ptrs(n_inputs);
+        std::vector<double> tot(n_totals);
+        for (int q = 0; q < n_inputs; ++q) { ptrs[q] = inputs[q]->values; args.push_back(&ptrs[q]); }
+        for (int q = 0; q < n_totals; ++q) { tot[q] = totals[q]; args.push_back(&tot[q]); }
+        long long n = size;
+        int nan_default = out_default_kind;
+        args.push_back(&out32); args.push_back(&st_out); args.push_back(&out64); args.push_back(&n); args.push_back(&nan_default);
+        const int blocks = (int)std::min<int64_t>(ceil_div(ceil_div(size, 4), 256), (int64_t)g.sm_count * 16);
+        CUresult cr = jit_api().LaunchKernel(k->fn, blocks, 1, 1, 256, 1, 1, 0, (CUstream)g.stream, args.data(), nullptr);
+        if (cr != CUDA_SUCCESS) {
+            const char* msg = "?";
+            jit_api().GetErrorString(cr, &msg);
+            return fail(OLAP_E_CUDA, "launching the formula kernel failed: %s", msg);
+        }
+        LAUNCHED();
+    }
+    end_op("eval/jit");
+    if (out_store) {
+        *out_store = result;
+        return finish_op();
+    }
+    if (size) {
+        OLAP_CUDA(cudaMemcpyAsync(out_host_f64, out64, (size_t)size * 8, cudaMemcpyDeviceToHost, g.stream));
+        OLAP_TRY(dev_free(out64));
+        OLAP_CUDA(cudaStreamSynchronize(g.stream));
+    }
+    return OLAP_OK;
+}
+
+}  // extern "C"

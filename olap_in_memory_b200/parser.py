@@ -19,8 +19,8 @@ is parity-unpinned and follows JavaScript ``Math`` semantics.
 
 An Expression offers the members the cube uses (src/cube.js:123-124, 253-256,
 336-338, 359, 1145): variables(), evaluate(), toString(), substitute(); plus
-``cuda_source()`` which lowers the tree to one double-precision CUDA expression
-for the fused elementwise kernel (JIT-compiled by the native library)."""
+``postfix()``, the serialised instruction list handed to olap_eval(), which the
+native library lowers to one fused double-precision sm_100a kernel (NVRTC)."""
 from __future__ import annotations
 
 import math
@@ -132,44 +132,44 @@ def _log(x):
     return math.log(x) if not math.isinf(x) else math.inf
 
 
-# name -> (arity or None for n-ary, python impl, CUDA template)
+# name -> (arity or None for n-ary, python impl with JS Math semantics)
 FUNCS = {
-    "abs": (1, _guard(abs), "fabs({0})"),
-    "ceil": (1, _guard(lambda x: x if x != x or math.isinf(x) else math.ceil(x)), "ceil({0})"),
-    "floor": (1, _guard(lambda x: x if x != x or math.isinf(x) else math.floor(x)), "floor({0})"),
-    "round": (1, _js_round, "floor({0} + 0.5)"),
-    "trunc": (1, _guard(lambda x: x if x != x or math.isinf(x) else math.trunc(x)), "trunc({0})"),
-    "sqrt": (1, _guard(lambda x: math.nan if x < 0 else math.sqrt(x)), "sqrt({0})"),
-    "cbrt": (1, _guard(lambda x: math.copysign(abs(x) ** (1.0 / 3.0), x)), "cbrt({0})"),
-    "exp": (1, _guard(math.exp), "exp({0})"),
-    "expm1": (1, _guard(math.expm1), "expm1({0})"),
-    "ln": (1, _log, "log({0})"),
-    "log": (1, _log, "log({0})"),
-    "log1p": (1, _guard(lambda x: -math.inf if x == -1 else math.log1p(x)), "log1p({0})"),
-    "log2": (1, lambda x: _log(x) / math.log(2) if x == x and x > 0 and not math.isinf(x) else _log(x), "log2({0})"),
-    "log10": (1, lambda x: math.log10(x) if x == x and x > 0 and not math.isinf(x) else _log(x), "log10({0})"),
-    "lg": (1, lambda x: math.log10(x) if x == x and x > 0 and not math.isinf(x) else _log(x), "log10({0})"),
-    "sin": (1, _guard(math.sin), "sin({0})"),
-    "cos": (1, _guard(math.cos), "cos({0})"),
-    "tan": (1, _guard(math.tan), "tan({0})"),
-    "asin": (1, _guard(math.asin), "asin({0})"),
-    "acos": (1, _guard(math.acos), "acos({0})"),
-    "atan": (1, _guard(math.atan), "atan({0})"),
-    "sinh": (1, _guard(math.sinh), "sinh({0})"),
-    "cosh": (1, _guard(math.cosh), "cosh({0})"),
-    "tanh": (1, _guard(math.tanh), "tanh({0})"),
-    "asinh": (1, _guard(math.asinh), "asinh({0})"),
-    "acosh": (1, _guard(math.acosh), "acosh({0})"),
-    "atanh": (1, _guard(lambda x: math.copysign(math.inf, x) if abs(x) == 1 else math.atanh(x)), "atanh({0})"),
-    "sign": (1, _sign, "olap_sign({0})"),
-    "isNaN": (1, lambda x: 1.0 if x != x else 0.0, "(isnan({0}) ? 1.0 : 0.0)"),
-    "pow": (2, _js_pow, "olap_pow({0}, {1})"),
-    "atan2": (2, _guard(math.atan2), "atan2({0}, {1})"),
-    "roundTo": (2, lambda x, n: _js_round(x * 10 ** n) / 10 ** n, "(floor({0} * pow(10.0, {1}) + 0.5) / pow(10.0, {1}))"),
-    "if": (3, lambda c, a, b: a if (c == c and c != 0) else b, "(olap_truthy({0}) ? ({1}) : ({2}))"),
-    "min": (None, _js_min, None),
-    "max": (None, _js_max, None),
-    "hypot": (None, _guard(lambda *a: math.hypot(*a)), None),
+    "abs": (1, _guard(abs)),
+    "ceil": (1, _guard(lambda x: x if x != x or math.isinf(x) else math.ceil(x))),
+    "floor": (1, _guard(lambda x: x if x != x or math.isinf(x) else math.floor(x))),
+    "round": (1, _js_round),
+    "trunc": (1, _guard(lambda x: x if x != x or math.isinf(x) else math.trunc(x))),
+    "sqrt": (1, _guard(lambda x: math.nan if x < 0 else math.sqrt(x))),
+    "cbrt": (1, _guard(lambda x: math.copysign(abs(x) ** (1.0 / 3.0), x))),
+    "exp": (1, _guard(math.exp)),
+    "expm1": (1, _guard(math.expm1)),
+    "ln": (1, _log),
+    "log": (1, _log),
+    "log1p": (1, _guard(lambda x: -math.inf if x == -1 else math.log1p(x))),
+    "log2": (1, lambda x: _log(x) / math.log(2) if x == x and x > 0 and not math.isinf(x) else _log(x)),
+    "log10": (1, lambda x: math.log10(x) if x == x and x > 0 and not math.isinf(x) else _log(x)),
+    "lg": (1, lambda x: math.log10(x) if x == x and x > 0 and not math.isinf(x) else _log(x)),
+    "sin": (1, _guard(math.sin)),
+    "cos": (1, _guard(math.cos)),
+    "tan": (1, _guard(math.tan)),
+    "asin": (1, _guard(math.asin)),
+    "acos": (1, _guard(math.acos)),
+    "atan": (1, _guard(math.atan)),
+    "sinh": (1, _guard(math.sinh)),
+    "cosh": (1, _guard(math.cosh)),
+    "tanh": (1, _guard(math.tanh)),
+    "asinh": (1, _guard(math.asinh)),
+    "acosh": (1, _guard(math.acosh)),
+    "atanh": (1, _guard(lambda x: math.copysign(math.inf, x) if abs(x) == 1 else math.atanh(x))),
+    "sign": (1, _sign),
+    "isNaN": (1, lambda x: 1.0 if x != x else 0.0),
+    "pow": (2, _js_pow),
+    "atan2": (2, _guard(math.atan2)),
+    "roundTo": (2, lambda x, n: _js_round(x * 10 ** n) / 10 ** n),
+    "if": (3, lambda c, a, b: a if (c == c and c != 0) else b),
+    "min": (None, _js_min),
+    "max": (None, _js_max),
+    "hypot": (None, _guard(lambda *a: math.hypot(*a))),
 }
 
 PREFIX_FUNCS = {k for k, v in FUNCS.items() if v[0] == 1 and k != "isNaN"}
@@ -183,16 +183,6 @@ _BIN_PY = {
     "^": _js_pow,
     "||": _coalesce_add,
 }
-_BIN_CU = {
-    "+": "({0} + {1})",
-    "-": "({0} - {1})",
-    "*": "({0} * {1})",
-    "/": "({0} / {1})",
-    "%": "fmod({0}, {1})",
-    "^": "olap_pow({0}, {1})",
-    "||": "olap_coalesce_add({0}, {1})",
-}
-
 
 class ParseError(ValueError):
     pass
@@ -324,14 +314,6 @@ def _fmt_num(v):
     return repr(v)
 
 
-def _c_literal(v):
-    if v != v:
-        return "olap_nan()"
-    if math.isinf(v):
-        return "olap_inf()" if v > 0 else "(-olap_inf())"
-    return repr(float(v))
-
-
 class Expression:
     def __init__(self, node):
         self.node = node
@@ -423,35 +405,40 @@ class Expression:
         return Expression(sub(self.node))
 
     # --- lowering for the fused device kernel -------------------------
-    def cuda_source(self, slot_of):
-        """One CUDA double expression.  `slot_of` maps a variable name to the
-        C identifier holding its value (a stored-measure cell or a total)."""
+    def postfix(self, slot_of):
+        """The formula as the space separated postfix text olap_eval() takes
+        (include/olap_gpu.h): `slot_of` maps a variable name to ``v<k>`` (cell of
+        input store k) or ``t<k>`` (k-th total)."""
+        out = []
 
-        def cu(n):
+        def emit(n):
             tag = n[0]
             if tag == "num":
-                return _c_literal(n[1])
-            if tag == "var":
-                return slot_of[n[1]]
-            if tag == "neg":
-                return f"(-{cu(n[1])})"
-            if tag == "bin":
-                return _BIN_CU[n[1]].format(cu(n[2]), cu(n[3]))
-            if tag == "cond":
-                return f"(olap_truthy({cu(n[1])}) ? ({cu(n[2])}) : ({cu(n[3])}))"
-            if tag == "call":
-                name, args = n[1], [cu(a) for a in n[2]]
-                if name in ("min", "max"):
-                    out = args[0] if len(args) > 1 else f"olap_{name}({args[0]}, {args[0]})"
-                    for a in args[1:]:
-                        out = f"olap_{name}({out}, {a})"
-                    return out
-                if name == "hypot":
-                    return "sqrt(" + " + ".join(f"({a}) * ({a})" for a in args) + ")"
-                return FUNCS[name][2].format(*args)
-            raise AssertionError(tag)
+                v = n[1]
+                out.append("#nan" if v != v else "#inf" if v == math.inf else "#-inf" if v == -math.inf else f"#{v!r}")
+            elif tag == "var":
+                out.append(slot_of[n[1]])
+            elif tag == "neg":
+                emit(n[1])
+                out.append("neg")
+            elif tag == "bin":
+                emit(n[2])
+                emit(n[3])
+                out.append(n[1])
+            elif tag == "cond":
+                emit(n[1])
+                emit(n[2])
+                emit(n[3])
+                out.append("?:")
+            elif tag == "call":
+                for a in n[2]:
+                    emit(a)
+                out.append(f"call:{n[1]}:{len(n[2])}")
+            else:
+                raise AssertionError(tag)
 
-        return cu(self.node)
+        emit(self.node)
+        return " ".join(out)
 
 
 class Parser:

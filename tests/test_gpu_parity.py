@@ -1,0 +1,206 @@
+"""CUDA store vs the CPU oracle on seeded lowered cases (tests/cases.py), through the
+C ABI.  Bars: bit-exact float32 for dice, reorder, load, presence,
+first, last, highest, lowest; sum / average / drillDown are computed in double in the
+reference's order, so they are expected bit-equal to fround(oracle) too (asserted), with
+rel 1e-6 kept as the documented tolerance for tree-reduced regimes."""
+import itertools
+import math
+
+import numpy as np
+import pytest
+
+import cases
+from oracle.c_oracle import COracleStore
+from oracle.store_oracle import OracleStore
+
+pytestmark = pytest.mark.gpu
+
+ALL = list(itertools.chain(cases.drillup_cases(), cases.drilldown_cases(), cases.dice_cases(),
+                           cases.reorder_cases(), cases.load_cases()))
+
+
+def _gpu():
+    from olap_in_memory_b200.store import GpuStore
+
+    return GpuStore
+
+
+@pytest.mark.parametrize("with_status", [True, False], ids=["status", "nostatus"])
+@pytest.mark.parametrize("case", ALL, ids=[f"{i}-{c['op']}" for i, c in enumerate(ALL)])
+def test_case_matches_oracle(case, with_status):
+    G = _gpu()
+    old = G.WITH_STATUS
+    G.WITH_STATUS = with_status
+    try:
+        got = cases.run_case(case, G)
+    finally:
+        G.WITH_STATUS = old
+    want = cases.run_case(case, COracleStore)
+    assert cases.bits_equal(got, want.astype(np.float32)), (
+        cases.describe(case) + f"\n got  {got[:16]}\n want {want[:16]}")
+
+
+def test_appendix_a_edge_vectors():
+    """SURVEY.md Appendix A1-A12, hand-derived from in-memory.js."""
+    G = _gpu()
+    nan = math.nan
+
+    def up(data, default, method):
+        s = G(len(data), "float32", default)
+        s.set_data_f32(np.asarray(data, np.float32))
+        return G.drillUp_lowered([s], [len(data)], [1], [np.zeros(len(data), np.int32)], [method])[0].data_f32()
+
+    assert up([-1, 0, -2], 0, "highest").tolist() == [-1.0]           # A1
+    assert up([2, 0, 4], 0, "average").tolist() == [3.0]              # A2
+    assert up([0, 5, 7], 0, "first").tolist() == [5.0]                # A3
+    assert up([2, 0, 3], 0, "product").tolist() == [6.0]              # A4
+    assert up([1, -1, 5], 0, "average").tolist() == [np.float32(5 / 3)]  # A5
+    assert up([10, 0, 20], nan, "average").tolist() == [10.0]         # A6
+    assert np.isnan(up([1, nan], 0, "highest")[0]) and np.isnan(up([1, nan], 0, "lowest")[0])  # A7
+    hi, lo = up([-0.0, 0.0], nan, "highest"), up([0.0, -0.0], nan, "lowest")  # A8
+    assert hi[0] == 0 and not np.signbit(hi[0]) and lo[0] == 0 and np.signbit(lo[0])
+
+    def down(data, default, typ, times):
+        s = G(len(data), typ, default)
+        s.set_data_f32(np.asarray(data, np.float32))
+        m = np.repeat(np.arange(len(data), dtype=np.int32), times)
+        return G.drillDown_lowered([s], [len(data)], [len(data) * times], [m], ["sum"])[0].data_f32()
+
+    a9 = down([0, 6], nan, "float32", 2)
+    assert np.isnan(a9[:2]).all() and a9[2:].tolist() == [3.0, 3.0]  # A9
+    assert down([nan, 6], 0, "float32", 2).tolist() == [0.0, 0.0, 3.0, 3.0]  # A10
+    assert down([-7], 0, "int32", 3).tolist() == [-3.0, -2.0, -3.0]  # A11
+    s = G(2, "float32", 0)
+    s.set_data_f32(np.asarray([10, 20], np.float32))
+    out = G.drillDown_lowered([s], [2, 1], [2, 3], [np.arange(2, dtype=np.int32), np.zeros(3, np.int32)], ["sum"],
+                              [[0.5, 0.3, 0.2, 0.1, 0.1, 0.8]])[0]
+    assert np.allclose(out.data_f32(), [5, 3, 2, 2, 2, 16], rtol=1e-6)  # A12
+    with pytest.raises(ValueError, match="distribution missing for index 4"):
+        G.drillDown_lowered([s], [2, 1], [2, 3], [np.arange(2, dtype=np.int32), np.zeros(3, np.int32)], ["sum"],
+                            [[0.5, 0.3, 0.2, 0.1, None, 0.8]])
+
+
+def test_declared_divergences():
+    """the device contract is ascending child index and 32-bit counts."""
+    G = _gpu()
+    s = G(3, "float32", 0)
+    s.set_data_f32(np.asarray([10, 20, 30], np.float32))
+    diced = G.dice_lowered([s], [3], [[2, 0, 1]])[0]
+    assert diced.data_f32().tolist() == [30.0, 10.0, 20.0]
+    zeros = [np.zeros(3, np.int32)]
+    assert G.drillUp_lowered([diced], [3], [1], zeros, ["first"])[0].data_f32().tolist() == [30.0]  # reference: 10
+    assert G.drillUp_lowered([diced], [3], [1], zeros, ["last"])[0].data_f32().tolist() == [20.0]   # reference: 30
+    big = G(65536, "float32", 0)
+    big.set_data_f32(np.full(65536, 2.0, np.float32))
+    avg = G.drillUp_lowered([big], [65536], [1], [np.zeros(65536, np.int32)], ["average"])[0]
+    assert avg.data_f32().tolist() == [2.0]  # reference: 131072 (Uint16 wrap)
+
+
+def test_store_accessors_and_sparse_roundtrip():
+    G = _gpu()
+    rng = np.random.default_rng(5)
+    for default in (0.0, math.nan):
+        data = cases.make_data(rng, 10007, default, 0.3, "int")
+        s = G(data.size, "float32", default)
+        s.set_data_f32(data)
+        o = OracleStore(data.size, "float32", default)
+        o.data = [float(x) for x in data]
+        assert cases.bits_equal(s.data_f32(), np.asarray(o.data, np.float32))
+        assert s.presence().tolist() == [1 if i in o._dataMap else 0 for i in range(data.size)]
+        assert s.status == o.status
+        keys, vals = s.export_sparse()
+        assert keys.tolist() == sorted(o._dataMap.keys())
+        assert cases.bits_equal(vals, np.asarray([o._dataMap[k] for k in keys.tolist()], np.float32))
+        if default == 0.0:
+            finite = np.where(np.isnan(data), 0, data)
+            assert not np.isnan(data).any() or np.isnan(s.total)
+            if not np.isnan(data).any():
+                assert math.isclose(s.total, float(finite.astype(np.float64).sum()), rel_tol=1e-9)
+        else:
+            assert math.isclose(s.total, o.total, rel_tol=1e-9)
+        assert s.getValue(17) == np.float32(o.getValue(17)) or (math.isnan(s.getValue(17)) and math.isnan(o.getValue(17)))
+        s.setValue(17, 123.5)
+        o.setValue(17, 123.5)
+        s.setValue(18, None)
+        o.setValue(18, None)
+        assert s.getValue(17) == 123.5 and cases.bits_equal(s.data_f32(), np.asarray(o.data, np.float32))
+        c = s.clone()
+        s.fill(7.0)
+        assert c.getValue(17) == 123.5 and s.getValue(17) == 7.0 and s.total == 7.0 * data.size
+        r = G(data.size, "float32", default)
+        r.import_sparse(*c.export_sparse())
+        assert cases.bits_equal(r.data_f32(), c.data_f32())
+    with pytest.raises(ValueError, match=r"value length is invalid: 4 !== 3"):
+        G(4).set_data_f32(np.zeros(3, np.float32))
+    with pytest.raises(ValueError, match="Invalid default value"):
+        G(4, "float32", 1)
+    with pytest.raises(ValueError, match="Invalid type"):
+        G(4, "float16", 0)
+    assert G(6, "uint32", 0).byteLength == 24 and G(6, "float64", 0).byteLength == 48
+    assert G(0).data == []
+
+
+def test_batched_measures_share_one_call():
+    """All stored measures of a cube in ONE olap_drill_up call, mixed methods."""
+    G = _gpu()
+    rng = np.random.default_rng(9)
+    dims, P = [40, 24], 6
+    m = cases.random_map(rng, 40, P, True)
+    methods = ["sum", "average", "highest", "lowest", "first", "last", "product"]
+    datas = [cases.make_data(rng, 960, 0.0, 0.7, "small" if k == "product" else "int") for k in methods]
+    stores = []
+    for d in datas:
+        s = G(960, "float32", 0.0)
+        s.set_data_f32(d)
+        stores.append(s)
+    outs = G.drillUp_lowered(stores, dims, [P, 24], [m, cases.identity(24)], methods)
+    for d, method, out in zip(datas, methods, outs):
+        o = COracleStore(960, "float32", 0.0)
+        o.set_data_f32(d)
+        want = o.drillUp_lowered(dims, [P, 24], [m, cases.identity(24)], method).data_f64()
+        assert cases.bits_equal(out.data_f32(), want.astype(np.float32)), method
+
+
+def test_status_plane_semantics():
+    """README.md:698-721: drillUp ORs children (0x3 = incomplete), drillDown adds 0x4."""
+    G = _gpu()
+    s = G(6, "float32", math.nan)
+    s.set_data_f32(np.asarray([1, math.nan, 3, math.nan, math.nan, 4], np.float32))
+    assert s.status == [2, 1, 2, 1, 1, 2]
+    up = G.drillUp_lowered([s], [3, 2], [3, 1], [cases.identity(3), np.zeros(2, np.int32)], ["sum"])[0]
+    assert up.status == [3, 3, 3] and up.data_f32().tolist() == [1.0, 3.0, 4.0]
+    up2 = G.drillUp_lowered([s], [3, 2], [1, 2], [np.zeros(3, np.int32), cases.identity(2)], ["sum"])[0]
+    assert up2.status == [3, 3]
+    dn = G.drillDown_lowered([up], [3], [6], [np.repeat(np.arange(3, dtype=np.int32), 2)], ["sum"])[0]
+    assert dn.status == [7, 7, 7, 7, 7, 7]
+
+
+def test_computed_measures():
+    G = _gpu()
+    from olap_in_memory_b200 import Cube, GenericDimension
+
+    rng = np.random.default_rng(11)
+    formulas = ["a + b", "a - b * c", "(a + b) / c", "a || b", "isNaN(a) + 2 * b", "a / a__total + max(b, c, 3)",
+                "min(a, b) ^ 2 % 7", "-a + abs(b - c)", "a ? b : c", "sqrt(abs(a)) + round(b / 3) + floor(c / 7)"]
+    for default in (0.0, math.nan):
+        def mk(store_cls):
+            cube = Cube([GenericDimension("x", "root", [str(i) for i in range(37)]),
+                         GenericDimension("y", "root", [str(i) for i in range(29)])], store_cls)
+            r = np.random.default_rng(3)
+            for name in ("a", "b", "c"):
+                cube.createStoredMeasure(name * 2, {}, "float32", default)
+                cube.setData(name * 2, cases.make_data(r, cube.storeSize, default, 0.8, "int").tolist())
+            for k, f in enumerate(formulas):
+                cube.createComputedMeasure(f"f{k}_m", re_sub(f))
+            return cube
+
+        def re_sub(f):
+            import re
+
+            return re.sub(r"\b([abc])\b", lambda mo: mo.group(1) * 2, f).replace("a__total", "aa__total")
+
+        gpu, cpu = mk(G), mk(OracleStore)
+        for k, f in enumerate(formulas):
+            got = np.asarray(gpu.getData(f"f{k}_m"))
+            want = np.asarray(cpu.getData(f"f{k}_m"))
+            assert np.allclose(got, want, rtol=1e-6, atol=0, equal_nan=True), (f, default)
