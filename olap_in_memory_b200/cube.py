@@ -208,6 +208,17 @@ class Cube:
             )
         raise KeyError(f"getData: no such measure {measureId}")
 
+    def evaluateToStore(self, measureId, type="float32", defaultValue=0):
+        """getData(computedId) kept on the device as a new store — the device-side half
+        of copyToStoredMeasure (cube.js:205-215), without the host round trip."""
+        expression = self.computedMeasures[measureId]
+        names = expression.variables()
+        cell_names = [n for n in names if "__total" not in n]
+        totals = {n: self.storedMeasures[n.replace("__total", "")].total for n in names if "__total" in n}
+        return self._store_cls.evaluate_to_store(
+            expression, cell_names, [self.storedMeasures[n] for n in cell_names], totals, type, defaultValue
+        )
+
     def getStatusMap(self, measureId):
         """Map cell index -> value of the cells that are set (cube.js:368-389)."""
         if measureId in self.storedMeasures:

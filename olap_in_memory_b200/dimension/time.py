@@ -19,6 +19,7 @@ class TimeDimension(AbstractDimension):
         self._end = TimeSlot.fromDate(TimeSlot.fromValue(end).lastDate, "day")
         self._items = {}
         self._rootIdxToGroupIdx = {}
+        self._drilled = {}  # attribute -> dimension; time dimensions are immutable
 
     @property
     def attributes(self):
@@ -45,14 +46,21 @@ class TimeDimension(AbstractDimension):
     def drillUp(self, newAttribute):
         if newAttribute == self.rootAttribute:
             return self
-        return TimeDimension(self.id, newAttribute, self._start.value, self._end.value, self.label)
+        return self._drill(newAttribute)
+
+    def _drill(self, newAttribute):
+        dim = self._drilled.get(newAttribute)
+        if dim is None:
+            dim = TimeDimension(self.id, newAttribute, self._start.value, self._end.value, self.label)
+            self._drilled[newAttribute] = dim
+        return dim
 
     def drillDown(self, newAttribute):
         if newAttribute == self.rootAttribute:
             return self
         if self._rootAttribute not in TimeSlot.upperSlots[newAttribute]:
             raise ValueError("Invalid periodicity.")
-        return TimeDimension(self.id, newAttribute, self._start.value, self._end.value, self.label)
+        return self._drill(newAttribute)
 
     def dice(self, attribute, items, reorder=False):
         if len(items) == 1:
