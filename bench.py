@@ -65,36 +65,43 @@ def synth(out, seed, measure, start=0):
 
 
 class Clocks(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
-
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons of one GPU through NVML every ~2 ms while the
+    timed regions run (the nvidia-smi CLI is too slow for sub-second regions)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.index, self.sm, self.reasons, self.max_mhz = index, [], 0, None
+        self.stop_flag = threading.Event()
+        self.busy = threading.Event()  # set while a timed region is running
 
     def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        except Exception:
+            return
         while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.rows.append(parts)
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+            if self.busy.is_set():
+                try:
+                    self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    self.reasons |= int(get_reasons(h))
+                except Exception:
+                    pass
+            time.sleep(0.002)
 
     def summary(self):
         self.stop_flag.set()
-        self.join(timeout=6)
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": max((int(r[1]) for r in self.rows if r[1].isdigit()), default=None),
-                "reasons": reasons, "samples": len(self.rows)}
+        self.join(timeout=2)
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                "hw_power_brake_slowdown": 0x80}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": self.max_mhz, "reasons": [k for k, v in bits.items() if self.reasons & v],
+                "samples": len(sm)}
 
 
 # ------------------------------------------------------------------ CPU arm (oracle port)
@@ -217,6 +224,7 @@ def run_ours(args, rank, world, local_rank):
         ms_up = None
         if step_device.measure:
             ms_up = lib.olap_last_op_ms()
+            step_device.path = lib.olap_last_op_path().decode()
         ratio = rolled.evaluateToStore("ratio")
         return rolled, ratio, ms_up
 
@@ -231,6 +239,9 @@ def run_ours(args, rank, world, local_rank):
         N.check(lib.olap_store_download_f32(ratio._h, host_out[3].ctypes.data, n_out))
         return float(host_out[3][0])
 
+    clocks = Clocks(local_rank)
+    clocks.start()
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -242,12 +253,14 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         timed.launches = lib.olap_kernel_launches()
+        clocks.busy.set()
         with torch.cuda.stream(stream):
             e0.record(stream)
             for _ in range(steps):
                 fn()
             e1.record(stream)
         barrier()
+        clocks.busy.clear()
         timed.launches = lib.olap_kernel_launches() - timed.launches
         ms = e0.elapsed_time(e1) / steps
         if world > 1:
@@ -266,8 +279,6 @@ def run_ours(args, rank, world, local_rank):
     assert np.array_equal(got, want.astype(np.float32)), "bench: drillUp result does not match the float64 reference"
     del rolled, ratio
 
-    clocks = Clocks(local_rank)
-    clocks.start()
     N.check(lib.olap_set_async(1))
     ms_value = timed(step_device, args.steps, args.warmup)
     launches = timed.launches  # kernels of libolapgpu.so launched inside the timed region
@@ -281,7 +292,7 @@ def run_ours(args, rank, world, local_rank):
         ups.append(ms_up)
     step_device.measure = False
     up_ms = float(np.mean(ups))
-    path = lib.olap_last_op_path().decode()
+    path = step_device.path
 
     ms_e2e = timed(step_e2e, max(1, min(args.steps, 5)), 1)
     clk = clocks.summary()
@@ -329,7 +340,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

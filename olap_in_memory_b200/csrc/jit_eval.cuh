@@ -185,7 +185,12 @@ inline std::string eval_source(const Lowered& lw, int n_inputs, int n_totals) {
          "  return a < b ? a : b; }\n"
          "__device__ __forceinline__ double olap_pow(double a, double b) {\n"
          "  if (b != b) return olap_nan(); if (b == 0.0) return 1.0;\n"
-         "  if (fabs(a) == 1.0 && isinf(b)) return olap_nan(); return pow(a, b); }\n"
+         "  if (fabs(a) == 1.0 && isinf(b)) return olap_nan();\n"
+         // integer exponents by squaring: exact whenever the result is representable
+         // (CUDA pow() is only 2-ulp accurate, which breaks e.g. (7 ^ 2) % 7)
+         "  if (b == trunc(b) && fabs(b) <= 1024.0) { double r = 1.0, x = a; long long e = (long long)fabs(b);\n"
+         "    while (e) { if (e & 1) r *= x; x *= x; e >>= 1; } return b < 0.0 ? 1.0 / r : r; }\n"
+         "  return pow(a, b); }\n"
          "__device__ __forceinline__ float olap_canon(float v, int nan_default) {\n"
          "  if (v != v) return __int_as_float(0x7fc00000); if (!nan_default && v == 0.0f) return 0.0f; return v; }\n";
     s << "__device__ __forceinline__ double olap_formula(";

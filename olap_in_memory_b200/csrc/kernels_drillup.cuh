@@ -76,14 +76,149 @@ struct Acc {
     }
 };
 
+// ---- branch-free lanes for the mid kernel -------------------------------------------
+// Unset cells hold the canonical default, which lets most methods fold the presence test
+// into the arithmetic:
+//  * zero default: an unset cell is +0.0, and x + 0.0 == x, so `sum` adds every child;
+//    set values are never 0, so "accumulator == 0" means "nothing yet" for
+//    first/last/highest/lowest.
+//  * NaN default: an unset cell is NaN and no set value is NaN, so "accumulator is NaN"
+//    means "nothing yet" for first/last/highest/lowest; `sum` masks NaN children to 0.
+// The only stateful corner is the reference's restart after the accumulator lands on the
+// default (in-memory.js:311-318): under a NaN default that is inf + -inf, handled by
+// `dead` below; under a zero default the restart is numerically a no-op.
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float min_nan(float a, float b) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+template <int METHOD, bool NANDEF>
+struct Lane {  // generic (product): the faithful state machine
+    Acc<METHOD> a;
+    __device__ __forceinline__ void step(float v) { a.step(v, NANDEF); }
+    __device__ __forceinline__ float result() const { return a.result(NANDEF); }
+};
+
+template <>
+struct Lane<OLAP_SUM, false> {
+    double acc = 0.0;
+    __device__ __forceinline__ void step(float v) { acc += (double)v; }
+    __device__ __forceinline__ float result() const { return canon_store((float)acc, 0); }
+};
+template <>
+struct Lane<OLAP_AVERAGE, false> {
+    double acc = 0.0;
+    uint32_t cnt = 0;
+    __device__ __forceinline__ void step(float v) {
+        acc += (double)v;
+        cnt += (v != 0.0f) ? 1u : 0u;  // NaN != 0: a stored NaN is a set cell
+    }
+    __device__ __forceinline__ float result() const { return canon_store(cnt ? (float)(acc / (double)cnt) : 0.0f, 0); }
+};
+template <>
+struct Lane<OLAP_SUM, true> {
+    double acc = -0.0;  // -0 is the identity of IEEE addition: a set -0 must stay -0
+    bool has = false;
+    __device__ __forceinline__ void step(float v) {
+        const bool pres = v == v;
+        const bool dead = acc != acc;  // inf + -inf was deleted: the next set child restarts
+        acc = ((pres && dead) ? -0.0 : acc) + (pres ? (double)v : -0.0);
+        has |= pres;
+    }
+    __device__ __forceinline__ float result() const { return has ? canon_store((float)acc, 1) : canon_nan(); }
+};
+template <>
+struct Lane<OLAP_AVERAGE, true> {
+    double acc = -0.0;
+    uint32_t cnt = 0;
+    __device__ __forceinline__ void step(float v) {
+        const bool pres = v == v;
+        const bool dead = acc != acc;
+        acc = ((pres && dead) ? -0.0 : acc) + (pres ? (double)v : -0.0);
+        cnt += pres ? 1u : 0u;
+    }
+    __device__ __forceinline__ float result() const { return cnt ? canon_store((float)(acc / (double)cnt), 1) : canon_nan(); }
+};
+template <>
+struct Lane<OLAP_HIGHEST, false> {
+    float acc = 0.0f;
+    __device__ __forceinline__ void step(float v) {
+        const float m = max_nan(acc, v);  // set values are never 0 here: no signed-zero case
+        acc = (v != 0.0f) ? ((acc == 0.0f) ? v : m) : acc;
+    }
+    __device__ __forceinline__ float result() const { return canon_store(acc, 0); }
+};
+template <>
+struct Lane<OLAP_LOWEST, false> {
+    float acc = 0.0f;
+    __device__ __forceinline__ void step(float v) {
+        const float m = min_nan(acc, v);
+        acc = (v != 0.0f) ? ((acc == 0.0f) ? v : m) : acc;
+    }
+    __device__ __forceinline__ float result() const { return canon_store(acc, 0); }
+};
+template <>
+struct Lane<OLAP_HIGHEST, true> {
+    float acc;
+    __device__ __forceinline__ Lane() : acc(canon_nan()) {}
+    __device__ __forceinline__ void step(float v) {
+        const float m = js_max(acc, v);  // Math.max(-0, +0) = +0
+        acc = (v == v) ? ((acc != acc) ? v : m) : acc;
+    }
+    __device__ __forceinline__ float result() const { return canon_store(acc, 1); }
+};
+template <>
+struct Lane<OLAP_LOWEST, true> {
+    float acc;
+    __device__ __forceinline__ Lane() : acc(canon_nan()) {}
+    __device__ __forceinline__ void step(float v) {
+        const float m = js_min(acc, v);
+        acc = (v == v) ? ((acc != acc) ? v : m) : acc;
+    }
+    __device__ __forceinline__ float result() const { return canon_store(acc, 1); }
+};
+template <>
+struct Lane<OLAP_FIRST, false> {
+    float acc = 0.0f;
+    __device__ __forceinline__ void step(float v) { acc = (acc == 0.0f) ? v : acc; }
+    __device__ __forceinline__ float result() const { return canon_store(acc, 0); }
+};
+template <>
+struct Lane<OLAP_FIRST, true> {
+    float acc;
+    __device__ __forceinline__ Lane() : acc(canon_nan()) {}
+    __device__ __forceinline__ void step(float v) { acc = (acc != acc) ? v : acc; }
+    __device__ __forceinline__ float result() const { return canon_store(acc, 1); }
+};
+template <>
+struct Lane<OLAP_LAST, false> {
+    float acc = 0.0f;
+    __device__ __forceinline__ void step(float v) { acc = (v != 0.0f) ? v : acc; }
+    __device__ __forceinline__ float result() const { return canon_store(acc, 0); }
+};
+template <>
+struct Lane<OLAP_LAST, true> {
+    float acc;
+    __device__ __forceinline__ Lane() : acc(canon_nan()) {}
+    __device__ __forceinline__ void step(float v) { acc = (v == v) ? v : acc; }
+    __device__ __forceinline__ float result() const { return canon_store(acc, 1); }
+};
+
 // ---- kernel A: one changed dimension, any I ----------------------------------
 // Thread (tx, ty) of a block owns output vector j = bx*blockDim.x + tx of row
 // o = by*blockDim.y + ty, where a row is the P*IV output vectors of one outer index.
-// Loads along I are 128-bit and fully coalesced when VEC == 4.
+// Loads along I are 128-bit and fully coalesced when VEC == 4; U children are in flight
+// per thread.  No shared memory: there is no reuse, every input byte is read once.
 struct UpMidParams {
     const UpMeasure* meas;
     const int32_t* pstart;    // [P+1]
-    const int32_t* children;  // [C] ascending per parent, or nullptr when ranges are contiguous
+    const int32_t* children;  // [C] ascending per parent (unused when RANGE)
     int64_t O;
     int32_t C, P;
     int64_t I;            // elements of the inner run handled by this launch
@@ -98,74 +233,92 @@ struct UpMidParams {
     int n_measures;
 };
 
-template <int METHOD, int VEC>
+template <int VEC>
+struct Cells {
+    float v[VEC];
+    uint32_t st;
+};
+
+template <int VEC, bool STATUS>
+__device__ __forceinline__ Cells<VEC> load_cells(const float* src, const uint8_t* st_src, int64_t off) {
+    Cells<VEC> c;
+    if (VEC == 4) {
+        const float4 t = ld_stream4(src + off);
+        c.v[0] = t.x; c.v[1 % VEC] = t.y; c.v[2 % VEC] = t.z; c.v[3 % VEC] = t.w;
+        c.st = STATUS ? ld_stream_u32(st_src + off) : 0u;
+    } else {
+        c.v[0] = ld_stream1(src + off);
+        c.st = STATUS ? (uint32_t)st_src[off] : 0u;
+    }
+    return c;
+}
+
+template <int METHOD, bool NANDEF, int VEC, bool RANGE, bool STATUS, int U>
 __device__ __forceinline__ void up_mid_body(const UpMidParams& p, const UpMeasure& m, int64_t o, uint32_t pi,
                                             uint32_t iv) {
-    const int nan_default = m.nan_default;
     const int32_t k0 = p.pstart[pi], k1 = p.pstart[pi + 1];
     const int64_t inner = p.i_base + (int64_t)iv * VEC;
     const float* src = m.in + o * p.in_row + inner;
-    const uint8_t* st_src = m.st_in ? m.st_in + o * p.in_row + inner : nullptr;
+    const uint8_t* st_src = STATUS ? m.st_in + o * p.in_row + inner : nullptr;
     const int64_t stride = p.I_total;
 
-    Acc<METHOD> a[VEC];
+    Lane<METHOD, NANDEF> lane[VEC];
     uint32_t st = 0;
 
-    constexpr int U = 4;  // children in flight per thread
+    // U children in flight per thread
     int32_t k = k0;
     for (; k + U <= k1; k += U) {
-        float v[U][VEC];
-        uint32_t s[U];
+        Cells<VEC> c[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int64_t c = p.children ? p.children[k + u] : (k + u);
-            if (VEC == 4) {
-                float4 t = ld_stream4(src + c * stride);
-                v[u][0] = t.x; v[u][1 % VEC] = t.y; v[u][2 % VEC] = t.z; v[u][3 % VEC] = t.w;
-                s[u] = st_src ? ld_stream_u32(st_src + c * stride) : 0u;
-            } else {
-                v[u][0] = ld_stream1(src + c * stride);
-                s[u] = st_src ? (uint32_t)st_src[c * stride] : 0u;
-            }
+            const int64_t child = RANGE ? (int64_t)(k + u) : (int64_t)p.children[k + u];
+            c[u] = load_cells<VEC, STATUS>(src, st_src, child * stride);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) a[e].step(v[u][e], nan_default);
-            st |= s[u];
+            for (int e = 0; e < VEC; ++e) lane[e].step(c[u].v[e]);
+            st |= c[u].st;
         }
     }
     for (; k < k1; ++k) {
-        const int64_t c = p.children ? p.children[k] : k;
-        if (VEC == 4) {
-            float4 t = ld_stream4(src + c * stride);
-            a[0].step(t.x, nan_default); a[1 % VEC].step(t.y, nan_default);
-            a[2 % VEC].step(t.z, nan_default); a[3 % VEC].step(t.w, nan_default);
-            if (st_src) st |= ld_stream_u32(st_src + c * stride);
-        } else {
-            a[0].step(ld_stream1(src + c * stride), nan_default);
-            if (st_src) st |= (uint32_t)st_src[c * stride];
-        }
+        const int64_t child = RANGE ? (int64_t)k : (int64_t)p.children[k];
+        const Cells<VEC> c = load_cells<VEC, STATUS>(src, st_src, child * stride);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) lane[e].step(c.v[e]);
+        st |= c.st;
     }
 
-    float* dst = m.out + o * p.out_row + (int64_t)pi * p.I_total + inner;
+    const int64_t out_off = o * p.out_row + (int64_t)pi * p.I_total + inner;
     if (VEC == 4) {
         float4 r;
-        r.x = a[0].result(nan_default); r.y = a[1 % VEC].result(nan_default);
-        r.z = a[2 % VEC].result(nan_default); r.w = a[3 % VEC].result(nan_default);
-        st_stream4(dst, r);
+        r.x = lane[0].result(); r.y = lane[1 % VEC].result(); r.z = lane[2 % VEC].result(); r.w = lane[3 % VEC].result();
+        st_stream4(m.out + out_off, r);
     } else {
-        *dst = a[0].result(nan_default);
+        m.out[out_off] = lane[0].result();
     }
-    if (m.st_out) {
-        uint8_t* st_dst = m.st_out + o * p.out_row + (int64_t)pi * p.I_total + inner;
+    if (STATUS) {
         if (k0 == k1) st = VEC == 4 ? 0x01010101u : 0x1u;  // no child at all: not set
-        if (VEC == 4) *reinterpret_cast<uint32_t*>(st_dst) = st;
-        else *st_dst = (uint8_t)st;
+        if (VEC == 4) *reinterpret_cast<uint32_t*>(m.st_out + out_off) = st;
+        else m.st_out[out_off] = (uint8_t)st;
     }
 }
 
-template <int VEC>
+template <bool NANDEF, int VEC, bool RANGE, bool STATUS, int U>
+__device__ __forceinline__ void up_mid_dispatch(const UpMidParams& p, const UpMeasure& m, int64_t o, uint32_t pi,
+                                                uint32_t iv) {
+    switch (m.method) {
+        case OLAP_SUM: up_mid_body<OLAP_SUM, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv); break;
+        case OLAP_AVERAGE: up_mid_body<OLAP_AVERAGE, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv); break;
+        case OLAP_HIGHEST: up_mid_body<OLAP_HIGHEST, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv); break;
+        case OLAP_LOWEST: up_mid_body<OLAP_LOWEST, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv); break;
+        case OLAP_FIRST: up_mid_body<OLAP_FIRST, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv); break;
+        case OLAP_LAST: up_mid_body<OLAP_LAST, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv); break;
+        default: up_mid_body<OLAP_PRODUCT, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv); break;
+    }
+}
+
+template <int VEC, bool RANGE, int U>
 __global__ void __launch_bounds__(256) drillup_mid_kernel(const __grid_constant__ UpMidParams p) {
     const uint32_t brow = blockIdx.x / p.blocks_per_row;  // uniform per block
     const uint32_t bcol = blockIdx.x - brow * p.blocks_per_row;
@@ -175,14 +328,13 @@ __global__ void __launch_bounds__(256) drillup_mid_kernel(const __grid_constant_
     const uint32_t pi = p.div_iv.div(j);
     const uint32_t iv = j - pi * p.IV;
     const UpMeasure m = p.meas[blockIdx.y];
-    switch (m.method) {
-        case OLAP_SUM: up_mid_body<OLAP_SUM, VEC>(p, m, o, pi, iv); break;
-        case OLAP_AVERAGE: up_mid_body<OLAP_AVERAGE, VEC>(p, m, o, pi, iv); break;
-        case OLAP_HIGHEST: up_mid_body<OLAP_HIGHEST, VEC>(p, m, o, pi, iv); break;
-        case OLAP_LOWEST: up_mid_body<OLAP_LOWEST, VEC>(p, m, o, pi, iv); break;
-        case OLAP_FIRST: up_mid_body<OLAP_FIRST, VEC>(p, m, o, pi, iv); break;
-        case OLAP_LAST: up_mid_body<OLAP_LAST, VEC>(p, m, o, pi, iv); break;
-        default: up_mid_body<OLAP_PRODUCT, VEC>(p, m, o, pi, iv); break;
+    const bool status = m.st_in != nullptr;
+    if (m.nan_default) {
+        if (status) up_mid_dispatch<true, VEC, RANGE, true, U>(p, m, o, pi, iv);
+        else up_mid_dispatch<true, VEC, RANGE, false, U>(p, m, o, pi, iv);
+    } else {
+        if (status) up_mid_dispatch<false, VEC, RANGE, true, U>(p, m, o, pi, iv);
+        else up_mid_dispatch<false, VEC, RANGE, false, U>(p, m, o, pi, iv);
     }
 }
 

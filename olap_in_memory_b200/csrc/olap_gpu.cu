@@ -236,7 +236,7 @@ static int launch_up_mid(const UpMeasure* d_meas, int n, const Csr& csr, const i
         UpMidParams p{};
         p.meas = d_meas;
         p.pstart = d_pstart;
-        p.children = csr.contiguous ? nullptr : d_children;
+        p.children = d_children;
         p.O = O; p.C = (int32_t)C; p.P = (int32_t)P;
         p.I = iv_n * VEC;
         p.I_total = I;
@@ -253,8 +253,18 @@ static int launch_up_mid(const UpMeasure* d_meas, int n, const Csr& csr, const i
         const int64_t gx = ceil_div(O, by) * p.blocks_per_row;
         if (gx > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "drillUp: grid too large (%lld blocks)", (long long)gx);
         dim3 grid((unsigned)gx, (unsigned)n), block(bx, by);
-        if (VEC == 4) drillup_mid_kernel<4><<<grid, block, 0, g.stream>>>(p);
-        else drillup_mid_kernel<1><<<grid, block, 0, g.stream>>>(p);
+        static const int U = [] { const char* e = getenv("OLAP_UP_U"); return e ? atoi(e) : 8; }();  // tuning knob
+#define OLAP_UP_LAUNCH(V, R)                                                                         \
+    do {                                                                                             \
+        if (U == 4) drillup_mid_kernel<V, R, 4><<<grid, block, 0, g.stream>>>(p);                    \
+        else drillup_mid_kernel<V, R, 8><<<grid, block, 0, g.stream>>>(p);                           \
+    } while (0)
+        if (VEC == 4) {
+            if (csr.contiguous) OLAP_UP_LAUNCH(4, true); else OLAP_UP_LAUNCH(4, false);
+        } else {
+            if (csr.contiguous) OLAP_UP_LAUNCH(1, true); else OLAP_UP_LAUNCH(1, false);
+        }
+#undef OLAP_UP_LAUNCH
         LAUNCHED();
     }
     return OLAP_OK;
@@ -681,7 +691,9 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
             const size_t o_ps = t.add(csr.pstart.data(), csr.pstart.size() * 4);
             const size_t o_ch = t.add(csr.children.data(), csr.children.size() * 4);
             OLAP_TRY(t.upload());
-            TileDecision tile = tile_plan(O, C, P, I, n);
+            bool any_status = false;
+            for (int k = 0; k < n; ++k) any_status |= meas[k].st_in != nullptr;
+            TileDecision tile = tile_plan(O, C, P, I, any_status);
             if (tile.use) {
                 path = "drillup/tile";
                 OLAP_TRY(launch_up_tile(t.ptr<UpMeasure>(o_meas), n, csr.contiguous, t.ptr<int32_t>(o_ps), t.ptr<int32_t>(o_ch), O, C, P, I, tile));
