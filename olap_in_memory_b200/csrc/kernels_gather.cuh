@@ -24,16 +24,23 @@ struct GatherMeasure {
     int method_is_sum;
 };
 
+// drillDown bookkeeping of one new item: siblings under its parent, rank among them
+// (ascending new index), and 1.0 / siblings.
+struct DownAux {
+    int32_t cnt, rank;
+    double inv;
+};
+
 // one new-side dimension of a gather: either linear (offset = coord * stride) or a table
 struct GDim {
     int64_t len = 1;
     bool linear = true;
     int64_t stride = 0;
     std::vector<int64_t> tbl;
-    std::vector<int2> aux;  // drillDown only
+    std::vector<DownAux> aux;  // drillDown only
 };
 
-enum GatherMode { G_COPY = 0, G_DOWN = 1 };
+enum GatherMode { G_COPY = 0, G_DOWN = 1, G_DOWN_FLOAT = 2 };  // G_DOWN_FLOAT: float cells, method sum, no distributions
 
 struct GatherParams {
     const GatherMeasure* meas;
@@ -42,7 +49,8 @@ struct GatherParams {
     FastDiv div[OLAP_MAX_DIMS];
     const int64_t* tbl[OLAP_MAX_DIMS];   // source offset contribution per new coordinate, or
     int64_t lin[OLAP_MAX_DIMS];          // nullptr: the contribution is coordinate * lin[d]
-    const int2* aux[OLAP_MAX_DIMS];      // drillDown: {siblings, rank among siblings}; nullable
+    const DownAux* aux[OLAP_MAX_DIMS];   // drillDown: siblings / rank / 1/siblings per new item; nullable
+    int n_aux;                           // how many dimensions carry aux
     int64_t I;                           // inner run (elements), contiguous on both sides
     uint32_t IV;                         // I / VEC
     FastDiv div_iv;
@@ -53,8 +61,12 @@ struct GatherParams {
 };
 
 // in-memory.js:383-427 for one cell: `v` parent value, `n` siblings, `k` rank.
+// `inv` = 1.0 / n, computed once per thread.  For the float path the reference computes
+// fround(v / n) in double; v * (1/n) differs from v / n by < 2^-52 relative, and v / n
+// (v float32, n < 2^20) is never that close to a float32 rounding boundary, so the float32
+// result is identical; larger n take the exact division.
 __device__ __forceinline__ float down_value(const GatherMeasure& m, const GatherParams& p, float v, uint32_t n,
-                                            uint32_t k, int64_t new_idx, bool& ok) {
+                                            double inv, uint32_t k, int64_t new_idx, bool& ok) {
     ok = false;
     if (v == 0.0f || v != v) return default_of(m.nan_default);  // `if (!oldValue) continue`
     double r;
@@ -70,13 +82,16 @@ __device__ __forceinline__ float down_value(const GatherMeasure& m, const Gather
         r = (double)v * w;
     } else if (m.method_is_sum) {
         if (m.int_rounding) {
-            const double dn = (double)n;
-            const double base = floor((double)v / dn);
-            const double step = fmod((double)v, dn) / dn;
+            // floor(v/n), v % n (sign of the dividend), then the reference's spreading rule
+            const double dv = (double)v, dn = (double)n;
+            const double quot = dv / dn;
+            const double base = floor(quot);
+            const double rem = fma(-trunc(quot), dn, dv);  // == fmod(v, n): exact in double
+            const double step = rem / dn;
             const bool last_is_same = floor((double)k * step) == floor(((double)k - 1.0) * step);
             r = last_is_same ? base : base + 1.0;
         } else {
-            r = (double)v / (double)n;
+            r = n < (1u << 20) ? (double)v * inv : (double)v / (double)n;
         }
     } else {
         r = (double)v;
@@ -94,6 +109,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
 
     int64_t src_off[U], dst_off[U];
     uint32_t sib[U], rank[U];
+    double inv_of[U];
     bool live[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -112,6 +128,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
         int64_t off = (int64_t)colv * VEC;
         dst_off[u] = row * p.I + off;
         uint32_t n = 1, k = 0;
+        double inv1 = 1.0;
         if (live[u]) {
             if (BIG) {
                 int64_t rest = row;
@@ -120,10 +137,11 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
                     const uint32_t c = (uint32_t)(rest - q * p.len[d]);
                     rest = q;
                     off += p.tbl[d] ? p.tbl[d][c] : (int64_t)c * p.lin[d];
-                    if (MODE == G_DOWN && p.aux[d]) {
-                        const int2 a = p.aux[d][c];
-                        k += (uint32_t)a.y * n;  // ranks compose last-dimension-fastest
-                        n *= (uint32_t)a.x;
+                    if (MODE != G_COPY && p.aux[d]) {
+                        const DownAux a = p.aux[d][c];
+                        k += (uint32_t)a.rank * n;  // ranks compose last-dimension-fastest
+                        n *= (uint32_t)a.cnt;
+                        inv1 = a.inv;
                     }
                 }
             } else {
@@ -133,10 +151,11 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
                     const uint32_t c = rest - q * p.len[d];
                     rest = q;
                     off += p.tbl[d] ? p.tbl[d][c] : (int64_t)c * p.lin[d];
-                    if (MODE == G_DOWN && p.aux[d]) {
-                        const int2 a = p.aux[d][c];
-                        k += (uint32_t)a.y * n;
-                        n *= (uint32_t)a.x;
+                    if (MODE != G_COPY && p.aux[d]) {
+                        const DownAux a = p.aux[d][c];
+                        k += (uint32_t)a.rank * n;
+                        n *= (uint32_t)a.cnt;
+                        inv1 = a.inv;
                     }
                 }
             }
@@ -144,6 +163,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
         src_off[u] = off;
         sib[u] = n;
         rank[u] = k;
+        inv_of[u] = inv1;
     }
 
     float v[U][VEC];
@@ -164,12 +184,23 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         if (!live[u]) continue;
-        if (MODE == G_DOWN) {
+        if (MODE != G_COPY) {
             uint32_t so = 0;
+            const double inv = p.n_aux == 1 ? inv_of[u] : 1.0 / (double)sib[u];
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
                 bool ok;
-                v[u][e] = down_value(m, p, v[u][e], sib[u], rank[u], dst_off[u] + e, ok);
+                if (MODE == G_DOWN_FLOAT) {
+                    // fround(v / n) for a truthy parent, else unset (in-memory.js:386-387, 419)
+                    const float x = v[u][e];
+                    const float r = canon_store((float)(sib[u] < (1u << 20) ? (double)x * inv : (double)x / (double)sib[u]),
+                                                m.nan_default);
+                    const bool truthy = x != 0.0f && x == x;
+                    v[u][e] = truthy ? r : default_of(m.nan_default);
+                    ok = truthy && present_f(r, m.nan_default);
+                } else {
+                    v[u][e] = down_value(m, p, v[u][e], sib[u], inv, rank[u], dst_off[u] + e, ok);
+                }
                 const uint32_t sb = (s[u] >> (8 * e)) & 0xffu;
                 so |= (ok ? ((sb | OLAP_STATUS_INTERPOLATED) & 0xffu) : (uint32_t)OLAP_STATUS_UNSET) << (8 * e);
             }

@@ -205,7 +205,7 @@ inline int launch_up_tile(const UpMeasure* d_meas, int n, bool contiguous, const
     static bool attr_set[2] = {false, false};
     auto kern = contiguous ? drillup_tile_kernel<true> : drillup_tile_kernel<false>;
     if (!attr_set[contiguous]) {
-        OLAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        OLAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
         attr_set[contiguous] = true;
     }
     kern<<<dim3((unsigned)tiles, (unsigned)n), 256, t.smem, g.stream>>>(p);
@@ -213,12 +213,325 @@ inline int launch_up_tile(const UpMeasure* d_meas, int n, bool contiguous, const
     return OLAP_OK;
 }
 
+// ---- reorder whose innermost axis moves: box-tiled permutation -------------------------
+// reorder (in-memory.js:178-211) is out[new] = in[old] for a permutation of the axes.
+// When the output's innermost axis is not the input's, a thread-per-output gather reads
+// with a large stride.  Here a CTA owns a BOX of the cube: a few axes with extent b_d > 1
+// chosen so that the box covers >= 32 contiguous cells of the INPUT's trailing axes and
+// >= 32 contiguous cells of the OUTPUT's trailing axes.  Phase 1 walks the box in input
+// order (coalesced loads) and drops each cell at its output-order position in shared
+// memory (row pitches padded to odd numbers against bank conflicts); phase 2 walks the box
+// in output order: linear shared-memory reads, coalesced stores.  The status plane rides
+// along as bytes.
+constexpr int kMaxBoxDims = 4;
+
+struct BoxDim {
+    uint32_t b;         // box extent along this axis (1 = padding entry)
+    FastDiv div;        // by b
+    uint32_t g_stride;  // box-relative global stride (source in phase 1, destination in phase 2)
+    uint32_t s_stride;  // shared-memory pitch, elements
+    uint32_t axis;      // output axis whose (possibly ragged) extent bounds this entry
+    uint32_t ext_mult;  // cells of fully covered inner axes merged into this entry
+};
+
+struct TransposeParams {
+    const GatherMeasure* meas;
+    int nb;                        // entries used in rd[] / wr[] (both padded to nb)
+    BoxDim rd[kMaxBoxDims], wr[kMaxBoxDims];  // input order / output order, innermost first
+    uint32_t box_cells;            // prod b
+    // grid decomposition: every output axis, outermost first
+    int n_axes;
+    uint32_t boxes[OLAP_MAX_DIMS];   // number of boxes along the axis
+    FastDiv div_boxes[OLAP_MAX_DIMS];
+    uint32_t len[OLAP_MAX_DIMS];     // axis length
+    uint32_t bsize[OLAP_MAX_DIMS];   // box extent (1 for axes outside the box)
+    int64_t src_stride[OLAP_MAX_DIMS], dst_stride[OLAP_MAX_DIMS];
+    uint32_t st_offset;              // byte offset of the status tile in shared memory
+};
+
 struct TransposePlan {
     bool use = false;
+    TransposeParams p{};
+    int64_t n_boxes = 0;
+    size_t smem = 0;
 };
-inline TransposePlan transpose_plan(const std::vector<GDim>&) { return TransposePlan{}; }
-inline int launch_transpose(const std::vector<GatherMeasure>&, int, const TransposePlan&) {
-    return fail(OLAP_E_UNSUPPORTED, "transpose path not built");
+
+template <int NB, bool CHECK>
+__device__ __forceinline__ bool box_decode(const BoxDim (&dims)[kMaxBoxDims], const uint32_t (&ext)[kMaxBoxDims],
+                                           uint32_t t, uint32_t& g_off, uint32_t& s_off) {
+    bool ok = true;
+    g_off = 0;
+    s_off = 0;
+#pragma unroll
+    for (int d = 0; d < NB; ++d) {
+        uint32_t c;
+        if (d == NB - 1) c = t;
+        else {
+            const uint32_t q = dims[d].div.div(t);
+            c = t - q * dims[d].b;
+            t = q;
+        }
+        if (CHECK) ok = ok && c < ext[d];
+        g_off += c * dims[d].g_stride;
+        s_off += c * dims[d].s_stride;
+    }
+    return ok;
+}
+
+template <int NB, bool STATUS, bool CHECK>
+__device__ __forceinline__ void transpose_phases(const TransposeParams& p, const float* __restrict__ src,
+                                                 const uint8_t* __restrict__ st_src, float* __restrict__ dst,
+                                                 uint8_t* __restrict__ st_dst, float* s_val, uint8_t* s_st,
+                                                 const uint32_t (&ext_rd)[kMaxBoxDims],
+                                                 const uint32_t (&ext_wr)[kMaxBoxDims]) {
+    constexpr int U = 4;
+    // ---- phase 1: input order -> shared memory (output-order positions)
+    for (uint32_t t0 = threadIdx.x; t0 < p.box_cells; t0 += 256 * U) {
+        float v[U];
+        uint8_t sb[U];
+        uint32_t pos[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t t = t0 + u * 256;
+            uint32_t off;
+            ok[u] = box_decode<NB, CHECK>(p.rd, ext_rd, t, off, pos[u]) && t < p.box_cells;
+            if (ok[u]) {
+                v[u] = ld_stream1(src + off);
+                if (STATUS) sb[u] = st_src[off];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (ok[u]) {
+                s_val[pos[u]] = v[u];
+                if (STATUS) s_st[pos[u]] = sb[u];
+            }
+    }
+    __syncthreads();
+    // ---- phase 2: output order <- shared memory
+    for (uint32_t t0 = threadIdx.x; t0 < p.box_cells; t0 += 256 * U) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t t = t0 + u * 256;
+            uint32_t off, sp;
+            const bool ok = box_decode<NB, CHECK>(p.wr, ext_wr, t, off, sp) && t < p.box_cells;
+            if (ok) {
+                dst[off] = s_val[sp];
+                if (STATUS) st_dst[off] = s_st[sp];
+            }
+        }
+    }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(256) transpose_kernel(const __grid_constant__ TransposeParams p) {
+    extern __shared__ __align__(16) unsigned char smem_t[];
+    __shared__ uint32_t s_ext[OLAP_MAX_DIMS];
+    __shared__ int64_t s_base[2];
+    __shared__ int s_full;
+    float* s_val = reinterpret_cast<float*>(smem_t);
+    uint8_t* s_st = smem_t + p.st_offset;
+    const GatherMeasure m = p.meas[blockIdx.y];
+    // ---- which box am I, and how much of it is inside the cube
+    if (threadIdx.x == 0) {
+        uint32_t rest = blockIdx.x;
+        int64_t src = 0, dst = 0;
+        int full = 1;
+        for (int a = p.n_axes - 1; a >= 0; --a) {
+            const uint32_t q = p.div_boxes[a].div(rest);
+            const uint32_t bi = rest - q * p.boxes[a];
+            rest = q;
+            const uint32_t start = bi * p.bsize[a];
+            src += (int64_t)start * p.src_stride[a];
+            dst += (int64_t)start * p.dst_stride[a];
+            const uint32_t e = min(p.bsize[a], p.len[a] - start);
+            s_ext[a] = e;
+            full &= e == p.bsize[a];
+        }
+        s_base[0] = src;
+        s_base[1] = dst;
+        s_full = full;
+    }
+    __syncthreads();
+    uint32_t ext_rd[kMaxBoxDims], ext_wr[kMaxBoxDims];
+#pragma unroll
+    for (int d = 0; d < NB; ++d) {
+        ext_rd[d] = p.rd[d].b > 1 ? s_ext[p.rd[d].axis] * p.rd[d].ext_mult : 1u;
+        ext_wr[d] = p.wr[d].b > 1 ? s_ext[p.wr[d].axis] * p.wr[d].ext_mult : 1u;
+    }
+    const float* src = m.in + s_base[0];
+    float* dst = m.out + s_base[1];
+    const uint8_t* st_src = m.st_in ? m.st_in + s_base[0] : nullptr;
+    uint8_t* st_dst = m.st_in ? m.st_out + s_base[1] : nullptr;
+    if (s_full) {
+        if (m.st_in) transpose_phases<NB, true, false>(p, src, st_src, dst, st_dst, s_val, s_st, ext_rd, ext_wr);
+        else transpose_phases<NB, false, false>(p, src, st_src, dst, st_dst, s_val, s_st, ext_rd, ext_wr);
+    } else {
+        if (m.st_in) transpose_phases<NB, true, true>(p, src, st_src, dst, st_dst, s_val, s_st, ext_rd, ext_wr);
+        else transpose_phases<NB, false, true>(p, src, st_src, dst, st_dst, s_val, s_st, ext_rd, ext_wr);
+    }
+}
+
+// `dims`: the output axes (outermost first) as linear GDims with their SOURCE strides.
+inline TransposePlan transpose_plan(const std::vector<GDim>& dims_in) {
+    TransposePlan plan;
+    static const int force = [] { const char* e = getenv("OLAP_TRANSPOSE"); return e ? atoi(e) : -1; }();
+    if (force == 0) return plan;
+    // drop unit axes and merge neighbours that stay adjacent (same rule as the gather path)
+    std::vector<GDim> dims;
+    for (const GDim& d : dims_in) {
+        if (!d.linear) return plan;
+        if (d.len == 1) continue;
+        if (!dims.empty() && dims.back().stride == d.len * d.stride) {
+            dims.back().len *= d.len;
+            dims.back().stride = d.stride;
+        } else dims.push_back(d);
+    }
+    const int k = (int)dims.size();
+    if (k < 2 || k > OLAP_MAX_DIMS) return plan;
+    if (dims.back().stride == 1) return plan;  // innermost axis unchanged: the vectorised gather streams it
+    for (const GDim& d : dims)
+        if (d.len > 0x7fffffffLL) return plan;
+    std::vector<int64_t> dst_stride(k);
+    int64_t acc = 1;
+    for (int i = k - 1; i >= 0; --i) { dst_stride[i] = acc; acc *= dims[i].len; }
+    // axes by ascending source stride = the input's trailing axes first
+    std::vector<int> by_src(k);
+    for (int i = 0; i < k; ++i) by_src[i] = i;
+    std::sort(by_src.begin(), by_src.end(), [&](int a, int b) { return dims[a].stride < dims[b].stride; });
+    std::vector<int64_t> b(k, 1);
+    const int64_t run_target = 64, cells_target = 4096, cells_max = 8192;
+    auto cells = [&] { int64_t c = 1; for (int i = 0; i < k; ++i) c *= b[i]; return c; };
+    // (1) cover the input's trailing axes until a contiguous input run of >= run_target cells
+    int64_t run = 1;
+    for (int idx : by_src) {
+        if (run >= run_target) break;
+        const int64_t want = std::min<int64_t>(dims[idx].len, ceil_div(run_target, run));
+        b[idx] = std::max(b[idx], want);
+        run *= b[idx];
+        if (b[idx] < dims[idx].len) break;  // a partially covered axis ends the contiguous run
+    }
+    // (2) same for the output's trailing axes
+    run = 1;
+    for (int i = k - 1; i >= 0; --i) {
+        if (run >= run_target) break;
+        const int64_t want = std::min<int64_t>(dims[i].len, ceil_div(run_target, run));
+        b[i] = std::max(b[i], want);
+        run *= b[i];
+        if (b[i] < dims[i].len) break;
+    }
+    if (cells() > cells_max) {
+        // shrink the two run axes evenly until the box fits
+        while (cells() > cells_max) {
+            int big = 0;
+            for (int i = 1; i < k; ++i) if (b[i] > b[big]) big = i;
+            if (b[big] <= 1) return plan;
+            b[big] = (b[big] + 1) / 2;
+        }
+    }
+    // (3) grow: widen partially covered axes, innermost output axes first, up to the target
+    for (int pass = 0; pass < 2 && cells() < cells_target; ++pass)
+        for (int i = k - 1; i >= 0 && cells() < cells_target; --i) {
+            if (pass == 0 && b[i] == 1) continue;  // first widen axes already in the box
+            const int64_t room = cells_target / (cells() / b[i]);
+            b[i] = std::max<int64_t>(b[i], std::min<int64_t>(dims[i].len, room));
+        }
+    std::vector<int> box_axes;
+    for (int i = 0; i < k; ++i) if (b[i] > 1) box_axes.push_back(i);
+    if (box_axes.empty()) return plan;
+
+    TransposeParams& p = plan.p;
+    // shared-memory layout: output order inside the box, pitches padded to odd
+    std::vector<uint32_t> pitch(k, 0);
+    uint32_t sacc = 1;
+    for (int i = k - 1; i >= 0; --i) {
+        if (b[i] <= 1) continue;
+        pitch[i] = sacc;
+        sacc *= (uint32_t)b[i];
+        if (sacc % 2 == 0) sacc += 1;
+    }
+    const size_t s_cells = sacc;
+    // phase-1 order: ascending source stride; phase-2 order: ascending destination stride.
+    // Neighbouring entries that are fully covered and contiguous (globally and in shared
+    // memory) are merged into one, which is what keeps the decode at 2-3 divisions.
+    struct Ent { int64_t b, g, s; int axis; bool whole; int64_t mult; };
+    auto build = [&](bool read) {
+        std::vector<int> order = box_axes;
+        std::sort(order.begin(), order.end(), [&](int x, int y) {
+            return read ? dims[x].stride < dims[y].stride : dst_stride[x] < dst_stride[y];
+        });
+        std::vector<Ent> ents;
+        for (int i : order) {
+            Ent e{b[i], read ? dims[i].stride : dst_stride[i], pitch[i], i, b[i] == dims[i].len, 1};
+            if (!ents.empty()) {
+                Ent& in = ents.back();
+                // `in` fully covered (no ragged edge), and e continues it in both address spaces
+                if (in.whole && e.g == in.g * in.b && e.s == in.s * in.b) {
+                    in.mult = in.b;  // valid cells of the merged entry: mult * extent(outer axis)
+                    in.b *= e.b;
+                    in.whole = e.whole;
+                    in.axis = e.axis;
+                    continue;
+                }
+            }
+            ents.push_back(e);
+        }
+        return ents;
+    };
+    std::vector<Ent> rd = build(true), wr = build(false);
+    const int nb = (int)std::max(rd.size(), wr.size());
+    if (nb > kMaxBoxDims) return plan;
+    auto fill = [&](const std::vector<Ent>& ents, BoxDim* out) {
+        for (int q = 0; q < kMaxBoxDims; ++q) {
+            if (q < (int)ents.size()) {
+                if (ents[q].g * (ents[q].b - 1) > 0x7fffffffLL) return false;
+                out[q] = BoxDim{(uint32_t)ents[q].b, FastDiv((uint32_t)ents[q].b), (uint32_t)ents[q].g,
+                                (uint32_t)ents[q].s, (uint32_t)ents[q].axis, (uint32_t)ents[q].mult};
+            } else out[q] = BoxDim{1u, FastDiv(1u), 0u, 0u, 0u, 1u};
+        }
+        return true;
+    };
+    if (!fill(rd, p.rd) || !fill(wr, p.wr)) return plan;
+    p.nb = std::max(nb, 2);
+    p.box_cells = (uint32_t)cells();
+    p.n_axes = k;
+    int64_t n_boxes = 1;
+    for (int i = 0; i < k; ++i) {
+        p.len[i] = (uint32_t)dims[i].len;
+        p.bsize[i] = (uint32_t)b[i];
+        p.boxes[i] = (uint32_t)ceil_div(dims[i].len, b[i]);
+        p.div_boxes[i] = FastDiv(p.boxes[i]);
+        p.src_stride[i] = dims[i].stride;
+        p.dst_stride[i] = dst_stride[i];
+        n_boxes *= p.boxes[i];
+    }
+    if (n_boxes > 0x7fffffffLL) return plan;
+    plan.n_boxes = n_boxes;
+    p.st_offset = (uint32_t)((s_cells * 4 + 15) & ~(size_t)15);
+    plan.smem = p.st_offset + ((s_cells + 15) & ~(size_t)15);
+    if (plan.smem > 200 * 1024) return plan;
+    plan.use = true;
+    return plan;
+}
+
+inline int launch_transpose(const GatherMeasure* d_meas, int n, TransposePlan& plan) {
+    plan.p.meas = d_meas;
+    static bool attr_set = false;
+    if (!attr_set) {
+        OLAP_CUDA(cudaFuncSetAttribute(transpose_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        OLAP_CUDA(cudaFuncSetAttribute(transpose_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        OLAP_CUDA(cudaFuncSetAttribute(transpose_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    const dim3 grid((unsigned)plan.n_boxes, (unsigned)n);
+    switch (plan.p.nb) {
+        case 2: transpose_kernel<2><<<grid, 256, plan.smem, g.stream>>>(plan.p); break;
+        case 3: transpose_kernel<3><<<grid, 256, plan.smem, g.stream>>>(plan.p); break;
+        default: transpose_kernel<4><<<grid, 256, plan.smem, g.stream>>>(plan.p); break;
+    }
+    ++g_launches;
+    return OLAP_OK;
 }
 
 }  // namespace olap

@@ -785,7 +785,7 @@ static int run_gather(int mode, olap_store* const* src, int n, std::vector<GDim>
             big = true;
         }
         if (!dims[d].linear) o_tbl[d] = t.add(dims[d].tbl.data(), dims[d].tbl.size() * 8);
-        if (!dims[d].aux.empty()) o_aux[d] = t.add(dims[d].aux.data(), dims[d].aux.size() * sizeof(int2));
+        if (!dims[d].aux.empty()) o_aux[d] = t.add(dims[d].aux.data(), dims[d].aux.size() * sizeof(DownAux));
         rows *= dims[d].len;
     }
     OLAP_TRY(t.upload());
@@ -796,7 +796,8 @@ static int run_gather(int mode, olap_store* const* src, int n, std::vector<GDim>
         p.div[d] = FastDiv((uint32_t)dims[d].len);
         p.tbl[d] = dims[d].linear ? nullptr : t.ptr<int64_t>(o_tbl[d]);
         p.lin[d] = dims[d].stride;
-        p.aux[d] = dims[d].aux.empty() ? nullptr : t.ptr<int2>(o_aux[d]);
+        p.aux[d] = dims[d].aux.empty() ? nullptr : t.ptr<DownAux>(o_aux[d]);
+        p.n_aux += dims[d].aux.empty() ? 0 : 1;
     }
     p.I = I;
     const int64_t IV = I / VEC;
@@ -819,13 +820,15 @@ static int run_gather(int mode, olap_store* const* src, int n, std::vector<GDim>
     if (gx > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "grid too large");
     dim3 grid((unsigned)gx, (unsigned)n);
 #define OLAP_GATHER(M, V, B) gather_kernel<M, V, B><<<grid, 256, 0, g.stream>>>(p)
-    if (mode == G_COPY) {
-        if (VEC == 4) { if (big) OLAP_GATHER(G_COPY, 4, true); else OLAP_GATHER(G_COPY, 4, false); }
-        else { if (big) OLAP_GATHER(G_COPY, 1, true); else OLAP_GATHER(G_COPY, 1, false); }
-    } else {
-        if (VEC == 4) { if (big) OLAP_GATHER(G_DOWN, 4, true); else OLAP_GATHER(G_DOWN, 4, false); }
-        else { if (big) OLAP_GATHER(G_DOWN, 1, true); else OLAP_GATHER(G_DOWN, 1, false); }
-    }
+#define OLAP_GATHER_VB(M)                                                                      \
+    do {                                                                                       \
+        if (VEC == 4) { if (big) OLAP_GATHER(M, 4, true); else OLAP_GATHER(M, 4, false); }     \
+        else { if (big) OLAP_GATHER(M, 1, true); else OLAP_GATHER(M, 1, false); }              \
+    } while (0)
+    if (mode == G_COPY) OLAP_GATHER_VB(G_COPY);
+    else if (mode == G_DOWN_FLOAT) OLAP_GATHER_VB(G_DOWN_FLOAT);
+    else OLAP_GATHER_VB(G_DOWN);
+#undef OLAP_GATHER_VB
 #undef OLAP_GATHER
     LAUNCHED();
     *path = VEC == 4 ? (big ? "gather/vec4-big" : "gather/vec4") : (big ? "gather/scalar-big" : "gather/scalar");
@@ -920,8 +923,12 @@ int olap_reorder(olap_store* const* src, int n, int ndim, const int64_t* old_len
         auto meas = gather_measures(src, out, n);
         TransposePlan tp = transpose_plan(dims);
         if (tp.use) {
-            path = "reorder/tile-transpose";
-            OLAP_TRY(launch_transpose(meas, n, tp));
+            path = "reorder/box-transpose";
+            TablePack t;
+            const size_t o_meas = t.add(meas.data(), sizeof(GatherMeasure) * n);
+            OLAP_TRY(t.upload());
+            OLAP_TRY(launch_transpose(t.ptr<GatherMeasure>(o_meas), n, tp));
+            OLAP_TRY(t.release());
         } else {
             OLAP_TRY(run_gather(G_COPY, src, n, dims, size, size, meas, nullptr, &path));
         }
@@ -959,9 +966,12 @@ int olap_drill_down(olap_store* const* src, int n, const int* methods, int ndim,
             std::vector<int32_t> count(old_len[d], 0);
             for (int64_t j = 0; j < new_len[d]; ++j) {
                 g_.tbl[j] = (int64_t)maps[d][j] * stride;
-                g_.aux[j].y = count[maps[d][j]]++;  // rank among siblings, ascending new index
+                g_.aux[j].rank = count[maps[d][j]]++;  // rank among siblings, ascending new index
             }
-            for (int64_t j = 0; j < new_len[d]; ++j) g_.aux[j].x = count[maps[d][j]];
+            for (int64_t j = 0; j < new_len[d]; ++j) {
+                g_.aux[j].cnt = count[maps[d][j]];
+                g_.aux[j].inv = 1.0 / (double)g_.aux[j].cnt;
+            }
         }
         stride *= old_len[d];
     }
@@ -990,7 +1000,10 @@ int olap_drill_down(olap_store* const* src, int n, const int* methods, int ndim,
             meas[k].method_is_sum = methods ? (methods[k] == OLAP_SUM) : 1;
             if (any_dist && dist[k]) { meas[k].dist = dpack.ptr<double>(o_dist[k]); meas[k].dist_len = dist_len[k]; }
         }
-        rc = run_gather(G_DOWN, src, n, dims, new_size, old_size, meas, any_dist ? dpack.ptr<int>(0) : nullptr, &path);
+        bool fast = !any_dist;
+        for (int k = 0; k < n; ++k) fast &= meas[k].method_is_sum && !meas[k].int_rounding;
+        rc = run_gather(fast ? G_DOWN_FLOAT : G_DOWN, src, n, dims, new_size, old_size, meas,
+                        any_dist ? dpack.ptr<int>(0) : nullptr, &path);
         if (rc == OLAP_OK && any_dist) {
             int flag = 0;
             OLAP_CUDA(cudaMemcpyAsync(&flag, dpack.ptr<int>(0), 4, cudaMemcpyDeviceToHost, g.stream));

@@ -167,6 +167,14 @@ def reorder_cases(seed=3):
     rng = np.random.default_rng(seed)
     import itertools
 
+    # big enough for several (ragged) boxes of the tiled transpose
+    for dims, perm in (([130, 70], [1, 0]), ([37, 50, 3, 70], [3, 2, 1, 0]), ([37, 50, 3, 70], [1, 3, 0, 2]),
+                       ([20, 30, 10, 10], [3, 2, 1, 0]), ([9, 300, 11], [2, 0, 1]), ([64, 64, 8], [0, 2, 1]),
+                       ([3, 5000], [1, 0]), ([10, 10, 10, 10, 10], [4, 3, 2, 1, 0])):
+        for default in (0.0, math.nan):
+            n = int(np.prod(dims))
+            yield dict(op="reorder", old_len=list(dims), new_to_old=list(perm), default=default,
+                       data=make_data(rng, n, default, 0.7, "int"), type="float32")
     for dims in ([2, 3], [4, 5, 6], [3, 1, 4, 8], [7, 16], [5, 4, 3, 2, 6]):
         perms = list(itertools.permutations(range(len(dims))))
         if len(perms) > 12:

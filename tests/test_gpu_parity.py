@@ -204,3 +204,26 @@ def test_computed_measures():
             got = np.asarray(gpu.getData(f"f{k}_m"))
             want = np.asarray(cpu.getData(f"f{k}_m"))
             assert np.allclose(got, want, rtol=1e-6, atol=0, equal_nan=True), (f, default)
+
+
+def test_kernel_paths_are_the_intended_ones():
+    """Shape classes of SURVEY.md Appendix B reach the kernel written for them."""
+    from olap_in_memory_b200 import _native as N
+
+    G = _gpu()
+    path = lambda: N.lib().olap_last_op_path().decode()
+    s = G(64 * 40 * 64, "float32", 0)
+    ident = cases.identity
+    m = cases.random_map(np.random.default_rng(0), 40, 5, True)
+    G.drillUp_lowered([s], [64, 40, 64], [64, 5, 64], [ident(64), m, ident(64)], ["sum"])
+    assert path() == "drillup/mid-vec4"
+    G.drillUp_lowered([s], [64 * 64, 40], [64 * 64, 5], [ident(64 * 64), m], ["sum"])
+    assert path() == "drillup/tile"
+    G.drillUp_lowered([s], [64, 40, 64], [2, 5, 64], [cases.random_map(np.random.default_rng(1), 64, 2, False), m, ident(64)], ["sum"])
+    assert path() == "drillup/generic"
+    G.reorder_lowered([s], [64, 40, 64], [1, 0, 2])
+    assert path() == "gather/vec4"
+    G.reorder_lowered([s], [64, 40, 64], [2, 1, 0])
+    assert path() == "reorder/box-transpose"
+    G.dice_lowered([s], [64, 40, 64], [ident(64), np.arange(0, 40, 2, dtype=np.int32), ident(64)])
+    assert path() == "gather/vec4"
