@@ -402,3 +402,111 @@ __global__ void __launch_bounds__(256) drillup_generic_kernel(const __grid_const
 }
 
 }  // namespace olap
+
+// =====================================================================================
+// drillDown with ONE changed dimension: [O, P, I] -> [O, C, I] (in-memory.js:336-430).
+// Mirror image of the mid kernel: one thread owns one PARENT vector, reads it once, and
+// writes it (scaled) to each of the parent's children, so the parent plane is read once
+// from HBM and every store is a coalesced 128-bit write along I.  `pstart/children` is
+// the CSR parent -> ascending new items; the rank of a child among its siblings
+// (contributionsIds, in-memory.js:406-426) is its position in that list.
+namespace olap {
+
+struct DownMeasure {
+    const float* in;
+    float* out;
+    const uint8_t* st_in;
+    uint8_t* st_out;
+    int nan_default;
+    int kind;  // 0: float sum (v / n)   1: copy (method != sum)   2: integer sum with spreading
+};
+
+struct DownMidParams {
+    const DownMeasure* meas;
+    const int32_t* pstart;    // [P+1]
+    const int32_t* children;  // [C] new items per parent, ascending
+    int64_t O;
+    int32_t C, P;
+    int64_t I_total, in_row, out_row, i_base;
+    uint32_t IV;
+    FastDiv div_iv;
+    uint32_t row_vecs;  // P * IV
+    uint32_t blocks_per_row;
+};
+
+template <int VEC, bool RANGE, bool STATUS>
+__device__ __forceinline__ void down_mid_body(const DownMidParams& p, const DownMeasure& m, int64_t o, uint32_t pi,
+                                              uint32_t iv) {
+    const int32_t k0 = p.pstart[pi], k1 = p.pstart[pi + 1];
+    if (k0 == k1) return;
+    const int64_t inner = p.i_base + (int64_t)iv * VEC;
+    const int64_t in_off = o * p.in_row + (int64_t)pi * p.I_total + inner;
+    const Cells<VEC> c = load_cells<VEC, STATUS>(m.in, m.st_in, in_off);
+    const int nan_default = m.nan_default;
+    const uint32_t n = (uint32_t)(k1 - k0);
+    const double dn = (double)n;
+    float r[VEC];
+    bool truthy[VEC];
+    double base[VEC], step[VEC];
+    uint32_t st_ok = 0;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        const float x = c.v[e];
+        truthy[e] = x != 0.0f && x == x;  // `if (!oldValue) continue` (in-memory.js:386-387)
+        if (m.kind == 0) r[e] = canon_store((float)((double)x / dn), nan_default);
+        else if (m.kind == 1) r[e] = x;
+        else {
+            const double q = (double)x / dn;
+            base[e] = floor(q);
+            step[e] = fma(-trunc(q), dn, (double)x) / dn;  // (v % n) / n
+            r[e] = 0.0f;
+        }
+        if (!truthy[e]) r[e] = default_of(nan_default);
+        const uint32_t sb = STATUS ? ((c.st >> (8 * e)) & 0xffu) : 0u;
+        const bool ok = truthy[e] && (m.kind == 2 || present_f(r[e], nan_default));
+        st_ok |= (ok ? ((sb | OLAP_STATUS_INTERPOLATED) & 0xffu) : (uint32_t)OLAP_STATUS_UNSET) << (8 * e);
+    }
+    float* dst = m.out + o * p.out_row + inner;
+    uint8_t* st_dst = STATUS ? m.st_out + o * p.out_row + inner : nullptr;
+    for (int32_t k = k0; k < k1; ++k) {
+        const int64_t child = RANGE ? (int64_t)k : (int64_t)p.children[k];
+        const int64_t off = child * p.I_total;
+        uint32_t st = st_ok;
+        if (m.kind == 2) {
+            const double kk = (double)(k - k0);
+            st = 0;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const bool last_is_same = floor(kk * step[e]) == floor((kk - 1.0) * step[e]);
+                const float val = canon_store((float)(last_is_same ? base[e] : base[e] + 1.0), nan_default);
+                r[e] = truthy[e] ? val : default_of(nan_default);
+                const uint32_t sb = STATUS ? ((c.st >> (8 * e)) & 0xffu) : 0u;
+                const bool ok = truthy[e] && present_f(val, nan_default);
+                st |= (ok ? ((sb | OLAP_STATUS_INTERPOLATED) & 0xffu) : (uint32_t)OLAP_STATUS_UNSET) << (8 * e);
+            }
+        }
+        if (VEC == 4) {
+            st_stream4(dst + off, make_float4(r[0], r[1 % VEC], r[2 % VEC], r[3 % VEC]));
+            if (STATUS) *reinterpret_cast<uint32_t*>(st_dst + off) = st;
+        } else {
+            dst[off] = r[0];
+            if (STATUS) st_dst[off] = (uint8_t)st;
+        }
+    }
+}
+
+template <int VEC, bool RANGE>
+__global__ void __launch_bounds__(256) drilldown_mid_kernel(const __grid_constant__ DownMidParams p) {
+    const uint32_t brow = blockIdx.x / p.blocks_per_row;
+    const uint32_t bcol = blockIdx.x - brow * p.blocks_per_row;
+    const int64_t o = (int64_t)brow * blockDim.y + threadIdx.y;
+    const uint32_t j = bcol * blockDim.x + threadIdx.x;
+    if (o >= p.O || j >= p.row_vecs) return;
+    const uint32_t pi = p.div_iv.div(j);
+    const uint32_t iv = j - pi * p.IV;
+    const DownMeasure m = p.meas[blockIdx.y];
+    if (m.st_in) down_mid_body<VEC, RANGE, true>(p, m, o, pi, iv);
+    else down_mid_body<VEC, RANGE, false>(p, m, o, pi, iv);
+}
+
+}  // namespace olap

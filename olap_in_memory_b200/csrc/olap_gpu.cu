@@ -270,6 +270,45 @@ static int launch_up_mid(const UpMeasure* d_meas, int n, const Csr& csr, const i
     return OLAP_OK;
 }
 
+static int launch_down_mid(const DownMeasure* d_meas, int n, const Csr& csr, const int32_t* d_pstart,
+                           const int32_t* d_children, int64_t O, int64_t P, int64_t C, int64_t I) {
+    const int VEC = (I % 4 == 0) ? 4 : 1;
+    const int64_t IV_total = I / VEC;
+    const int64_t max_row = ((int64_t)1 << 30);
+    int64_t chunk_iv = IV_total;
+    if (P * IV_total > max_row) chunk_iv = std::max<int64_t>(1, max_row / P);
+    for (int64_t iv0 = 0; iv0 < IV_total; iv0 += chunk_iv) {
+        const int64_t iv_n = std::min(chunk_iv, IV_total - iv0);
+        DownMidParams p{};
+        p.meas = d_meas;
+        p.pstart = d_pstart;
+        p.children = d_children;
+        p.O = O; p.C = (int32_t)C; p.P = (int32_t)P;
+        p.I_total = I;
+        p.in_row = P * I;
+        p.out_row = C * I;
+        p.i_base = iv0 * VEC;
+        p.IV = (uint32_t)iv_n;
+        p.div_iv = FastDiv((uint32_t)iv_n);
+        p.row_vecs = (uint32_t)(P * iv_n);
+        const uint32_t bx = std::min<uint32_t>(256, next_pow2(p.row_vecs));
+        const uint32_t by = 256 / bx;
+        p.blocks_per_row = (uint32_t)ceil_div(p.row_vecs, bx);
+        const int64_t gx = ceil_div(O, by) * p.blocks_per_row;
+        if (gx > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "drillDown: grid too large (%lld blocks)", (long long)gx);
+        dim3 grid((unsigned)gx, (unsigned)n), block(bx, by);
+        if (VEC == 4) {
+            if (csr.contiguous) drilldown_mid_kernel<4, true><<<grid, block, 0, g.stream>>>(p);
+            else drilldown_mid_kernel<4, false><<<grid, block, 0, g.stream>>>(p);
+        } else {
+            if (csr.contiguous) drilldown_mid_kernel<1, true><<<grid, block, 0, g.stream>>>(p);
+            else drilldown_mid_kernel<1, false><<<grid, block, 0, g.stream>>>(p);
+        }
+        LAUNCHED();
+    }
+    return OLAP_OK;
+}
+
 }  // namespace olap
 
 using namespace olap;
@@ -948,6 +987,8 @@ int olap_drill_down(olap_store* const* src, int n, const int* methods, int ndim,
     OLAP_TRY(product(new_len, ndim, &new_size, "olap_drill_down"));
     if (old_size != size) return fail(OLAP_E_INVALID, "olap_drill_down: dimensions describe %lld cells, store has %lld", (long long)old_size, (long long)size);
     std::vector<GDim> dims(ndim);
+    std::vector<int> changed;
+    int64_t inner_of_changed = 1;
     int64_t stride = 1;
     for (int d = ndim - 1; d >= 0; --d) {
         GDim& g_ = dims[d];
@@ -960,6 +1001,8 @@ int olap_drill_down(olap_store* const* src, int n, const int* methods, int ndim,
         }
         if (identity) { g_.linear = true; g_.stride = stride; }
         else {
+            changed.push_back(d);
+            inner_of_changed = stride;  // product of the (old == new) lengths after d when d is the only change
             g_.linear = false;
             g_.tbl.resize(new_len[d]);
             g_.aux.resize(new_len[d]);
@@ -985,6 +1028,31 @@ int olap_drill_down(olap_store* const* src, int n, const int* methods, int ndim,
     int rc = OLAP_OK;
     if (new_size && old_size == 0) {
         for (int k = 0; k < n; ++k) { olap_store t = *out[k]; t.status = st_out_of(out, k); OLAP_TRY(fill_default(&t)); }
+    } else if (new_size && !any_dist && changed.size() == 1 &&
+               ((inner_of_changed % 4 == 0 && inner_of_changed >= 32) || inner_of_changed >= 128)) {
+        // one changed dimension with a long inner run: parent-driven kernel
+        const int d = changed[0];
+        int64_t O = 1;
+        for (int q = 0; q < d; ++q) O *= old_len[q];
+        // CSR parent -> new items: build from the new->old map
+        const Csr csr = build_csr(maps[d], new_len[d], old_len[d]);
+        std::vector<DownMeasure> dm(n);
+        for (int k = 0; k < n; ++k) {
+            const bool is_int = src[k]->type == OLAP_INT32 || src[k]->type == OLAP_UINT32;
+            const bool is_sum = methods ? methods[k] == OLAP_SUM : true;
+            const uint8_t* si = out[k]->status ? st_in_of(src, k) : nullptr;
+            dm[k] = DownMeasure{src[k]->values, out[k]->values, si, si ? st_out_of(out, k) : nullptr,
+                                src[k]->default_kind, !is_sum ? 1 : (is_int ? 2 : 0)};
+        }
+        TablePack t;
+        const size_t o_meas = t.add(dm.data(), sizeof(DownMeasure) * n);
+        const size_t o_ps = t.add(csr.pstart.data(), csr.pstart.size() * 4);
+        const size_t o_ch = t.add(csr.children.data(), csr.children.size() * 4);
+        OLAP_TRY(t.upload());
+        path = inner_of_changed % 4 == 0 ? "drilldown/mid-vec4" : "drilldown/mid-scalar";
+        OLAP_TRY(launch_down_mid(t.ptr<DownMeasure>(o_meas), n, csr, t.ptr<int32_t>(o_ps), t.ptr<int32_t>(o_ch), O,
+                                 old_len[d], new_len[d], inner_of_changed));
+        OLAP_TRY(t.release());
     } else if (new_size) {
         auto meas = gather_measures(src, out, n);
         TablePack dpack;

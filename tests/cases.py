@@ -108,6 +108,9 @@ def drilldown_cases(seed=1):
         ([3], 0, 9, True),
         ([6, 1, 4], 1, 5, True),   # addDimension: CatchAll(1) -> 5 items
         ([3, 5], 1, 12, False),    # non-monotone new->old map
+        ([4, 64], 0, 11, True),    # long inner run: parent-driven kernel, vec4
+        ([3, 5, 32], 1, 9, False),
+        ([2, 3, 130], 1, 7, True),  # long inner run, scalar
     ]
     for dims, d, C, mono in shapes:
         for default in (0.0, math.nan):
