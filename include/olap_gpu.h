@@ -73,6 +73,9 @@ extern "C" {
 #define OLAP_FIRST 4
 #define OLAP_LAST 5
 #define OLAP_PRODUCT 6
+/* extension (not a reference method): number of set children per parent, as a float.
+ * Used to finish `average` when the drilled dimension is sharded across GPUs. */
+#define OLAP_COUNT 7
 
 /* status flags (README.md:698-721) */
 #define OLAP_STATUS_UNSET 0x1

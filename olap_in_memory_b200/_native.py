@@ -21,6 +21,7 @@ TYPES = {"int32": 0, "uint32": 1, "float32": 2, "float64": 3}
 TYPE_NAMES = {v: k for k, v in TYPES.items()}
 DEFAULT_ZERO, DEFAULT_NAN = 0, 1
 METHODS = {"sum": 0, "average": 1, "highest": 2, "lowest": 3, "first": 4, "last": 5, "product": 6}
+COUNT = 7  # extension, see OLAP_COUNT in include/olap_gpu.h
 
 
 class OlapError(RuntimeError):

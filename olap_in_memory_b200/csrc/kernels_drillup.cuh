@@ -47,7 +47,7 @@ struct Acc {
             has = true;
             return;
         }
-        if (METHOD == OLAP_FIRST) return;
+        if (METHOD == OLAP_FIRST || METHOD == OLAP_COUNT) return;
         if (METHOD == OLAP_LAST) {
             acc = (double)v;
             return;
@@ -72,6 +72,7 @@ struct Acc {
         }
         double r = acc;
         if (METHOD == OLAP_AVERAGE && cnt) r = acc / (double)cnt;
+        if (METHOD == OLAP_COUNT) r = (double)cnt;
         return canon_store((float)r, nan_default);
     }
 };
@@ -145,6 +146,16 @@ struct Lane<OLAP_AVERAGE, true> {
     }
     __device__ __forceinline__ float result() const { return cnt ? canon_store((float)(acc / (double)cnt), 1) : canon_nan(); }
 };
+template <bool NANDEF>
+struct CountLane {
+    uint32_t cnt = 0;
+    __device__ __forceinline__ void step(float v) { cnt += present_f(v, NANDEF) ? 1u : 0u; }
+    __device__ __forceinline__ float result() const { return cnt ? (float)cnt : default_of(NANDEF); }
+};
+template <>
+struct Lane<OLAP_COUNT, false> : CountLane<false> {};
+template <>
+struct Lane<OLAP_COUNT, true> : CountLane<true> {};
 template <>
 struct Lane<OLAP_HIGHEST, false> {
     float acc = 0.0f;
@@ -314,6 +325,7 @@ __device__ __forceinline__ void up_mid_dispatch(const UpMidParams& p, const UpMe
         case OLAP_LOWEST: up_mid_body<OLAP_LOWEST, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv); break;
         case OLAP_FIRST: up_mid_body<OLAP_FIRST, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv); break;
         case OLAP_LAST: up_mid_body<OLAP_LAST, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv); break;
+        case OLAP_COUNT: up_mid_body<OLAP_COUNT, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv); break;
         default: up_mid_body<OLAP_PRODUCT, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv); break;
     }
 }
@@ -397,6 +409,7 @@ __global__ void __launch_bounds__(256) drillup_generic_kernel(const __grid_const
         case OLAP_LOWEST: up_gen_body<OLAP_LOWEST>(p, m, j); break;
         case OLAP_FIRST: up_gen_body<OLAP_FIRST>(p, m, j); break;
         case OLAP_LAST: up_gen_body<OLAP_LAST>(p, m, j); break;
+        case OLAP_COUNT: up_gen_body<OLAP_COUNT>(p, m, j); break;
         default: up_gen_body<OLAP_PRODUCT>(p, m, j); break;
     }
 }

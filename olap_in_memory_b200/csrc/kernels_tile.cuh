@@ -140,6 +140,7 @@ __device__ __forceinline__ void up_tile_dispatch(const UpTileParams& p, const Up
         case OLAP_LOWEST: up_tile_reduce<OLAP_LOWEST, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows); break;
         case OLAP_FIRST: up_tile_reduce<OLAP_FIRST, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows); break;
         case OLAP_LAST: up_tile_reduce<OLAP_LAST, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows); break;
+        case OLAP_COUNT: up_tile_reduce<OLAP_COUNT, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows); break;
         default: up_tile_reduce<OLAP_PRODUCT, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows); break;
     }
 }

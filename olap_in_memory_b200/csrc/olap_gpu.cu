@@ -691,7 +691,7 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
     OLAP_TRY(product(new_len, ndim, &new_size, "olap_drill_up"));
     if (old_size != size) return fail(OLAP_E_INVALID, "olap_drill_up: dimensions describe %lld cells, store has %lld", (long long)old_size, (long long)size);
     for (int k = 0; k < n; ++k)
-        if (methods[k] < OLAP_SUM || methods[k] > OLAP_PRODUCT) return fail(OLAP_E_INVALID, "Unsupported aggregation method: %d", methods[k]);
+        if (methods[k] < OLAP_SUM || methods[k] > OLAP_COUNT) return fail(OLAP_E_INVALID, "Unsupported aggregation method: %d", methods[k]);
     std::vector<int> changed;
     for (int d = 0; d < ndim; ++d) {
         if (old_len[d] > 0x7fffffffLL || new_len[d] > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "olap_drill_up: dimension %d longer than 2^31-1", d);

@@ -1,0 +1,422 @@
+"""Cubes larger than one GPU: rows of the flattened outermost dimensions are split
+contiguously across the ranks of a torch.distributed group (one process per GPU).
+
+The reference has no notion of this: a cube there is one JS Map.  The
+contract kept here is that a ShardedCube behaves like ONE Cube whose cells happen to live
+on several devices:
+
+* transforms of a dimension inside the shard (index >= `prefix`) are shard-local store
+  calls — no communication at all;
+* drillUp of a sharded dimension = local partial rollup of my rows into the FULL output
+  row space, one all-to-all that hands every rank the W partials of its own output rows
+  (the bytes a reduce-scatter would move), then a local, ordered combine of the W
+  partials with the very same drillUp kernel (`sum` of sums, `highest` of highests,
+  `first`/`last` in rank order = ascending row order, `average` = sum of sums / sum of
+  counts).  Presence and status merge exactly as in the single-GPU kernel because the
+  partials are ordinary stores.
+* `total` = local totals + one all-reduce of a double.
+
+torch.distributed is plumbing: NCCL moves the planes (zero-copy views of the device
+stores, olap_in_memory_b200/interop.py); every arithmetic step is a store call."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .cube import Cube  # noqa: F401  (re-exported for convenience)
+
+
+def split_rows(total, world):
+    """Contiguous, balanced row ranges: sizes differ by at most one."""
+    base, extra = divmod(total, world)
+    bounds = [0]
+    for r in range(world):
+        bounds.append(bounds[-1] + base + (1 if r < extra else 0))
+    return bounds
+
+
+def _prod(xs):
+    p = 1
+    for x in xs:
+        p *= int(x)
+    return p
+
+
+def _is_device_store(store):
+    return hasattr(store, "_h")
+
+
+class _Comm:
+    """The three collectives the path needs, over torch.distributed (nccl on GPUs, gloo in
+    the CPU tests) or as no-ops for a single rank."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.on = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if self.on else 0
+        self.world = dist.get_world_size(group) if self.on else 1
+
+    def all_to_all(self, out, inp, out_splits, in_splits):
+        if self.world == 1:
+            out.copy_(inp)
+            return
+        if out.is_cuda:
+            self.dist.all_to_all_single(out, inp, out_splits, in_splits, group=self.group)
+            return
+        # gloo has no all_to_all: pairwise exchange
+        import torch
+
+        in_off = np.concatenate([[0], np.cumsum(in_splits)])
+        out_off = np.concatenate([[0], np.cumsum(out_splits)])
+        reqs = []
+        for peer in range(self.world):
+            src = inp[in_off[peer]:in_off[peer + 1]]
+            dst = out[out_off[peer]:out_off[peer + 1]]
+            if peer == self.rank:
+                dst.copy_(src)
+                continue
+            if src.numel():
+                reqs.append(self.dist.isend(src.contiguous(), peer, group=self.group))
+            if dst.numel():
+                reqs.append(self.dist.irecv(dst, peer, group=self.group))
+        for r in reqs:
+            r.wait()
+        del torch
+
+    def all_reduce_sum(self, value, device=None):
+        if self.world == 1:
+            return value
+        import torch
+
+        t = torch.tensor([value], dtype=torch.float64, device=device or "cpu")
+        self.dist.all_reduce(t, group=self.group)
+        return float(t.item())
+
+    def all_gather(self, tensor, sizes):
+        if self.world == 1:
+            return tensor.clone()
+        import torch
+
+        parts = [torch.empty(int(s), dtype=tensor.dtype, device=tensor.device) for s in sizes]
+        if len(set(int(s) for s in sizes)) == 1:
+            self.dist.all_gather(parts, tensor.contiguous(), group=self.group)
+        else:  # ragged: pad to the largest
+            m = max(int(s) for s in sizes)
+            padded = torch.zeros(m, dtype=tensor.dtype, device=tensor.device)
+            padded[: tensor.numel()] = tensor
+            bufs = [torch.empty(m, dtype=tensor.dtype, device=tensor.device) for _ in sizes]
+            self.dist.all_gather(bufs, padded, group=self.group)
+            parts = [b[: int(s)] for b, s in zip(bufs, sizes)]
+        return torch.cat(parts)
+
+
+class ShardedCube:
+    def __init__(self, dimensions, prefix=1, store_cls=None, group=None, _row_bounds=None):
+        if store_cls is None:
+            from .store import GpuStore
+
+            store_cls = GpuStore
+        self.dimensions = list(dimensions)
+        self.prefix = int(prefix)
+        if not 1 <= self.prefix <= len(self.dimensions):
+            raise ValueError("prefix must cover 1..ndim leading dimensions")
+        self._store_cls = store_cls
+        self.comm = _Comm(group)
+        self.rank, self.world = self.comm.rank, self.comm.world
+        self.rows_total = _prod(d.numItems for d in self.dimensions[: self.prefix])
+        self.inner_lens = [d.numItems for d in self.dimensions[self.prefix:]]
+        self.inner = _prod(self.inner_lens)
+        self.row_bounds = _row_bounds or split_rows(self.rows_total, self.world)
+        self.row0, self.row1 = self.row_bounds[self.rank], self.row_bounds[self.rank + 1]
+        self.storedMeasures = {}
+        self.storedMeasuresRules = {}
+
+    # ------------------------------------------------------------------ basics
+    @property
+    def rows_local(self):
+        return self.row1 - self.row0
+
+    @property
+    def localSize(self):
+        return self.rows_local * self.inner
+
+    @property
+    def storeSize(self):
+        return self.rows_total * self.inner
+
+    @property
+    def dimensionIds(self):
+        return [d.id for d in self.dimensions]
+
+    def getDimensionIndex(self, dimensionId):
+        for i, d in enumerate(self.dimensions):
+            if d.id == dimensionId:
+                return i
+        return -1
+
+    def createStoredMeasure(self, measureId, rules=None, type="float32", defaultValue=0):
+        self.storedMeasures[measureId] = self._store_cls(self.localSize, type, defaultValue)
+        self.storedMeasuresRules[measureId] = {} if rules is None else rules
+
+    def setLocalData(self, measureId, values):
+        """Cells of MY rows, row-major (length rows_local * inner)."""
+        self._set(self.storedMeasures[measureId], values)
+
+    def setData(self, measureId, values):
+        """Full-cube data given on every rank: each keeps its own rows (tests, small cubes)."""
+        values = np.asarray(values)
+        self.setLocalData(measureId, values[self.row0 * self.inner: self.row1 * self.inner])
+
+    def getLocalData(self, measureId):
+        return self._get(self.storedMeasures[measureId])
+
+    def getData(self, measureId):
+        """Whole cube gathered on every rank (verification / small results only)."""
+        import torch
+
+        local = torch.from_numpy(np.ascontiguousarray(self.getLocalData(measureId), dtype=np.float64))
+        sizes = [(self.row_bounds[r + 1] - self.row_bounds[r]) * self.inner for r in range(self.world)]
+        if self.world > 1 and _is_device_store(next(iter(self.storedMeasures.values()))):
+            local = local.cuda()
+        return self.comm.all_gather(local, sizes).cpu().numpy()
+
+    def getTotal(self, measureId):
+        store = self.storedMeasures[measureId]
+        device = "cuda" if _is_device_store(store) and self.world > 1 else None
+        return self.comm.all_reduce_sum(store.total, device)
+
+    @staticmethod
+    def _set(store, values):
+        if hasattr(store, "set_data_f32"):
+            store.set_data_f32(np.asarray(values, dtype=np.float32))
+        else:
+            store.data = [float(v) for v in values]
+
+    @staticmethod
+    def _get(store):
+        if hasattr(store, "data_f32"):
+            return store.data_f32().astype(np.float64)
+        return np.asarray(store.data, dtype=np.float64)
+
+    def _derive(self, dimensions, row_bounds=None):
+        out = ShardedCube(dimensions, self.prefix, self._store_cls, self.comm.group, row_bounds)
+        out.storedMeasuresRules = dict(self.storedMeasuresRules)
+        return out
+
+    # ----------------------------------------------------------- lowered store calls
+    def _call(self, name, stores, *args):
+        fn = getattr(self._store_cls, name)
+        if _is_device_store(stores[0]):
+            return fn(stores, *args)  # batched static form of the device store
+        per_store = []
+        for k, s in enumerate(stores):
+            a = [x[k] if isinstance(x, _Per) else x for x in args]
+            per_store.append(fn(s, *a))
+        return per_store
+
+    def _local_lens(self):
+        return [self.rows_local] + self.inner_lens
+
+    # ------------------------------------------------------------------ transforms
+    def drillUp(self, dimensionId, attribute):
+        idx = self.getDimensionIndex(dimensionId)
+        old_dim = self.dimensions[idx]
+        if old_dim.rootAttribute == attribute:
+            return self
+        new_dim = old_dim.drillUp(attribute)
+        if new_dim is old_dim:
+            return self
+        new_dims = list(self.dimensions)
+        new_dims[idx] = new_dim
+        ids = list(self.storedMeasures)
+        methods = [self.storedMeasuresRules[m].get(dimensionId) or "sum" for m in ids]
+        group_map = np.asarray(old_dim.getGroupIndexFromRootIndexMap(new_dim.rootAttribute), dtype=np.int32)
+        if idx >= self.prefix:
+            return self._drill_up_local(new_dims, idx, group_map, ids, methods)
+        return self._drill_up_sharded(new_dims, idx, group_map, ids, methods)
+
+    def _drill_up_local(self, new_dims, idx, group_map, ids, methods):
+        """The drilled dimension lies inside my shard: no communication."""
+        out = self._derive(new_dims, self.row_bounds)
+        old_len = self._local_lens()
+        new_len = [self.rows_local] + [d.numItems for d in new_dims[self.prefix:]]
+        maps = [np.arange(n, dtype=np.int32) for n in old_len]
+        maps[1 + idx - self.prefix] = group_map
+        stores = [self.storedMeasures[m] for m in ids]
+        if stores:
+            results = self._call("drillUp_lowered", stores, old_len, new_len, maps, _Per(methods))
+            out.storedMeasures = dict(zip(ids, results))
+        return out
+
+    def _row_map(self, idx, group_map, new_prefix_lens):
+        """my local row -> global row of the drilled cube"""
+        old_prefix_lens = [d.numItems for d in self.dimensions[: self.prefix]]
+        rows = np.arange(self.row0, self.row1, dtype=np.int64)
+        coords = []
+        rest = rows
+        for n in reversed(old_prefix_lens):
+            coords.append(rest % n)
+            rest = rest // n
+        coords.reverse()
+        coords[idx] = group_map[coords[idx]].astype(np.int64)
+        new_row = np.zeros_like(rows)
+        for c, n in zip(coords, new_prefix_lens):
+            new_row = new_row * n + c
+        return new_row.astype(np.int32)
+
+    def _drill_up_sharded(self, new_dims, idx, group_map, ids, methods):
+        """The drilled dimension is (part of) the sharded row axis."""
+        import torch
+
+        new_prefix_lens = [d.numItems for d in new_dims[: self.prefix]]
+        new_rows_total = _prod(new_prefix_lens)
+        out_bounds = split_rows(new_rows_total, self.world)
+        out = self._derive(new_dims, out_bounds)
+        if not ids:
+            return out
+        W, inner = self.world, self.inner
+        my_out_rows = out_bounds[self.rank + 1] - out_bounds[self.rank]
+        row_map = self._row_map(idx, group_map, new_prefix_lens)
+        old_len = self._local_lens()
+        new_len = [new_rows_total] + self.inner_lens
+        maps = [row_map] + [np.arange(n, dtype=np.int32) for n in self.inner_lens]
+
+        # 1. local partial rollup of my rows into the full output row space; `average`
+        #    travels as (sum, count)
+        plan = []  # (measure, method used for the partial, role)
+        for m, method in zip(ids, methods):
+            if method == "average":
+                plan.append((m, "sum", "avg_sum"))
+                plan.append((m, "__count", "avg_cnt"))
+            else:
+                plan.append((m, method, "plain"))
+        stores = [self.storedMeasures[m] for m, _, _ in plan]
+        partials = self._partials(stores, old_len, new_len, maps, [meth for _, meth, _ in plan])
+
+        # 2. one all-to-all per plane: rank r receives the W partials of ITS output rows
+        in_splits = [(out_bounds[r + 1] - out_bounds[r]) * inner for r in range(W)]
+        out_splits = [my_out_rows * inner] * W
+        received = []
+        for part, src_store in zip(partials, stores):
+            recv = self._store_cls(W * my_out_rows * inner, src_store._type, src_store._defaultValue)
+            self._exchange(part, recv, in_splits, out_splits)
+            received.append(recv)
+        del partials
+
+        # 3. ordered combine of the W partials: a drillUp over the rank axis
+        comb_old = [W, my_out_rows] + self.inner_lens
+        comb_new = [1, my_out_rows] + self.inner_lens
+        comb_maps = [np.zeros(W, dtype=np.int32)] + [np.arange(n, dtype=np.int32) for n in comb_old[1:]]
+        comb_methods = ["sum" if role != "plain" else meth for _, meth, role in plan]
+        combined = self._call("drillUp_lowered", received, comb_old, comb_new, comb_maps, _Per(comb_methods))
+        del received
+        k = 0
+        for m, method in zip(ids, methods):
+            if method == "average":
+                out.storedMeasures[m] = self._divide(combined[k], combined[k + 1])
+                k += 2
+            else:
+                out.storedMeasures[m] = combined[k]
+                k += 1
+        del torch
+        return out
+
+    def _partials(self, stores, old_len, new_len, maps, methods):
+        if _is_device_store(stores[0]):
+            return self._store_cls.drillUp_lowered(stores, old_len, new_len, maps, methods)
+        out = []
+        for s, method in zip(stores, methods):
+            if method == "__count":  # CPU stand-in stores have no count method: roll up an indicator
+                ind = type(s)(s.size, s._type, s._defaultValue)
+                present = set(s._dataMap.keys())
+                ind.data = [1.0 if i in present else s._defaultValue for i in range(s.size)]
+                out.append(ind.drillUp_lowered(old_len, new_len, maps, "sum"))
+            else:
+                out.append(s.drillUp_lowered(old_len, new_len, maps, method))
+        return out
+
+    def _exchange(self, part, recv, in_splits, out_splits):
+        import torch
+
+        if _is_device_store(part):
+            from . import interop
+
+            torch.cuda.current_stream().synchronize()
+            self.comm.all_to_all(interop.values_tensor(recv), interop.values_tensor(part), out_splits, in_splits)
+            st_in, st_out = interop.status_tensor(part), interop.status_tensor(recv)
+            if st_in is not None and st_out is not None:
+                self.comm.all_to_all(st_out, st_in, out_splits, in_splits)
+            torch.cuda.synchronize()
+        else:
+            src = torch.tensor(part.data, dtype=torch.float64)
+            dst = torch.empty(sum(out_splits), dtype=torch.float64)
+            self.comm.all_to_all(dst, src, out_splits, in_splits)
+            recv.data = dst.tolist()
+
+    def _divide(self, sums, counts):
+        """average = sum of sums / sum of counts; no contribution -> unset (in-memory.js:323-331)."""
+        if _is_device_store(sums):
+            # `c ? s / c : default` as the postfix program of olap_eval (one fused kernel)
+            default = "#nan" if sums._defaultValue != sums._defaultValue else "#0.0"
+            return self._store_cls.eval_program(f"v1 v0 v1 / {default} ?:", [sums, counts], [], sums._type,
+                                                sums._defaultValue)
+        out = type(sums)(sums.size, sums._type, sums._defaultValue)
+        s, c = sums.data, counts.data
+        out.data = [sv / cv if (cv == cv and cv != 0) else sums._defaultValue for sv, cv in zip(s, c)]
+        return out
+
+    def dice(self, dimensionId, attribute, items, reorder=False):
+        """Dice of a dimension inside the shard (shard-local)."""
+        idx = self.getDimensionIndex(dimensionId)
+        if idx < self.prefix:
+            raise NotImplementedError("dice on a sharded dimension re-partitions rows; not in this round (SURVEY §8e)")
+        old_dim = self.dimensions[idx]
+        new_dim = old_dim.dice(attribute, items, reorder)
+        if new_dim is old_dim:
+            return self
+        new_dims = list(self.dimensions)
+        new_dims[idx] = new_dim
+        out = self._derive(new_dims, self.row_bounds)
+        old_idx = old_dim.getItemsToIdx()
+        keep = [np.arange(n, dtype=np.int32) for n in self._local_lens()]
+        keep[1 + idx - self.prefix] = np.asarray([old_idx[i] for i in new_dim.getItems()], dtype=np.int32)
+        ids = list(self.storedMeasures)
+        if ids:
+            res = self._call("dice_lowered", [self.storedMeasures[m] for m in ids], self._local_lens(), keep)
+            out.storedMeasures = dict(zip(ids, res))
+        return out
+
+    def drillDown(self, dimensionId, attribute):
+        """drillDown of a dimension inside the shard (shard-local)."""
+        idx = self.getDimensionIndex(dimensionId)
+        if idx < self.prefix:
+            raise NotImplementedError("drillDown of a sharded dimension re-partitions rows; not in this round")
+        old_dim = self.dimensions[idx]
+        if old_dim.rootAttribute == attribute:
+            return self
+        new_dim = old_dim.drillDown(attribute)
+        new_dims = list(self.dimensions)
+        new_dims[idx] = new_dim
+        out = self._derive(new_dims, self.row_bounds)
+        old_len = self._local_lens()
+        new_len = [self.rows_local] + [d.numItems for d in new_dims[self.prefix:]]
+        maps = [np.arange(n, dtype=np.int32) for n in new_len]
+        maps[1 + idx - self.prefix] = np.asarray(new_dim.getGroupIndexFromRootIndexMap(old_dim.rootAttribute), np.int32)
+        ids = list(self.storedMeasures)
+        methods = [self.storedMeasuresRules[m].get(dimensionId) or "sum" for m in ids]
+        if ids:
+            stores = [self.storedMeasures[m] for m in ids]
+            if _is_device_store(stores[0]):
+                res = self._store_cls.drillDown_lowered(stores, old_len, new_len, maps, methods)
+            else:
+                res = [s.drillDown_lowered(old_len, new_len, maps, meth) for s, meth in zip(stores, methods)]
+            out.storedMeasures = dict(zip(ids, res))
+        return out
+
+
+class _Per(list):
+    """One value per store (methods)."""

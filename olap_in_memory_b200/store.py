@@ -28,6 +28,8 @@ def _default_kind(defaultValue):
 
 def _method_code(method):
     name = "sum" if method is None else method
+    if name == "__count":  # internal: set children per parent (sharded average)
+        return N.COUNT
     code = N.METHODS.get(name)
     if code is None:
         raise N.OlapValueError(f"Unsupported aggregation method: {name}")  # in-memory.js:294-296
@@ -339,11 +341,16 @@ class GpuStore:
         """copyToStoredMeasure without leaving the device (cube.js:205-215)."""
         total_names = list(totals.keys())
         program = GpuStore._program(expression, cell_names, total_names)
-        tot = (C.c_double * max(1, len(total_names)))(*[totals[t] for t in total_names])
+        return GpuStore.eval_program(program, stores, [totals[t] for t in total_names], type, defaultValue)
+
+    @staticmethod
+    def eval_program(program, stores, totals, type="float32", defaultValue=0):
+        """Run a postfix formula program (include/olap_gpu.h, olap_eval) into a new store."""
+        tot = (C.c_double * max(1, len(totals)))(*totals)
         out = C.c_void_p()
         N.check(
             N.lib().olap_eval(
-                program.encode(), N.store_array([s._h for s in stores]), len(stores), tot, len(total_names),
+                program.encode(), N.store_array([s._h for s in stores]), len(stores), tot, len(totals),
                 None, N.TYPES[type], _default_kind(defaultValue), C.byref(out),
             )
         )

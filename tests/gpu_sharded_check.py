@@ -1,0 +1,57 @@
+"""Run under torchrun (one rank per GPU): the sharded cube on real devices over NCCL must
+match one CPU-oracle cube.  `pytest -m gpu` launches this through test_gpu_sharded.py when
+the box has >= 2 GPUs; with gpurun:  gpurun --gpus 2 -- python -m torch.distributed.run
+--nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/gpu_sharded_check.py"""
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from test_sharded_gloo import METHODS, _collect, _dims, _fill  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from olap_in_memory_b200 import Cube, _native
+    from olap_in_memory_b200.sharded import ShardedCube
+    from oracle.store_oracle import OracleStore
+
+    _native.init(local)
+    failures = 0
+    for prefix, default in ((1, 0.0), (2, math.nan), (2, 0.0)):
+        cube = ShardedCube(_dims(), prefix=prefix)
+        _fill(cube, default)
+        got = _collect(cube, list(cube.storedMeasures))
+        ref = Cube(_dims(), OracleStore)
+        _fill(ref, default)
+        want = _collect(ref, ref.storedMeasureIds)
+        for key in want:
+            if key == "total":
+                ok = math.isclose(got[key], want[key], rel_tol=1e-6) or (math.isnan(got[key]) and math.isnan(want[key]))
+            elif key[0] == "chain" and key[2] in ("m_first", "m_last"):
+                ok = True  # declared divergence of the reference's Map order
+            else:
+                ok = np.allclose(got[key], want[key], rtol=1e-6, atol=0, equal_nan=True)
+            if not ok:
+                failures += 1
+                if rank == 0:
+                    print("MISMATCH", prefix, default, key, np.asarray(got[key]).ravel()[:6], np.asarray(want[key]).ravel()[:6])
+    t = torch.tensor([failures], device="cuda")
+    dist.all_reduce(t)
+    if rank == 0:
+        print(f"gpu_sharded_check: world={world} failures={int(t.item())} launches={_native.lib().olap_kernel_launches()}")
+    dist.destroy_process_group()
+    sys.exit(1 if int(t.item()) else 0)
+
+
+if __name__ == "__main__":
+    main()
