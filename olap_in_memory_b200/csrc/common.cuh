@@ -56,6 +56,7 @@ extern Ctx g;
 extern std::atomic<int64_t> g_launches;
 
 int ensure_ctx();
+void mark_kernels_begin();       // records the op's start event before its first kernel
 int finish_op();                       // sync unless async; surfaces launch errors
 int dev_alloc(void** p, size_t bytes); // stream-ordered
 int dev_free(void* p);

@@ -209,6 +209,7 @@ inline int launch_up_tile(const UpMeasure* d_meas, int n, bool contiguous, const
         OLAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
         attr_set[contiguous] = true;
     }
+    mark_kernels_begin();
     kern<<<dim3((unsigned)tiles, (unsigned)n), 256, t.smem, g.stream>>>(p);
     ++g_launches;
     return OLAP_OK;
@@ -526,6 +527,7 @@ inline int launch_transpose(const GatherMeasure* d_meas, int n, TransposePlan& p
         attr_set = true;
     }
     const dim3 grid((unsigned)plan.n_boxes, (unsigned)n);
+    mark_kernels_begin();
     switch (plan.p.nb) {
         case 2: transpose_kernel<2><<<grid, 256, plan.smem, g.stream>>>(plan.p); break;
         case 3: transpose_kernel<3><<<grid, 256, plan.smem, g.stream>>>(plan.p); break;

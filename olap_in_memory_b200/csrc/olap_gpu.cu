@@ -32,6 +32,7 @@ int fail(int code, const char* fmt, ...) {
 }
 
 #define LAUNCHED() (++::olap::g_launches)
+#define KERNELS_BEGIN() ::olap::mark_kernels_begin()
 
 int ensure_ctx() {
     if (g.ready) {
@@ -43,10 +44,16 @@ int ensure_ctx() {
     return olap_init(0);
 }
 
-static void begin_op() {
-    if (g.ev0) cudaEventRecord(g.ev0, g.stream);
+// ev0 is recorded right before the FIRST kernel of an op (after the small table upload),
+// ev1 after the last one: olap_last_op_ms() is kernel time, not host-side preparation.
+static bool g_op_started = false;
+static void begin_op() { g_op_started = false; }
+void mark_kernels_begin() {
+    if (!g_op_started && g.ev0) cudaEventRecord(g.ev0, g.stream);
+    g_op_started = true;
 }
 static void end_op(const char* path) {
+    mark_kernels_begin();  // an op without kernels still gets a (zero-length) bracket
     if (g.ev1) cudaEventRecord(g.ev1, g.stream);
     g.timing_pending = true;
     g.last_path = path;
@@ -253,6 +260,7 @@ static int launch_up_mid(const UpMeasure* d_meas, int n, const Csr& csr, const i
         const int64_t gx = ceil_div(O, by) * p.blocks_per_row;
         if (gx > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "drillUp: grid too large (%lld blocks)", (long long)gx);
         dim3 grid((unsigned)gx, (unsigned)n), block(bx, by);
+        KERNELS_BEGIN();
         static const int U = [] { const char* e = getenv("OLAP_UP_U"); return e ? atoi(e) : 8; }();  // tuning knob
 #define OLAP_UP_LAUNCH(V, R)                                                                         \
     do {                                                                                             \
@@ -297,6 +305,7 @@ static int launch_down_mid(const DownMeasure* d_meas, int n, const Csr& csr, con
         const int64_t gx = ceil_div(O, by) * p.blocks_per_row;
         if (gx > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "drillDown: grid too large (%lld blocks)", (long long)gx);
         dim3 grid((unsigned)gx, (unsigned)n), block(bx, by);
+        KERNELS_BEGIN();
         if (VEC == 4) {
             if (csr.contiguous) drilldown_mid_kernel<4, true><<<grid, block, 0, g.stream>>>(p);
             else drilldown_mid_kernel<4, false><<<grid, block, 0, g.stream>>>(p);
@@ -760,6 +769,7 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
             for (int d = 0; d < ndim; ++d) { p.pstart[d] = t.ptr<int32_t>(o_ps[d]); p.children[d] = t.ptr<int32_t>(o_ch[d]); }
             const int64_t gx = ceil_div(new_size, 256);
             if (gx > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "olap_drill_up: grid too large");
+            KERNELS_BEGIN();
             drillup_generic_kernel<<<dim3((unsigned)gx, (unsigned)n), 256, 0, g.stream>>>(p);
             LAUNCHED();
         }
@@ -858,6 +868,7 @@ static int run_gather(int mode, olap_store* const* src, int n, std::vector<GDim>
     const int64_t gx = ceil_div(p.n_vec, 512);
     if (gx > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "grid too large");
     dim3 grid((unsigned)gx, (unsigned)n);
+    KERNELS_BEGIN();
 #define OLAP_GATHER(M, V, B) gather_kernel<M, V, B><<<grid, 256, 0, g.stream>>>(p)
 #define OLAP_GATHER_VB(M)                                                                      \
     do {                                                                                       \
@@ -1122,6 +1133,7 @@ int olap_load(olap_store* dst, const olap_store* src, int ndim, const int64_t* m
         p.nd = ndim; p.n = his_size;
         const int64_t gx = ceil_div(his_size, 256);
         if (gx > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "olap_load: grid too large");
+        KERNELS_BEGIN();
         load_scatter_kernel<<<(unsigned)gx, 256, 0, g.stream>>>(p);
         LAUNCHED();
         OLAP_TRY(t.release());
@@ -1170,6 +1182,7 @@ int olap_eval(const char* program, olap_store* const* inputs, int n_inputs, cons
         int nan_default = out_default_kind;
         args.push_back(&out32); args.push_back(&st_out); args.push_back(&out64); args.push_back(&n); args.push_back(&nan_default);
         const int blocks = (int)std::min<int64_t>(ceil_div(ceil_div(size, 4), 256), (int64_t)g.sm_count * 16);
+        KERNELS_BEGIN();
         CUresult cr = jit_api().LaunchKernel(k->fn, blocks, 1, 1, 256, 1, 1, 0, (CUstream)g.stream, args.data(), nullptr);
         if (cr != CUDA_SUCCESS) {
             const char* msg = "?";
