@@ -104,6 +104,13 @@ struct Lane {  // generic (product): the faithful state machine
     Acc<METHOD> a;
     __device__ __forceinline__ void step(float v) { a.step(v, NANDEF); }
     __device__ __forceinline__ float result() const { return a.result(NANDEF); }
+    // fold a LATER chunk of the same parent's children into this one (split reductions)
+    __device__ __forceinline__ void merge(const Lane& o) {
+        if (!o.a.has) { a.cnt += o.a.cnt; return; }
+        if (!a.has) { const uint32_t c = a.cnt; a = o.a; a.cnt += c; return; }
+        if (METHOD == OLAP_PRODUCT) { a.acc *= o.a.acc; a.has = present_d(a.acc, NANDEF); }
+        a.cnt += o.a.cnt;
+    }
 };
 
 template <>
@@ -111,6 +118,7 @@ struct Lane<OLAP_SUM, false> {
     double acc = 0.0;
     __device__ __forceinline__ void step(float v) { acc += (double)v; }
     __device__ __forceinline__ float result() const { return canon_store((float)acc, 0); }
+    __device__ __forceinline__ void merge(const Lane& o) { acc += o.acc; }
 };
 template <>
 struct Lane<OLAP_AVERAGE, false> {
@@ -121,6 +129,7 @@ struct Lane<OLAP_AVERAGE, false> {
         cnt += (v != 0.0f) ? 1u : 0u;  // NaN != 0: a stored NaN is a set cell
     }
     __device__ __forceinline__ float result() const { return canon_store(cnt ? (float)(acc / (double)cnt) : 0.0f, 0); }
+    __device__ __forceinline__ void merge(const Lane& o) { acc += o.acc; cnt += o.cnt; }
 };
 template <>
 struct Lane<OLAP_SUM, true> {
@@ -133,6 +142,11 @@ struct Lane<OLAP_SUM, true> {
         has |= pres;
     }
     __device__ __forceinline__ float result() const { return has ? canon_store((float)acc, 1) : canon_nan(); }
+    __device__ __forceinline__ void merge(const Lane& o) {
+        if (!o.has) return;
+        acc = (has && acc == acc) ? acc + o.acc : o.acc;
+        has = true;
+    }
 };
 template <>
 struct Lane<OLAP_AVERAGE, true> {
@@ -145,12 +159,18 @@ struct Lane<OLAP_AVERAGE, true> {
         cnt += pres ? 1u : 0u;
     }
     __device__ __forceinline__ float result() const { return cnt ? canon_store((float)(acc / (double)cnt), 1) : canon_nan(); }
+    __device__ __forceinline__ void merge(const Lane& o) {
+        if (!o.cnt) return;
+        acc = (cnt && acc == acc) ? acc + o.acc : o.acc;
+        cnt += o.cnt;
+    }
 };
 template <bool NANDEF>
 struct CountLane {
     uint32_t cnt = 0;
     __device__ __forceinline__ void step(float v) { cnt += present_f(v, NANDEF) ? 1u : 0u; }
     __device__ __forceinline__ float result() const { return cnt ? (float)cnt : default_of(NANDEF); }
+    __device__ __forceinline__ void merge(const CountLane& o) { cnt += o.cnt; }
 };
 template <>
 struct Lane<OLAP_COUNT, false> : CountLane<false> {};
@@ -164,6 +184,7 @@ struct Lane<OLAP_HIGHEST, false> {
         acc = (v != 0.0f) ? ((acc == 0.0f) ? v : m) : acc;
     }
     __device__ __forceinline__ float result() const { return canon_store(acc, 0); }
+    __device__ __forceinline__ void merge(const Lane& o) { step(o.acc); }
 };
 template <>
 struct Lane<OLAP_LOWEST, false> {
@@ -173,6 +194,7 @@ struct Lane<OLAP_LOWEST, false> {
         acc = (v != 0.0f) ? ((acc == 0.0f) ? v : m) : acc;
     }
     __device__ __forceinline__ float result() const { return canon_store(acc, 0); }
+    __device__ __forceinline__ void merge(const Lane& o) { step(o.acc); }
 };
 template <>
 struct Lane<OLAP_HIGHEST, true> {
@@ -183,6 +205,7 @@ struct Lane<OLAP_HIGHEST, true> {
         acc = (v == v) ? ((acc != acc) ? v : m) : acc;
     }
     __device__ __forceinline__ float result() const { return canon_store(acc, 1); }
+    __device__ __forceinline__ void merge(const Lane& o) { step(o.acc); }
 };
 template <>
 struct Lane<OLAP_LOWEST, true> {
@@ -193,12 +216,14 @@ struct Lane<OLAP_LOWEST, true> {
         acc = (v == v) ? ((acc != acc) ? v : m) : acc;
     }
     __device__ __forceinline__ float result() const { return canon_store(acc, 1); }
+    __device__ __forceinline__ void merge(const Lane& o) { step(o.acc); }
 };
 template <>
 struct Lane<OLAP_FIRST, false> {
     float acc = 0.0f;
     __device__ __forceinline__ void step(float v) { acc = (acc == 0.0f) ? v : acc; }
     __device__ __forceinline__ float result() const { return canon_store(acc, 0); }
+    __device__ __forceinline__ void merge(const Lane& o) { step(o.acc); }
 };
 template <>
 struct Lane<OLAP_FIRST, true> {
@@ -206,12 +231,14 @@ struct Lane<OLAP_FIRST, true> {
     __device__ __forceinline__ Lane() : acc(canon_nan()) {}
     __device__ __forceinline__ void step(float v) { acc = (acc != acc) ? v : acc; }
     __device__ __forceinline__ float result() const { return canon_store(acc, 1); }
+    __device__ __forceinline__ void merge(const Lane& o) { step(o.acc); }
 };
 template <>
 struct Lane<OLAP_LAST, false> {
     float acc = 0.0f;
     __device__ __forceinline__ void step(float v) { acc = (v != 0.0f) ? v : acc; }
     __device__ __forceinline__ float result() const { return canon_store(acc, 0); }
+    __device__ __forceinline__ void merge(const Lane& o) { step(o.acc); }
 };
 template <>
 struct Lane<OLAP_LAST, true> {
@@ -219,6 +246,7 @@ struct Lane<OLAP_LAST, true> {
     __device__ __forceinline__ Lane() : acc(canon_nan()) {}
     __device__ __forceinline__ void step(float v) { acc = (v == v) ? v : acc; }
     __device__ __forceinline__ float result() const { return canon_store(acc, 1); }
+    __device__ __forceinline__ void merge(const Lane& o) { step(o.acc); }
 };
 
 // ---- kernel A: one changed dimension, any I ----------------------------------
@@ -347,6 +375,115 @@ __global__ void __launch_bounds__(256) drillup_mid_kernel(const __grid_constant_
     } else {
         if (status) up_mid_dispatch<false, VEC, RANGE, true, U>(p, m, o, pi, iv);
         else up_mid_dispatch<false, VEC, RANGE, false, U>(p, m, o, pi, iv);
+    }
+}
+
+// ---- kernel A/split: few outputs, long child lists (drillUp to 'all', year, ...) ------
+// When O*P*I/4 threads cannot fill the chip, G thread rows share one output vector: row g
+// reduces the g-th contiguous chunk of the parent's children (same coalesced 128-bit loads
+// as kernel A), lane states meet in shared memory and row 0 folds them IN CHUNK ORDER, so
+// first/last stay exact and the double sums only change their association.
+template <int METHOD, bool NANDEF, int VEC, bool RANGE, bool STATUS>
+__device__ __forceinline__ void up_split_body(const UpMidParams& p, const UpMeasure& m, int64_t o, uint32_t pi,
+                                              uint32_t iv, bool live, unsigned char* smem_raw) {
+    typedef Lane<METHOD, NANDEF> L;
+    const int G = blockDim.y, g = threadIdx.y, tx = threadIdx.x;
+    L* s_lane = reinterpret_cast<L*>(smem_raw);                                   // [G][32][VEC]
+    uint32_t* s_st = reinterpret_cast<uint32_t*>(smem_raw + (size_t)G * 32 * VEC * sizeof(L));  // [G][32]
+    L lane[VEC];
+    uint32_t st = 0;
+    int32_t k0 = 0, k1 = 0;
+    const int64_t inner = p.i_base + (int64_t)iv * VEC;
+    if (live) {
+        k0 = p.pstart[pi];
+        k1 = p.pstart[pi + 1];
+        const int32_t per = (k1 - k0 + G - 1) / G;
+        const int32_t ks = min(k1, k0 + g * per), ke = min(k1, ks + per);
+        const float* src = m.in + o * p.in_row + inner;
+        const uint8_t* st_src = STATUS ? m.st_in + o * p.in_row + inner : nullptr;
+        constexpr int U = 4;
+        int32_t k = ks;
+        for (; k + U <= ke; k += U) {
+            Cells<VEC> c[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t child = RANGE ? (int64_t)(k + u) : (int64_t)p.children[k + u];
+                c[u] = load_cells<VEC, STATUS>(src, st_src, child * p.I_total);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) lane[e].step(c[u].v[e]);
+                st |= c[u].st;
+            }
+        }
+        for (; k < ke; ++k) {
+            const int64_t child = RANGE ? (int64_t)k : (int64_t)p.children[k];
+            const Cells<VEC> c = load_cells<VEC, STATUS>(src, st_src, child * p.I_total);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) lane[e].step(c.v[e]);
+            st |= c.st;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) s_lane[((size_t)g * 32 + tx) * VEC + e] = lane[e];
+    s_st[g * 32 + tx] = st;
+    __syncthreads();
+    if (g != 0 || !live) return;
+    for (int q = 1; q < G; ++q) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) lane[e].merge(s_lane[((size_t)q * 32 + tx) * VEC + e]);
+        st |= s_st[q * 32 + tx];
+    }
+    const int64_t out_off = o * p.out_row + (int64_t)pi * p.I_total + inner;
+    if (VEC == 4) {
+        float4 r;
+        r.x = lane[0].result(); r.y = lane[1 % VEC].result(); r.z = lane[2 % VEC].result(); r.w = lane[3 % VEC].result();
+        st_stream4(m.out + out_off, r);
+    } else {
+        m.out[out_off] = lane[0].result();
+    }
+    if (STATUS) {
+        if (k0 == k1) st = VEC == 4 ? 0x01010101u : 0x1u;
+        if (VEC == 4) *reinterpret_cast<uint32_t*>(m.st_out + out_off) = st;
+        else m.st_out[out_off] = (uint8_t)st;
+    }
+}
+
+template <bool NANDEF, int VEC, bool RANGE, bool STATUS>
+__device__ __forceinline__ void up_split_dispatch(const UpMidParams& p, const UpMeasure& m, int64_t o, uint32_t pi,
+                                                  uint32_t iv, bool live, unsigned char* smem_raw) {
+    switch (m.method) {
+        case OLAP_SUM: up_split_body<OLAP_SUM, NANDEF, VEC, RANGE, STATUS>(p, m, o, pi, iv, live, smem_raw); break;
+        case OLAP_AVERAGE: up_split_body<OLAP_AVERAGE, NANDEF, VEC, RANGE, STATUS>(p, m, o, pi, iv, live, smem_raw); break;
+        case OLAP_HIGHEST: up_split_body<OLAP_HIGHEST, NANDEF, VEC, RANGE, STATUS>(p, m, o, pi, iv, live, smem_raw); break;
+        case OLAP_LOWEST: up_split_body<OLAP_LOWEST, NANDEF, VEC, RANGE, STATUS>(p, m, o, pi, iv, live, smem_raw); break;
+        case OLAP_FIRST: up_split_body<OLAP_FIRST, NANDEF, VEC, RANGE, STATUS>(p, m, o, pi, iv, live, smem_raw); break;
+        case OLAP_LAST: up_split_body<OLAP_LAST, NANDEF, VEC, RANGE, STATUS>(p, m, o, pi, iv, live, smem_raw); break;
+        case OLAP_COUNT: up_split_body<OLAP_COUNT, NANDEF, VEC, RANGE, STATUS>(p, m, o, pi, iv, live, smem_raw); break;
+        default: up_split_body<OLAP_PRODUCT, NANDEF, VEC, RANGE, STATUS>(p, m, o, pi, iv, live, smem_raw); break;
+    }
+}
+
+// blockDim = (32, G); one outer row per block row: blockIdx.x = o * blocks_per_row + column block
+template <int VEC, bool RANGE>
+__global__ void __launch_bounds__(1024) drillup_split_kernel(const __grid_constant__ UpMidParams p) {
+    extern __shared__ __align__(16) unsigned char smem_split[];
+    const uint32_t brow = blockIdx.x / p.blocks_per_row;
+    const uint32_t bcol = blockIdx.x - brow * p.blocks_per_row;
+    const int64_t o = brow;
+    const uint32_t j = bcol * 32 + threadIdx.x;
+    const bool live = j < p.row_vecs;
+    const uint32_t pi = live ? p.div_iv.div(j) : 0u;
+    const uint32_t iv = live ? j - pi * p.IV : 0u;
+    const UpMeasure m = p.meas[blockIdx.y];
+    const bool status = m.st_in != nullptr;
+    if (m.nan_default) {
+        if (status) up_split_dispatch<true, VEC, RANGE, true>(p, m, o, pi, iv, live, smem_split);
+        else up_split_dispatch<true, VEC, RANGE, false>(p, m, o, pi, iv, live, smem_split);
+    } else {
+        if (status) up_split_dispatch<false, VEC, RANGE, true>(p, m, o, pi, iv, live, smem_split);
+        else up_split_dispatch<false, VEC, RANGE, false>(p, m, o, pi, iv, live, smem_split);
     }
 }
 

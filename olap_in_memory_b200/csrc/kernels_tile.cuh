@@ -56,6 +56,8 @@ struct UpTileParams {
     int32_t bulk_values;    // tile starts are 16-byte aligned for the float plane
     int32_t bulk_status;    // ... and for the status plane
     uint32_t st_offset;     // byte offset of the status tile in dynamic shared memory
+    uint32_t merge_offset;  // byte offset of the split-merge scratch (G > 1)
+    int32_t G, logG;        // threads sharing one output (power of two)
 };
 
 struct TileDecision {
@@ -63,7 +65,8 @@ struct TileDecision {
     int R = 1;
     bool bulk_values = false, bulk_status = false;
     size_t smem = 0;
-    uint32_t st_offset = 0;
+    uint32_t st_offset = 0, merge_offset = 0;
+    int G = 1;
 };
 
 // Use the tile kernel when the inner run is short and at least one row fits in shared memory.
@@ -99,16 +102,66 @@ inline TileDecision tile_plan(int64_t O, int64_t C, int64_t P, int64_t I, bool a
     const size_t vbytes = ((size_t)R * row_in * 4 + 15) & ~(size_t)15;
     t.st_offset = (uint32_t)vbytes;
     t.smem = vbytes + (any_status ? (((size_t)R * row_in + 15) & ~(size_t)15) : 0) + 16;
+    // few outputs per tile and long child lists: let G threads share an output
+    const int64_t n_out = R * P * I, avg_children = std::max<int64_t>(1, C / std::max<int64_t>(P, 1));
+    int G = 1;
+    while (G < 256 && n_out * G * 2 <= 256 && avg_children >= 8 * G) G *= 2;
+    t.G = G;
+    if (G > 1) {
+        t.merge_offset = (uint32_t)t.smem;
+        t.smem += 256 * 16 + 256;
+    }
     t.use = true;
     return t;
 }
 
 template <int METHOD, bool NANDEF, bool RANGE, bool STATUS>
 __device__ __forceinline__ void up_tile_reduce(const UpTileParams& p, const UpMeasure& m, const float* s_val,
-                                               const uint8_t* s_st, int64_t o0, int rows) {
+                                               const uint8_t* s_st, int64_t o0, int rows, unsigned char* s_merge) {
+    typedef Lane<METHOD, NANDEF> L;
     const int n_out = rows * p.row_out;
     float* out = m.out + o0 * p.row_out;
     uint8_t* st_out = STATUS ? m.st_out + o0 * p.row_out : nullptr;
+    if (p.G > 1) {
+        // few outputs per tile: G consecutive threads share one output, each reduces one
+        // contiguous chunk of the children, thread 0 of the group folds the chunks in order
+        L* s_lane = reinterpret_cast<L*>(s_merge);
+        uint8_t* s_stm = s_merge + 256 * sizeof(L);
+        const int j = threadIdx.x >> p.logG, gq = threadIdx.x & (p.G - 1);
+        L lane;
+        uint32_t st = 0;
+        int32_t k0 = 0, k1 = 0;
+        if (j < n_out) {
+            const uint32_t r = p.div_row_out.div((uint32_t)j);
+            const uint32_t q = (uint32_t)j - r * (uint32_t)p.row_out;
+            const uint32_t pi = p.div_i.div(q);
+            const uint32_t i = q - pi * (uint32_t)p.I;
+            k0 = p.pstart[pi];
+            k1 = p.pstart[pi + 1];
+            const int32_t per = (k1 - k0 + p.G - 1) >> p.logG;
+            const int32_t ks = min(k1, k0 + gq * per), ke = min(k1, ks + per);
+            const uint32_t base = r * (uint32_t)p.row_in + i;
+#pragma unroll 4
+            for (int32_t k = ks; k < ke; ++k) {
+                const uint32_t c = RANGE ? (uint32_t)k : (uint32_t)p.children[k];
+                const uint32_t idx = base + c * (uint32_t)p.I;
+                lane.step(s_val[idx]);
+                if (STATUS) st |= s_st[idx];
+            }
+        }
+        s_lane[threadIdx.x] = lane;
+        s_stm[threadIdx.x] = (uint8_t)st;
+        __syncthreads();
+        if (j < n_out && gq == 0) {
+            for (int q2 = 1; q2 < p.G; ++q2) {
+                lane.merge(s_lane[threadIdx.x + q2]);
+                st |= s_stm[threadIdx.x + q2];
+            }
+            out[j] = lane.result();
+            if (STATUS) st_out[j] = (uint8_t)(k0 == k1 ? OLAP_STATUS_UNSET : st);
+        }
+        return;
+    }
     for (int j = threadIdx.x; j < n_out; j += blockDim.x) {
         const uint32_t r = p.div_row_out.div((uint32_t)j);
         const uint32_t q = (uint32_t)j - r * (uint32_t)p.row_out;
@@ -116,7 +169,7 @@ __device__ __forceinline__ void up_tile_reduce(const UpTileParams& p, const UpMe
         const uint32_t i = q - pi * (uint32_t)p.I;
         const int32_t k0 = p.pstart[pi], k1 = p.pstart[pi + 1];
         const uint32_t base = r * (uint32_t)p.row_in + i;
-        Lane<METHOD, NANDEF> lane;
+        L lane;
         uint32_t st = 0;
 #pragma unroll 4
         for (int32_t k = k0; k < k1; ++k) {
@@ -132,16 +185,16 @@ __device__ __forceinline__ void up_tile_reduce(const UpTileParams& p, const UpMe
 
 template <bool NANDEF, bool RANGE, bool STATUS>
 __device__ __forceinline__ void up_tile_dispatch(const UpTileParams& p, const UpMeasure& m, const float* s_val,
-                                                 const uint8_t* s_st, int64_t o0, int rows) {
+                                                 const uint8_t* s_st, int64_t o0, int rows, unsigned char* s_merge) {
     switch (m.method) {
-        case OLAP_SUM: up_tile_reduce<OLAP_SUM, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows); break;
-        case OLAP_AVERAGE: up_tile_reduce<OLAP_AVERAGE, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows); break;
-        case OLAP_HIGHEST: up_tile_reduce<OLAP_HIGHEST, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows); break;
-        case OLAP_LOWEST: up_tile_reduce<OLAP_LOWEST, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows); break;
-        case OLAP_FIRST: up_tile_reduce<OLAP_FIRST, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows); break;
-        case OLAP_LAST: up_tile_reduce<OLAP_LAST, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows); break;
-        case OLAP_COUNT: up_tile_reduce<OLAP_COUNT, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows); break;
-        default: up_tile_reduce<OLAP_PRODUCT, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows); break;
+        case OLAP_SUM: up_tile_reduce<OLAP_SUM, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows, s_merge); break;
+        case OLAP_AVERAGE: up_tile_reduce<OLAP_AVERAGE, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows, s_merge); break;
+        case OLAP_HIGHEST: up_tile_reduce<OLAP_HIGHEST, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows, s_merge); break;
+        case OLAP_LOWEST: up_tile_reduce<OLAP_LOWEST, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows, s_merge); break;
+        case OLAP_FIRST: up_tile_reduce<OLAP_FIRST, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows, s_merge); break;
+        case OLAP_LAST: up_tile_reduce<OLAP_LAST, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows, s_merge); break;
+        case OLAP_COUNT: up_tile_reduce<OLAP_COUNT, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows, s_merge); break;
+        default: up_tile_reduce<OLAP_PRODUCT, NANDEF, RANGE, STATUS>(p, m, s_val, s_st, o0, rows, s_merge); break;
     }
 }
 
@@ -153,6 +206,7 @@ __global__ void __launch_bounds__(256) drillup_tile_kernel(const __grid_constant
     const UpMeasure m = p.meas[blockIdx.y];
     const bool status = m.st_in != nullptr;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + p.st_offset + (status ? (((size_t)p.R * p.row_in + 15) & ~(size_t)15) : 0));
+    unsigned char* s_merge = smem + p.merge_offset;
 
     const int64_t o0 = (int64_t)blockIdx.x * p.R;
     const int rows = (int)min((int64_t)p.R, p.O - o0);
@@ -177,11 +231,11 @@ __global__ void __launch_bounds__(256) drillup_tile_kernel(const __grid_constant
     __syncthreads();
 
     if (m.nan_default) {
-        if (status) up_tile_dispatch<true, RANGE, true>(p, m, s_val, s_st, o0, rows);
-        else up_tile_dispatch<true, RANGE, false>(p, m, s_val, s_st, o0, rows);
+        if (status) up_tile_dispatch<true, RANGE, true>(p, m, s_val, s_st, o0, rows, s_merge);
+        else up_tile_dispatch<true, RANGE, false>(p, m, s_val, s_st, o0, rows, s_merge);
     } else {
-        if (status) up_tile_dispatch<false, RANGE, true>(p, m, s_val, s_st, o0, rows);
-        else up_tile_dispatch<false, RANGE, false>(p, m, s_val, s_st, o0, rows);
+        if (status) up_tile_dispatch<false, RANGE, true>(p, m, s_val, s_st, o0, rows, s_merge);
+        else up_tile_dispatch<false, RANGE, false>(p, m, s_val, s_st, o0, rows, s_merge);
     }
 }
 
@@ -201,6 +255,10 @@ inline int launch_up_tile(const UpMeasure* d_meas, int n, bool contiguous, const
     p.bulk_values = t.bulk_values;
     p.bulk_status = t.bulk_status;
     p.st_offset = t.st_offset;
+    p.merge_offset = t.merge_offset;
+    p.G = t.G;
+    p.logG = 0;
+    while ((1 << p.logG) < t.G) ++p.logG;
     const int64_t tiles = ceil_div(O, t.R);
     if (tiles > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "drillUp: grid too large (%lld tiles)", (long long)tiles);
     static bool attr_set[2] = {false, false};

@@ -254,6 +254,36 @@ static int launch_up_mid(const UpMeasure* d_meas, int n, const Csr& csr, const i
         p.div_iv = FastDiv((uint32_t)iv_n);
         p.row_vecs = (uint32_t)(P * iv_n);
         p.n_measures = n;
+        // too few output vectors to fill the chip and long child lists: split each parent's
+        // children over G thread rows (drillup_split_kernel)
+        static const int split_knob = [] { const char* e = getenv("OLAP_SPLIT"); return e ? atoi(e) : -1; }();
+        const int64_t threads = O * (int64_t)p.row_vecs;
+        const int64_t want_threads = (int64_t)g.sm_count * 2048;
+        const int64_t avg_children = std::max<int64_t>(1, C / std::max<int64_t>(P, 1));
+        int G = 1;
+        while (G < 32 && threads * G * 4 <= want_threads && avg_children >= 8 * G) G *= 2;
+        if (split_knob >= 0) G = split_knob;
+        if (G >= 2 && O * ceil_div(p.row_vecs, 32) <= 0x7fffffffLL) {
+            p.blocks_per_row = (uint32_t)ceil_div(p.row_vecs, 32);
+            const size_t smem = (size_t)G * 32 * VEC * 16 + (size_t)G * 32 * 4;
+            dim3 grid((unsigned)(O * p.blocks_per_row), (unsigned)n), block(32, G);
+            KERNELS_BEGIN();
+#define OLAP_SPLIT_LAUNCH(V, R)                                                                            \
+    do {                                                                                                   \
+        static bool attr = false;                                                                          \
+        if (!attr) {                                                                                       \
+            OLAP_CUDA(cudaFuncSetAttribute(drillup_split_kernel<V, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           32 * 32 * 4 * 16 + 32 * 32 * 4));                               \
+            attr = true;                                                                                   \
+        }                                                                                                  \
+        drillup_split_kernel<V, R><<<grid, block, smem, g.stream>>>(p);                                    \
+    } while (0)
+            if (VEC == 4) { if (csr.contiguous) OLAP_SPLIT_LAUNCH(4, true); else OLAP_SPLIT_LAUNCH(4, false); }
+            else { if (csr.contiguous) OLAP_SPLIT_LAUNCH(1, true); else OLAP_SPLIT_LAUNCH(1, false); }
+#undef OLAP_SPLIT_LAUNCH
+            LAUNCHED();
+            continue;
+        }
         const uint32_t bx = std::min<uint32_t>(256, next_pow2(p.row_vecs));
         const uint32_t by = 256 / bx;
         p.blocks_per_row = (uint32_t)ceil_div(p.row_vecs, bx);

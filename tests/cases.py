@@ -70,6 +70,10 @@ def drillup_cases(seed=0):
         ([4, 1, 6], 1, 1, True),         # C == P == 1 (slice's removeDimension)
         ([2, 700, 4], 1, 3, True),       # long segments
         ([1200, 3], 0, 2, False),
+        ([1000, 8], 0, 1, True),         # few outputs, long child lists: split kernel (mid)
+        ([1000, 8], 0, 3, False),
+        ([4, 2000], 1, 1, True),         # ... split inside the tile kernel
+        ([3, 1500, 2], 1, 2, False),
     ]
     for dims, d, P, mono in shapes:
         for default in (0.0, math.nan):
