@@ -216,6 +216,107 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
     }
 }
 
+// ---- scalar gathers, amortised: gather_rows_kernel ------------------------------------
+// When the innermost output axis cannot be moved with 128-bit accesses (it is diced /
+// drilled itself, or shorter than 4), the per-element cost of gather_kernel is the full
+// index decode.  Here a CTA owns RB consecutive output rows (a row = the innermost axis, L
+// cells): RB threads decode one row each (source offset, drillDown sibling count / rank)
+// into shared memory, the innermost axis' table sits in shared memory too, and every
+// element then costs one division by L, two shared-memory reads, one load, one store.
+// Output is written as one contiguous span.
+constexpr int kRowsMaxL = 1024;
+constexpr int kRowsPerBlock = 256;
+
+struct RowsTail {
+    uint32_t L;
+    FastDiv div_l;
+    const int64_t* tbl;   // source offset per innermost coordinate (nullptr: coordinate * lin)
+    int64_t lin;
+    const DownAux* aux;   // drillDown aux of the innermost axis (nullable)
+    uint32_t RB;          // rows per CTA
+    int64_t rows;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const __grid_constant__ GatherParams p,
+                                                          const __grid_constant__ RowsTail tail) {
+    __shared__ int64_t s_off[kRowsPerBlock];
+    __shared__ uint32_t s_n[kRowsPerBlock], s_k[kRowsPerBlock];
+    __shared__ int64_t s_tbl[kRowsMaxL];
+    __shared__ DownAux s_aux[MODE == G_COPY ? 1 : kRowsMaxL];
+    const GatherMeasure m = p.meas[blockIdx.y];
+    const int64_t row0 = (int64_t)blockIdx.x * tail.RB;
+    const uint32_t rows = (uint32_t)min((int64_t)tail.RB, tail.rows - row0);
+    for (uint32_t c = threadIdx.x; c < tail.L; c += 256) {
+        s_tbl[c] = tail.tbl ? tail.tbl[c] : (int64_t)c * tail.lin;
+        if (MODE != G_COPY) s_aux[c] = tail.aux ? tail.aux[c] : DownAux{1, 0, 1.0};
+    }
+    if (threadIdx.x < rows) {
+        uint32_t rest = (uint32_t)(row0 + threadIdx.x);
+        int64_t off = 0;
+        uint32_t n = 1, k = 0;
+        for (int d = p.nd - 1; d >= 0; --d) {
+            const uint32_t q = p.div[d].div(rest);
+            const uint32_t c = rest - q * p.len[d];
+            rest = q;
+            off += p.tbl[d] ? p.tbl[d][c] : (int64_t)c * p.lin[d];
+            if (MODE != G_COPY && p.aux[d]) {
+                const DownAux a = p.aux[d][c];
+                k += (uint32_t)a.rank * n;
+                n *= (uint32_t)a.cnt;
+            }
+        }
+        s_off[threadIdx.x] = off;
+        s_n[threadIdx.x] = n;
+        s_k[threadIdx.x] = k;
+    }
+    __syncthreads();
+    const uint32_t cells = rows * tail.L;
+    const int64_t base = row0 * tail.L;
+    constexpr int U = 4;
+    for (uint32_t t0 = threadIdx.x; t0 < cells; t0 += 256 * U) {
+        float v[U];
+        uint32_t sb[U], rr[U], cc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t t = t0 + u * 256;
+            if (t < cells) {
+                rr[u] = tail.div_l.div(t);
+                cc[u] = t - rr[u] * tail.L;
+                const int64_t off = s_off[rr[u]] + s_tbl[cc[u]];
+                v[u] = ld_stream1(m.in + off);
+                sb[u] = m.st_in ? (uint32_t)m.st_in[off] : 0u;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t t = t0 + u * 256;
+            if (t >= cells) continue;
+            float r = v[u];
+            uint32_t so = sb[u];
+            if (MODE != G_COPY) {
+                const DownAux a = s_aux[cc[u]];
+                const uint32_t n = s_n[rr[u]] * (uint32_t)a.cnt;
+                const uint32_t k = s_k[rr[u]] * (uint32_t)a.cnt + (uint32_t)a.rank;
+                const double inv = s_n[rr[u]] == 1 ? a.inv : 1.0 / (double)n;
+                bool ok;
+                if (MODE == G_DOWN_FLOAT) {
+                    const float x = v[u];
+                    const float q = canon_store((float)(n < (1u << 20) ? (double)x * inv : (double)x / (double)n), m.nan_default);
+                    const bool truthy = x != 0.0f && x == x;
+                    r = truthy ? q : default_of(m.nan_default);
+                    ok = truthy && present_f(q, m.nan_default);
+                } else {
+                    r = down_value(m, p, v[u], n, inv, k, base + t, ok);
+                }
+                so = ok ? ((sb[u] | OLAP_STATUS_INTERPOLATED) & 0xffu) : (uint32_t)OLAP_STATUS_UNSET;
+            }
+            m.out[base + t] = r;
+            if (m.st_out) m.st_out[base + t] = (uint8_t)so;
+        }
+    }
+}
+
 // ---- load: input-driven scatter  dst[mine(his)] = src[his]  (in-memory.js:159-175).
 // Tables hold my offset contribution per his coordinate, or -1 when I lack the item
 // (then the cell is dropped).  His items are distinct, so the scatter is injective.

@@ -842,6 +842,63 @@ static int run_gather(int mode, olap_store* const* src, int n, std::vector<GDim>
     }
     if ((int)dims.size() > OLAP_MAX_DIMS) return fail(OLAP_E_UNSUPPORTED, "too many dimensions");
     int VEC = (I % 4 == 0) ? 4 : 1;
+    // scalar case: the amortised row kernel (innermost axis = short run or a table axis)
+    static const int rows_knob = [] { const char* e = getenv("OLAP_ROWS"); return e ? atoi(e) : 1; }();
+    if (VEC == 1 && rows_knob && (I > 1 || !dims.empty())) {
+        GDim last;
+        std::vector<GDim> outer = dims;
+        if (I > 1) { last.len = I; last.linear = true; last.stride = 1; }
+        else { last = outer.back(); outer.pop_back(); }
+        int64_t rows = 1;
+        bool fits = last.len <= kRowsMaxL && last.len >= 1;
+        for (auto& d : outer) { rows *= d.len; fits &= d.len <= 0x7fffffffLL; }
+        if (fits && rows < ((int64_t)1 << 31)) {
+            GatherParams p{};
+            RowsTail tail{};
+            TablePack t;
+            std::vector<GatherMeasure> meas = meas_in;
+            for (auto& m : meas) { m.in += const_off; if (m.st_in) m.st_in += const_off; }
+            const size_t o_meas = t.add(meas.data(), sizeof(GatherMeasure) * n);
+            std::vector<size_t> o_tbl(outer.size(), 0), o_aux(outer.size(), 0);
+            for (size_t d = 0; d < outer.size(); ++d) {
+                if (!outer[d].linear) o_tbl[d] = t.add(outer[d].tbl.data(), outer[d].tbl.size() * 8);
+                if (!outer[d].aux.empty()) o_aux[d] = t.add(outer[d].aux.data(), outer[d].aux.size() * sizeof(DownAux));
+            }
+            const size_t o_ltbl = last.linear ? 0 : t.add(last.tbl.data(), last.tbl.size() * 8);
+            const size_t o_laux = last.aux.empty() ? 0 : t.add(last.aux.data(), last.aux.size() * sizeof(DownAux));
+            OLAP_TRY(t.upload());
+            p.meas = t.ptr<GatherMeasure>(o_meas);
+            p.nd = (int)outer.size();
+            for (size_t d = 0; d < outer.size(); ++d) {
+                p.len[d] = (uint32_t)outer[d].len;
+                p.div[d] = FastDiv((uint32_t)outer[d].len);
+                p.tbl[d] = outer[d].linear ? nullptr : t.ptr<int64_t>(o_tbl[d]);
+                p.lin[d] = outer[d].stride;
+                p.aux[d] = outer[d].aux.empty() ? nullptr : t.ptr<DownAux>(o_aux[d]);
+            }
+            p.new_size = new_size;
+            p.old_size = old_size;
+            p.error_flag = d_error;
+            tail.L = (uint32_t)last.len;
+            tail.div_l = FastDiv((uint32_t)last.len);
+            tail.tbl = last.linear ? nullptr : t.ptr<int64_t>(o_ltbl);
+            tail.lin = last.stride;
+            tail.aux = last.aux.empty() ? nullptr : t.ptr<DownAux>(o_laux);
+            tail.RB = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(kRowsPerBlock, 4096 / last.len));
+            tail.rows = rows;
+            const int64_t gx = ceil_div(rows, tail.RB);
+            if (gx > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "grid too large");
+            dim3 grid((unsigned)gx, (unsigned)n);
+            KERNELS_BEGIN();
+            if (mode == G_COPY) gather_rows_kernel<G_COPY><<<grid, 256, 0, g.stream>>>(p, tail);
+            else if (mode == G_DOWN_FLOAT) gather_rows_kernel<G_DOWN_FLOAT><<<grid, 256, 0, g.stream>>>(p, tail);
+            else gather_rows_kernel<G_DOWN><<<grid, 256, 0, g.stream>>>(p, tail);
+            LAUNCHED();
+            *path = "gather/rows";
+            OLAP_TRY(t.release());
+            return OLAP_OK;
+        }
+    }
     // every offset must keep 16-byte alignment for the 128-bit path
     if (VEC == 4) {
         if (const_off % 4) VEC = 1;
