@@ -8,6 +8,9 @@
 // R*P*I results leave as one contiguous, coalesced span.  Several CTAs are resident per
 // SM, so one CTA's copy overlaps its neighbours' reduction without an explicit pipeline.
 #pragma once
+#include <algorithm>
+#include <numeric>
+
 #include "common.cuh"
 #include "kernels_drillup.cuh"
 #include "kernels_gather.cuh"
@@ -87,8 +90,8 @@ inline TileDecision tile_plan(int64_t O, int64_t C, int64_t P, int64_t I, bool a
         if (r == 0) r = mult;
         return r;
     };
-    const int64_t mult_v = 4 / std::__gcd<int64_t>(row_in % 4 == 0 ? 4 : row_in % 4, 4);
-    const int64_t mult_s = 16 / std::__gcd<int64_t>(row_in % 16 == 0 ? 16 : row_in % 16, 16);
+    const int64_t mult_v = 4 / std::gcd<int64_t, int64_t>(row_in % 4 == 0 ? 4 : row_in % 4, 4);
+    const int64_t mult_s = 16 / std::gcd<int64_t, int64_t>(row_in % 16 == 0 ? 16 : row_in % 16, 16);
     int64_t Rs = round_to(any_status ? mult_s : mult_v);
     if (Rs * row_in * per_cell <= hard) {
         R = Rs;
@@ -299,6 +302,7 @@ struct TransposeParams {
     int nb;                        // entries used in rd[] / wr[] (both padded to nb)
     BoxDim rd[kMaxBoxDims], wr[kMaxBoxDims];  // input order / output order, innermost first
     uint32_t box_cells;            // prod b
+    uint32_t runs_in, runs_out;    // prod of b over entries 1.. of rd / wr
     // grid decomposition: every output axis, outermost first
     int n_axes;
     uint32_t boxes[OLAP_MAX_DIMS];   // number of boxes along the axis
@@ -316,14 +320,15 @@ struct TransposePlan {
     size_t smem = 0;
 };
 
+// Decode the index of a RUN (everything but entry 0) into global / shared offsets.
 template <int NB, bool CHECK>
-__device__ __forceinline__ bool box_decode(const BoxDim (&dims)[kMaxBoxDims], const uint32_t (&ext)[kMaxBoxDims],
+__device__ __forceinline__ bool run_decode(const BoxDim (&dims)[kMaxBoxDims], const uint32_t (&ext)[kMaxBoxDims],
                                            uint32_t t, uint32_t& g_off, uint32_t& s_off) {
     bool ok = true;
     g_off = 0;
     s_off = 0;
 #pragma unroll
-    for (int d = 0; d < NB; ++d) {
+    for (int d = 1; d < NB; ++d) {
         uint32_t c;
         if (d == NB - 1) c = t;
         else {
@@ -338,47 +343,55 @@ __device__ __forceinline__ bool box_decode(const BoxDim (&dims)[kMaxBoxDims], co
     return ok;
 }
 
+// One WARP per run: the run is entry 0 of the order (contiguous in global memory), the
+// lanes walk it, and the decode of the run's position is paid once per run, not per cell.
 template <int NB, bool STATUS, bool CHECK>
 __device__ __forceinline__ void transpose_phases(const TransposeParams& p, const float* __restrict__ src,
                                                  const uint8_t* __restrict__ st_src, float* __restrict__ dst,
                                                  uint8_t* __restrict__ st_dst, float* s_val, uint8_t* s_st,
                                                  const uint32_t (&ext_rd)[kMaxBoxDims],
                                                  const uint32_t (&ext_wr)[kMaxBoxDims]) {
-    constexpr int U = 4;
-    // ---- phase 1: input order -> shared memory (output-order positions)
-    for (uint32_t t0 = threadIdx.x; t0 < p.box_cells; t0 += 256 * U) {
-        float v[U];
-        uint8_t sb[U];
-        uint32_t pos[U];
-        bool ok[U];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ---- phase 1: input runs -> shared memory
+    {
+        const uint32_t len = CHECK ? ext_rd[0] : p.rd[0].b;
+        const uint32_t gs = p.rd[0].g_stride, ss = p.rd[0].s_stride;
+        for (uint32_t run = warp; run < p.runs_in; run += 8) {
+            uint32_t g_off, s_off;
+            if (!run_decode<NB, CHECK>(p.rd, ext_rd, run, g_off, s_off)) continue;
+            for (uint32_t pos0 = lane; pos0 < len; pos0 += 128) {
+                float v[4];
+                uint8_t sb[4];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t t = t0 + u * 256;
-            uint32_t off;
-            ok[u] = box_decode<NB, CHECK>(p.rd, ext_rd, t, off, pos[u]) && t < p.box_cells;
-            if (ok[u]) {
-                v[u] = ld_stream1(src + off);
-                if (STATUS) sb[u] = st_src[off];
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t pos = pos0 + u * 32;
+                    if (pos < len) {
+                        v[u] = ld_stream1(src + g_off + pos * gs);
+                        if (STATUS) sb[u] = st_src[g_off + pos * gs];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t pos = pos0 + u * 32;
+                    if (pos < len) {
+                        s_val[s_off + pos * ss] = v[u];
+                        if (STATUS) s_st[s_off + pos * ss] = sb[u];
+                    }
+                }
             }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (ok[u]) {
-                s_val[pos[u]] = v[u];
-                if (STATUS) s_st[pos[u]] = sb[u];
-            }
     }
     __syncthreads();
-    // ---- phase 2: output order <- shared memory
-    for (uint32_t t0 = threadIdx.x; t0 < p.box_cells; t0 += 256 * U) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t t = t0 + u * 256;
-            uint32_t off, sp;
-            const bool ok = box_decode<NB, CHECK>(p.wr, ext_wr, t, off, sp) && t < p.box_cells;
-            if (ok) {
-                dst[off] = s_val[sp];
-                if (STATUS) st_dst[off] = s_st[sp];
+    // ---- phase 2: shared memory -> output runs
+    {
+        const uint32_t len = CHECK ? ext_wr[0] : p.wr[0].b;
+        const uint32_t gs = p.wr[0].g_stride, ss = p.wr[0].s_stride;
+        for (uint32_t run = warp; run < p.runs_out; run += 8) {
+            uint32_t g_off, s_off;
+            if (!run_decode<NB, CHECK>(p.wr, ext_wr, run, g_off, s_off)) continue;
+            for (uint32_t pos = lane; pos < len; pos += 32) {
+                dst[g_off + pos * gs] = s_val[s_off + pos * ss];
+                if (STATUS) st_dst[g_off + pos * gs] = s_st[s_off + pos * ss];
             }
         }
     }
@@ -461,14 +474,19 @@ inline TransposePlan transpose_plan(const std::vector<GDim>& dims_in) {
     for (int i = 0; i < k; ++i) by_src[i] = i;
     std::sort(by_src.begin(), by_src.end(), [&](int a, int b) { return dims[a].stride < dims[b].stride; });
     std::vector<int64_t> b(k, 1);
-    const int64_t run_target = 64, cells_target = 4096, cells_max = 8192;
+    const int64_t run_target = 64, cells_target = 4096, cells_max = 6144;
     auto cells = [&] { int64_t c = 1; for (int i = 0; i < k; ++i) c *= b[i]; return c; };
+    // an extent near `want` that splits the axis into equal parts (no ragged edge boxes)
+    auto even_extent = [&](int64_t len, int64_t want) {
+        want = std::max<int64_t>(1, std::min(want, len));
+        const int64_t parts = std::max<int64_t>(1, len / want);
+        return ceil_div(len, parts);
+    };
     // (1) cover the input's trailing axes until a contiguous input run of >= run_target cells
     int64_t run = 1;
     for (int idx : by_src) {
         if (run >= run_target) break;
-        const int64_t want = std::min<int64_t>(dims[idx].len, ceil_div(run_target, run));
-        b[idx] = std::max(b[idx], want);
+        b[idx] = std::max(b[idx], even_extent(dims[idx].len, ceil_div(run_target, run)));
         run *= b[idx];
         if (b[idx] < dims[idx].len) break;  // a partially covered axis ends the contiguous run
     }
@@ -476,40 +494,56 @@ inline TransposePlan transpose_plan(const std::vector<GDim>& dims_in) {
     run = 1;
     for (int i = k - 1; i >= 0; --i) {
         if (run >= run_target) break;
-        const int64_t want = std::min<int64_t>(dims[i].len, ceil_div(run_target, run));
-        b[i] = std::max(b[i], want);
+        b[i] = std::max(b[i], even_extent(dims[i].len, ceil_div(run_target, run)));
         run *= b[i];
         if (b[i] < dims[i].len) break;
     }
-    if (cells() > cells_max) {
-        // shrink the two run axes evenly until the box fits
-        while (cells() > cells_max) {
-            int big = 0;
-            for (int i = 1; i < k; ++i) if (b[i] > b[big]) big = i;
-            if (b[big] <= 1) return plan;
-            b[big] = (b[big] + 1) / 2;
-        }
+    // largest even-split extent strictly below `cur`
+    auto shrink = [&](int64_t len, int64_t cur) {
+        int64_t parts = ceil_div(len, cur) + 1, extent = ceil_div(len, parts);
+        while (extent >= cur && parts < len) extent = ceil_div(len, ++parts);
+        return std::max<int64_t>(1, std::min(extent, cur - 1));
+    };
+    while (cells() > cells_max) {  // shrink the largest extent until the box fits
+        int big = 0;
+        for (int i = 1; i < k; ++i) if (b[i] > b[big]) big = i;
+        if (b[big] <= 1) return plan;
+        b[big] = shrink(dims[big].len, b[big]);
     }
-    // (3) grow: widen partially covered axes, innermost output axes first, up to the target
+    // (3) grow towards the target: widen axes already in the box, innermost output axes first
     for (int pass = 0; pass < 2 && cells() < cells_target; ++pass)
         for (int i = k - 1; i >= 0 && cells() < cells_target; --i) {
-            if (pass == 0 && b[i] == 1) continue;  // first widen axes already in the box
-            const int64_t room = cells_target / (cells() / b[i]);
-            b[i] = std::max<int64_t>(b[i], std::min<int64_t>(dims[i].len, room));
+            if (pass == 0 && b[i] == 1) continue;
+            if (b[i] >= dims[i].len) continue;
+            const int64_t room = cells_max / (cells() / b[i]);
+            const int64_t cand = even_extent(dims[i].len, std::min<int64_t>(dims[i].len, room));
+            if (cand > b[i] && cells() / b[i] * cand <= cells_max) b[i] = cand;
         }
     std::vector<int> box_axes;
     for (int i = 0; i < k; ++i) if (b[i] > 1) box_axes.push_back(i);
     if (box_axes.empty()) return plan;
 
     TransposeParams& p = plan.p;
-    // shared-memory layout: output order inside the box, pitches padded to odd
+    // shared-memory layout: INPUT order inside the box (ascending source stride), so that a
+    // whole contiguous input run is also contiguous in shared memory; the pitch is padded to
+    // an odd number wherever the next axis is not a continuation of the run, which makes the
+    // strided shared-memory reads of phase 2 bank-conflict free.
     std::vector<uint32_t> pitch(k, 0);
     uint32_t sacc = 1;
-    for (int i = k - 1; i >= 0; --i) {
+    for (size_t q = 0; q < by_src.size(); ++q) {
+        const int i = by_src[q];
         if (b[i] <= 1) continue;
         pitch[i] = sacc;
         sacc *= (uint32_t)b[i];
-        if (sacc % 2 == 0) sacc += 1;
+        // continuation = next box axis in input order is source-contiguous with this fully covered one
+        bool continues = false;
+        for (size_t q2 = q + 1; q2 < by_src.size(); ++q2) {
+            const int j = by_src[q2];
+            if (b[j] <= 1) continue;
+            continues = b[i] == dims[i].len && dims[j].stride == dims[i].stride * dims[i].len;
+            break;
+        }
+        if (!continues && sacc % 2 == 0) sacc += 1;
     }
     const size_t s_cells = sacc;
     // phase-1 order: ascending source stride; phase-2 order: ascending destination stride.
@@ -555,6 +589,8 @@ inline TransposePlan transpose_plan(const std::vector<GDim>& dims_in) {
     if (!fill(rd, p.rd) || !fill(wr, p.wr)) return plan;
     p.nb = std::max(nb, 2);
     p.box_cells = (uint32_t)cells();
+    p.runs_in = p.runs_out = 1;
+    for (int q = 1; q < kMaxBoxDims; ++q) { p.runs_in *= p.rd[q].b; p.runs_out *= p.wr[q].b; }
     p.n_axes = k;
     int64_t n_boxes = 1;
     for (int i = 0; i < k; ++i) {
