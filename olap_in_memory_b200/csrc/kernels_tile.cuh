@@ -295,6 +295,11 @@ struct BoxDim {
     uint32_t s_stride;  // shared-memory pitch, elements
     uint32_t axis;      // output axis whose (possibly ragged) extent bounds this entry
     uint32_t ext_mult;  // cells of fully covered inner axes merged into this entry
+    // entry 0 only: the run may span TWO globally contiguous axes that are not contiguous in
+    // shared memory: position -> (pos / by) * s_outer + (pos % by) * s_stride
+    uint32_t by;        // cells of the inner axis of the run (== b when the run is one axis)
+    FastDiv div_by;
+    uint32_t s_outer;   // shared-memory pitch of the outer axis of the run
 };
 
 struct TransposeParams {
@@ -303,6 +308,10 @@ struct TransposeParams {
     BoxDim rd[kMaxBoxDims], wr[kMaxBoxDims];  // input order / output order, innermost first
     uint32_t box_cells;            // prod b
     uint32_t runs_in, runs_out;    // prod of b over entries 1.. of rd / wr
+    // box-relative {global, shared} offsets of every run, precomputed on the host: identical
+    // for every full box, so the kernel's per-cell work is a table read plus the position
+    const uint2* rd_tab;
+    const uint2* wr_tab;
     // grid decomposition: every output axis, outermost first
     int n_axes;
     uint32_t boxes[OLAP_MAX_DIMS];   // number of boxes along the axis
@@ -311,6 +320,8 @@ struct TransposeParams {
     uint32_t bsize[OLAP_MAX_DIMS];   // box extent (1 for axes outside the box)
     int64_t src_stride[OLAP_MAX_DIMS], dst_stride[OLAP_MAX_DIMS];
     uint32_t st_offset;              // byte offset of the status tile in shared memory
+    uint32_t tab_offset;             // byte offset of the staged run tables in shared memory
+    int rd_vec4;                     // phase 1 may use 128-bit loads along the input run
 };
 
 struct TransposePlan {
@@ -318,6 +329,7 @@ struct TransposePlan {
     TransposeParams p{};
     int64_t n_boxes = 0;
     size_t smem = 0;
+    std::vector<uint2> rd_tab, wr_tab;  // host copies, uploaded by the caller
 };
 
 // Decode the index of a RUN (everything but entry 0) into global / shared offsets.
@@ -343,56 +355,241 @@ __device__ __forceinline__ bool run_decode(const BoxDim (&dims)[kMaxBoxDims], co
     return ok;
 }
 
-// One WARP per run: the run is entry 0 of the order (contiguous in global memory), the
-// lanes walk it, and the decode of the run's position is paid once per run, not per cell.
+// Walk the box one RUN at a time (entry 0 of the order is contiguous in global memory).
+// Long runs are cut into 128-cell chunks, one warp each; runs shorter than a warp are
+// packed several to a warp.  Each lane resolves up to 4 cells per pass: `offs` receives
+// their global / shared-memory offsets, the return value is the bit mask of valid slots.
+struct CellOffs {
+    uint32_t g[4], s[4];
+};
+
+template <int NB, bool CHECK>
+struct RunWalker {
+    const BoxDim (&dims)[kMaxBoxDims];
+    const uint32_t (&ext)[kMaxBoxDims];
+    uint32_t n_runs, len, warp, lane;
+    bool long_runs;
+    uint32_t chunks, tasks;            // long runs
+    uint32_t w_log, per_pass, passes;  // short runs
+    __device__ __forceinline__ RunWalker(const BoxDim (&d)[kMaxBoxDims], const uint32_t (&e)[kMaxBoxDims], uint32_t runs)
+        : dims(d), ext(e), n_runs(runs) {
+        warp = threadIdx.x >> 5;
+        lane = threadIdx.x & 31;
+        len = CHECK ? ext[0] : dims[0].b;
+        long_runs = dims[0].b >= 32;
+        chunks = (dims[0].b + 127) >> 7;
+        tasks = n_runs * chunks;
+        w_log = 0;
+        while ((1u << w_log) < dims[0].b) ++w_log;
+        per_pass = 32u >> w_log;
+        passes = (n_runs + per_pass - 1) / per_pass;
+    }
+    __device__ __forceinline__ uint32_t s_pos(uint32_t pos) const {
+        const uint32_t hi = dims[0].div_by.div(pos);
+        return hi * dims[0].s_outer + (pos - hi * dims[0].by) * dims[0].s_stride;
+    }
+    // number of outer iterations this warp performs
+    __device__ __forceinline__ uint32_t iterations() const {
+        const uint32_t total = long_runs ? tasks : (passes + 3) / 4;
+        return total > warp ? (total - warp + 7) / 8 : 0;
+    }
+    __device__ __forceinline__ uint32_t resolve(uint32_t it, CellOffs& o) const {
+        uint32_t mask = 0;
+        const uint32_t idx = warp + it * 8;
+        if (long_runs) {
+            const uint32_t run = idx / chunks, chunk = idx - run * chunks;
+            uint32_t g_off, s_off;
+            if (!run_decode<NB, CHECK>(dims, ext, run, g_off, s_off)) return 0;
+            const uint32_t p0 = (chunk << 7) + lane;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t pos = p0 + u * 32;
+                if (pos < len) {
+                    o.g[u] = g_off + pos * dims[0].g_stride;
+                    o.s[u] = s_off + s_pos(pos);
+                    mask |= 1u << u;
+                }
+            }
+        } else {
+            const uint32_t sub = lane >> w_log, pos = lane & ((1u << w_log) - 1u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t run = (idx * 4 + u) * per_pass + sub;
+                uint32_t g_off, s_off;
+                if (run < n_runs && pos < len && run_decode<NB, CHECK>(dims, ext, run, g_off, s_off)) {
+                    o.g[u] = g_off + pos * dims[0].g_stride;
+                    o.s[u] = s_off + s_pos(pos);
+                    mask |= 1u << u;
+                }
+            }
+        }
+        return mask;
+    }
+};
+
+// Full boxes (the common case): run offsets come from the host-built tables.  128 lane
+// slots per warp pass; runs shorter than 128 cells are packed 128/W to a pass (W = run
+// length rounded up to a power of two), longer ones are cut into 128-cell chunks.
+struct RunGeom {
+    uint32_t len, w_log, per_pass, passes, chunks;
+    bool packed;
+};
+__device__ __forceinline__ RunGeom run_geom(const BoxDim& e0, uint32_t n_runs, uint32_t unit = 1) {
+    RunGeom r;
+    r.len = e0.b / unit;  // positions are counted in units of `unit` cells
+    r.packed = r.len < 128;
+    r.w_log = 0;
+    while ((1u << r.w_log) < r.len && r.w_log < 7) ++r.w_log;
+    r.per_pass = 128u >> r.w_log;
+    r.chunks = (r.len + 127) >> 7;
+    r.passes = r.packed ? (n_runs + r.per_pass - 1) / r.per_pass : n_runs * r.chunks;
+    return r;
+}
+// slot in [0,128) of pass `pass` -> (run, pos); false when the slot is padding
+__device__ __forceinline__ bool slot_cell(const RunGeom& r, uint32_t n_runs, uint32_t pass, uint32_t slot,
+                                          uint32_t& run, uint32_t& pos) {
+    if (r.packed) {
+        run = pass * r.per_pass + (slot >> r.w_log);
+        pos = slot & ((1u << r.w_log) - 1u);
+        return run < n_runs && pos < r.len;
+    }
+    run = pass / r.chunks;
+    pos = (pass - run * r.chunks) * 128u + slot;
+    return pos < r.len;
+}
+__device__ __forceinline__ uint32_t run_spos(const BoxDim& e0, uint32_t pos) {
+    if (e0.by == e0.b) return pos * e0.s_stride;
+    const uint32_t hi = e0.div_by.div(pos);
+    return hi * e0.s_outer + (pos - hi * e0.by) * e0.s_stride;
+}
+
+template <bool STATUS>
+__device__ __forceinline__ void transpose_full_box(const TransposeParams& p, const float* __restrict__ src,
+                                                   const uint8_t* __restrict__ st_src, float* __restrict__ dst,
+                                                   uint8_t* __restrict__ st_dst, float* s_val, uint8_t* s_st,
+                                                   const uint2* s_rd, const uint2* s_wr) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (p.rd_vec4) {
+        // 128-bit loads along the input run (4 cells per lane slot, 4 slots in flight)
+        const RunGeom r = run_geom(p.rd[0], p.runs_in, 4);
+        for (uint32_t pass = warp; pass < r.passes; pass += 8) {
+            float4 v[4];
+            uint32_t sb[4], so[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint32_t run, pos;
+                ok[u] = slot_cell(r, p.runs_in, pass, u * 32 + lane, run, pos);
+                if (ok[u]) {
+                    const uint2 t = s_rd[run];
+                    const uint32_t g = t.x + pos * 4;
+                    so[u] = t.y + pos * 4 * p.rd[0].s_stride;
+                    v[u] = ld_stream4(src + g);
+                    if (STATUS) sb[u] = ld_stream_u32(st_src + g);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (ok[u]) {
+                    const uint32_t ss = p.rd[0].s_stride;
+                    s_val[so[u]] = v[u].x; s_val[so[u] + ss] = v[u].y;
+                    s_val[so[u] + 2 * ss] = v[u].z; s_val[so[u] + 3 * ss] = v[u].w;
+                    if (STATUS) {
+                        s_st[so[u]] = (uint8_t)sb[u]; s_st[so[u] + ss] = (uint8_t)(sb[u] >> 8);
+                        s_st[so[u] + 2 * ss] = (uint8_t)(sb[u] >> 16); s_st[so[u] + 3 * ss] = (uint8_t)(sb[u] >> 24);
+                    }
+                }
+        }
+    } else {
+        const RunGeom r = run_geom(p.rd[0], p.runs_in);
+        const uint32_t gs = p.rd[0].g_stride;
+        for (uint32_t pass = warp; pass < r.passes; pass += 8) {
+            float v[4];
+            uint8_t sb[4];
+            uint32_t so[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint32_t run, pos;
+                ok[u] = slot_cell(r, p.runs_in, pass, u * 32 + lane, run, pos);
+                if (ok[u]) {
+                    const uint2 t = s_rd[run];
+                    const uint32_t g = t.x + pos * gs;
+                    so[u] = t.y + run_spos(p.rd[0], pos);
+                    v[u] = ld_stream1(src + g);
+                    if (STATUS) sb[u] = st_src[g];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (ok[u]) {
+                    s_val[so[u]] = v[u];
+                    if (STATUS) s_st[so[u]] = sb[u];
+                }
+        }
+    }
+    __syncthreads();
+    {
+        const RunGeom r = run_geom(p.wr[0], p.runs_out);
+        const uint32_t gs = p.wr[0].g_stride;
+        for (uint32_t pass = warp; pass < r.passes; pass += 8) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint32_t run, pos;
+                if (slot_cell(r, p.runs_out, pass, u * 32 + lane, run, pos)) {
+                    const uint2 t = s_wr[run];
+                    const uint32_t g = t.x + pos * gs, so = t.y + run_spos(p.wr[0], pos);
+                    dst[g] = s_val[so];
+                    if (STATUS) st_dst[g] = s_st[so];
+                }
+            }
+        }
+    }
+}
+
 template <int NB, bool STATUS, bool CHECK>
 __device__ __forceinline__ void transpose_phases(const TransposeParams& p, const float* __restrict__ src,
                                                  const uint8_t* __restrict__ st_src, float* __restrict__ dst,
                                                  uint8_t* __restrict__ st_dst, float* s_val, uint8_t* s_st,
                                                  const uint32_t (&ext_rd)[kMaxBoxDims],
                                                  const uint32_t (&ext_wr)[kMaxBoxDims]) {
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // ---- phase 1: input runs -> shared memory
+    // ---- phase 1: input runs -> shared memory (4 loads in flight per lane)
     {
-        const uint32_t len = CHECK ? ext_rd[0] : p.rd[0].b;
-        const uint32_t gs = p.rd[0].g_stride, ss = p.rd[0].s_stride;
-        for (uint32_t run = warp; run < p.runs_in; run += 8) {
-            uint32_t g_off, s_off;
-            if (!run_decode<NB, CHECK>(p.rd, ext_rd, run, g_off, s_off)) continue;
-            for (uint32_t pos0 = lane; pos0 < len; pos0 += 128) {
-                float v[4];
-                uint8_t sb[4];
+        const RunWalker<NB, CHECK> w(p.rd, ext_rd, p.runs_in);
+        const uint32_t n_it = w.iterations();
+        for (uint32_t it = 0; it < n_it; ++it) {
+            CellOffs o;
+            const uint32_t mask = w.resolve(it, o);
+            float v[4];
+            uint8_t sb[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t pos = pos0 + u * 32;
-                    if (pos < len) {
-                        v[u] = ld_stream1(src + g_off + pos * gs);
-                        if (STATUS) sb[u] = st_src[g_off + pos * gs];
-                    }
+            for (int u = 0; u < 4; ++u)
+                if (mask & (1u << u)) {
+                    v[u] = __ldg(src + o.g[u]);
+                    if (STATUS) sb[u] = __ldg(st_src + o.g[u]);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t pos = pos0 + u * 32;
-                    if (pos < len) {
-                        s_val[s_off + pos * ss] = v[u];
-                        if (STATUS) s_st[s_off + pos * ss] = sb[u];
-                    }
+            for (int u = 0; u < 4; ++u)
+                if (mask & (1u << u)) {
+                    s_val[o.s[u]] = v[u];
+                    if (STATUS) s_st[o.s[u]] = sb[u];
                 }
-            }
         }
     }
     __syncthreads();
     // ---- phase 2: shared memory -> output runs
     {
-        const uint32_t len = CHECK ? ext_wr[0] : p.wr[0].b;
-        const uint32_t gs = p.wr[0].g_stride, ss = p.wr[0].s_stride;
-        for (uint32_t run = warp; run < p.runs_out; run += 8) {
-            uint32_t g_off, s_off;
-            if (!run_decode<NB, CHECK>(p.wr, ext_wr, run, g_off, s_off)) continue;
-            for (uint32_t pos = lane; pos < len; pos += 32) {
-                dst[g_off + pos * gs] = s_val[s_off + pos * ss];
-                if (STATUS) st_dst[g_off + pos * gs] = s_st[s_off + pos * ss];
-            }
+        const RunWalker<NB, CHECK> w(p.wr, ext_wr, p.runs_out);
+        const uint32_t n_it = w.iterations();
+        for (uint32_t it = 0; it < n_it; ++it) {
+            CellOffs o;
+            const uint32_t mask = w.resolve(it, o);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (mask & (1u << u)) {
+                    dst[o.g[u]] = s_val[o.s[u]];
+                    if (STATUS) st_dst[o.g[u]] = s_st[o.s[u]];
+                }
         }
     }
 }
@@ -438,8 +635,14 @@ __global__ void __launch_bounds__(256) transpose_kernel(const __grid_constant__ 
     const uint8_t* st_src = m.st_in ? m.st_in + s_base[0] : nullptr;
     uint8_t* st_dst = m.st_in ? m.st_out + s_base[1] : nullptr;
     if (s_full) {
-        if (m.st_in) transpose_phases<NB, true, false>(p, src, st_src, dst, st_dst, s_val, s_st, ext_rd, ext_wr);
-        else transpose_phases<NB, false, false>(p, src, st_src, dst, st_dst, s_val, s_st, ext_rd, ext_wr);
+        // stage the (box independent) run tables next to the tile
+        uint2* s_rd = reinterpret_cast<uint2*>(smem_t + p.tab_offset);
+        uint2* s_wr = s_rd + p.runs_in;
+        for (uint32_t i = threadIdx.x; i < p.runs_in; i += 256) s_rd[i] = __ldg(p.rd_tab + i);
+        for (uint32_t i = threadIdx.x; i < p.runs_out; i += 256) s_wr[i] = __ldg(p.wr_tab + i);
+        __syncthreads();
+        if (m.st_in) transpose_full_box<true>(p, src, st_src, dst, st_dst, s_val, s_st, s_rd, s_wr);
+        else transpose_full_box<false>(p, src, st_src, dst, st_dst, s_val, s_st, s_rd, s_wr);
     } else {
         if (m.st_in) transpose_phases<NB, true, true>(p, src, st_src, dst, st_dst, s_val, s_st, ext_rd, ext_wr);
         else transpose_phases<NB, false, true>(p, src, st_src, dst, st_dst, s_val, s_st, ext_rd, ext_wr);
@@ -516,7 +719,9 @@ inline TransposePlan transpose_plan(const std::vector<GDim>& dims_in) {
             if (pass == 0 && b[i] == 1) continue;
             if (b[i] >= dims[i].len) continue;
             const int64_t room = cells_max / (cells() / b[i]);
-            const int64_t cand = even_extent(dims[i].len, std::min<int64_t>(dims[i].len, room));
+            // even split with an extent of AT MOST `room`
+            const int64_t want = std::max<int64_t>(1, std::min<int64_t>(dims[i].len, room));
+            const int64_t cand = ceil_div(dims[i].len, ceil_div(dims[i].len, want));
             if (cand > b[i] && cells() / b[i] * cand <= cells_max) b[i] = cand;
         }
     std::vector<int> box_axes;
@@ -574,23 +779,70 @@ inline TransposePlan transpose_plan(const std::vector<GDim>& dims_in) {
         return ents;
     };
     std::vector<Ent> rd = build(true), wr = build(false);
+    // compound run: let entry 0 also swallow entry 1 when the two are contiguous in GLOBAL
+    // memory (they are not in shared memory, or build() would have merged them already)
+    struct Run { int64_t by, s_outer; };
+    auto compound = [&](std::vector<Ent>& ents) {
+        Run r{ents[0].b, 0};
+        if (ents.size() >= 2 && ents[0].whole && ents[0].mult == 1 && ents[1].mult == 1 &&
+            ents[1].g == ents[0].g * ents[0].b && ents[0].b * ents[1].b <= 0x7fffffffLL) {
+            r.by = ents[0].b;
+            r.s_outer = ents[1].s;
+            ents[0].mult = ents[0].b;  // extent of the run = by * extent(outer axis)
+            ents[0].b *= ents[1].b;
+            ents[0].axis = ents[1].axis;
+            ents[0].whole = ents[1].whole;
+            ents.erase(ents.begin() + 1);
+        }
+        return r;
+    };
+    const Run run_rd = compound(rd), run_wr = compound(wr);
     const int nb = (int)std::max(rd.size(), wr.size());
     if (nb > kMaxBoxDims) return plan;
-    auto fill = [&](const std::vector<Ent>& ents, BoxDim* out) {
+    auto fill = [&](const std::vector<Ent>& ents, const Run& run, BoxDim* out) {
         for (int q = 0; q < kMaxBoxDims; ++q) {
             if (q < (int)ents.size()) {
                 if (ents[q].g * (ents[q].b - 1) > 0x7fffffffLL) return false;
                 out[q] = BoxDim{(uint32_t)ents[q].b, FastDiv((uint32_t)ents[q].b), (uint32_t)ents[q].g,
-                                (uint32_t)ents[q].s, (uint32_t)ents[q].axis, (uint32_t)ents[q].mult};
-            } else out[q] = BoxDim{1u, FastDiv(1u), 0u, 0u, 0u, 1u};
+                                (uint32_t)ents[q].s, (uint32_t)ents[q].axis, (uint32_t)ents[q].mult,
+                                (uint32_t)ents[q].b, FastDiv((uint32_t)ents[q].b), 0u};
+            } else out[q] = BoxDim{1u, FastDiv(1u), 0u, 0u, 0u, 1u, 1u, FastDiv(1u), 0u};
         }
+        out[0].by = (uint32_t)run.by;
+        out[0].div_by = FastDiv((uint32_t)run.by);
+        out[0].s_outer = (uint32_t)run.s_outer;
         return true;
     };
-    if (!fill(rd, p.rd) || !fill(wr, p.wr)) return plan;
+    if (!fill(rd, run_rd, p.rd) || !fill(wr, run_wr, p.wr)) return plan;
     p.nb = std::max(nb, 2);
     p.box_cells = (uint32_t)cells();
     p.runs_in = p.runs_out = 1;
     for (int q = 1; q < kMaxBoxDims; ++q) { p.runs_in *= p.rd[q].b; p.runs_out *= p.wr[q].b; }
+    auto table = [&](const BoxDim* e, uint32_t runs, std::vector<uint2>& tab) {
+        tab.resize(runs);
+        for (uint32_t run = 0; run < runs; ++run) {
+            uint32_t t = run, g_off = 0, s_off = 0;
+            for (int d = 1; d < kMaxBoxDims; ++d) {
+                const uint32_t c = t % e[d].b;
+                t /= e[d].b;
+                g_off += c * e[d].g_stride;
+                s_off += c * e[d].s_stride;
+            }
+            tab[run] = make_uint2(g_off, s_off);
+        }
+    };
+    table(p.rd, p.runs_in, plan.rd_tab);
+    table(p.wr, p.runs_out, plan.wr_tab);
+    // 128-bit loads along the input run: the run is a single axis group contiguous in global
+    // memory, a multiple of 4 cells long, and every other source stride keeps 16-byte alignment
+    p.rd_vec4 = p.rd[0].g_stride == 1 && p.rd[0].b % 4 == 0 && p.rd[0].by == p.rd[0].b;
+    for (int i = 0; i < k; ++i)
+        if (dims[i].stride != 1 && (dims[i].stride % 4 != 0)) {
+            // an axis outside the run with an unaligned stride breaks alignment unless it is
+            // part of the run itself (then its stride is covered by the run's contiguity)
+            bool in_run = b[i] > 1 && dims[i].stride < p.rd[0].b;
+            if (!in_run) p.rd_vec4 = 0;
+        }
     p.n_axes = k;
     int64_t n_boxes = 1;
     for (int i = 0; i < k; ++i) {
@@ -605,14 +857,18 @@ inline TransposePlan transpose_plan(const std::vector<GDim>& dims_in) {
     if (n_boxes > 0x7fffffffLL) return plan;
     plan.n_boxes = n_boxes;
     p.st_offset = (uint32_t)((s_cells * 4 + 15) & ~(size_t)15);
-    plan.smem = p.st_offset + ((s_cells + 15) & ~(size_t)15);
+    p.tab_offset = (uint32_t)(p.st_offset + ((s_cells + 15) & ~(size_t)15));
+    plan.smem = p.tab_offset + ((size_t)p.runs_in + p.runs_out) * sizeof(uint2);
     if (plan.smem > 200 * 1024) return plan;
     plan.use = true;
     return plan;
 }
 
-inline int launch_transpose(const GatherMeasure* d_meas, int n, TransposePlan& plan) {
+inline int launch_transpose(const GatherMeasure* d_meas, const uint2* d_rd_tab, const uint2* d_wr_tab, int n,
+                            TransposePlan& plan) {
     plan.p.meas = d_meas;
+    plan.p.rd_tab = d_rd_tab;
+    plan.p.wr_tab = d_wr_tab;
     static bool attr_set = false;
     if (!attr_set) {
         OLAP_CUDA(cudaFuncSetAttribute(transpose_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -1063,8 +1063,10 @@ int olap_reorder(olap_store* const* src, int n, int ndim, const int64_t* old_len
             path = "reorder/box-transpose";
             TablePack t;
             const size_t o_meas = t.add(meas.data(), sizeof(GatherMeasure) * n);
+            const size_t o_rd = t.add(tp.rd_tab.data(), tp.rd_tab.size() * sizeof(uint2));
+            const size_t o_wr = t.add(tp.wr_tab.data(), tp.wr_tab.size() * sizeof(uint2));
             OLAP_TRY(t.upload());
-            OLAP_TRY(launch_transpose(t.ptr<GatherMeasure>(o_meas), n, tp));
+            OLAP_TRY(launch_transpose(t.ptr<GatherMeasure>(o_meas), t.ptr<uint2>(o_rd), t.ptr<uint2>(o_wr), n, tp));
             OLAP_TRY(t.release());
         } else {
             OLAP_TRY(run_gather(G_COPY, src, n, dims, size, size, meas, nullptr, &path));

@@ -35,7 +35,7 @@ static int check_perm(const std::vector<int64_t>& len, const std::vector<int>& p
         boxes *= p.boxes[a];
     }
     if (cells != p.box_cells || cells > 8192 || boxes != plan.n_boxes) { printf("bad cells %lld\n", (long long)cells); return 1; }
-    if (plan.smem > 200 * 1024) { printf("smem\n"); return 1; }
+    if (plan.smem > 200 * 1024 || plan.rd_tab.size() != p.runs_in || plan.wr_tab.size() != p.runs_out) { printf("smem/tables\n"); return 1; }
     // entry-0 strides must be the contiguous ones
     if (p.rd[0].g_stride != 1 && p.rd[0].b > 1) { printf("rd[0] not contiguous\n"); return 1; }
     if (p.wr[0].g_stride != 1 && p.wr[0].b > 1) { printf("wr[0] not contiguous\n"); return 1; }
