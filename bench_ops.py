@@ -170,6 +170,12 @@ def main():
         lambda: GpuStore.drillDown_lowered([s], [Od * 100, 10], [Od * 100, 304], [ident(Od * 100), m2d], ["sum"]),
         B * (10 + 304) * Od * 100, 304 * Od * 100)
     del s
+    Ob = int(5e4 * sc)  # the config-3 sized interpolation: 5e7 cells -> 1.52e9 cells
+    s = store(Ob * 10 * 100, 0.0)
+    run(f"drilldown/mid month->day float [{Ob},10->304,100]",
+        lambda: GpuStore.drillDown_lowered([s], [Ob, 10, 100], [Ob, 304, 100], [ident(Ob), m2d, ident(100)], ["sum"]),
+        B * (10 + 304) * Ob * 100, 304 * Ob * 100)
+    del s
     si = store(Od * 10 * 100, 0.0, typ="uint32")
     run(f"drilldown/mid month->day uint32 [{Od},10->304,100]",
         lambda: GpuStore.drillDown_lowered([si], [Od, 10, 100], [Od, 304, 100], [ident(Od), m2d, ident(100)], ["sum"]),

@@ -110,6 +110,10 @@ int olap_host_alloc(size_t bytes, void** out);
 int olap_host_free(void* p);
 
 /* ---- store life cycle: `new InMemoryStore(size, type, defaultValue)` in-memory.js:48-64 */
+/* with_status: bit 0 = allocate the status plane; bit 1 (OLAP_CREATE_UNINITIALISED) = do not
+ * fill the planes with the default — only for a store whose every cell is about to be
+ * overwritten (receive buffers of the multi-GPU exchange). */
+#define OLAP_CREATE_UNINITIALISED 2
 int olap_store_create(int64_t size, int type, int default_kind, int with_status, olap_store** out);
 /* n stores of equal size carved from one allocation (a cube's stored measures).
  * shared_status != 0: one status plane shared by all n stores. */

@@ -455,7 +455,8 @@ int olap_store_create_batch(int n, int64_t size, const int* types, const int* de
     if (size < 0) return fail(OLAP_E_INVALID, "olap_store_create_batch: negative size");
     for (int k = 0; k < n; ++k) OLAP_TRY(check_type_default(types[k], default_kinds[k]));
     OLAP_TRY(ensure_ctx());
-    OLAP_TRY(alloc_batch(n, size, types, default_kinds, with_status != 0, shared_status != 0, out));
+    OLAP_TRY(alloc_batch(n, size, types, default_kinds, (with_status & 1) != 0, shared_status != 0, out));
+    if (with_status & 2) return finish_op();  // OLAP_CREATE_UNINITIALISED: the caller overwrites every cell
     for (int k = 0; k < n; ++k) {
         olap_store tmp = *out[k];
         tmp.status = st_out_of(out, k);

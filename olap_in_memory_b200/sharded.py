@@ -279,6 +279,15 @@ class ShardedCube:
         if not ids:
             return out
         W, inner = self.world, self.inner
+        if W == 1:
+            # a single rank owns every row: the "partial" rollup is the result
+            row_map = self._row_map(idx, group_map, new_prefix_lens)
+            maps = [row_map] + [np.arange(n, dtype=np.int32) for n in self.inner_lens]
+            stores = [self.storedMeasures[m] for m in ids]
+            results = self._call("drillUp_lowered", stores, self._local_lens(), [new_rows_total] + self.inner_lens,
+                                 maps, _Per(methods))
+            out.storedMeasures = dict(zip(ids, results))
+            return out
         my_out_rows = out_bounds[self.rank + 1] - out_bounds[self.rank]
         row_map = self._row_map(idx, group_map, new_prefix_lens)
         old_len = self._local_lens()
@@ -302,7 +311,11 @@ class ShardedCube:
         out_splits = [my_out_rows * inner] * W
         received = []
         for part, src_store in zip(partials, stores):
-            recv = self._store_cls(W * my_out_rows * inner, src_store._type, src_store._defaultValue)
+            if _is_device_store(src_store):  # every cell is overwritten by the exchange: skip the default fill
+                recv = self._store_cls(W * my_out_rows * inner, src_store._type, src_store._defaultValue,
+                                       uninitialised=True)
+            else:
+                recv = self._store_cls(W * my_out_rows * inner, src_store._type, src_store._defaultValue)
             self._exchange(part, recv, in_splits, out_splits)
             received.append(recv)
         del partials

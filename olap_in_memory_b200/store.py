@@ -44,7 +44,8 @@ class GpuStore:
     #: allocate a status byte per cell next to the Float32 cells (README.md:698-721)
     WITH_STATUS = True
 
-    def __init__(self, size, type="float32", defaultValue=math.nan, *, _handle=None, with_status=None):
+    def __init__(self, size, type="float32", defaultValue=math.nan, *, _handle=None, with_status=None,
+                 uninitialised=False):
         if _handle is not None:
             self._h = _handle
         else:
@@ -53,7 +54,8 @@ class GpuStore:
                 raise N.OlapValueError("Invalid type")  # in-memory.js:59-60
             out = C.c_void_p()
             status = self.WITH_STATUS if with_status is None else with_status
-            N.check(N.lib().olap_store_create(int(size), N.TYPES[type], kind, int(bool(status)), C.byref(out)))
+            flags = int(bool(status)) | (2 if uninitialised else 0)  # OLAP_CREATE_UNINITIALISED
+            N.check(N.lib().olap_store_create(int(size), N.TYPES[type], kind, flags, C.byref(out)))
             self._h = out.value
         lib = N.lib()
         self._size = lib.olap_store_size(self._h)
