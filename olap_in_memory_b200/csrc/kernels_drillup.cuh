@@ -165,6 +165,31 @@ struct Lane<OLAP_AVERAGE, true> {
         cnt += o.cnt;
     }
 };
+// product: same key-exists state machine as the reference (a product that lands on the
+// default — underflow to 0, inf * 0 — is deleted and the next set child restarts it),
+// written with selects instead of branches
+template <bool NANDEF>
+struct ProductLane {
+    double acc = 1.0;
+    bool has = false;
+    __device__ __forceinline__ void step(float v) {
+        const bool pres = present_f(v, NANDEF);
+        const double next = has ? acc * (double)v : (double)v;
+        acc = pres ? next : acc;
+        has = pres ? present_d(next, NANDEF) : has;
+    }
+    __device__ __forceinline__ float result() const { return has ? canon_store((float)acc, NANDEF) : default_of(NANDEF); }
+    __device__ __forceinline__ void merge(const ProductLane& o) {
+        if (!o.has) return;
+        const double next = has ? acc * o.acc : o.acc;
+        acc = next;
+        has = present_d(next, NANDEF);
+    }
+};
+template <>
+struct Lane<OLAP_PRODUCT, false> : ProductLane<false> {};
+template <>
+struct Lane<OLAP_PRODUCT, true> : ProductLane<true> {};
 template <bool NANDEF>
 struct CountLane {
     uint32_t cnt = 0;
