@@ -327,7 +327,7 @@ def run_ours(args, rank, world, local_rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_value, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(),
             "e2e": {"value": e2e_value, "unit": "cells/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": measures * n_in * 4, "d2h_bytes_per_step": 4 * n_out * 4},
+                    "h2d_bytes_per_step": world * measures * n_in * 4, "d2h_bytes_per_step": world * 4 * n_out * 4},
             "gpu_launches": int(launches), "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": path, "kernel_ms": up_ms, "algorithmic_bytes": algo_bytes,

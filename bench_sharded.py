@@ -83,7 +83,9 @@ def main():
         if "sharded" in label and world > 1:
             # average travels as (sum, count): 4 planes for 3 measures
             planes = 4
-            row["nvlink_GBs_per_gpu"] = round(5 * planes * n_out * (world - 1) / world / world / (ms * 1e-3) / 1e9, 1)
+            # every rank holds a partial of the FULL output and sends (W-1)/W of it
+            row["nvlink_bytes_sent_per_gpu"] = 5 * planes * n_out * (world - 1) // world
+            row["nvlink_GBs_per_gpu"] = round(row["nvlink_bytes_sent_per_gpu"] / (ms * 1e-3) / 1e9, 1)
         rows.append(row)
         if rank == 0:
             print(json.dumps(row), flush=True)
