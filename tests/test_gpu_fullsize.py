@@ -142,3 +142,59 @@ def test_config3_style_round_trips():
     if st is not None:
         pres = interop.values_tensor(s2) != 0
         assert bool(torch.all(st[pres] == 6)) and bool(torch.all(st[~pres] == 1))  # set + interpolated
+
+
+def test_more_than_2_31_cells():
+    """Linear indices are int64 (SURVEY 'hard parts'): a 2.4e9-cell store through the mid
+    drillUp kernel, the 64-bit scalar gather (reorder that keeps a short inner run) and the
+    tile kernel with > 2^31 input cells; checked by totals, order relations and sampled cells."""
+    torch, interop, G, _ = _setup()
+    old = G.WITH_STATUS
+    G.WITH_STATUS = False  # 4 B/cell keeps the case at ~10 GB
+    try:
+        A, B, C = 3, 40000, 20000  # 2.4e9 cells
+        n = A * B * C
+        assert n > 2 ** 31
+        src = G(n, "float32", 0.0)
+        v = interop.values_tensor(src)
+        g = torch.Generator(device="cuda").manual_seed(11)
+        chunk = 1 << 28
+        for lo in range(0, n, chunk):
+            hi = min(n, lo + chunk)
+            v[lo:hi] = torch.randint(1, 100, (hi - lo,), generator=g, device="cuda").float()
+        torch.cuda.synchronize()
+        x = v.view(A, B, C)
+        # mid kernel: axis 1, 40000 -> 4 groups of 10000
+        m = (np.arange(B) // 10000).astype(np.int32)
+        ident = lambda k: np.arange(k, dtype=np.int32)
+        up = G.drillUp_lowered([src], [A, B, C], [A, 4, C], [ident(A), m, ident(C)], ["sum"])[0]
+        r = interop.values_tensor(up).view(A, 4, C)
+        cols = torch.tensor([0, 7777, C - 1], device="cuda")
+        want = x[:, :, cols].double().view(A, 4, 10000, 3).sum(dim=2)
+        assert bool(torch.equal(r[:, :, cols].double(), want))
+        assert math.isclose(up.total, src.total, rel_tol=1e-12)
+        # the last cells of the store (offsets beyond 2^31) are really addressed
+        assert float(r[A - 1, 3, C - 1]) == float(x[A - 1, 30000:, C - 1].double().sum())
+        del up, r
+        # tile kernel: innermost axis 20000 -> 2 (rows of 20000 cells, 1.2e5 rows)
+        m2 = (np.arange(C) // 10000).astype(np.int32)
+        up2 = G.drillUp_lowered([src], [A * 4, B // 4, C], [A * 4, B // 4, 2],
+                                [ident(A * 4), ident(B // 4), m2], ["highest"])[0]
+        r2 = interop.values_tensor(up2).view(A, B, 2)
+        rows = torch.tensor([0, 12345, B - 1], device="cuda")
+        want2 = x[:, rows, :].view(A, 3, 2, 10000).amax(dim=3)
+        assert bool(torch.equal(r2[:, rows, :], want2))
+        del up2, r2
+        # scalar gather with 64-bit offsets: view as [A, B, K, 5] and swap the middle axes
+        # (inner run of 5 cells, 4.8e8 rows, source offsets beyond 2^31)
+        K = C // 5
+        re = G.reorder_lowered([src], [A, B, K, 5], [0, 2, 1, 3])[0]
+        from olap_in_memory_b200 import _native
+
+        assert _native.lib().olap_last_op_path().decode() in ("gather/scalar-big", "gather/rows")
+        y = interop.values_tensor(re).view(A, K, B, 5)
+        x4 = x.view(A, B, K, 5)
+        for k_ in (0, 1234, K - 1):
+            assert bool(torch.equal(y[:, k_], x4[:, :, k_]))
+    finally:
+        G.WITH_STATUS = old
