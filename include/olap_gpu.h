@@ -104,6 +104,10 @@ double olap_last_op_ms(void);
 /* Name of the kernel path the most recent transform took (for tests/profiles). */
 const char* olap_last_op_path(void);
 
+/* Debug aid: with OLAP_GUARD=1 in the environment every plane is followed by a guard region
+ * that is checked when the store is destroyed; returns the number of overwritten guard bytes. */
+int64_t olap_guard_violations(void);
+
 /* Page-locked host buffers for the data boundary: uploads/downloads from these run at
  * PCIe speed (the N-API shim backs Float32Array results with them). */
 int olap_host_alloc(size_t bytes, void** out);

@@ -57,6 +57,7 @@ SIGNATURES = {
     "olap_kernel_launches": (C.c_int64, []),
     "olap_last_op_ms": (C.c_double, []),
     "olap_last_op_path": (C.c_char_p, []),
+    "olap_guard_violations": (C.c_int64, []),
     "olap_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "olap_host_free": (C.c_int, [C.c_void_p]),
     "olap_store_create": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, pp_store]),

@@ -83,10 +83,18 @@ int dev_free(void* p) {
 
 static size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 
+// OLAP_GUARD=1 (debug aid; compute-sanitizer is not available on every pool): every plane is
+// followed by a 256-byte guard filled with 0xA5; destroying a store checks its guards and
+// olap_guard_violations() reports how many bytes were overwritten.
+static const bool g_guard = [] { const char* e = getenv("OLAP_GUARD"); return e && atoi(e) != 0; }();
+static std::atomic<int64_t> g_guard_violations{0};
+constexpr size_t kGuardBytes = 256;
+
 int alloc_batch(int n, int64_t size, const int* types, const int* default_kinds, bool with_status,
                 bool shared_status, olap_store** out) {
-    const size_t vplane = pad256((size_t)size * sizeof(float));
-    const size_t splane = with_status ? pad256((size_t)size) : 0;
+    const size_t guard = g_guard ? kGuardBytes : 0;
+    const size_t vplane = pad256((size_t)size * sizeof(float)) + guard;
+    const size_t splane = with_status ? pad256((size_t)size) + guard : 0;
     const int n_status = with_status ? (shared_status ? 1 : n) : 0;
     const size_t bytes = vplane * n + splane * n_status;
     Arena* arena = new Arena();
@@ -95,6 +103,7 @@ int alloc_batch(int n, int64_t size, const int* types, const int* default_kinds,
     arena->bytes = bytes;
     arena->refs = n;
     char* base = static_cast<char*>(arena->base);
+    if (g_guard && bytes) cudaMemsetAsync(base, 0xA5, bytes, g.stream);
     for (int k = 0; k < n; ++k) {
         olap_store* s = new olap_store();
         s->size = size;
@@ -106,6 +115,20 @@ int alloc_batch(int n, int64_t size, const int* types, const int* default_kinds,
         out[k] = s;
     }
     return OLAP_OK;
+}
+
+// bytes of the guard (and of the alignment padding before it) that no longer hold 0xA5
+static void check_guards(const olap_store* s) {
+    if (!g_guard || !g.ready) return;
+    auto check = [&](const char* plane, size_t used) {
+        const size_t span = pad256(used) + kGuardBytes - used;
+        std::vector<unsigned char> host(span);
+        if (cudaMemcpyAsync(host.data(), plane + used, span, cudaMemcpyDeviceToHost, g.stream) != cudaSuccess) return;
+        if (cudaStreamSynchronize(g.stream) != cudaSuccess) return;
+        for (unsigned char c : host) g_guard_violations += c != 0xA5;
+    };
+    check(reinterpret_cast<const char*>(s->values), (size_t)s->size * 4);
+    if (s->status) check(reinterpret_cast<const char*>(s->status), (size_t)s->size);
 }
 
 size_t TablePack::add(const void* data, size_t bytes) {
@@ -469,8 +492,11 @@ int olap_store_create(int64_t size, int type, int default_kind, int with_status,
     return olap_store_create_batch(1, size, &type, &default_kind, with_status, 0, out);
 }
 
+int64_t olap_guard_violations(void) { return g_guard_violations.load(); }
+
 int olap_store_destroy(olap_store* s) {
     if (!s) return OLAP_OK;
+    check_guards(s);
     Arena* a = s->arena;
     delete s;
     if (a && --a->refs == 0) {
