@@ -46,11 +46,16 @@ struct Ctx {
     bool timing_pending = false;
     double last_ms = 0.0;
     const char* last_path = "";
-    // pinned staging for small per-query tables (index maps, CSR, descriptors)
-    char* pin = nullptr;
-    size_t pin_cap = 0;
-    cudaEvent_t pin_free = nullptr;  // recorded after the last copy out of `pin`
-    bool pin_busy = false;
+    // pinned staging for small per-query tables (index maps, CSR, descriptors): a ring of
+    // slots so that the host can prepare several calls ahead of the device in async mode
+    static constexpr int kPinSlots = 8;
+    struct PinSlot {
+        char* ptr = nullptr;
+        size_t cap = 0;
+        cudaEvent_t free_ev = nullptr;  // recorded after the copy out of this slot
+        bool busy = false;
+    } pin[kPinSlots];
+    int pin_next = 0;
 };
 extern Ctx g;
 extern std::atomic<int64_t> g_launches;
@@ -133,6 +138,16 @@ __device__ __forceinline__ void st_stream4(float* p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                  "f"(v.w)
                  : "memory");
+}
+__device__ __forceinline__ float2 ld_stream2(const float* p) {
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_stream_u16(const void* p) {
+    uint16_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));
+    return (uint32_t)r;
 }
 __device__ __forceinline__ uint32_t ld_stream_u32(const void* p) {
     uint32_t r;

@@ -310,11 +310,33 @@ __device__ __forceinline__ Cells<VEC> load_cells(const float* src, const uint8_t
         const float4 t = ld_stream4(src + off);
         c.v[0] = t.x; c.v[1 % VEC] = t.y; c.v[2 % VEC] = t.z; c.v[3 % VEC] = t.w;
         c.st = STATUS ? ld_stream_u32(st_src + off) : 0u;
+    } else if (VEC == 2) {
+        const float2 t = ld_stream2(src + off);
+        c.v[0] = t.x; c.v[1 % VEC] = t.y;
+        c.st = STATUS ? ld_stream_u16(st_src + off) : 0u;
     } else {
         c.v[0] = ld_stream1(src + off);
         c.st = STATUS ? (uint32_t)st_src[off] : 0u;
     }
     return c;
+}
+
+// VEC results (+ VEC status bytes packed in `st`) to consecutive cells
+template <int VEC>
+__device__ __forceinline__ void store_cells(float* dst, const float (&r)[VEC]) {
+    if (VEC == 4) st_stream4(dst, make_float4(r[0], r[1 % VEC], r[2 % VEC], r[3 % VEC]));
+    else if (VEC == 2) *reinterpret_cast<float2*>(dst) = make_float2(r[0], r[1 % VEC]);
+    else *dst = r[0];
+}
+template <int VEC>
+__device__ __forceinline__ void store_status(uint8_t* dst, uint32_t st) {
+    if (VEC == 4) *reinterpret_cast<uint32_t*>(dst) = st;
+    else if (VEC == 2) *reinterpret_cast<uint16_t*>(dst) = (uint16_t)st;
+    else *dst = (uint8_t)st;
+}
+template <int VEC>
+__device__ __forceinline__ uint32_t unset_status() {  // OLAP_STATUS_UNSET in each of the VEC bytes
+    return VEC == 4 ? 0x01010101u : (VEC == 2 ? 0x0101u : 0x01u);
 }
 
 template <int METHOD, bool NANDEF, int VEC, bool RANGE, bool STATUS, int U>
@@ -354,18 +376,11 @@ __device__ __forceinline__ void up_mid_body(const UpMidParams& p, const UpMeasur
     }
 
     const int64_t out_off = o * p.out_row + (int64_t)pi * p.I_total + inner;
-    if (VEC == 4) {
-        float4 r;
-        r.x = lane[0].result(); r.y = lane[1 % VEC].result(); r.z = lane[2 % VEC].result(); r.w = lane[3 % VEC].result();
-        st_stream4(m.out + out_off, r);
-    } else {
-        m.out[out_off] = lane[0].result();
-    }
-    if (STATUS) {
-        if (k0 == k1) st = VEC == 4 ? 0x01010101u : 0x1u;  // no child at all: not set
-        if (VEC == 4) *reinterpret_cast<uint32_t*>(m.st_out + out_off) = st;
-        else m.st_out[out_off] = (uint8_t)st;
-    }
+    float r[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) r[e] = lane[e].result();
+    store_cells<VEC>(m.out + out_off, r);
+    if (STATUS) store_status<VEC>(m.st_out + out_off, k0 == k1 ? unset_status<VEC>() : st);  // no child: not set
 }
 
 template <bool NANDEF, int VEC, bool RANGE, bool STATUS, int U>
@@ -461,18 +476,11 @@ __device__ __forceinline__ void up_split_body(const UpMidParams& p, const UpMeas
         st |= s_st[q * 32 + tx];
     }
     const int64_t out_off = o * p.out_row + (int64_t)pi * p.I_total + inner;
-    if (VEC == 4) {
-        float4 r;
-        r.x = lane[0].result(); r.y = lane[1 % VEC].result(); r.z = lane[2 % VEC].result(); r.w = lane[3 % VEC].result();
-        st_stream4(m.out + out_off, r);
-    } else {
-        m.out[out_off] = lane[0].result();
-    }
-    if (STATUS) {
-        if (k0 == k1) st = VEC == 4 ? 0x01010101u : 0x1u;
-        if (VEC == 4) *reinterpret_cast<uint32_t*>(m.st_out + out_off) = st;
-        else m.st_out[out_off] = (uint8_t)st;
-    }
+    float r[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) r[e] = lane[e].result();
+    store_cells<VEC>(m.out + out_off, r);
+    if (STATUS) store_status<VEC>(m.st_out + out_off, k0 == k1 ? unset_status<VEC>() : st);
 }
 
 template <bool NANDEF, int VEC, bool RANGE, bool STATUS>
@@ -660,13 +668,8 @@ __device__ __forceinline__ void down_mid_body(const DownMidParams& p, const Down
                 st |= (ok ? ((sb | OLAP_STATUS_INTERPOLATED) & 0xffu) : (uint32_t)OLAP_STATUS_UNSET) << (8 * e);
             }
         }
-        if (VEC == 4) {
-            st_stream4(dst + off, make_float4(r[0], r[1 % VEC], r[2 % VEC], r[3 % VEC]));
-            if (STATUS) *reinterpret_cast<uint32_t*>(st_dst + off) = st;
-        } else {
-            dst[off] = r[0];
-            if (STATUS) st_dst[off] = (uint8_t)st;
-        }
+        store_cells<VEC>(dst + off, r);
+        if (STATUS) store_status<VEC>(st_dst + off, st);
     }
 }
 

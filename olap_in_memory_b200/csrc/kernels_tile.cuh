@@ -77,7 +77,7 @@ inline TileDecision tile_plan(int64_t O, int64_t C, int64_t P, int64_t I, bool a
     TileDecision t;
     static const int force = [] { const char* e = getenv("OLAP_TILE"); return e ? atoi(e) : -1; }();  // tuning knob
     if (force == 0) return t;
-    if (I >= 32 && (I % 4 == 0 || I >= 128)) return t;  // the vectorised mid kernel streams these
+    if (I >= 32 && (I % 4 == 0 || (I % 2 == 0 && I >= 64) || I >= 128)) return t;  // the vectorised mid kernel streams these
     const int64_t row_in = C * I;
     const int64_t per_cell = any_status ? 5 : 4;
     const int64_t budget = 48 * 1024, hard = 200 * 1024;

@@ -142,22 +142,25 @@ int TablePack::upload() {
     const size_t bytes = host.size();
     OLAP_TRY(dev_alloc(&dev, bytes));
     if (!bytes) return OLAP_OK;
-    if (g.pin_busy) {
-        OLAP_CUDA(cudaEventSynchronize(g.pin_free));
-        g.pin_busy = false;
+    Ctx::PinSlot& slot = g.pin[g.pin_next];
+    g.pin_next = (g.pin_next + 1) % Ctx::kPinSlots;
+    if (slot.busy) {
+        OLAP_CUDA(cudaEventSynchronize(slot.free_ev));
+        slot.busy = false;
     }
-    if (g.pin_cap < bytes) {
-        if (g.pin) cudaFreeHost(g.pin);
-        g.pin = nullptr;
-        g.pin_cap = 0;
-        const size_t cap = std::max(bytes * 2, (size_t)1 << 20);
-        OLAP_CUDA(cudaHostAlloc((void**)&g.pin, cap, cudaHostAllocDefault));
-        g.pin_cap = cap;
+    if (slot.cap < bytes) {
+        if (slot.ptr) cudaFreeHost(slot.ptr);
+        slot.ptr = nullptr;
+        slot.cap = 0;
+        const size_t cap = std::max(bytes * 2, (size_t)256 << 10);
+        OLAP_CUDA(cudaHostAlloc((void**)&slot.ptr, cap, cudaHostAllocDefault));
+        slot.cap = cap;
     }
-    memcpy(g.pin, host.data(), bytes);
-    OLAP_CUDA(cudaMemcpyAsync(dev, g.pin, bytes, cudaMemcpyHostToDevice, g.stream));
-    OLAP_CUDA(cudaEventRecord(g.pin_free, g.stream));
-    g.pin_busy = true;
+    if (!slot.free_ev) OLAP_CUDA(cudaEventCreateWithFlags(&slot.free_ev, cudaEventDisableTiming));
+    memcpy(slot.ptr, host.data(), bytes);
+    OLAP_CUDA(cudaMemcpyAsync(dev, slot.ptr, bytes, cudaMemcpyHostToDevice, g.stream));
+    OLAP_CUDA(cudaEventRecord(slot.free_ev, g.stream));
+    slot.busy = true;
     return OLAP_OK;
 }
 
@@ -255,7 +258,7 @@ static uint32_t next_pow2(uint32_t v) {
 
 static int launch_up_mid(const UpMeasure* d_meas, int n, const Csr& csr, const int32_t* d_pstart,
                          const int32_t* d_children, int64_t O, int64_t C, int64_t P, int64_t I) {
-    const int VEC = (I % 4 == 0) ? 4 : 1;
+    const int VEC = (I % 4 == 0) ? 4 : (I % 2 == 0 ? 2 : 1);
     const int64_t IV_total = I / VEC;
     // chunk the inner run so that one row of output vectors fits 32-bit math
     const int64_t max_row = ((int64_t)1 << 30);
@@ -302,6 +305,7 @@ static int launch_up_mid(const UpMeasure* d_meas, int n, const Csr& csr, const i
         drillup_split_kernel<V, R><<<grid, block, smem, g.stream>>>(p);                                    \
     } while (0)
             if (VEC == 4) { if (csr.contiguous) OLAP_SPLIT_LAUNCH(4, true); else OLAP_SPLIT_LAUNCH(4, false); }
+            else if (VEC == 2) { if (csr.contiguous) OLAP_SPLIT_LAUNCH(2, true); else OLAP_SPLIT_LAUNCH(2, false); }
             else { if (csr.contiguous) OLAP_SPLIT_LAUNCH(1, true); else OLAP_SPLIT_LAUNCH(1, false); }
 #undef OLAP_SPLIT_LAUNCH
             LAUNCHED();
@@ -322,6 +326,8 @@ static int launch_up_mid(const UpMeasure* d_meas, int n, const Csr& csr, const i
     } while (0)
         if (VEC == 4) {
             if (csr.contiguous) OLAP_UP_LAUNCH(4, true); else OLAP_UP_LAUNCH(4, false);
+        } else if (VEC == 2) {
+            if (csr.contiguous) OLAP_UP_LAUNCH(2, true); else OLAP_UP_LAUNCH(2, false);
         } else {
             if (csr.contiguous) OLAP_UP_LAUNCH(1, true); else OLAP_UP_LAUNCH(1, false);
         }
@@ -333,7 +339,7 @@ static int launch_up_mid(const UpMeasure* d_meas, int n, const Csr& csr, const i
 
 static int launch_down_mid(const DownMeasure* d_meas, int n, const Csr& csr, const int32_t* d_pstart,
                            const int32_t* d_children, int64_t O, int64_t P, int64_t C, int64_t I) {
-    const int VEC = (I % 4 == 0) ? 4 : 1;
+    const int VEC = (I % 4 == 0) ? 4 : (I % 2 == 0 ? 2 : 1);
     const int64_t IV_total = I / VEC;
     const int64_t max_row = ((int64_t)1 << 30);
     int64_t chunk_iv = IV_total;
@@ -362,6 +368,9 @@ static int launch_down_mid(const DownMeasure* d_meas, int n, const Csr& csr, con
         if (VEC == 4) {
             if (csr.contiguous) drilldown_mid_kernel<4, true><<<grid, block, 0, g.stream>>>(p);
             else drilldown_mid_kernel<4, false><<<grid, block, 0, g.stream>>>(p);
+        } else if (VEC == 2) {
+            if (csr.contiguous) drilldown_mid_kernel<2, true><<<grid, block, 0, g.stream>>>(p);
+            else drilldown_mid_kernel<2, false><<<grid, block, 0, g.stream>>>(p);
         } else {
             if (csr.contiguous) drilldown_mid_kernel<1, true><<<grid, block, 0, g.stream>>>(p);
             else drilldown_mid_kernel<1, false><<<grid, block, 0, g.stream>>>(p);
@@ -403,7 +412,6 @@ int olap_init(int device) {
     g.stream = g.own_stream;
     OLAP_CUDA(cudaEventCreate(&g.ev0));
     OLAP_CUDA(cudaEventCreate(&g.ev1));
-    OLAP_CUDA(cudaEventCreateWithFlags(&g.pin_free, cudaEventDisableTiming));
     cudaMemPool_t pool;
     OLAP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t keep = UINT64_MAX;  // keep freed blocks cached: transforms allocate every call
@@ -456,7 +464,8 @@ const char* olap_last_op_path(void) { return g.last_path; }
 // ---- pinned host buffers for the data boundary (so H2D/D2H run at PCIe speed) ----
 int olap_host_alloc(size_t bytes, void** out) {
     OLAP_TRY(ensure_ctx());
-    OLAP_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    static const bool wc = [] { const char* e = getenv("OLAP_PIN_WC"); return e && atoi(e) != 0; }();  // experiment knob
+    OLAP_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
     return OLAP_OK;
 }
 int olap_host_free(void* p) {
@@ -803,7 +812,7 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
                 path = "drillup/tile";
                 OLAP_TRY(launch_up_tile(t.ptr<UpMeasure>(o_meas), n, csr.contiguous, t.ptr<int32_t>(o_ps), t.ptr<int32_t>(o_ch), O, C, P, I, tile));
             } else {
-                path = (I % 4 == 0) ? "drillup/mid-vec4" : "drillup/mid-scalar";
+                path = (I % 4 == 0) ? "drillup/mid-vec4" : (I % 2 == 0 ? "drillup/mid-vec2" : "drillup/mid-scalar");
                 OLAP_TRY(launch_up_mid(t.ptr<UpMeasure>(o_meas), n, csr, t.ptr<int32_t>(o_ps), t.ptr<int32_t>(o_ch), O, C, P, I));
             }
         } else {
@@ -1156,7 +1165,8 @@ int olap_drill_down(olap_store* const* src, int n, const int* methods, int ndim,
     if (new_size && old_size == 0) {
         for (int k = 0; k < n; ++k) { olap_store t = *out[k]; t.status = st_out_of(out, k); OLAP_TRY(fill_default(&t)); }
     } else if (new_size && !any_dist && changed.size() == 1 &&
-               ((inner_of_changed % 4 == 0 && inner_of_changed >= 32) || inner_of_changed >= 128)) {
+               ((inner_of_changed % 4 == 0 && inner_of_changed >= 32) || (inner_of_changed % 2 == 0 && inner_of_changed >= 64) ||
+                inner_of_changed >= 128)) {
         // one changed dimension with a long inner run: parent-driven kernel
         const int d = changed[0];
         int64_t O = 1;
@@ -1176,7 +1186,7 @@ int olap_drill_down(olap_store* const* src, int n, const int* methods, int ndim,
         const size_t o_ps = t.add(csr.pstart.data(), csr.pstart.size() * 4);
         const size_t o_ch = t.add(csr.children.data(), csr.children.size() * 4);
         OLAP_TRY(t.upload());
-        path = inner_of_changed % 4 == 0 ? "drilldown/mid-vec4" : "drilldown/mid-scalar";
+        path = inner_of_changed % 4 == 0 ? "drilldown/mid-vec4" : (inner_of_changed % 2 == 0 ? "drilldown/mid-vec2" : "drilldown/mid-scalar");
         OLAP_TRY(launch_down_mid(t.ptr<DownMeasure>(o_meas), n, csr, t.ptr<int32_t>(o_ps), t.ptr<int32_t>(o_ch), O,
                                  old_len[d], new_len[d], inner_of_changed));
         OLAP_TRY(t.release());

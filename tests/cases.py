@@ -74,6 +74,8 @@ def drillup_cases(seed=0):
         ([1000, 8], 0, 3, False),
         ([4, 2000], 1, 1, True),         # ... split inside the tile kernel
         ([3, 1500, 2], 1, 2, False),
+        ([20, 66], 0, 3, True),          # inner run even but not a multiple of 4: 64-bit accesses
+        ([5, 9, 70], 1, 2, False),
     ]
     for dims, d, P, mono in shapes:
         for default in (0.0, math.nan):
@@ -114,7 +116,8 @@ def drilldown_cases(seed=1):
         ([3, 5], 1, 12, False),    # non-monotone new->old map
         ([4, 64], 0, 11, True),    # long inner run: parent-driven kernel, vec4
         ([3, 5, 32], 1, 9, False),
-        ([2, 3, 130], 1, 7, True),  # long inner run, scalar
+        ([2, 3, 130], 1, 7, True),  # long inner run, 64-bit accesses
+        ([2, 3, 129], 1, 5, True),  # long inner run, scalar
     ]
     for dims, d, C, mono in shapes:
         for default in (0.0, math.nan):
