@@ -279,8 +279,11 @@ struct Lane<OLAP_LAST, true> {
 // o = by*blockDim.y + ty, where a row is the P*IV output vectors of one outer index.
 // Loads along I are 128-bit and fully coalesced when VEC == 4; U children are in flight
 // per thread.  No shared memory: there is no reuse, every input byte is read once.
+constexpr int kInlineMeasures = 16;  // measure descriptors that travel in the kernel parameters
+
 struct UpMidParams {
-    const UpMeasure* meas;
+    const UpMeasure* meas;                      // device table, or nullptr: use meas_inline
+    UpMeasure meas_inline[kInlineMeasures];
     const int32_t* pstart;    // [P+1]
     const int32_t* children;  // [C] ascending per parent (unused when RANGE)
     int64_t O;
@@ -407,7 +410,7 @@ __global__ void __launch_bounds__(256) drillup_mid_kernel(const __grid_constant_
     if (o >= p.O || j >= p.row_vecs) return;
     const uint32_t pi = p.div_iv.div(j);
     const uint32_t iv = j - pi * p.IV;
-    const UpMeasure m = p.meas[blockIdx.y];
+    const UpMeasure m = p.meas ? p.meas[blockIdx.y] : p.meas_inline[blockIdx.y];
     const bool status = m.st_in != nullptr;
     if (m.nan_default) {
         if (status) up_mid_dispatch<true, VEC, RANGE, true, U>(p, m, o, pi, iv);
@@ -509,7 +512,7 @@ __global__ void __launch_bounds__(1024) drillup_split_kernel(const __grid_consta
     const bool live = j < p.row_vecs;
     const uint32_t pi = live ? p.div_iv.div(j) : 0u;
     const uint32_t iv = live ? j - pi * p.IV : 0u;
-    const UpMeasure m = p.meas[blockIdx.y];
+    const UpMeasure m = p.meas ? p.meas[blockIdx.y] : p.meas_inline[blockIdx.y];
     const bool status = m.st_in != nullptr;
     if (m.nan_default) {
         if (status) up_split_dispatch<true, VEC, RANGE, true>(p, m, o, pi, iv, live, smem_split);

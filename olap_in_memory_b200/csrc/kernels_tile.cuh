@@ -48,7 +48,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 struct UpTileParams {
-    const UpMeasure* meas;
+    const UpMeasure* meas;                      // device table, or nullptr: use meas_inline
+    UpMeasure meas_inline[kInlineMeasures];
     const int32_t* pstart;
     const int32_t* children;
     int64_t O;
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(256) drillup_tile_kernel(const __grid_constant
     extern __shared__ __align__(128) unsigned char smem[];
     float* s_val = reinterpret_cast<float*>(smem);
     uint8_t* s_st = smem + p.st_offset;
-    const UpMeasure m = p.meas[blockIdx.y];
+    const UpMeasure m = p.meas ? p.meas[blockIdx.y] : p.meas_inline[blockIdx.y];
     const bool status = m.st_in != nullptr;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + p.st_offset + (status ? (((size_t)p.R * p.row_in + 15) & ~(size_t)15) : 0));
     unsigned char* s_merge = smem + p.merge_offset;
@@ -242,11 +243,12 @@ __global__ void __launch_bounds__(256) drillup_tile_kernel(const __grid_constant
     }
 }
 
-inline int launch_up_tile(const UpMeasure* d_meas, int n, bool contiguous, const int32_t* d_pstart,
-                          const int32_t* d_children, int64_t O, int64_t C, int64_t P, int64_t I,
-                          const TileDecision& t) {
+inline int launch_up_tile(const UpMeasure* d_meas, const UpMeasure* h_meas, int n, bool contiguous,
+                          const int32_t* d_pstart, const int32_t* d_children, int64_t O, int64_t C, int64_t P,
+                          int64_t I, const TileDecision& t) {
     UpTileParams p{};
     p.meas = d_meas;
+    if (!d_meas) for (int k = 0; k < n; ++k) p.meas_inline[k] = h_meas[k];
     p.pstart = d_pstart;
     p.children = d_children;
     p.O = O; p.C = (int32_t)C; p.P = (int32_t)P; p.I = (int32_t)I;

@@ -170,6 +170,37 @@ int TablePack::release() {
     return rc;
 }
 
+// Device copies of map-derived tables, keyed by content (a few recent ones are kept).
+struct CachedTable {
+    std::vector<char> host;
+    void* dev = nullptr;
+    uint64_t stamp = 0;
+};
+static int cached_tables(const TablePack& pack, const char** dev_out) {
+    static CachedTable cache[8];
+    static uint64_t clock = 0;
+    ++clock;
+    CachedTable* victim = &cache[0];
+    for (auto& e : cache) {
+        if (e.dev && e.host.size() == pack.host.size() && !memcmp(e.host.data(), pack.host.data(), pack.host.size())) {
+            e.stamp = clock;
+            *dev_out = static_cast<const char*>(e.dev);
+            return OLAP_OK;
+        }
+        if (e.stamp < victim->stamp) victim = &e;
+    }
+    if (victim->dev) OLAP_TRY(dev_free(victim->dev));  // stream-ordered: earlier kernels finish first
+    victim->dev = nullptr;
+    TablePack up;
+    up.host = pack.host;
+    OLAP_TRY(up.upload());
+    victim->dev = up.dev;
+    victim->host = pack.host;
+    victim->stamp = clock;
+    *dev_out = static_cast<const char*>(up.dev);
+    return OLAP_OK;
+}
+
 static int grid_for(int64_t n, int per_block) {
     const int64_t want = ceil_div(n, per_block);
     const int64_t cap = (int64_t)g.sm_count * 32;
@@ -256,8 +287,8 @@ static uint32_t next_pow2(uint32_t v) {
     return p;
 }
 
-static int launch_up_mid(const UpMeasure* d_meas, int n, const Csr& csr, const int32_t* d_pstart,
-                         const int32_t* d_children, int64_t O, int64_t C, int64_t P, int64_t I) {
+static int launch_up_mid(const UpMeasure* d_meas, const UpMeasure* h_meas, int n, const Csr& csr,
+                         const int32_t* d_pstart, const int32_t* d_children, int64_t O, int64_t C, int64_t P, int64_t I) {
     const int VEC = (I % 4 == 0) ? 4 : (I % 2 == 0 ? 2 : 1);
     const int64_t IV_total = I / VEC;
     // chunk the inner run so that one row of output vectors fits 32-bit math
@@ -268,6 +299,7 @@ static int launch_up_mid(const UpMeasure* d_meas, int n, const Csr& csr, const i
         const int64_t iv_n = std::min(chunk_iv, IV_total - iv0);
         UpMidParams p{};
         p.meas = d_meas;
+        if (!d_meas) for (int k = 0; k < n; ++k) p.meas_inline[k] = h_meas[k];
         p.pstart = d_pstart;
         p.children = d_children;
         p.O = O; p.C = (int32_t)C; p.P = (int32_t)P;
@@ -802,18 +834,28 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
             const int64_t C = ndim ? old_len[d] : 1, P = ndim ? new_len[d] : 1;
             static const int32_t zero = 0;
             const Csr csr = build_csr(ndim ? maps[d] : &zero, C, P);
-            const size_t o_ps = t.add(csr.pstart.data(), csr.pstart.size() * 4);
-            const size_t o_ch = t.add(csr.children.data(), csr.children.size() * 4);
-            OLAP_TRY(t.upload());
+            // the CSR depends only on the map: keep it on the device across calls (a cube is
+            // usually drilled the same way many times); measure descriptors change every call
+            // (new output planes) and travel in the kernel parameters when they fit
+            TablePack stat;
+            const size_t o_ps = stat.add(csr.pstart.data(), csr.pstart.size() * 4);
+            const size_t o_ch = stat.add(csr.children.data(), csr.children.size() * 4);
+            const char* d_stat = nullptr;
+            OLAP_TRY(cached_tables(stat, &d_stat));
+            const bool inline_meas = n <= kInlineMeasures;
+            if (!inline_meas) OLAP_TRY(t.upload());
+            const UpMeasure* d_meas = inline_meas ? nullptr : t.ptr<UpMeasure>(o_meas);
+            const int32_t* d_ps = reinterpret_cast<const int32_t*>(d_stat + o_ps);
+            const int32_t* d_ch = reinterpret_cast<const int32_t*>(d_stat + o_ch);
             bool any_status = false;
             for (int k = 0; k < n; ++k) any_status |= meas[k].st_in != nullptr;
             TileDecision tile = tile_plan(O, C, P, I, any_status);
             if (tile.use) {
                 path = "drillup/tile";
-                OLAP_TRY(launch_up_tile(t.ptr<UpMeasure>(o_meas), n, csr.contiguous, t.ptr<int32_t>(o_ps), t.ptr<int32_t>(o_ch), O, C, P, I, tile));
+                OLAP_TRY(launch_up_tile(d_meas, meas.data(), n, csr.contiguous, d_ps, d_ch, O, C, P, I, tile));
             } else {
                 path = (I % 4 == 0) ? "drillup/mid-vec4" : (I % 2 == 0 ? "drillup/mid-vec2" : "drillup/mid-scalar");
-                OLAP_TRY(launch_up_mid(t.ptr<UpMeasure>(o_meas), n, csr, t.ptr<int32_t>(o_ps), t.ptr<int32_t>(o_ch), O, C, P, I));
+                OLAP_TRY(launch_up_mid(d_meas, meas.data(), n, csr, d_ps, d_ch, O, C, P, I));
             }
         } else {
             path = "drillup/generic";
