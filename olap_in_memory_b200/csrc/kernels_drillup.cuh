@@ -131,21 +131,26 @@ struct Lane<OLAP_AVERAGE, false> {
     __device__ __forceinline__ float result() const { return canon_store(cnt ? (float)(acc / (double)cnt) : 0.0f, 0); }
     __device__ __forceinline__ void merge(const Lane& o) { acc += o.acc; cnt += o.cnt; }
 };
+// NaN default: unset children are NaN and are masked to -0 (the identity of IEEE addition,
+// so a lone set -0 stays -0).  The reference's restart after inf + -inf (the NaN sum equals
+// the default, the key is deleted, the next set child starts over: in-memory.js:311-318) is
+// NOT tracked in the hot loop: a NaN accumulator with set children (`poisoned`) sends the
+// output through the faithful state machine once more (exact_redo below) — it needs both
+// +inf and -inf among the children of one parent.
 template <>
 struct Lane<OLAP_SUM, true> {
-    double acc = -0.0;  // -0 is the identity of IEEE addition: a set -0 must stay -0
+    double acc = -0.0;
     bool has = false;
     __device__ __forceinline__ void step(float v) {
         const bool pres = v == v;
-        const bool dead = acc != acc;  // inf + -inf was deleted: the next set child restarts
-        acc = ((pres && dead) ? -0.0 : acc) + (pres ? (double)v : -0.0);
+        acc += (double)(pres ? v : -0.0f);
         has |= pres;
     }
+    __device__ __forceinline__ bool poisoned() const { return has && acc != acc; }
     __device__ __forceinline__ float result() const { return has ? canon_store((float)acc, 1) : canon_nan(); }
     __device__ __forceinline__ void merge(const Lane& o) {
-        if (!o.has) return;
-        acc = (has && acc == acc) ? acc + o.acc : o.acc;
-        has = true;
+        acc += o.acc;
+        has |= o.has;
     }
 };
 template <>
@@ -154,14 +159,13 @@ struct Lane<OLAP_AVERAGE, true> {
     uint32_t cnt = 0;
     __device__ __forceinline__ void step(float v) {
         const bool pres = v == v;
-        const bool dead = acc != acc;
-        acc = ((pres && dead) ? -0.0 : acc) + (pres ? (double)v : -0.0);
+        acc += (double)(pres ? v : -0.0f);
         cnt += pres ? 1u : 0u;
     }
+    __device__ __forceinline__ bool poisoned() const { return cnt && acc != acc; }
     __device__ __forceinline__ float result() const { return cnt ? canon_store((float)(acc / (double)cnt), 1) : canon_nan(); }
     __device__ __forceinline__ void merge(const Lane& o) {
-        if (!o.cnt) return;
-        acc = (cnt && acc == acc) ? acc + o.acc : o.acc;
+        acc += o.acc;
         cnt += o.cnt;
     }
 };
@@ -274,6 +278,24 @@ struct Lane<OLAP_LAST, true> {
     __device__ __forceinline__ void merge(const Lane& o) { step(o.acc); }
 };
 
+// Lanes that can be poisoned (see Lane<OLAP_SUM, true>) report it; the others never are.
+template <int METHOD, bool NANDEF>
+__device__ __forceinline__ bool lane_poisoned(const Lane<METHOD, NANDEF>& l) {
+    if constexpr (NANDEF && (METHOD == OLAP_SUM || METHOD == OLAP_AVERAGE)) return l.poisoned();
+    else return false;
+}
+// Faithful recomputation of ONE output cell: children k0..k1 of its parent, ascending.
+template <int METHOD, bool RANGE>
+__device__ __noinline__ float exact_redo(const float* cell0, int64_t stride, const int32_t* children, int32_t k0,
+                                         int32_t k1) {
+    Acc<METHOD> a;
+    for (int32_t k = k0; k < k1; ++k) {
+        const int64_t child = RANGE ? (int64_t)k : (int64_t)children[k];
+        a.step(cell0[child * stride], 1);
+    }
+    return a.result(1);
+}
+
 // ---- kernel A: one changed dimension, any I ----------------------------------
 // Thread (tx, ty) of a block owns output vector j = bx*blockDim.x + tx of row
 // o = by*blockDim.y + ty, where a row is the P*IV output vectors of one outer index.
@@ -381,7 +403,8 @@ __device__ __forceinline__ void up_mid_body(const UpMidParams& p, const UpMeasur
     const int64_t out_off = o * p.out_row + (int64_t)pi * p.I_total + inner;
     float r[VEC];
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) r[e] = lane[e].result();
+    for (int e = 0; e < VEC; ++e)
+        r[e] = lane_poisoned(lane[e]) ? exact_redo<METHOD, RANGE>(src + e, stride, p.children, k0, k1) : lane[e].result();
     store_cells<VEC>(m.out + out_off, r);
     if (STATUS) store_status<VEC>(m.st_out + out_off, k0 == k1 ? unset_status<VEC>() : st);  // no child: not set
 }
@@ -481,7 +504,10 @@ __device__ __forceinline__ void up_split_body(const UpMidParams& p, const UpMeas
     const int64_t out_off = o * p.out_row + (int64_t)pi * p.I_total + inner;
     float r[VEC];
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) r[e] = lane[e].result();
+    for (int e = 0; e < VEC; ++e)
+        r[e] = lane_poisoned(lane[e])
+                   ? exact_redo<METHOD, RANGE>(m.in + o * p.in_row + inner + e, p.I_total, p.children, k0, k1)
+                   : lane[e].result();
     store_cells<VEC>(m.out + out_off, r);
     if (STATUS) store_status<VEC>(m.st_out + out_off, k0 == k1 ? unset_status<VEC>() : st);
 }

@@ -133,7 +133,7 @@ __device__ __forceinline__ void up_tile_reduce(const UpTileParams& p, const UpMe
         uint8_t* s_stm = s_merge + 256 * sizeof(L);
         const int j = threadIdx.x >> p.logG, gq = threadIdx.x & (p.G - 1);
         L lane;
-        uint32_t st = 0;
+        uint32_t st = 0, redo_base = 0;
         int32_t k0 = 0, k1 = 0;
         if (j < n_out) {
             const uint32_t r = p.div_row_out.div((uint32_t)j);
@@ -145,6 +145,7 @@ __device__ __forceinline__ void up_tile_reduce(const UpTileParams& p, const UpMe
             const int32_t per = (k1 - k0 + p.G - 1) >> p.logG;
             const int32_t ks = min(k1, k0 + gq * per), ke = min(k1, ks + per);
             const uint32_t base = r * (uint32_t)p.row_in + i;
+            redo_base = base;
 #pragma unroll 4
             for (int32_t k = ks; k < ke; ++k) {
                 const uint32_t c = RANGE ? (uint32_t)k : (uint32_t)p.children[k];
@@ -161,7 +162,7 @@ __device__ __forceinline__ void up_tile_reduce(const UpTileParams& p, const UpMe
                 lane.merge(s_lane[threadIdx.x + q2]);
                 st |= s_stm[threadIdx.x + q2];
             }
-            out[j] = lane.result();
+            out[j] = lane_poisoned(lane) ? exact_redo<METHOD, RANGE>(s_val + redo_base, p.I, p.children, k0, k1) : lane.result();
             if (STATUS) st_out[j] = (uint8_t)(k0 == k1 ? OLAP_STATUS_UNSET : st);
         }
         return;
@@ -182,7 +183,7 @@ __device__ __forceinline__ void up_tile_reduce(const UpTileParams& p, const UpMe
             lane.step(s_val[idx]);
             if (STATUS) st |= s_st[idx];
         }
-        out[j] = lane.result();
+        out[j] = lane_poisoned(lane) ? exact_redo<METHOD, RANGE>(s_val + base, p.I, p.children, k0, k1) : lane.result();
         if (STATUS) st_out[j] = (uint8_t)(k0 == k1 ? OLAP_STATUS_UNSET : st);
     }
 }

@@ -227,3 +227,34 @@ def test_kernel_paths_are_the_intended_ones():
     assert path() == "reorder/box-transpose"
     G.dice_lowered([s], [64, 40, 64], [ident(64), np.arange(0, 40, 2, dtype=np.int32), ident(64)])
     assert path() == "gather/vec4"
+
+
+def test_inf_minus_inf_restart_under_nan_default():
+    """in-memory.js:311-318: under a NaN default inf + -inf = NaN deletes the key and the next
+    set child restarts the accumulator — on every drillUp kernel path."""
+    G = _gpu()
+    inf = math.inf
+    column = [3.0, inf, -inf, 5.0, 7.0, math.nan, -inf, inf]  # -> restart at 5: 12; then -inf+inf deletes again
+    for C_, I_, dims_of in ((8, 64, lambda: ([8, 64], 0)), (8, 1, lambda: ([5, 8], 1)), (8, 6, lambda: ([8, 6], 0))):
+        old_len, d = dims_of()
+        n = int(np.prod(old_len))
+        data = np.full(n, 2.0, np.float32).reshape(old_len)
+        column2 = [inf, -inf, 5.0, 7.0, 1.0, math.nan, 1.0, 1.0]  # restart at 5 -> 15
+        if d == 0:
+            data[:, 0] = column
+            data[:, 1] = column2
+        else:
+            data[0, :] = column
+            data[1, :] = column2
+        for method in ("sum", "average"):
+            s = G(n, "float32", math.nan)
+            s.set_data_f32(data.ravel())
+            o = COracleStore(n, "float32", math.nan)
+            o.set_data_f32(data.ravel())
+            new_len = list(old_len)
+            new_len[d] = 1
+            maps = [cases.identity(x) for x in old_len]
+            maps[d] = np.zeros(old_len[d], np.int32)
+            got = G.drillUp_lowered([s], old_len, new_len, maps, [method])[0].data_f32()
+            want = o.drillUp_lowered(old_len, new_len, maps, method).data_f64()
+            assert cases.bits_equal(got, want.astype(np.float32)), (old_len, method, got[:4], want[:4])
