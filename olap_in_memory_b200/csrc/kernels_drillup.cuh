@@ -717,3 +717,109 @@ __global__ void __launch_bounds__(256) drilldown_mid_kernel(const __grid_constan
 }
 
 }  // namespace olap
+
+// =====================================================================================
+// drillDown of the INNERMOST axis: [O, P] -> [O, C] (time innermost, I == 1).
+// A CTA owns RB consecutive rows: their RB*P parents and the per-child tables (parent,
+// rank) sit in shared memory; every thread produces 4 consecutive children and writes them
+// with one 128-bit store (the output span of a CTA is contiguous).
+namespace olap {
+
+struct DownInnerParams {
+    const DownMeasure* meas;
+    const int32_t* parent_of;  // [C] new item -> parent
+    const int32_t* rank_of;    // [C] rank among siblings
+    const int32_t* cnt_of;     // [P] siblings per parent
+    int64_t O;
+    int32_t P, C;
+    uint32_t RB;               // rows per CTA
+    FastDiv div_c;
+    int vec4;                  // C % 4 == 0: 128-bit stores
+};
+
+// Everything that depends only on the PARENT (value / n, integer base and step, status) is
+// computed once per parent while staging; a child cell then costs two shared-memory reads.
+template <bool STATUS>
+__device__ __forceinline__ void down_inner_body(const DownInnerParams& p, const DownMeasure& m, unsigned char* smem) {
+    const uint32_t n_par = p.RB * (uint32_t)p.P;
+    double* s_step = reinterpret_cast<double*>(smem);                 // [RB * P]  integer spreading only
+    float* s_res = reinterpret_cast<float*>(s_step + n_par);          // [RB * P]  child value (or floor(v/n))
+    int32_t* s_parent = reinterpret_cast<int32_t*>(s_res + n_par);    // [C]
+    int32_t* s_rank = s_parent + p.C;                                 // [C]
+    uint8_t* s_st = reinterpret_cast<uint8_t*>(s_rank + p.C);         // [RB * P]  child status
+    uint8_t* s_truthy = s_st + n_par;                                 // [RB * P]
+    const int64_t row0 = (int64_t)blockIdx.x * p.RB;
+    const uint32_t rows = (uint32_t)min((int64_t)p.RB, p.O - row0);
+    const int nan_default = m.nan_default;
+    for (uint32_t i = threadIdx.x; i < rows * (uint32_t)p.P; i += blockDim.x) {
+        const float x = m.in[row0 * p.P + i];
+        const uint32_t sb = STATUS ? m.st_in[row0 * p.P + i] : 0u;
+        const uint32_t par = i % (uint32_t)p.P;
+        const double dn = (double)p.cnt_of[par];
+        const bool truthy = x != 0.0f && x == x;  // `if (!oldValue) continue` (in-memory.js:386-387)
+        float r;
+        bool ok = truthy;
+        if (m.kind == 0) { r = canon_store((float)((double)x / dn), nan_default); ok = truthy && present_f(r, nan_default); }
+        else if (m.kind == 1) r = x;
+        else {
+            const double q = (double)x / dn;
+            r = (float)floor(q);
+            s_step[i] = fma(-trunc(q), dn, (double)x) / dn;  // (v % n) / n
+        }
+        s_res[i] = truthy ? r : default_of(nan_default);
+        s_truthy[i] = truthy;
+        s_st[i] = (uint8_t)(ok ? ((sb | OLAP_STATUS_INTERPOLATED) & 0xffu) : (uint32_t)OLAP_STATUS_UNSET);
+    }
+    for (uint32_t c = threadIdx.x; c < (uint32_t)p.C; c += blockDim.x) {
+        s_parent[c] = p.parent_of[c];
+        s_rank[c] = p.rank_of[c];
+    }
+    __syncthreads();
+    const uint32_t cells = rows * (uint32_t)p.C;
+    float* out = m.out + row0 * p.C;
+    uint8_t* st_out = STATUS ? m.st_out + row0 * p.C : nullptr;
+    auto cell = [&](uint32_t r, uint32_t c, uint32_t& so) {
+        const uint32_t i = r * (uint32_t)p.P + (uint32_t)s_parent[c];
+        float v = s_res[i];
+        so = s_st[i];
+        if (m.kind == 2 && s_truthy[i]) {
+            const double k = (double)s_rank[c], step = s_step[i];
+            const bool last_is_same = floor(k * step) == floor((k - 1.0) * step);
+            v = canon_store(last_is_same ? v : v + 1.0f, nan_default);
+            if (STATUS && !present_f(v, nan_default)) so = OLAP_STATUS_UNSET;
+        }
+        return v;
+    };
+    if (p.vec4) {
+        for (uint32_t t = threadIdx.x * 4; t < cells; t += blockDim.x * 4) {
+            const uint32_t r = p.div_c.div(t);
+            const uint32_t c0 = t - r * (uint32_t)p.C;  // C % 4 == 0: the 4 cells share the row
+            float v[4];
+            uint32_t st = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                uint32_t so;
+                v[e] = cell(r, c0 + e, so);
+                st |= so << (8 * e);
+            }
+            st_stream4(out + t, make_float4(v[0], v[1], v[2], v[3]));
+            if (STATUS) *reinterpret_cast<uint32_t*>(st_out + t) = st;
+        }
+    } else {
+        for (uint32_t t = threadIdx.x; t < cells; t += blockDim.x) {
+            const uint32_t r = p.div_c.div(t);
+            uint32_t so;
+            out[t] = cell(r, t - r * (uint32_t)p.C, so);
+            if (STATUS) st_out[t] = (uint8_t)so;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) drilldown_inner_kernel(const __grid_constant__ DownInnerParams p) {
+    extern __shared__ __align__(16) unsigned char smem_di[];
+    const DownMeasure m = p.meas[blockIdx.y];
+    if (m.st_in) down_inner_body<true>(p, m, smem_di);
+    else down_inner_body<false>(p, m, smem_di);
+}
+
+}  // namespace olap

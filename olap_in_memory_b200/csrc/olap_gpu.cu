@@ -412,6 +412,31 @@ static int launch_down_mid(const DownMeasure* d_meas, int n, const Csr& csr, con
     return OLAP_OK;
 }
 
+static int launch_down_inner(const DownMeasure* d_meas, int n, const int32_t* d_parent, const int32_t* d_rank,
+                             const int32_t* d_cnt, int64_t O, int64_t P, int64_t C) {
+    DownInnerParams p{};
+    p.meas = d_meas;
+    p.parent_of = d_parent;
+    p.rank_of = d_rank;
+    p.cnt_of = d_cnt;
+    p.O = O; p.P = (int32_t)P; p.C = (int32_t)C;
+    p.RB = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(O, 8192 / C));
+    if (C % 4 != 0 || ((int64_t)p.RB * C) % 4 != 0) p.vec4 = 0; else p.vec4 = 1;
+    p.div_c = FastDiv((uint32_t)C);
+    const size_t smem = (size_t)p.RB * P * (8 + 4 + 2) + (size_t)C * 8 + 16;
+    const int64_t gx = ceil_div(O, p.RB);
+    if (gx > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "drillDown: grid too large");
+    static bool attr = false;
+    if (!attr) {
+        OLAP_CUDA(cudaFuncSetAttribute(drilldown_inner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr = true;
+    }
+    KERNELS_BEGIN();
+    drilldown_inner_kernel<<<dim3((unsigned)gx, (unsigned)n), 256, smem, g.stream>>>(p);
+    LAUNCHED();
+    return OLAP_OK;
+}
+
 }  // namespace olap
 
 using namespace olap;
@@ -1231,6 +1256,33 @@ int olap_drill_down(olap_store* const* src, int n, const int* methods, int ndim,
         path = inner_of_changed % 4 == 0 ? "drilldown/mid-vec4" : (inner_of_changed % 2 == 0 ? "drilldown/mid-vec2" : "drilldown/mid-scalar");
         OLAP_TRY(launch_down_mid(t.ptr<DownMeasure>(o_meas), n, csr, t.ptr<int32_t>(o_ps), t.ptr<int32_t>(o_ch), O,
                                  old_len[d], new_len[d], inner_of_changed));
+        OLAP_TRY(t.release());
+    } else if (new_size && !any_dist && changed.size() == 1 && inner_of_changed == 1 && new_len[changed[0]] <= 8192 &&
+               old_len[changed[0]] <= 8192) {
+        // the drilled dimension is the innermost one: row kernel with 128-bit stores
+        const int d = changed[0];
+        int64_t O = 1;
+        for (int q = 0; q < d; ++q) O *= old_len[q];
+        const int64_t P = old_len[d], C = new_len[d];
+        std::vector<int32_t> rank(C), cnt(P, 0);
+        for (int64_t j = 0; j < C; ++j) rank[j] = cnt[maps[d][j]]++;
+        std::vector<DownMeasure> dm(n);
+        for (int k = 0; k < n; ++k) {
+            const bool is_int = src[k]->type == OLAP_INT32 || src[k]->type == OLAP_UINT32;
+            const bool is_sum = methods ? methods[k] == OLAP_SUM : true;
+            const uint8_t* si = out[k]->status ? st_in_of(src, k) : nullptr;
+            dm[k] = DownMeasure{src[k]->values, out[k]->values, si, si ? st_out_of(out, k) : nullptr,
+                                src[k]->default_kind, !is_sum ? 1 : (is_int ? 2 : 0)};
+        }
+        TablePack t;
+        const size_t o_meas = t.add(dm.data(), sizeof(DownMeasure) * n);
+        const size_t o_par = t.add(maps[d], (size_t)C * 4);
+        const size_t o_rank = t.add(rank.data(), (size_t)C * 4);
+        const size_t o_cnt = t.add(cnt.data(), (size_t)P * 4);
+        OLAP_TRY(t.upload());
+        path = "drilldown/inner-rows";
+        OLAP_TRY(launch_down_inner(t.ptr<DownMeasure>(o_meas), n, t.ptr<int32_t>(o_par), t.ptr<int32_t>(o_rank),
+                                   t.ptr<int32_t>(o_cnt), O, P, C));
         OLAP_TRY(t.release());
     } else if (new_size) {
         auto meas = gather_measures(src, out, n);
