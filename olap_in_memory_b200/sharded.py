@@ -87,6 +87,31 @@ class _Comm:
             r.wait()
         del torch
 
+    def all_to_all_many(self, pairs, out_splits, in_splits):
+        """Several planes with the same split sizes exchanged as ONE grouped NCCL launch
+        (all sends and receives of all planes are in flight together)."""
+        if self.world == 1 or not pairs[0][0].is_cuda:
+            for out, inp in pairs:
+                self.all_to_all(out, inp, out_splits, in_splits)
+            return
+        in_off = np.concatenate([[0], np.cumsum(in_splits)])
+        out_off = np.concatenate([[0], np.cumsum(out_splits)])
+        ops = []
+        for out, inp in pairs:
+            for step in range(1, self.world):  # stagger the peers so that no rank is a hot spot
+                dst_peer = (self.rank + step) % self.world
+                src_peer = (self.rank - step) % self.world
+                src = inp[in_off[dst_peer]:in_off[dst_peer + 1]]
+                dst = out[out_off[src_peer]:out_off[src_peer + 1]]
+                if src.numel():
+                    ops.append(self.dist.P2POp(self.dist.isend, src, dst_peer, self.group))
+                if dst.numel():
+                    ops.append(self.dist.P2POp(self.dist.irecv, dst, src_peer, self.group))
+            out[out_off[self.rank]:out_off[self.rank + 1]].copy_(inp[in_off[self.rank]:in_off[self.rank + 1]])
+        if ops:
+            for req in self.dist.batch_isend_irecv(ops):
+                req.wait()
+
     def all_reduce_sum(self, value, device=None):
         if self.world == 1:
             return value
@@ -310,14 +335,14 @@ class ShardedCube:
         in_splits = [(out_bounds[r + 1] - out_bounds[r]) * inner for r in range(W)]
         out_splits = [my_out_rows * inner] * W
         received = []
-        for part, src_store in zip(partials, stores):
+        for src_store in stores:
             if _is_device_store(src_store):  # every cell is overwritten by the exchange: skip the default fill
                 recv = self._store_cls(W * my_out_rows * inner, src_store._type, src_store._defaultValue,
                                        uninitialised=True)
             else:
                 recv = self._store_cls(W * my_out_rows * inner, src_store._type, src_store._defaultValue)
-            self._exchange(part, recv, in_splits, out_splits)
             received.append(recv)
+        self._exchange_all(partials, received, in_splits, out_splits)
         del partials
 
         # 3. ordered combine of the W partials: a drillUp over the rank axis
@@ -351,6 +376,26 @@ class ShardedCube:
             else:
                 out.append(s.drillUp_lowered(old_len, new_len, maps, method))
         return out
+
+    def _exchange_all(self, parts, recvs, in_splits, out_splits):
+        """All planes (values and status) of all partials in one grouped exchange."""
+        if not _is_device_store(parts[0]):
+            for part, recv in zip(parts, recvs):
+                self._exchange(part, recv, in_splits, out_splits)
+            return
+        import torch
+
+        from . import interop
+
+        pairs = []
+        for part, recv in zip(parts, recvs):
+            pairs.append((interop.values_tensor(recv), interop.values_tensor(part)))
+            st_in, st_out = interop.status_tensor(part), interop.status_tensor(recv)
+            if st_in is not None and st_out is not None:
+                pairs.append((st_out, st_in))
+        torch.cuda.current_stream().synchronize()
+        self.comm.all_to_all_many(pairs, out_splits, in_splits)
+        torch.cuda.synchronize()
 
     def _exchange(self, part, recv, in_splits, out_splits):
         import torch
