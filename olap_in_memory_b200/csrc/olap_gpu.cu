@@ -350,7 +350,10 @@ static int launch_up_mid(const UpMeasure* d_meas, const UpMeasure* h_meas, int n
         if (gx > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "drillUp: grid too large (%lld blocks)", (long long)gx);
         dim3 grid((unsigned)gx, (unsigned)n), block(bx, by);
         KERNELS_BEGIN();
-        static const int U = [] { const char* e = getenv("OLAP_UP_U"); return e ? atoi(e) : 8; }();  // tuning knob
+        // 8 children in flight per thread (80 registers) for long child lists, 4 (60 registers,
+        // one more resident CTA per SM) when a parent has only a handful of children
+        static const int U_knob = [] { const char* e = getenv("OLAP_UP_U"); return e ? atoi(e) : 0; }();
+        const int U = U_knob ? U_knob : (C / std::max<int64_t>(P, 1) < 8 ? 4 : 8);
 #define OLAP_UP_LAUNCH(V, R)                                                                         \
     do {                                                                                             \
         if (U == 4) drillup_mid_kernel<V, R, 4><<<grid, block, 0, g.stream>>>(p);                    \
