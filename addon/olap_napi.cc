@@ -143,7 +143,6 @@ static napi_value Download(napi_env env, napi_callback_info info) {
 static napi_value DrillUp(napi_env env, napi_callback_info info) {
     GET_ARGS();
     auto src = store_list(env, a.v[0]);
-    auto methods = map_list(env, a.v[1]);  // unused path; methods arrive as one Int32Array
     napi_typedarray_type t;
     size_t len;
     void* mdata;
@@ -153,7 +152,6 @@ static napi_value DrillUp(napi_env env, napi_callback_info info) {
     std::vector<olap_store*> out(src.size());
     OLAP_CALL(olap_drill_up(src.data(), (int)src.size(), static_cast<const int*>(mdata), (int)old_len.size(),
                             old_len.data(), new_len.data(), maps.data(), out.data()));
-    (void)methods;
     return store_array_out(env, out);
 }
 

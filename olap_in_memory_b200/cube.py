@@ -281,16 +281,28 @@ class Cube:
         self.setData(measureId, formatter.fromNestedObject(value, self.dimensions))
 
     def hydrateFromSparseNestedObject(self, measureId, obj, offset=0, dimOffset=0):
+        """cube.js:472-491.  The reference calls setValue per leaf; here the leaves are
+        collected first and written with ONE batched store call when the store has one."""
+        store = self.storedMeasures[measureId]
+        indexes, values = [], []
+        self._collect_sparse(obj, offset, dimOffset, indexes, values)
+        if hasattr(store, "setValues") and len(indexes) > 1:
+            d = float(store._defaultValue)
+            store.setValues(indexes, [d if v is None else v for v in values])
+        else:
+            for index, value in zip(indexes, values):
+                store.setValue(index, value)
+
+    def _collect_sparse(self, obj, offset, dimOffset, indexes, values):
         if dimOffset == len(self.dimensions):
-            self.storedMeasures[measureId].setValue(offset, obj)
+            indexes.append(offset)
+            values.append(obj)
             return
         dimension = self.dimensions[dimOffset]
         for key, child in obj.items():
             item_offset = dimension.getRootIndexFromRootItem(key)
             if item_offset != -1:
-                self.hydrateFromSparseNestedObject(
-                    measureId, child, offset * dimension.numItems + item_offset, dimOffset + 1
-                )
+                self._collect_sparse(child, offset * dimension.numItems + item_offset, dimOffset + 1, indexes, values)
 
     def _check_coords(self, who, coords):
         if any(not coords.get(d) for d in self.dimensionIds):
