@@ -258,3 +258,60 @@ def test_inf_minus_inf_restart_under_nan_default():
             got = G.drillUp_lowered([s], old_len, new_len, maps, [method])[0].data_f32()
             want = o.drillUp_lowered(old_len, new_len, maps, method).data_f64()
             assert cases.bits_equal(got, want.astype(np.float32)), (old_len, method, got[:4], want[:4])
+
+
+def test_more_measures_than_fit_in_kernel_parameters():
+    """> 16 measures in one olap_drill_up call take the device-table path for descriptors."""
+    G = _gpu()
+    rng = np.random.default_rng(21)
+    dims, P, n_meas = [30, 40], 4, 20
+    m = cases.random_map(rng, 30, P, False)
+    methods = [cases.METHODS[k % 6] for k in range(n_meas)]
+    datas = [cases.make_data(rng, 1200, 0.0, 0.7, "int") for _ in range(n_meas)]
+    stores = []
+    for d in datas:
+        s = G(1200, "float32", 0.0)
+        s.set_data_f32(d)
+        stores.append(s)
+    outs = G.drillUp_lowered(stores, dims, [P, 40], [m, cases.identity(40)], methods)
+    for d, method, out in zip(datas, methods, outs):
+        o = COracleStore(1200, "float32", 0.0)
+        o.set_data_f32(d)
+        want = o.drillUp_lowered(dims, [P, 40], [m, cases.identity(40)], method).data_f64()
+        assert cases.bits_equal(out.data_f32(), want.astype(np.float32)), method
+
+
+def test_shared_status_plane_layout():
+    """north-star layout (a): the measures of a cube in ONE allocation with ONE status plane
+    shared by all of them (olap_store_create_batch(..., shared_status=1)); transforms keep the
+    sharing and touch the plane once."""
+    import ctypes as C
+
+    from olap_in_memory_b200 import _native as N
+
+    G = _gpu()
+    lib = N.lib()
+    n, size = 3, 6 * 8
+    handles = (C.c_void_p * n)()
+    types = (C.c_int * n)(2, 2, 2)
+    kinds = (C.c_int * n)(0, 0, 0)
+    N.check(lib.olap_store_create_batch(n, size, types, kinds, 1, 1, handles))
+    stores = [G._wrap(handles[k]) for k in range(n)]
+    ptrs = {lib.olap_store_status_ptr(s._h) for s in stores}
+    assert len(ptrs) == 1 and None not in ptrs
+    v0 = lib.olap_store_values_ptr(stores[0]._h)
+    assert lib.olap_store_values_ptr(stores[1]._h) - v0 == 256  # 48 floats = 192 B padded to 256
+    data = np.arange(1, size + 1, dtype=np.float32)
+    data[5] = 0.0  # same fill pattern for every measure: that is when one plane is exact
+    for k, s in enumerate(stores):
+        s.set_data_f32(data * (k + 1))
+    assert stores[2].status[5] == 1 and stores[0].status[4] == 2
+    m = np.asarray([0, 0, 1, 1, 2, 2], np.int32)
+    outs = G.drillUp_lowered(stores, [6, 8], [3, 8], [m, cases.identity(8)], ["sum", "highest", "last"])
+    assert len({lib.olap_store_status_ptr(o._h) for o in outs}) == 1
+    x = data.reshape(6, 8)
+    assert outs[0].data_f32().reshape(3, 8).tolist() == (x[0::2] + x[1::2]).tolist()
+    assert outs[1].data_f32().reshape(3, 8).tolist() == (2 * np.maximum(x[0::2], x[1::2])).tolist()
+    assert outs[2].data_f32().reshape(3, 8).tolist() == (3 * x[1::2]).tolist()
+    st = np.asarray(outs[1].status).reshape(3, 8)
+    assert st[0, 5] == 3 and (np.delete(st.ravel(), 5) == 2).all()
