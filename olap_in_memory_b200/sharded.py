@@ -88,29 +88,12 @@ class _Comm:
         del torch
 
     def all_to_all_many(self, pairs, out_splits, in_splits):
-        """Several planes with the same split sizes exchanged as ONE grouped NCCL launch
-        (all sends and receives of all planes are in flight together)."""
-        if self.world == 1 or not pairs[0][0].is_cuda:
-            for out, inp in pairs:
-                self.all_to_all(out, inp, out_splits, in_splits)
-            return
-        in_off = np.concatenate([[0], np.cumsum(in_splits)])
-        out_off = np.concatenate([[0], np.cumsum(out_splits)])
-        ops = []
+        """Exchange several planes that share the same split sizes.  One NCCL all-to-all per
+        plane: on 8 B200 that measured FASTER (60 ms for 20 GB partials) than putting every
+        send/receive of every plane into one grouped launch (73 ms) — fewer concurrent
+        peer-to-peer channels contend less."""
         for out, inp in pairs:
-            for step in range(1, self.world):  # stagger the peers so that no rank is a hot spot
-                dst_peer = (self.rank + step) % self.world
-                src_peer = (self.rank - step) % self.world
-                src = inp[in_off[dst_peer]:in_off[dst_peer + 1]]
-                dst = out[out_off[src_peer]:out_off[src_peer + 1]]
-                if src.numel():
-                    ops.append(self.dist.P2POp(self.dist.isend, src, dst_peer, self.group))
-                if dst.numel():
-                    ops.append(self.dist.P2POp(self.dist.irecv, dst, src_peer, self.group))
-            out[out_off[self.rank]:out_off[self.rank + 1]].copy_(inp[in_off[self.rank]:in_off[self.rank + 1]])
-        if ops:
-            for req in self.dist.batch_isend_irecv(ops):
-                req.wait()
+            self.all_to_all(out, inp, out_splits, in_splits)
 
     def all_reduce_sum(self, value, device=None):
         if self.world == 1:
