@@ -130,16 +130,27 @@ __global__ void __launch_bounds__(kStoreThreads) total_kernel(const float* __res
         s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
+    if (s_last) {
+        // the last block folds the per-block partials cooperatively (fixed order for a given grid)
         double a = 0.0;
         unsigned long long c = 0;
-        for (unsigned b = 0; b < gridDim.x; ++b) {
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
             a += ((volatile double*)partial_sum)[b];
             c += ((volatile unsigned long long*)partial_cnt)[b];
         }
-        *out_sum = a;
-        *out_cnt = c;
-        *ticket = 0;
+        a = warp_sum(a);
+        c = warp_sum_u64(c);
+        __syncthreads();
+        if (l == 0) { s_sum[w] = a; s_cnt[w] = c; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double ta = 0.0;
+            unsigned long long tc = 0;
+            for (int k = 0; k < kStoreThreads / 32; ++k) { ta += s_sum[k]; tc += s_cnt[k]; }
+            *out_sum = ta;
+            *out_cnt = tc;
+            *ticket = 0;
+        }
     }
 }
 
