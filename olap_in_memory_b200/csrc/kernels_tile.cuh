@@ -290,6 +290,9 @@ inline int launch_up_tile(const UpMeasure* d_meas, const UpMeasure* h_meas, int 
 // in output order: linear shared-memory reads, coalesced stores.  The status plane rides
 // along as bytes.
 constexpr int kMaxBoxDims = 4;
+#ifndef OLAP_TRANSPOSE_MIN_BLOCKS
+#define OLAP_TRANSPOSE_MIN_BLOCKS 6  // <= 42 registers: 6 CTAs per SM keep more loads in flight (8 spills too much: measured slower)
+#endif
 
 struct BoxDim {
     uint32_t b;         // box extent along this axis (1 = padding entry)
@@ -598,7 +601,7 @@ __device__ __forceinline__ void transpose_phases(const TransposeParams& p, const
 }
 
 template <int NB>
-__global__ void __launch_bounds__(256) transpose_kernel(const __grid_constant__ TransposeParams p) {
+__global__ void __launch_bounds__(256, OLAP_TRANSPOSE_MIN_BLOCKS) transpose_kernel(const __grid_constant__ TransposeParams p) {
     extern __shared__ __align__(16) unsigned char smem_t[];
     __shared__ uint32_t s_ext[OLAP_MAX_DIMS];
     __shared__ int64_t s_base[2];
