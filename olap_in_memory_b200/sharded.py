@@ -20,8 +20,6 @@ torch.distributed is plumbing: NCCL moves the planes (zero-copy views of the dev
 stores, olap_in_memory_b200/interop.py); every arithmetic step is a store call."""
 from __future__ import annotations
 
-import math
-
 import numpy as np
 
 from .cube import Cube  # noqa: F401  (re-exported for convenience)
@@ -68,8 +66,6 @@ class _Comm:
             self.dist.all_to_all_single(out, inp, out_splits, in_splits, group=self.group)
             return
         # gloo has no all_to_all: pairwise exchange
-        import torch
-
         in_off = np.concatenate([[0], np.cumsum(in_splits)])
         out_off = np.concatenate([[0], np.cumsum(out_splits)])
         reqs = []
@@ -85,7 +81,6 @@ class _Comm:
                 reqs.append(self.dist.irecv(dst, peer, group=self.group))
         for r in reqs:
             r.wait()
-        del torch
 
     def all_to_all_many(self, pairs, out_splits, in_splits):
         """Exchange several planes that share the same split sizes.  One NCCL all-to-all per
@@ -278,8 +273,6 @@ class ShardedCube:
 
     def _drill_up_sharded(self, new_dims, idx, group_map, ids, methods):
         """The drilled dimension is (part of) the sharded row axis."""
-        import torch
-
         new_prefix_lens = [d.numItems for d in new_dims[: self.prefix]]
         new_rows_total = _prod(new_prefix_lens)
         out_bounds = split_rows(new_rows_total, self.world)
@@ -343,7 +336,6 @@ class ShardedCube:
             else:
                 out.storedMeasures[m] = combined[k]
                 k += 1
-        del torch
         return out
 
     def _partials(self, stores, old_len, new_len, maps, methods):
