@@ -108,7 +108,8 @@ class COracleStore:
 
     @data.setter
     def data(self, values):
-        arr = np.ascontiguousarray(values, dtype=np.float64)
+        d = float(self._defaultValue)  # undefined / null unset the cell (in-memory.js:124-125)
+        arr = np.fromiter((d if v is None else v for v in values), dtype=np.float64, count=len(values))
         if lib().ostore_set_data(self._h, arr.ctypes.data, arr.size) != 0:
             raise ValueError(f"value length is invalid: {self._size} !== {arr.size}")
 
@@ -172,3 +173,58 @@ class COracleStore:
     def load_lowered(self, other, my_len, his_len, his_to_mine):
         alive, ptrs = _maps([[-1 if v is None else v for v in m] for m in his_to_mine])
         lib().ostore_load(self._h, other._h, len(my_len), _i64(my_len), _i64(his_len), ptrs)
+
+    # ---- the reference's dimension-object interface (in-memory.js:139-430), lowered like
+    # ---- the device store lowers it, so that Cube(dims, store_cls=COracleStore) runs the
+    # ---- reference algorithm in C (bench_cube_benchmark.py's CPU column)
+    @property
+    def byteLength(self):
+        return self._size * (8 if self._type == "float64" else 4)
+
+    @property
+    def _dataMap(self):
+        keys, vals = self.entries()
+        return dict(zip(keys.tolist(), vals.tolist()))
+
+    @property
+    def status(self):
+        present = set(self.entries()[0].tolist())
+        return [2 if i in present else 1 for i in range(self._size)]
+
+    def reorder(self, oldDimensions, newDimensions):
+        return self.reorder_lowered([d.numItems for d in oldDimensions],
+                                    [next(i for i, d in enumerate(oldDimensions) if d is nd) for nd in newDimensions])
+
+    def dice(self, oldDimensions, newDimensions):
+        keep = []
+        for i, new_dim in enumerate(newDimensions):
+            old_idx = oldDimensions[i].getItemsToIdx()
+            keep.append([old_idx[item] for item in new_dim.getItems()])
+        return self.dice_lowered([d.numItems for d in oldDimensions], keep)
+
+    def drillUp(self, oldDimensions, newDimensions, method="sum"):
+        maps = [oldDimensions[i].getGroupIndexFromRootIndexMap(nd.rootAttribute) for i, nd in enumerate(newDimensions)]
+        return self.drillUp_lowered([d.numItems for d in oldDimensions], [d.numItems for d in newDimensions], maps, method)
+
+    def drillDown(self, oldDimensions, newDimensions, method="sum", distributions=None):
+        maps = [newDimensions[i].getGroupIndexFromRootIndexMap(od.rootAttribute) for i, od in enumerate(oldDimensions)]
+        return self.drillDown_lowered([d.numItems for d in oldDimensions], [d.numItems for d in newDimensions], maps,
+                                      method, distributions)
+
+    def load(self, otherStore, myDimensions, hisDimensions):
+        his_to_mine = []
+        for i, his in enumerate(hisDimensions):
+            mine = myDimensions[i].getItemsToIdx()
+            his_to_mine.append([mine.get(item) for item in his.getItems()])
+        self.load_lowered(otherStore, [d.numItems for d in myDimensions], [d.numItems for d in hisDimensions], his_to_mine)
+
+    @staticmethod
+    def evaluate(expression, cell_names, stores, totals, size):
+        cols = [s.data_f64() for s in stores]
+        params = dict(totals)
+        out = [0.0] * size
+        for i in range(size):
+            for name, col in zip(cell_names, cols):
+                params[name] = col[i]
+            out[i] = expression.evaluate(params)
+        return out
