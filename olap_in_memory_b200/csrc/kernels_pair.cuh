@@ -1,0 +1,352 @@
+// Reorder (in-memory.js:178-211) when the innermost axis moves and the cube offers two
+// DISJOINT axis groups of >= 32 cells: the input's trailing axes (a contiguous INPUT run of A
+// cells) and the output's trailing axes (a contiguous OUTPUT run of B cells).  A CTA owns the
+// A x B tile spanned by the two groups (every other axis has extent 1):
+//
+//   phase 1  every thread owns 4x4 micro-tiles: four 128-bit loads along four input runs (and
+//            four 32-bit loads of their status bytes), a register transpose (free for floats,
+//            8 PRMT for the bytes) and four 128-bit / 32-bit shared-memory stores into an
+//            OUTPUT-ordered tile  s[i & 3][i >> 2][j]  (pitch 4*odd: conflict-free);
+//   phase 2  128-bit shared-memory loads along j, 128-bit coalesced stores along output runs.
+//
+// ~3 thread-instructions per cell instead of ~70 for the generic box kernel, every global
+// access is 16 bytes per lane, every run a contiguous span.  CTAs are numbered so that
+// neighbours in the input's memory order (and then in the output's) run at the same time:
+// runs that start or end inside a DRAM atom share it through L2 instead of fetching it twice.
+// Needs run lengths and strides that are multiples of 4 cells; everything else stays on
+// transpose_kernel (kernels_tile.cuh).
+#pragma once
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_gather.cuh"
+
+namespace olap {
+
+struct PairParams {
+    const GatherMeasure* meas;
+    uint32_t A, B;            // cells of a full tile along the input run / output run
+    uint32_t nIg, nJq;        // A / 4, B / 4
+    FastDiv div_nIg, div_nJq;
+    uint32_t PB;              // shared-memory pitch of one [k][ig] row, cells (4 * odd)
+    const uint32_t* src_row;  // [B] tile-relative source offset / 4 of output-run position j
+    const uint32_t* dst_row;  // [A] tile-relative destination offset / 4 of input-run position i
+    int in_axis, out_axis;    // grid slot of the partially covered axis of each group, or -1
+    uint32_t in_mult, out_mult;  // cells of the fully covered axes of the group
+    // grid decomposition: slots in traversal order, the LAST slot varies fastest
+    int n_axes;
+    uint32_t boxes[OLAP_MAX_DIMS];
+    FastDiv div_boxes[OLAP_MAX_DIMS];
+    uint32_t len[OLAP_MAX_DIMS], bsize[OLAP_MAX_DIMS];
+    int64_t src_stride[OLAP_MAX_DIMS], dst_stride[OLAP_MAX_DIMS];
+    uint32_t st_offset, tab_offset;  // byte offsets of the status tile / the staged tables
+};
+
+struct PairPlan {
+    bool use = false;
+    PairParams p{};
+    int64_t n_boxes = 0;
+    size_t smem = 0;
+    std::vector<uint32_t> src_row, dst_row;
+};
+
+// Memory accessors: the device flavour streams through L1; the host flavour lets
+// tests/host/plan_check.cu run the very same phase code on the CPU.
+struct PairDevMem {
+    static __device__ __forceinline__ float4 ld4(const float* q) { return ld_stream4(q); }
+    static __device__ __forceinline__ uint32_t ld_u32(const uint8_t* q) { return ld_stream_u32(q); }
+    static __device__ __forceinline__ void st4(float* q, float4 v) { st_stream4(q, v); }
+};
+struct PairHostMem {
+    static __host__ __device__ float4 ld4(const float* q) { return *reinterpret_cast<const float4*>(q); }
+    static __host__ __device__ uint32_t ld_u32(const uint8_t* q) { return *reinterpret_cast<const uint32_t*>(q); }
+    static __host__ __device__ void st4(float* q, float4 v) { *reinterpret_cast<float4*>(q) = v; }
+};
+// PRMT: byte n of the result is byte (sel >> 4n & 7) of {x, y}
+__host__ __device__ __forceinline__ uint32_t pair_prmt(uint32_t x, uint32_t y, uint32_t sel) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(x, y, sel);
+#else
+    const uint64_t xy = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int n = 0; n < 4; ++n) r |= (uint32_t)((xy >> (8 * ((sel >> (4 * n)) & 7))) & 0xff) << (8 * n);
+    return r;
+#endif
+}
+
+// Which tile is block `block`: source / destination base offsets and the valid run lengths.
+__host__ __device__ __forceinline__ void pair_decode(const PairParams& p, uint32_t block, int64_t& src, int64_t& dst,
+                                                     uint32_t& a_eff, uint32_t& b_eff) {
+    uint32_t rest = block;
+    a_eff = p.A;
+    b_eff = p.B;
+    src = dst = 0;
+    for (int a = p.n_axes - 1; a >= 0; --a) {
+        const uint32_t q = p.div_boxes[a].div(rest);
+        const uint32_t bi = rest - q * p.boxes[a];
+        rest = q;
+        const uint32_t start = bi * p.bsize[a];
+        src += (int64_t)start * p.src_stride[a];
+        dst += (int64_t)start * p.dst_stride[a];
+        const uint32_t rem = p.len[a] - start, e = p.bsize[a] < rem ? p.bsize[a] : rem;
+        if (a == p.in_axis) a_eff = e * p.in_mult;
+        if (a == p.out_axis) b_eff = e * p.out_mult;
+    }
+}
+
+// ---- phase 1: 4 input runs x 4 cells per micro-tile -> output-ordered shared tile
+template <bool STATUS, class Mem>
+__host__ __device__ __forceinline__ void pair_phase1(const PairParams& p, uint32_t tid, const float* src,
+                                                     const uint8_t* st_src, float* s_val, uint8_t* s_st,
+                                                     const uint32_t* s_src_row, uint32_t n_ig, uint32_t n_jq) {
+    const uint32_t plane = p.nIg * p.PB;
+    const uint32_t n_mt = p.nIg * p.nJq;
+    for (uint32_t mt = tid; mt < n_mt; mt += 256) {
+        const uint32_t jg = p.div_nIg.div(mt), ig = mt - jg * p.nIg;
+        if (ig < n_ig && jg < n_jq) {
+            const uint4 ro = *reinterpret_cast<const uint4*>(s_src_row + 4 * jg);
+            const size_t o0 = ((size_t)ro.x + ig) << 2, o1 = ((size_t)ro.y + ig) << 2;
+            const size_t o2 = ((size_t)ro.z + ig) << 2, o3 = ((size_t)ro.w + ig) << 2;
+            const float4 v0 = Mem::ld4(src + o0), v1 = Mem::ld4(src + o1);
+            const float4 v2 = Mem::ld4(src + o2), v3 = Mem::ld4(src + o3);
+            uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+            if (STATUS) {
+                b0 = Mem::ld_u32(st_src + o0); b1 = Mem::ld_u32(st_src + o1);
+                b2 = Mem::ld_u32(st_src + o2); b3 = Mem::ld_u32(st_src + o3);
+            }
+            const uint32_t sidx = ig * p.PB + 4 * jg;
+            *reinterpret_cast<float4*>(s_val + sidx) = make_float4(v0.x, v1.x, v2.x, v3.x);
+            *reinterpret_cast<float4*>(s_val + sidx + plane) = make_float4(v0.y, v1.y, v2.y, v3.y);
+            *reinterpret_cast<float4*>(s_val + sidx + 2 * plane) = make_float4(v0.z, v1.z, v2.z, v3.z);
+            *reinterpret_cast<float4*>(s_val + sidx + 3 * plane) = make_float4(v0.w, v1.w, v2.w, v3.w);
+            if (STATUS) {
+                // 4x4 byte transpose: word k collects byte k of the four rows
+                const uint32_t p01 = pair_prmt(b0, b1, 0x5140), q01 = pair_prmt(b0, b1, 0x7362);
+                const uint32_t p23 = pair_prmt(b2, b3, 0x5140), q23 = pair_prmt(b2, b3, 0x7362);
+                *reinterpret_cast<uint32_t*>(s_st + sidx) = pair_prmt(p01, p23, 0x5410);
+                *reinterpret_cast<uint32_t*>(s_st + sidx + plane) = pair_prmt(p01, p23, 0x7632);
+                *reinterpret_cast<uint32_t*>(s_st + sidx + 2 * plane) = pair_prmt(q01, q23, 0x5410);
+                *reinterpret_cast<uint32_t*>(s_st + sidx + 3 * plane) = pair_prmt(q01, q23, 0x7632);
+            }
+        }
+    }
+}
+
+// ---- phase 2: output runs, 4 cells per lane
+template <bool STATUS, class Mem>
+__host__ __device__ __forceinline__ void pair_phase2(const PairParams& p, uint32_t tid, float* dst, uint8_t* st_dst,
+                                                     const float* s_val, const uint8_t* s_st,
+                                                     const uint32_t* s_dst_row, uint32_t a_eff, uint32_t n_jq) {
+    const uint32_t n_it = p.A * p.nJq;
+    for (uint32_t it = tid; it < n_it; it += 256) {
+        const uint32_t i = p.div_nJq.div(it), jq = it - i * p.nJq;
+        if (i < a_eff && jq < n_jq) {
+            const uint32_t sidx = ((i & 3u) * p.nIg + (i >> 2)) * p.PB + 4 * jq;
+            const float4 v = *reinterpret_cast<const float4*>(s_val + sidx);
+            const size_t g = ((size_t)s_dst_row[i] + jq) << 2;
+            Mem::st4(dst + g, v);
+            if (STATUS) *reinterpret_cast<uint32_t*>(st_dst + g) = *reinterpret_cast<const uint32_t*>(s_st + sidx);
+        }
+    }
+}
+
+template <bool STATUS>
+__device__ __forceinline__ void pair_body(const PairParams& p, const GatherMeasure& m, unsigned char* smem_p,
+                                          const int64_t* s_base, const uint32_t* s_eff) {
+    float* s_val = reinterpret_cast<float*>(smem_p);
+    uint8_t* s_st = smem_p + p.st_offset;
+    const uint32_t* s_src_row = reinterpret_cast<const uint32_t*>(smem_p + p.tab_offset);
+    const uint32_t* s_dst_row = s_src_row + p.B;
+    pair_phase1<STATUS, PairDevMem>(p, threadIdx.x, m.in + s_base[0], STATUS ? m.st_in + s_base[0] : nullptr, s_val,
+                                    s_st, s_src_row, s_eff[0] >> 2, s_eff[1] >> 2);
+    __syncthreads();
+    pair_phase2<STATUS, PairDevMem>(p, threadIdx.x, m.out + s_base[1], STATUS ? m.st_out + s_base[1] : nullptr, s_val,
+                                    s_st, s_dst_row, s_eff[0], s_eff[1] >> 2);
+}
+
+__global__ void __launch_bounds__(256, 4) transpose_pair_kernel(const __grid_constant__ PairParams p) {
+    extern __shared__ __align__(16) unsigned char smem_p[];
+    __shared__ int64_t s_base[2];
+    __shared__ uint32_t s_eff[2];
+    uint32_t* s_src_row = reinterpret_cast<uint32_t*>(smem_p + p.tab_offset);
+    uint32_t* s_dst_row = s_src_row + p.B;
+    const GatherMeasure m = p.meas[blockIdx.y];
+    if (threadIdx.x == 0) pair_decode(p, blockIdx.x, s_base[0], s_base[1], s_eff[0], s_eff[1]);
+    for (uint32_t i = threadIdx.x; i < p.B; i += 256) s_src_row[i] = __ldg(p.src_row + i);
+    for (uint32_t i = threadIdx.x; i < p.A; i += 256) s_dst_row[i] = __ldg(p.dst_row + i);
+    __syncthreads();
+    if (m.st_in) pair_body<true>(p, m, smem_p, s_base, s_eff);
+    else pair_body<false>(p, m, smem_p, s_base, s_eff);
+}
+
+// `dims_in`: the output axes (outermost first) as linear GDims carrying their SOURCE strides.
+inline PairPlan transpose_pair_plan(const std::vector<GDim>& dims_in) {
+    PairPlan plan;
+    static const int force = [] { const char* e = getenv("OLAP_TRANSPOSE_PAIR"); return e ? atoi(e) : -1; }();
+    if (force == 0) return plan;
+    static const int64_t cap = [] { const char* e = getenv("OLAP_PAIR_CAP"); return e ? (int64_t)atoi(e) : (int64_t)100; }();
+    std::vector<GDim> dims;
+    for (const GDim& d : dims_in) {
+        if (!d.linear) return plan;
+        if (d.len == 1) continue;
+        if (!dims.empty() && dims.back().stride == d.len * d.stride) {
+            dims.back().len *= d.len;
+            dims.back().stride = d.stride;
+        } else dims.push_back(d);
+    }
+    const int k = (int)dims.size();
+    if (k < 2 || k > OLAP_MAX_DIMS) return plan;
+    if (dims.back().stride == 1) return plan;  // innermost axis stays: the vectorised gather streams it
+    for (const GDim& d : dims)
+        if (d.len > 0x7fffffffLL) return plan;
+    std::vector<int64_t> dst_stride(k);
+    int64_t acc = 1;
+    for (int i = k - 1; i >= 0; --i) { dst_stride[i] = acc; acc *= dims[i].len; }
+    std::vector<int> by_src(k), by_dst(k);
+    for (int i = 0; i < k; ++i) { by_src[i] = i; by_dst[i] = k - 1 - i; }
+    std::sort(by_src.begin(), by_src.end(), [&](int a, int b) { return dims[a].stride < dims[b].stride; });
+    if (dims[by_src[0]].stride != 1) return plan;
+
+    // a group: trailing axes taken whole while the run stays <= cap, then one partial axis
+    struct Group { std::vector<int> axes; int64_t mult = 1, ext = 1, run = 1; bool partial = false; };
+    auto grow = [&](const std::vector<int>& order, Group& gr) {
+        int64_t pr = 1;
+        for (int ax : order) {
+            const int64_t L = dims[ax].len;
+            if (pr * L <= cap) {
+                gr.axes.push_back(ax);
+                pr *= L;
+                gr.mult = pr;  // every axis whole so far
+                gr.ext = 1;
+                gr.partial = false;
+                if (pr >= 64) break;
+                continue;
+            }
+            // partial axis: an extent e with (pr * e) % 4 == 0 for full and ragged tiles,
+            // preferring an even split of the axis
+            const int64_t e_max = std::min<int64_t>(L, cap / pr);
+            int64_t pick = 0;
+            for (int64_t e = e_max; e >= std::max<int64_t>(1, e_max / 2); --e) {
+                if ((pr * e) % 4 || ((L % e) * pr) % 4) continue;
+                if (L % e == 0) { pick = e; break; }
+                if (!pick) pick = e;
+            }
+            if (!pick) return false;
+            if ((pr * L) % 4) return false;  // strides of the axes outside the group
+            gr.axes.push_back(ax);
+            gr.mult = pr;
+            gr.ext = pick;
+            gr.partial = true;
+            pr *= pick;
+            break;
+        }
+        gr.run = pr;
+        return pr >= 32 && pr % 4 == 0;
+    };
+    Group gi, go;
+    if (!grow(by_src, gi) || !grow(by_dst, go)) return plan;
+    for (int a : gi.axes)
+        for (int b : go.axes)
+            if (a == b) return plan;
+    if ((int)(gi.axes.size() + go.axes.size()) < k) {
+        // some axis lies outside both groups: its strides are multiples of the whole groups
+        int64_t full_i = 1, full_o = 1;
+        for (int a : gi.axes) full_i *= dims[a].len;
+        for (int a : go.axes) full_o *= dims[a].len;
+        if (full_i % 4 || full_o % 4) return plan;
+    }
+    // strides seen from the other group must keep 16-byte alignment too
+    for (int a : go.axes) if (dims[a].stride % 4) return plan;   // source rows
+    for (int a : gi.axes) if (dst_stride[a] % 4) return plan;    // destination rows
+
+    PairParams& p = plan.p;
+    p.A = (uint32_t)gi.run;
+    p.B = (uint32_t)go.run;
+    p.nIg = p.A / 4;
+    p.nJq = p.B / 4;
+    p.div_nIg = FastDiv(p.nIg);
+    p.div_nJq = FastDiv(p.nJq);
+    uint32_t pq = p.nJq | 1u;  // odd number of 16-byte chunks per row
+    p.PB = pq * 4;
+    // extent of every axis inside the tile
+    std::vector<int64_t> b(k, 1);
+    for (size_t q = 0; q < gi.axes.size(); ++q) b[gi.axes[q]] = (gi.partial && q + 1 == gi.axes.size()) ? gi.ext : dims[gi.axes[q]].len;
+    for (size_t q = 0; q < go.axes.size(); ++q) b[go.axes[q]] = (go.partial && q + 1 == go.axes.size()) ? go.ext : dims[go.axes[q]].len;
+    // tables: position along a group -> offset on the OTHER side, in units of 4 cells
+    auto table = [&](const Group& gr, bool src_side, std::vector<uint32_t>& tab) {
+        tab.resize((size_t)gr.run);
+        for (int64_t pos = 0; pos < gr.run; ++pos) {
+            int64_t t = pos, off = 0;
+            for (int ax : gr.axes) {
+                const int64_t c = t % b[ax];
+                t /= b[ax];
+                off += c * (src_side ? dims[ax].stride : dst_stride[ax]);
+            }
+            if (off % 4 || off / 4 > 0xffffffffLL) return false;
+            tab[(size_t)pos] = (uint32_t)(off / 4);
+        }
+        return true;
+    };
+    if (!table(go, true, plan.src_row) || !table(gi, false, plan.dst_row)) return plan;
+    // traversal order of the grid: fastest = the axis along which tiles are neighbours in the
+    // input, then the one along which they are neighbours in the output, then the rest
+    std::vector<int> order;  // fastest first
+    auto boxes_of = [&](int ax) { return ceil_div(dims[ax].len, b[ax]); };
+    static const int order_knob = [] { const char* e = getenv("OLAP_PAIR_ORDER"); return e ? atoi(e) : 0; }();
+    if (order_knob == 0)
+    for (int ax : by_src) if (boxes_of(ax) > 1) { order.push_back(ax); break; }
+    if (order_knob == 0 || order_knob == 2)
+    for (int ax : by_dst) if (boxes_of(ax) > 1 && std::find(order.begin(), order.end(), ax) == order.end()) { order.push_back(ax); break; }
+    if (order_knob == 2)
+        for (int ax : by_src) if (boxes_of(ax) > 1 && std::find(order.begin(), order.end(), ax) == order.end()) { order.push_back(ax); break; }
+    for (int ax : by_dst) if (std::find(order.begin(), order.end(), ax) == order.end()) order.push_back(ax);
+    p.n_axes = k;
+    p.in_axis = p.out_axis = -1;
+    int64_t n_boxes = 1;
+    for (int q = 0; q < k; ++q) {
+        const int ax = order[q], slot = k - 1 - q;
+        p.len[slot] = (uint32_t)dims[ax].len;
+        p.bsize[slot] = (uint32_t)b[ax];
+        p.boxes[slot] = (uint32_t)boxes_of(ax);
+        p.div_boxes[slot] = FastDiv(p.boxes[slot]);
+        p.src_stride[slot] = dims[ax].stride;
+        p.dst_stride[slot] = dst_stride[ax];
+        n_boxes *= p.boxes[slot];
+        if (gi.partial && ax == gi.axes.back()) p.in_axis = slot;
+        if (go.partial && ax == go.axes.back()) p.out_axis = slot;
+    }
+    p.in_mult = (uint32_t)gi.mult;
+    p.out_mult = (uint32_t)go.mult;
+    if (!gi.partial) p.in_mult = p.A;
+    if (!go.partial) p.out_mult = p.B;
+    if (n_boxes > 0x7fffffffLL) return plan;
+    plan.n_boxes = n_boxes;
+    const size_t cells = (size_t)p.A * p.PB;
+    p.st_offset = (uint32_t)(cells * 4);
+    p.tab_offset = (uint32_t)(p.st_offset + ((cells + 15) & ~(size_t)15));
+    plan.smem = p.tab_offset + ((size_t)p.A + p.B) * sizeof(uint32_t);
+    if (plan.smem > 100 * 1024) return plan;
+    plan.use = true;
+    return plan;
+}
+
+inline int launch_transpose_pair(const GatherMeasure* d_meas, const uint32_t* d_src_row, const uint32_t* d_dst_row,
+                                 int n, PairPlan& plan) {
+    plan.p.meas = d_meas;
+    plan.p.src_row = d_src_row;
+    plan.p.dst_row = d_dst_row;
+    static bool attr_set = false;
+    if (!attr_set) {
+        OLAP_CUDA(cudaFuncSetAttribute(transpose_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    const dim3 grid((unsigned)plan.n_boxes, (unsigned)n);
+    mark_kernels_begin();
+    transpose_pair_kernel<<<grid, 256, plan.smem, g.stream>>>(plan.p);
+    ++g_launches;
+    return OLAP_OK;
+}
+
+}  // namespace olap

@@ -850,16 +850,32 @@ inline TransposePlan transpose_plan(const std::vector<GDim>& dims_in) {
             if (!in_run) p.rd_vec4 = 0;
         }
     p.n_axes = k;
-    int64_t n_boxes = 1;
-    for (int i = 0; i < k; ++i) {
-        p.len[i] = (uint32_t)dims[i].len;
-        p.bsize[i] = (uint32_t)b[i];
-        p.boxes[i] = (uint32_t)ceil_div(dims[i].len, b[i]);
-        p.div_boxes[i] = FastDiv(p.boxes[i]);
-        p.src_stride[i] = dims[i].stride;
-        p.dst_stride[i] = dst_stride[i];
-        n_boxes *= p.boxes[i];
+    // grid slots in traversal order (the LAST slot varies fastest): boxes that are neighbours in
+    // the input's memory order run back to back, then neighbours in the output's order, so runs
+    // that begin or end inside a DRAM atom share it through L2 (OLAP_BOX_ORDER=0: output order)
+    static const bool neighbour_order = [] { const char* e = getenv("OLAP_BOX_ORDER"); return !e || atoi(e) != 0; }();
+    std::vector<int> order;  // fastest first
+    if (neighbour_order) {
+        for (int ax : by_src) if (b[ax] < dims[ax].len) { order.push_back(ax); break; }
+        for (int ax = k - 1; ax >= 0; --ax)
+            if (b[ax] < dims[ax].len && std::find(order.begin(), order.end(), ax) == order.end()) { order.push_back(ax); break; }
     }
+    for (int ax = k - 1; ax >= 0; --ax) if (std::find(order.begin(), order.end(), ax) == order.end()) order.push_back(ax);
+    std::vector<uint32_t> slot_of(k);
+    int64_t n_boxes = 1;
+    for (int q = 0; q < k; ++q) {
+        const int i = order[q], slot = k - 1 - q;
+        slot_of[i] = (uint32_t)slot;
+        p.len[slot] = (uint32_t)dims[i].len;
+        p.bsize[slot] = (uint32_t)b[i];
+        p.boxes[slot] = (uint32_t)ceil_div(dims[i].len, b[i]);
+        p.div_boxes[slot] = FastDiv(p.boxes[slot]);
+        p.src_stride[slot] = dims[i].stride;
+        p.dst_stride[slot] = dst_stride[i];
+        n_boxes *= p.boxes[slot];
+    }
+    for (size_t q = 0; q < rd.size(); ++q) p.rd[q].axis = slot_of[p.rd[q].axis];
+    for (size_t q = 0; q < wr.size(); ++q) p.wr[q].axis = slot_of[p.wr[q].axis];
     if (n_boxes > 0x7fffffffLL) return plan;
     plan.n_boxes = n_boxes;
     p.st_offset = (uint32_t)((s_cells * 4 + 15) & ~(size_t)15);

@@ -13,6 +13,7 @@
 #include "kernels_drillup.cuh"
 #include "kernels_gather.cuh"
 #include "kernels_store.cuh"
+#include "kernels_pair.cuh"
 #include "kernels_tile.cuh"
 
 namespace olap {
@@ -1164,8 +1165,19 @@ int olap_reorder(olap_store* const* src, int n, int ndim, const int64_t* old_len
     const char* path = "reorder/empty";
     if (size) {
         auto meas = gather_measures(src, out, n);
-        TransposePlan tp = transpose_plan(dims);
-        if (tp.use) {
+        PairPlan pp = transpose_pair_plan(dims);
+        TransposePlan tp;
+        if (!pp.use) tp = transpose_plan(dims);
+        if (pp.use) {
+            path = "reorder/pair-transpose";
+            TablePack t;
+            const size_t o_meas = t.add(meas.data(), sizeof(GatherMeasure) * n);
+            const size_t o_src = t.add(pp.src_row.data(), pp.src_row.size() * sizeof(uint32_t));
+            const size_t o_dst = t.add(pp.dst_row.data(), pp.dst_row.size() * sizeof(uint32_t));
+            OLAP_TRY(t.upload());
+            OLAP_TRY(launch_transpose_pair(t.ptr<GatherMeasure>(o_meas), t.ptr<uint32_t>(o_src), t.ptr<uint32_t>(o_dst), n, pp));
+            OLAP_TRY(t.release());
+        } else if (tp.use) {
             path = "reorder/box-transpose";
             TablePack t;
             const size_t o_meas = t.add(meas.data(), sizeof(GatherMeasure) * n);

@@ -180,7 +180,11 @@ def reorder_cases(seed=3):
     # big enough for several (ragged) boxes of the tiled transpose
     for dims, perm in (([130, 70], [1, 0]), ([37, 50, 3, 70], [3, 2, 1, 0]), ([37, 50, 3, 70], [1, 3, 0, 2]),
                        ([20, 30, 10, 10], [3, 2, 1, 0]), ([9, 300, 11], [2, 0, 1]), ([64, 64, 8], [0, 2, 1]),
-                       ([3, 5000], [1, 0]), ([10, 10, 10, 10, 10], [4, 3, 2, 1, 0])):
+                       ([3, 5000], [1, 0]), ([10, 10, 10, 10, 10], [4, 3, 2, 1, 0]),
+                       # two disjoint 4-aligned axis groups: the pair transpose, ragged tiles included
+                       ([100, 104], [1, 0]), ([332, 100], [1, 0]), ([12, 32, 32, 44], [3, 2, 1, 0]),
+                       ([52, 7, 92], [2, 1, 0]), ([44, 4, 25, 8], [3, 2, 1, 0]), ([20, 12, 10, 10, 10], [4, 3, 1, 2, 0]),
+                       ([72, 200, 12], [2, 0, 1]), ([8, 8, 8, 8, 8], [2, 4, 0, 3, 1])):
         for default in (0.0, math.nan):
             n = int(np.prod(dims))
             yield dict(op="reorder", old_len=list(dims), new_to_old=list(perm), default=default,

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <numeric>
 
+#include "../../olap_in_memory_b200/csrc/kernels_pair.cuh"
 #include "../../olap_in_memory_b200/csrc/kernels_tile.cuh"
 
 namespace olap {
@@ -45,8 +46,82 @@ static int check_perm(const std::vector<int64_t>& len, const std::vector<int>& p
     return 0;
 }
 
+// Run transpose_pair_kernel's own phase code on the CPU (PairHostMem) and compare with the
+// plain permutation: checks the planner's tables, the grid order, ragged tiles and the 4x4
+// micro-tile addressing without a GPU.  Returns -1 when the pair planner declines the shape.
+static int emulate_pair(const std::vector<int64_t>& len, const std::vector<int>& perm) {
+    const int k = (int)len.size();
+    std::vector<int64_t> stride(k), out_len(k), out_stride(k);
+    int64_t acc = 1;
+    for (int i = k - 1; i >= 0; --i) { stride[i] = acc; acc *= len[i]; }
+    const int64_t N = acc;
+    std::vector<GDim> dims(k);
+    for (int i = 0; i < k; ++i) { dims[i].len = len[perm[i]]; dims[i].linear = true; dims[i].stride = stride[perm[i]]; out_len[i] = len[perm[i]]; }
+    PairPlan plan = transpose_pair_plan(dims);
+    if (!plan.use) return -1;
+    PairParams& p = plan.p;
+    if (p.A % 4 || p.B % 4 || (p.PB / 4) % 2 == 0 || p.PB < p.B || plan.smem > 100 * 1024) { printf("pair geometry\n"); return 1; }
+    if (N > (1 << 24)) return 0;  // geometry only
+    p.src_row = plan.src_row.data();
+    p.dst_row = plan.dst_row.data();
+    // 16-byte aligned planes
+    std::vector<float4> in4((N + 3) / 4 + 1), out4((N + 3) / 4 + 1);
+    std::vector<uint32_t> sti((N + 3) / 4 + 1), sto((N + 3) / 4 + 1, 0xeeeeeeeeu);
+    float* in = reinterpret_cast<float*>(in4.data());
+    float* out = reinterpret_cast<float*>(out4.data());
+    uint8_t* st_in = reinterpret_cast<uint8_t*>(sti.data());
+    uint8_t* st_out = reinterpret_cast<uint8_t*>(sto.data());
+    for (int64_t i = 0; i < N; ++i) { in[i] = (float)i; out[i] = -1.0f; st_in[i] = (uint8_t)(i * 7 + 3); }
+    std::vector<float4> smem(plan.smem / 16 + 1);
+    unsigned char* sm = reinterpret_cast<unsigned char*>(smem.data());
+    float* s_val = reinterpret_cast<float*>(sm);
+    uint8_t* s_st = sm + p.st_offset;
+    uint32_t* s_src_row = reinterpret_cast<uint32_t*>(sm + p.tab_offset);
+    uint32_t* s_dst_row = s_src_row + p.B;
+    for (uint32_t i = 0; i < p.B; ++i) s_src_row[i] = p.src_row[i];
+    for (uint32_t i = 0; i < p.A; ++i) s_dst_row[i] = p.dst_row[i];
+    for (int64_t box = 0; box < plan.n_boxes; ++box) {
+        int64_t sb, db;
+        uint32_t a_eff, b_eff;
+        pair_decode(p, (uint32_t)box, sb, db, a_eff, b_eff);
+        if (a_eff % 4 || b_eff % 4 || sb % 4 || db % 4) { printf("pair alignment\n"); return 1; }
+        for (uint32_t tid = 0; tid < 256; ++tid)
+            pair_phase1<true, PairHostMem>(p, tid, in + sb, st_in + sb, s_val, s_st, s_src_row, a_eff >> 2, b_eff >> 2);
+        for (uint32_t tid = 0; tid < 256; ++tid)
+            pair_phase2<true, PairHostMem>(p, tid, out + db, st_out + db, s_val, s_st, s_dst_row, a_eff, b_eff >> 2);
+    }
+    // expected: out[new index] = in[sum coord * source stride]
+    std::vector<int64_t> c(k, 0);
+    for (int64_t o = 0; o < N; ++o) {
+        int64_t srci = 0;
+        for (int i = 0; i < k; ++i) srci += c[i] * dims[i].stride;
+        if (out[o] != in[srci] || st_out[o] != st_in[srci]) { printf("pair mismatch at %lld\n", (long long)o); return 1; }
+        for (int i = k - 1; i >= 0; --i) { if (++c[i] < out_len[i]) break; c[i] = 0; }
+    }
+    return 0;
+}
+
 int main() {
-    int bad = 0, n = 0;
+    int bad = 0, n = 0, n_pair = 0;
+    {
+        const std::vector<std::vector<int64_t>> pshapes = {
+            {20, 20, 20, 10, 10, 10}, {100, 100, 100, 10, 10, 10}, {64, 64}, {128, 36}, {36, 128}, {100, 104}, {3652, 32, 32},
+            {12, 32, 32, 44}, {8, 8, 8, 8, 8}, {4, 100, 4, 100}, {1000, 1000}, {72, 200, 12}, {10, 10, 10, 10, 10, 10}, {332, 100},
+            {52, 7, 92}, {44, 4, 25, 8}};
+        for (const auto& len : pshapes) {
+            std::vector<int> perm(len.size());
+            std::iota(perm.begin(), perm.end(), 0);
+            int count = 0;
+            do {
+                const int r = emulate_pair(len, perm);
+                if (r > 0) ++bad;
+                if (r == 0) ++n_pair;
+                ++n;
+            } while (std::next_permutation(perm.begin(), perm.end()) && ++count < 130);
+        }
+        printf("pair transposes emulated: %d\n", n_pair);
+        if (n_pair < 20) { printf("pair planner declined almost everything\n"); ++bad; }
+    }
     const std::vector<std::vector<int64_t>> shapes = {
         {100, 100, 100, 10, 10, 10}, {3, 5000}, {5000, 3}, {7, 11, 13}, {2, 2, 2, 2, 2, 2, 2, 2}, {1000, 1000},
         {64, 64, 8}, {9, 300, 11}, {37, 50, 3, 70}, {3, 3}, {129, 3, 257}, {10, 10, 10, 10, 10, 10, 10, 10, 10},

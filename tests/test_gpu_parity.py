@@ -224,6 +224,8 @@ def test_kernel_paths_are_the_intended_ones():
     G.reorder_lowered([s], [64, 40, 64], [1, 0, 2])
     assert path() == "gather/vec4"
     G.reorder_lowered([s], [64, 40, 64], [2, 1, 0])
+    assert path() == "reorder/pair-transpose"
+    G.reorder_lowered([G(63 * 40 * 65, "float32", 0)], [63, 40, 65], [2, 1, 0])
     assert path() == "reorder/box-transpose"
     G.dice_lowered([s], [64, 40, 64], [ident(64), np.arange(0, 40, 2, dtype=np.int32), ident(64)])
     assert path() == "gather/vec4"
