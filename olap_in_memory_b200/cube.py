@@ -265,17 +265,29 @@ class Cube:
     def getNestedObject(self, measureId, withTotals=False):
         if not withTotals or len(self.dimensions) == 0:
             return formatter.toNestedObject(self.getData(measureId), None, self.dimensions)
-        result = {}
-        for mask in range(2 ** len(self.dimensions)):
-            sub = self
-            for i, dim in enumerate(self.dimensions):
-                if mask & (1 << i):
-                    sub = sub.drillUp(dim.id, "all")
-            _deep_merge(result, sub.getNestedObject(measureId, False))
-        return result
+        return self.getNestedObjects([measureId], True)[measureId]
+
+    def _totals_lattice(self):
+        """Every sub-cube of cube.js:429-439 / 454-462 (dimension i rolled up to 'all' iff bit
+        i of the mask is set), each computed ONCE: the reference rebuilds mask j from the full
+        cube (D * 2^(D-1) store passes); its chain for j is the chain for j without its highest
+        bit followed by one more drillUp, so walking the masks as a tree gives the same
+        operations in the same order with 2^D - 1 passes over ever smaller stores."""
+        def walk(cube, mask, start):
+            yield mask, cube
+            for i in range(start, len(self.dimensions)):
+                yield from walk(cube.drillUp(self.dimensions[i].id, "all"), mask | (1 << i), i + 1)
+
+        return walk(self, 0, 0)
 
     def getNestedObjects(self, measureIds, withTotals=False):
-        return {m: self.getNestedObject(m, withTotals) for m in measureIds}
+        if not withTotals or len(self.dimensions) == 0:
+            return {m: formatter.toNestedObject(self.getData(m), None, self.dimensions) for m in measureIds}
+        parts = {mask: {m: sub.getNestedObject(m, False) for m in measureIds} for mask, sub in self._totals_lattice()}
+        result = {}
+        for mask in sorted(parts):  # merge in the reference's order (ascending mask)
+            _deep_merge(result, parts[mask])
+        return result
 
     def setNestedObject(self, measureId, value):
         self.setData(measureId, formatter.fromNestedObject(value, self.dimensions))
