@@ -111,6 +111,20 @@ def main():
     run(f"drillup/time-inner day->all sum [{I},3652,1]",
         lambda: GpuStore.drillUp_lowered([s], [I, 3652], [I, 1], [ident(I), np.zeros(3652, np.int32)], ["sum"]),
         B * (3652 + 1) * I, 3652 * I)
+    # long rows, few parents (drillup/long): collapse of the whole cube, 100 000 customers -> 8 segments
+    nL = 3652 * I
+    run(f"drillup/long collapse sum [1,{nL},1]",
+        lambda: GpuStore.drillUp_lowered([s], [nL], [1], [np.zeros(nL, np.int32)], ["sum"]), B * (nL + 1), nL)
+    run(f"drillup/long collapse first [1,{nL},1]",
+        lambda: GpuStore.drillUp_lowered([s], [nL], [1], [np.zeros(nL, np.int32)], ["first"]), B * (nL + 1), nL)
+    del s
+    Oc, Cc = nL // 100000, 100000
+    s = store(Oc * Cc, 0.0)
+    seg8 = np.random.default_rng(0).integers(0, 8, Cc).astype(np.int32)
+    run(f"drillup/long customers->segment sum [{Oc},{Cc},1]",
+        lambda: GpuStore.drillUp_lowered([s], [Oc, Cc], [Oc, 8], [ident(Oc), seg8], ["sum"]), B * (Cc + 8) * Oc, Cc * Oc)
+    run(f"drillup/long customers->segment average [{Oc},{Cc},1]",
+        lambda: GpuStore.drillUp_lowered([s], [Oc, Cc], [Oc, 8], [ident(Oc), seg8], ["average"]), B * (Cc + 8) * Oc, Cc * Oc)
     del s
     # univac-style: 10-item generic dims, 1e9 cells at scale 1 (identity axes are split so
     # that no map is longer than 1e4 entries)

@@ -96,41 +96,52 @@ __host__ __device__ __forceinline__ void pair_decode(const PairParams& p, uint32
     }
 }
 
-// ---- phase 1: 4 input runs x 4 cells per micro-tile -> output-ordered shared tile
+// ---- phase 1: one 4x4 micro-tile per thread.  The loads (four input runs x 4 cells, and
+// their status bytes) land in registers, so a persistent CTA can issue the NEXT tile's loads
+// before it drains the current tile from shared memory: loads stay in flight all the time.
+struct PairRegs {
+    float4 v0, v1, v2, v3;
+    uint32_t b0, b1, b2, b3;
+    uint32_t sidx;  // shared-memory index of the micro-tile, or 0xffffffff: nothing loaded
+};
+
 template <bool STATUS, class Mem>
-__host__ __device__ __forceinline__ void pair_phase1(const PairParams& p, uint32_t tid, const float* src,
-                                                     const uint8_t* st_src, float* s_val, uint8_t* s_st,
-                                                     const uint32_t* s_src_row, uint32_t n_ig, uint32_t n_jq) {
-    const uint32_t plane = p.nIg * p.PB;
-    const uint32_t n_mt = p.nIg * p.nJq;
-    for (uint32_t mt = tid; mt < n_mt; mt += 256) {
-        const uint32_t jg = p.div_nIg.div(mt), ig = mt - jg * p.nIg;
-        if (ig < n_ig && jg < n_jq) {
-            const uint4 ro = *reinterpret_cast<const uint4*>(s_src_row + 4 * jg);
-            const size_t o0 = ((size_t)ro.x + ig) << 2, o1 = ((size_t)ro.y + ig) << 2;
-            const size_t o2 = ((size_t)ro.z + ig) << 2, o3 = ((size_t)ro.w + ig) << 2;
-            const float4 v0 = Mem::ld4(src + o0), v1 = Mem::ld4(src + o1);
-            const float4 v2 = Mem::ld4(src + o2), v3 = Mem::ld4(src + o3);
-            uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-            if (STATUS) {
-                b0 = Mem::ld_u32(st_src + o0); b1 = Mem::ld_u32(st_src + o1);
-                b2 = Mem::ld_u32(st_src + o2); b3 = Mem::ld_u32(st_src + o3);
-            }
-            const uint32_t sidx = ig * p.PB + 4 * jg;
-            *reinterpret_cast<float4*>(s_val + sidx) = make_float4(v0.x, v1.x, v2.x, v3.x);
-            *reinterpret_cast<float4*>(s_val + sidx + plane) = make_float4(v0.y, v1.y, v2.y, v3.y);
-            *reinterpret_cast<float4*>(s_val + sidx + 2 * plane) = make_float4(v0.z, v1.z, v2.z, v3.z);
-            *reinterpret_cast<float4*>(s_val + sidx + 3 * plane) = make_float4(v0.w, v1.w, v2.w, v3.w);
-            if (STATUS) {
-                // 4x4 byte transpose: word k collects byte k of the four rows
-                const uint32_t p01 = pair_prmt(b0, b1, 0x5140), q01 = pair_prmt(b0, b1, 0x7362);
-                const uint32_t p23 = pair_prmt(b2, b3, 0x5140), q23 = pair_prmt(b2, b3, 0x7362);
-                *reinterpret_cast<uint32_t*>(s_st + sidx) = pair_prmt(p01, p23, 0x5410);
-                *reinterpret_cast<uint32_t*>(s_st + sidx + plane) = pair_prmt(p01, p23, 0x7632);
-                *reinterpret_cast<uint32_t*>(s_st + sidx + 2 * plane) = pair_prmt(q01, q23, 0x5410);
-                *reinterpret_cast<uint32_t*>(s_st + sidx + 3 * plane) = pair_prmt(q01, q23, 0x7632);
-            }
+__host__ __device__ __forceinline__ void pair_load(const PairParams& p, uint32_t tid, const float* src,
+                                                   const uint8_t* st_src, const uint32_t* s_src_row, uint32_t n_ig,
+                                                   uint32_t n_jq, PairRegs& r) {
+    const uint32_t jg = p.div_nIg.div(tid), ig = tid - jg * p.nIg;
+    r.sidx = 0xffffffffu;
+    if (ig < n_ig && jg < n_jq) {
+        const uint4 ro = *reinterpret_cast<const uint4*>(s_src_row + 4 * jg);
+        const size_t o0 = ((size_t)ro.x + ig) << 2, o1 = ((size_t)ro.y + ig) << 2;
+        const size_t o2 = ((size_t)ro.z + ig) << 2, o3 = ((size_t)ro.w + ig) << 2;
+        r.v0 = Mem::ld4(src + o0); r.v1 = Mem::ld4(src + o1);
+        r.v2 = Mem::ld4(src + o2); r.v3 = Mem::ld4(src + o3);
+        if (STATUS) {
+            r.b0 = Mem::ld_u32(st_src + o0); r.b1 = Mem::ld_u32(st_src + o1);
+            r.b2 = Mem::ld_u32(st_src + o2); r.b3 = Mem::ld_u32(st_src + o3);
         }
+        r.sidx = ig * p.PB + 4 * jg;
+    }
+}
+
+// register transpose (free for the floats, 8 PRMT for the bytes) into the OUTPUT-ordered tile
+template <bool STATUS>
+__host__ __device__ __forceinline__ void pair_stash(const PairParams& p, const PairRegs& r, float* s_val, uint8_t* s_st) {
+    if (r.sidx == 0xffffffffu) return;
+    const uint32_t plane = p.nIg * p.PB, sidx = r.sidx;
+    *reinterpret_cast<float4*>(s_val + sidx) = make_float4(r.v0.x, r.v1.x, r.v2.x, r.v3.x);
+    *reinterpret_cast<float4*>(s_val + sidx + plane) = make_float4(r.v0.y, r.v1.y, r.v2.y, r.v3.y);
+    *reinterpret_cast<float4*>(s_val + sidx + 2 * plane) = make_float4(r.v0.z, r.v1.z, r.v2.z, r.v3.z);
+    *reinterpret_cast<float4*>(s_val + sidx + 3 * plane) = make_float4(r.v0.w, r.v1.w, r.v2.w, r.v3.w);
+    if (STATUS) {
+        // 4x4 byte transpose: word k collects byte k of the four rows
+        const uint32_t p01 = pair_prmt(r.b0, r.b1, 0x5140), q01 = pair_prmt(r.b0, r.b1, 0x7362);
+        const uint32_t p23 = pair_prmt(r.b2, r.b3, 0x5140), q23 = pair_prmt(r.b2, r.b3, 0x7362);
+        *reinterpret_cast<uint32_t*>(s_st + sidx) = pair_prmt(p01, p23, 0x5410);
+        *reinterpret_cast<uint32_t*>(s_st + sidx + plane) = pair_prmt(p01, p23, 0x7632);
+        *reinterpret_cast<uint32_t*>(s_st + sidx + 2 * plane) = pair_prmt(q01, q23, 0x5410);
+        *reinterpret_cast<uint32_t*>(s_st + sidx + 3 * plane) = pair_prmt(q01, q23, 0x7632);
     }
 }
 
@@ -138,9 +149,10 @@ __host__ __device__ __forceinline__ void pair_phase1(const PairParams& p, uint32
 template <bool STATUS, class Mem>
 __host__ __device__ __forceinline__ void pair_phase2(const PairParams& p, uint32_t tid, float* dst, uint8_t* st_dst,
                                                      const float* s_val, const uint8_t* s_st,
-                                                     const uint32_t* s_dst_row, uint32_t a_eff, uint32_t n_jq) {
+                                                     const uint32_t* s_dst_row, uint32_t a_eff, uint32_t n_jq,
+                                                     uint32_t n_threads) {
     const uint32_t n_it = p.A * p.nJq;
-    for (uint32_t it = tid; it < n_it; it += 256) {
+    for (uint32_t it = tid; it < n_it; it += n_threads) {
         const uint32_t i = p.div_nJq.div(it), jq = it - i * p.nJq;
         if (i < a_eff && jq < n_jq) {
             const uint32_t sidx = ((i & 3u) * p.nIg + (i >> 2)) * p.PB + 4 * jq;
@@ -152,37 +164,62 @@ __host__ __device__ __forceinline__ void pair_phase2(const PairParams& p, uint32
     }
 }
 
-template <bool STATUS>
+constexpr int kPairThreads = 640;  // >= micro-tiles of the largest tile (25 x 25)
+
+// Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...; NM micro-tiles per thread.
+template <bool STATUS, int NM>
 __device__ __forceinline__ void pair_body(const PairParams& p, const GatherMeasure& m, unsigned char* smem_p,
-                                          const int64_t* s_base, const uint32_t* s_eff) {
+                                          uint32_t n_boxes) {
     float* s_val = reinterpret_cast<float*>(smem_p);
     uint8_t* s_st = smem_p + p.st_offset;
     const uint32_t* s_src_row = reinterpret_cast<const uint32_t*>(smem_p + p.tab_offset);
     const uint32_t* s_dst_row = s_src_row + p.B;
-    pair_phase1<STATUS, PairDevMem>(p, threadIdx.x, m.in + s_base[0], STATUS ? m.st_in + s_base[0] : nullptr, s_val,
-                                    s_st, s_src_row, s_eff[0] >> 2, s_eff[1] >> 2);
-    __syncthreads();
-    pair_phase2<STATUS, PairDevMem>(p, threadIdx.x, m.out + s_base[1], STATUS ? m.st_out + s_base[1] : nullptr, s_val,
-                                    s_st, s_dst_row, s_eff[0], s_eff[1] >> 2);
+    uint32_t tile = blockIdx.x;
+    int64_t sb, db;
+    uint32_t a_eff, b_eff;
+    PairRegs r[NM];
+    pair_decode(p, tile, sb, db, a_eff, b_eff);
+#pragma unroll
+    for (int q = 0; q < NM; ++q)
+        pair_load<STATUS, PairDevMem>(p, threadIdx.x + q * blockDim.x, m.in + sb, STATUS ? m.st_in + sb : nullptr,
+                                      s_src_row, a_eff >> 2, b_eff >> 2, r[q]);
+    while (true) {
+#pragma unroll
+        for (int q = 0; q < NM; ++q) pair_stash<STATUS>(p, r[q], s_val, s_st);
+        __syncthreads();  // the tile is complete in shared memory
+        const int64_t db_cur = db;
+        const uint32_t a_cur = a_eff, nj_cur = b_eff >> 2;
+        tile += gridDim.x;
+        const bool more = tile < n_boxes;
+        if (more) {  // next tile's loads fly while this one drains
+            pair_decode(p, tile, sb, db, a_eff, b_eff);
+#pragma unroll
+            for (int q = 0; q < NM; ++q)
+                pair_load<STATUS, PairDevMem>(p, threadIdx.x + q * blockDim.x, m.in + sb,
+                                              STATUS ? m.st_in + sb : nullptr, s_src_row, a_eff >> 2, b_eff >> 2, r[q]);
+        }
+        pair_phase2<STATUS, PairDevMem>(p, threadIdx.x, m.out + db_cur, STATUS ? m.st_out + db_cur : nullptr, s_val,
+                                        s_st, s_dst_row, a_cur, nj_cur, blockDim.x);
+        if (!more) break;
+        __syncthreads();  // everyone has drained the tile
+    }
 }
 
-__global__ void __launch_bounds__(256, 4) transpose_pair_kernel(const __grid_constant__ PairParams p) {
+template <int NM>
+__global__ void __launch_bounds__(kPairThreads, NM == 1 ? 2 : 1) transpose_pair_kernel(const __grid_constant__ PairParams p, uint32_t n_boxes) {
     extern __shared__ __align__(16) unsigned char smem_p[];
-    __shared__ int64_t s_base[2];
-    __shared__ uint32_t s_eff[2];
     uint32_t* s_src_row = reinterpret_cast<uint32_t*>(smem_p + p.tab_offset);
     uint32_t* s_dst_row = s_src_row + p.B;
     const GatherMeasure m = p.meas[blockIdx.y];
-    if (threadIdx.x == 0) pair_decode(p, blockIdx.x, s_base[0], s_base[1], s_eff[0], s_eff[1]);
-    for (uint32_t i = threadIdx.x; i < p.B; i += 256) s_src_row[i] = __ldg(p.src_row + i);
-    for (uint32_t i = threadIdx.x; i < p.A; i += 256) s_dst_row[i] = __ldg(p.dst_row + i);
+    for (uint32_t i = threadIdx.x; i < p.B; i += blockDim.x) s_src_row[i] = __ldg(p.src_row + i);
+    for (uint32_t i = threadIdx.x; i < p.A; i += blockDim.x) s_dst_row[i] = __ldg(p.dst_row + i);
     __syncthreads();
-    if (m.st_in) pair_body<true>(p, m, smem_p, s_base, s_eff);
-    else pair_body<false>(p, m, smem_p, s_base, s_eff);
+    if (m.st_in) pair_body<true, NM>(p, m, smem_p, n_boxes);
+    else pair_body<false, NM>(p, m, smem_p, n_boxes);
 }
 
 // `dims_in`: the output axes (outermost first) as linear GDims carrying their SOURCE strides.
-inline PairPlan transpose_pair_plan(const std::vector<GDim>& dims_in) {
+inline PairPlan transpose_pair_plan_for(const std::vector<GDim>& dims_in, int64_t cap_in, int64_t cap_out) {
     PairPlan plan;
     static const int force = [] { const char* e = getenv("OLAP_TRANSPOSE_PAIR"); return e ? atoi(e) : -1; }();
     if (force == 0) return plan;
@@ -211,22 +248,23 @@ inline PairPlan transpose_pair_plan(const std::vector<GDim>& dims_in) {
 
     // a group: trailing axes taken whole while the run stays <= cap, then one partial axis
     struct Group { std::vector<int> axes; int64_t mult = 1, ext = 1, run = 1; bool partial = false; };
-    auto grow = [&](const std::vector<int>& order, Group& gr) {
+    auto grow = [&](const std::vector<int>& order, Group& gr, int64_t cap_g, int64_t want) {
         int64_t pr = 1;
         for (int ax : order) {
             const int64_t L = dims[ax].len;
-            if (pr * L <= cap) {
+            if (pr * L <= cap_g) {
                 gr.axes.push_back(ax);
                 pr *= L;
                 gr.mult = pr;  // every axis whole so far
                 gr.ext = 1;
                 gr.partial = false;
-                if (pr >= 64) break;
+                if (pr >= want) break;
                 continue;
             }
             // partial axis: an extent e with (pr * e) % 4 == 0 for full and ragged tiles,
             // preferring an even split of the axis
-            const int64_t e_max = std::min<int64_t>(L, cap / pr);
+            const int64_t e_max = std::min<int64_t>(L, cap_g / pr);
+            if (e_max < 2 && pr >= 32) break;  // nothing to gain from a sliver of the next axis
             int64_t pick = 0;
             for (int64_t e = e_max; e >= std::max<int64_t>(1, e_max / 2); --e) {
                 if ((pr * e) % 4 || ((L % e) * pr) % 4) continue;
@@ -246,7 +284,10 @@ inline PairPlan transpose_pair_plan(const std::vector<GDim>& dims_in) {
         return pr >= 32 && pr % 4 == 0;
     };
     Group gi, go;
-    if (!grow(by_src, gi) || !grow(by_dst, go)) return plan;
+    // either run may be asked to be longer than the other (two micro-tiles per thread, one CTA
+    // per SM): fewer, longer DRAM bursts on that side
+    if (!grow(by_src, gi, std::max(cap, cap_in), cap_in ? cap_in : 64) ||
+        !grow(by_dst, go, std::max(cap, cap_out), cap_out ? cap_out : 64)) return plan;
     for (int a : gi.axes)
         for (int b : go.axes)
             if (a == b) return plan;
@@ -327,8 +368,27 @@ inline PairPlan transpose_pair_plan(const std::vector<GDim>& dims_in) {
     p.st_offset = (uint32_t)(cells * 4);
     p.tab_offset = (uint32_t)(p.st_offset + ((cells + 15) & ~(size_t)15));
     plan.smem = p.tab_offset + ((size_t)p.A + p.B) * sizeof(uint32_t);
-    if (plan.smem > 100 * 1024) return plan;
+    if (plan.smem > 200 * 1024 || p.nIg * p.nJq > 3u * kPairThreads) return plan;
+    if (plan.smem > 100 * 1024 && p.nIg * p.nJq <= (uint32_t)kPairThreads) return plan;
     plan.use = true;
+    return plan;
+}
+
+// Measured on the 100^3 x 10^3 reversal (profiles/README.md): longer runs mean fewer, longer
+// DRAM bursts.  A 200-cell OUTPUT run (800-byte value bursts, 200-byte status bursts) beats
+// the square 100 x 100 tile by 17 %, a 200-cell input run by 9 %; the square tile is the
+// fallback when a longer run would collide with the other group.
+inline PairPlan transpose_pair_plan(const std::vector<GDim>& dims_in) {
+    static const int64_t want_in = [] { const char* e = getenv("OLAP_PAIR_IN"); return e ? (int64_t)atoi(e) : (int64_t)-1; }();
+    static const int64_t want_out = [] { const char* e = getenv("OLAP_PAIR_OUT"); return e ? (int64_t)atoi(e) : (int64_t)-1; }();
+    if (want_in >= 0 || want_out >= 0) {  // tuning knobs
+        PairPlan plan = transpose_pair_plan_for(dims_in, std::max<int64_t>(0, want_in), std::max<int64_t>(0, want_out));
+        if (plan.use) return plan;
+        return transpose_pair_plan_for(dims_in, 0, 0);
+    }
+    PairPlan plan = transpose_pair_plan_for(dims_in, 0, 200);
+    if (!plan.use) plan = transpose_pair_plan_for(dims_in, 200, 0);
+    if (!plan.use) plan = transpose_pair_plan_for(dims_in, 0, 0);
     return plan;
 }
 
@@ -339,12 +399,23 @@ inline int launch_transpose_pair(const GatherMeasure* d_meas, const uint32_t* d_
     plan.p.dst_row = d_dst_row;
     static bool attr_set = false;
     if (!attr_set) {
-        OLAP_CUDA(cudaFuncSetAttribute(transpose_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        OLAP_CUDA(cudaFuncSetAttribute(transpose_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        OLAP_CUDA(cudaFuncSetAttribute(transpose_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        OLAP_CUDA(cudaFuncSetAttribute(transpose_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    const dim3 grid((unsigned)plan.n_boxes, (unsigned)n);
+    // persistent CTAs, each walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+    const uint32_t n_mt = plan.p.nIg * plan.p.nJq;
+    const int nm = (int)ceil_div(n_mt, kPairThreads);
+    static const int per_sm_knob = [] { const char* e = getenv("OLAP_PAIR_CTAS"); return e ? atoi(e) : 1; }();
+    const int per_sm = nm >= 2 ? 1 : per_sm_knob;
+    const int64_t ctas = std::min<int64_t>(plan.n_boxes, std::max<int64_t>(1, ceil_div((int64_t)g.sm_count * per_sm, n)));
+    const unsigned threads = (unsigned)((ceil_div(n_mt, nm) + 31) / 32 * 32);
+    const dim3 grid((unsigned)ctas, (unsigned)n);
     mark_kernels_begin();
-    transpose_pair_kernel<<<grid, 256, plan.smem, g.stream>>>(plan.p);
+    if (nm == 1) transpose_pair_kernel<1><<<grid, threads, plan.smem, g.stream>>>(plan.p, (uint32_t)plan.n_boxes);
+    else if (nm == 3) transpose_pair_kernel<3><<<grid, threads, plan.smem, g.stream>>>(plan.p, (uint32_t)plan.n_boxes);
+    else transpose_pair_kernel<2><<<grid, threads, plan.smem, g.stream>>>(plan.p, (uint32_t)plan.n_boxes);
     ++g_launches;
     return OLAP_OK;
 }

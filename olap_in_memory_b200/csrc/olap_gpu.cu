@@ -15,6 +15,7 @@
 #include "kernels_store.cuh"
 #include "kernels_pair.cuh"
 #include "kernels_tile.cuh"
+#include "kernels_long.cuh"
 
 namespace olap {
 
@@ -269,8 +270,12 @@ struct Csr {
     bool contiguous = true;
 };
 
-static Csr build_csr(const int32_t* map, int64_t C, int64_t P) {
+static Csr build_csr(const int32_t* map, int64_t C, int64_t P, bool lean = false) {
     Csr c;
+    if (P == 1 && lean) {  // everything rolls up to one parent: the child list is 0..C-1, never materialised
+        c.pstart = {0, (int32_t)C};
+        return c;
+    }
     c.pstart.assign(P + 1, 0);
     for (int64_t i = 0; i < C; ++i) c.pstart[map[i] + 1]++;
     for (int64_t p = 0; p < P; ++p) c.pstart[p + 1] += c.pstart[p];
@@ -862,26 +867,42 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
             for (int q = d + 1; q < ndim; ++q) I *= old_len[q];
             const int64_t C = ndim ? old_len[d] : 1, P = ndim ? new_len[d] : 1;
             static const int32_t zero = 0;
-            const Csr csr = build_csr(ndim ? maps[d] : &zero, C, P);
+            const Csr csr = build_csr(ndim ? maps[d] : &zero, C, P, true);
             // the CSR depends only on the map: keep it on the device across calls (a cube is
             // usually drilled the same way many times); measure descriptors change every call
             // (new output planes) and travel in the kernel parameters when they fit
+            bool any_status = false;
+            for (int k = 0; k < n; ++k) any_status |= meas[k].st_in != nullptr;
+            const TileDecision tile = tile_plan(O, C, P, I, any_status);
+            LongDecision lng;
+            if (!tile.use) lng = long_plan(O, C, P, I, any_status, n, g.sm_count);
             TablePack stat;
             const size_t o_ps = stat.add(csr.pstart.data(), csr.pstart.size() * 4);
-            const size_t o_ch = stat.add(csr.children.data(), csr.children.size() * 4);
+            // a contiguous map needs no child list on the device (children[k] == k)
+            const size_t o_ch = csr.contiguous ? 0 : stat.add(csr.children.data(), csr.children.size() * 4);
+            size_t o_seg = 0;
+            if (lng.use) {
+                const std::vector<int32_t> seg = long_seg_table(csr.pstart, csr.children, csr.contiguous, C, P, lng);
+                o_seg = stat.add(seg.data(), seg.size() * 4);
+            }
             const char* d_stat = nullptr;
             OLAP_TRY(cached_tables(stat, &d_stat));
             const bool inline_meas = n <= kInlineMeasures;
             if (!inline_meas) OLAP_TRY(t.upload());
             const UpMeasure* d_meas = inline_meas ? nullptr : t.ptr<UpMeasure>(o_meas);
             const int32_t* d_ps = reinterpret_cast<const int32_t*>(d_stat + o_ps);
-            const int32_t* d_ch = reinterpret_cast<const int32_t*>(d_stat + o_ch);
-            bool any_status = false;
-            for (int k = 0; k < n; ++k) any_status |= meas[k].st_in != nullptr;
-            TileDecision tile = tile_plan(O, C, P, I, any_status);
+            const int32_t* d_ch = csr.contiguous ? nullptr : reinterpret_cast<const int32_t*>(d_stat + o_ch);
             if (tile.use) {
                 path = "drillup/tile";
                 OLAP_TRY(launch_up_tile(d_meas, meas.data(), n, csr.contiguous, d_ps, d_ch, O, C, P, I, tile));
+            } else if (lng.use) {
+                path = "drillup/long";
+                void* scratch = nullptr;
+                if (lng.SS > 1) OLAP_TRY(dev_alloc(&scratch, (size_t)lng.scratch_stride * n));
+                OLAP_TRY(launch_up_long(d_meas, meas.data(), n, csr.contiguous, d_ps, d_ch,
+                                        reinterpret_cast<const int32_t*>(d_stat + o_seg), O, C, P, I, lng,
+                                        static_cast<unsigned char*>(scratch)));
+                if (scratch) OLAP_TRY(dev_free(scratch));
             } else {
                 path = (I % 4 == 0) ? "drillup/mid-vec4" : (I % 2 == 0 ? "drillup/mid-vec2" : "drillup/mid-scalar");
                 OLAP_TRY(launch_up_mid(d_meas, meas.data(), n, csr, d_ps, d_ch, O, C, P, I));

@@ -13,6 +13,8 @@ There is no CPU fallback: without the CUDA library every store call raises."""
 from __future__ import annotations
 
 import copy
+
+import numpy as np
 import itertools
 import re
 
@@ -523,17 +525,87 @@ class Cube:
         return self.dice(dimensionId, attribute, [value]).removeDimension(dimensionId)
 
     def collapse(self):
+        """cube.js:320-324."""
+        fused = self._remove_fused(self.dimensionIds)
+        if fused is not None:
+            return fused
         cube = self
         for d in self.dimensionIds:
             cube = cube.slice(d, "all", "all")
         return cube
 
     def aggregateByDimensions(self, excludeDimensionIds):
+        """cube.js:560-566."""
+        fused = self._remove_fused([d for d in self.dimensionIds if d not in excludeDimensionIds])
+        if fused is not None:
+            return fused
         cube = self
         for d in self.dimensionIds:
             if d not in excludeDimensionIds:
                 cube = cube.slice(d, "all", "all")
         return cube
+
+    # Rolling several dimensions up to 'all' (collapse, aggregateByDimensions, keepDimensions,
+    # removeDimensions) is a chain of single-dimension store passes in the reference.  When
+    # the order of the passes cannot matter — every stored measure aggregates ALL the removed
+    # dimensions with the same order-free rule (sum under a zero default, highest, lowest) —
+    # a store class that sets FUSED_ROLLUPS gets ONE pass per run of adjacent removed
+    # dimensions instead: the run is presented to the store as a single merged axis rolled up
+    # to one parent (the store interface already takes any lengths, in-memory.js:270-274).
+    # Sums are then accumulated in double across the whole run and rounded once, which is what
+    # the reference's double-valued chain does.  Anything else takes the reference's chain.
+    _FUSED_MAX_CHILDREN = 1 << 24
+
+    def _remove_fused(self, dimensionIds):
+        cls = self._store_cls
+        if not getattr(cls, "FUSED_ROLLUPS", False) or len(dimensionIds) < 2:
+            return None
+        remove = [d for d in self.dimensionIds if d in set(dimensionIds)]
+        if len(remove) != len(dimensionIds) or len(remove) < 2:
+            return None
+        ids = self.storedMeasureIds
+        methods = []
+        for m in ids:
+            rule = {self.storedMeasuresRules[m].get(d) or "sum" for d in remove}
+            store = self.storedMeasures[m]
+            default_is_nan = store._defaultValue != store._defaultValue
+            if len(rule) != 1 or next(iter(rule)) not in ("sum", "highest", "lowest"):
+                return None
+            if next(iter(rule)) == "sum" and default_is_nan:
+                return None  # the restart rule (in-memory.js:311-318) depends on the pass order
+            methods.append(next(iter(rule)))
+        # runs of adjacent removed dimensions, innermost run first
+        lens = [d.numItems for d in self.dimensions]
+        runs, i = [], 0
+        while i < len(lens):
+            if self.dimensions[i].id in remove:
+                j = i
+                while j < len(lens) and self.dimensions[j].id in remove:
+                    j += 1
+                runs.append((i, j))
+                i = j
+            else:
+                i += 1
+        if any(int(np.prod(lens[a:b])) > self._FUSED_MAX_CHILDREN or int(np.prod(lens[a:b])) == 0 for a, b in runs):
+            return None
+        stores = [self.storedMeasures[m] for m in ids]
+        for a, b in reversed(runs):
+            merged = int(np.prod(lens[a:b]))
+            old_len = lens[:a] + [merged] + lens[b:]
+            new_len = lens[:a] + [1] + lens[b:]
+            maps = [np.arange(n, dtype=np.int32) for n in old_len]
+            maps[a] = np.zeros(merged, np.int32)
+            if stores:
+                stores = cls.drillUp_lowered(stores, old_len, new_len, maps, methods)
+            lens = lens[:a] + lens[b:]
+        out = Cube([d for d in self.dimensions if d.id not in remove], cls)
+        out.storedMeasures = dict(zip(ids, stores))
+        out.computedMeasures.update(self.computedMeasures)
+        out.storedMeasuresRules = copy.deepcopy(self.storedMeasuresRules)
+        for rule in out.storedMeasuresRules.values():
+            for d in remove:
+                rule.pop(d, None)
+        return out
 
     def reorderDimensions(self, dimensionIds):
         """Permute the axes (cube.js:757-783)."""
@@ -550,6 +622,10 @@ class Cube:
         return self.reorderDimensions([dim2 if d == dim1 else dim1 if d == dim2 else d for d in self.dimensionIds])
 
     def keepDimensions(self, dimensionIds):
+        """cube.js:890-899."""
+        fused = self._remove_fused([d.id for d in self.dimensions if d.id not in dimensionIds])
+        if fused is not None:
+            return fused
         cube = self
         for dimension in self.dimensions:
             if dimension.id not in dimensionIds:
@@ -557,6 +633,10 @@ class Cube:
         return cube
 
     def removeDimensions(self, dimensionIds):
+        """cube.js:901-908."""
+        fused = self._remove_fused(list(dimensionIds))
+        if fused is not None:
+            return fused
         cube = self
         for d in dimensionIds:
             cube = cube.removeDimension(d)

@@ -43,6 +43,7 @@ def _lens(dims):
 class GpuStore:
     #: allocate a status byte per cell next to the Float32 cells (README.md:698-721)
     WITH_STATUS = True
+    FUSED_ROLLUPS = True  # Cube may present a run of removed dimensions as one merged axis (cube.py)
 
     def __init__(self, size, type="float32", defaultValue=math.nan, *, _handle=None, with_status=None,
                  uninitialised=False):

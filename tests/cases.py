@@ -104,6 +104,38 @@ def drillup_cases(seed=0):
                method="sum", default=0.0, data=np.zeros(0, np.float32), type="float32")
 
 
+def drillup_long_cases(seed=7):
+    """Rows too long for one shared-memory tile with a short inner run and few parents:
+    drillup_long_kernel (segments, ordered fold, scratch + merge kernel)."""
+    rng = np.random.default_rng(seed)
+    shapes = [
+        ([60000], 0, 1, True),         # 1-D -> all: one row, many CTAs, merge kernel
+        ([3, 50001], 1, 4, False),     # rows that start off 16-byte boundaries, random parents
+        ([2, 30000, 3], 1, 5, True),   # I = 3
+        ([45000, 2], 0, 3, False),     # O = 1, I = 2
+        ([2, 11000, 7], 1, 2, True),   # I = 7
+        ([1, 300000], 1, 200, False),  # 200 parents x 1500 children, outputs > 128: thread-per-output path
+    ]
+    for dims, d, P, mono in shapes:
+        for default in (0.0, math.nan):
+            for method in METHODS:
+                kind = "small" if method == "product" else ("int" if rng.random() < 0.5 else "real")
+                if method == "product" and dims[d] // P > 3000:
+                    continue  # products of thousands of factors leave float range
+                n = int(np.prod(dims))
+                maps = [identity(x) for x in dims]
+                maps[d] = random_map(rng, dims[d], P, mono)
+                new_len = list(dims)
+                new_len[d] = P
+                data = make_data(rng, n, default, fill=rng.choice([1.0, 0.6, 0.05]), kind=kind)
+                if default != default and method in ("sum", "average"):
+                    # the restart corner (in-memory.js:311-318): +inf and -inf under one parent
+                    data[rng.integers(0, n, 3)] = np.inf
+                    data[rng.integers(0, n, 3)] = -np.inf
+                yield dict(op="drillUp", old_len=list(dims), new_len=new_len, maps=maps, method=method,
+                           default=default, data=data, type="float32")
+
+
 def drilldown_cases(seed=1):
     rng = np.random.default_rng(seed)
     shapes = [

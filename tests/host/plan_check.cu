@@ -60,7 +60,7 @@ static int emulate_pair(const std::vector<int64_t>& len, const std::vector<int>&
     PairPlan plan = transpose_pair_plan(dims);
     if (!plan.use) return -1;
     PairParams& p = plan.p;
-    if (p.A % 4 || p.B % 4 || (p.PB / 4) % 2 == 0 || p.PB < p.B || plan.smem > 100 * 1024) { printf("pair geometry\n"); return 1; }
+    if (p.A % 4 || p.B % 4 || (p.PB / 4) % 2 == 0 || p.PB < p.B || plan.smem > 200 * 1024) { printf("pair geometry\n"); return 1; }
     if (N > (1 << 24)) return 0;  // geometry only
     p.src_row = plan.src_row.data();
     p.dst_row = plan.dst_row.data();
@@ -85,10 +85,17 @@ static int emulate_pair(const std::vector<int64_t>& len, const std::vector<int>&
         uint32_t a_eff, b_eff;
         pair_decode(p, (uint32_t)box, sb, db, a_eff, b_eff);
         if (a_eff % 4 || b_eff % 4 || sb % 4 || db % 4) { printf("pair alignment\n"); return 1; }
-        for (uint32_t tid = 0; tid < 256; ++tid)
-            pair_phase1<true, PairHostMem>(p, tid, in + sb, st_in + sb, s_val, s_st, s_src_row, a_eff >> 2, b_eff >> 2);
-        for (uint32_t tid = 0; tid < 256; ++tid)
-            pair_phase2<true, PairHostMem>(p, tid, out + db, st_out + db, s_val, s_st, s_dst_row, a_eff, b_eff >> 2);
+        const uint32_t n_mt = p.nIg * p.nJq, nm = (n_mt + kPairThreads - 1) / kPairThreads;
+        const uint32_t threads = ((n_mt + nm - 1) / nm + 31) / 32 * 32;
+        if (threads > (uint32_t)kPairThreads) { printf("pair threads\n"); return 1; }
+        for (uint32_t tid = 0; tid < threads; ++tid)
+            for (uint32_t q = 0; q < nm; ++q) {
+                PairRegs r;
+                pair_load<true, PairHostMem>(p, tid + q * threads, in + sb, st_in + sb, s_src_row, a_eff >> 2, b_eff >> 2, r);
+                pair_stash<true>(p, r, s_val, s_st);
+            }
+        for (uint32_t tid = 0; tid < threads; ++tid)
+            pair_phase2<true, PairHostMem>(p, tid, out + db, st_out + db, s_val, s_st, s_dst_row, a_eff, b_eff >> 2, threads);
     }
     // expected: out[new index] = in[sum coord * source stride]
     std::vector<int64_t> c(k, 0);

@@ -198,3 +198,42 @@ def test_more_than_2_31_cells():
             assert bool(torch.equal(y[:, k_], x4[:, :, k_]))
     finally:
         G.WITH_STATUS = old
+
+
+@pytest.mark.parametrize("O,Cn,I_,Pn", [(1, 100_000_000, 1, 1), (1500, 45_000, 1, 3), (4, 2_000_000, 5, 2)])
+def test_long_rows_against_torch(O, Cn, I_, Pn):
+    """drillup/long (rows too long for a tile, few parents): a 1e8-cell collapse, the
+    one-CTA-per-row regime without merge pass, and a short inner run — against torch."""
+    from olap_in_memory_b200 import _native as N
+
+    torch, interop, G, _ = _setup()
+    n = O * Cn * I_
+    src = _filled(torch, interop, G, n, 0.0, 0.6, 11)
+    cut = np.sort(np.random.default_rng(3).integers(1, Cn, Pn - 1)) if Pn > 1 else np.array([], np.int64)
+    m = np.searchsorted(cut, np.arange(Cn), side="right").astype(np.int32)
+    ident = lambda k: np.arange(k, dtype=np.int32)
+    methods = ["sum", "highest", "first", "last", "average"]
+    outs = G.drillUp_lowered([src] * len(methods), [O, Cn, I_], [O, Pn, I_], [ident(O), m, ident(I_)], methods)
+    assert N.lib().olap_last_op_path().decode() == "drillup/long"
+    x = interop.values_tensor(src).view(O, Cn, I_)
+    bounds = [0] + cut.tolist() + [Cn]
+    for p_ in range(Pn):
+        seg = x[:, bounds[p_]:bounds[p_ + 1], :]
+        pres = seg != 0
+        want_sum = seg.double().sum(1)
+        cnt = pres.sum(1)
+        got = {k: interop.values_tensor(o).view(O, Pn, I_)[:, p_, :] for k, o in zip(methods, outs)}
+        assert bool(torch.equal(got["sum"], want_sum.float()))
+        assert bool(torch.equal(got["highest"], seg.max(1).values))  # values are >= 0, unset cells are 0
+        avg = torch.where(cnt > 0, want_sum / cnt.clamp(min=1).double(), torch.zeros_like(want_sum)).float()
+        assert bool(torch.equal(got["average"], avg))
+        idx = torch.arange(seg.shape[1], device="cuda").view(1, -1, 1)
+        first_i = torch.where(pres, idx, seg.shape[1]).min(1).values.clamp(max=seg.shape[1] - 1)
+        last_i = torch.where(pres, idx, -1).max(1).values.clamp(min=0)
+        assert bool(torch.equal(got["first"], torch.gather(seg, 1, first_i.unsqueeze(1)).squeeze(1)))
+        assert bool(torch.equal(got["last"], torch.gather(seg, 1, last_i.unsqueeze(1)).squeeze(1)))
+        st = interop.status_tensor(outs[0])
+        if st is not None:
+            sp = st.view(O, Pn, I_)[:, p_, :]
+            full = cnt == seg.shape[1]
+            assert bool(torch.all(sp[full] == 2)) and bool(torch.all(sp[(cnt > 0) & ~full] == 3)) and bool(torch.all(sp[cnt == 0] == 1))

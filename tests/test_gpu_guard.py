@@ -19,7 +19,7 @@ from olap_in_memory_b200.store import GpuStore
 n = 0
 for with_status in (True, False):
     GpuStore.WITH_STATUS = with_status
-    for case in itertools.chain((c for c, _ in golden_io.load()), cases.drillup_cases(), cases.drilldown_cases(),
+    for case in itertools.chain((c for c, _ in golden_io.load()), cases.drillup_cases(), cases.drillup_long_cases(), cases.drilldown_cases(),
                                 cases.dice_cases(), cases.reorder_cases(), cases.load_cases()):
         cases.run_case(case, GpuStore)
         n += 1

@@ -15,7 +15,7 @@ from oracle.store_oracle import OracleStore
 
 pytestmark = pytest.mark.gpu
 
-ALL = list(itertools.chain(cases.drillup_cases(), cases.drilldown_cases(), cases.dice_cases(),
+ALL = list(itertools.chain(cases.drillup_cases(), cases.drillup_long_cases(), cases.drilldown_cases(), cases.dice_cases(),
                            cases.reorder_cases(), cases.load_cases()))
 
 
