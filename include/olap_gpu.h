@@ -167,7 +167,9 @@ int olap_store_import_sparse(olap_store* s, const int64_t* keys, const float* va
 /* ---- transforms (each returns n NEW stores in out[0..n)) -------------------- */
 /* `drillUp(oldDims, newDims, method)` in-memory.js:265-334, called per measure by
  * Cube.drillUp (cube.js:1012-1020).  maps[d][i] = new item index of old item i of
- * dimension d, length old_len[d] (in-memory.js:270-274).  methods[k] per store. */
+ * dimension d, length old_len[d] (in-memory.js:270-274).  methods[k] per store.
+ * maps[d] may be NULL for a dimension that does not change (old_len == new_len) or that
+ * rolls up to ONE item (new_len == 1): no table has to be built or checked for it. */
 int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, const int64_t* old_len,
                   const int64_t* new_len, const int32_t* const* maps, olap_store** out);
 /* `drillDown(oldDims, newDims, method, distributions)` in-memory.js:336-430

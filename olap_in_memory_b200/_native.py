@@ -147,6 +147,6 @@ def store_array(handles):
 
 def map_arrays(maps):
     """list of int sequences -> (keepalive numpy arrays, int32** argument)"""
-    keep = [np.ascontiguousarray(np.asarray(m, dtype=np.int32)) for m in maps]
-    ptrs = (p_i32 * max(1, len(keep)))(*[a.ctypes.data_as(p_i32) for a in keep])
+    keep = [None if m is None else np.ascontiguousarray(np.asarray(m, dtype=np.int32)) for m in maps]
+    ptrs = (p_i32 * max(1, len(keep)))(*[p_i32() if a is None else a.ctypes.data_as(p_i32) for a in keep])
     return keep, ptrs

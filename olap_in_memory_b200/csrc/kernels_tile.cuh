@@ -328,6 +328,7 @@ struct TransposeParams {
     uint32_t st_offset;              // byte offset of the status tile in shared memory
     uint32_t tab_offset;             // byte offset of the staged run tables in shared memory
     int rd_vec4;                     // phase 1 may use 128-bit loads along the input run
+    int wr_vec4;                     // phase 2 may use 128-bit stores along the output run
 };
 
 struct TransposePlan {
@@ -535,7 +536,35 @@ __device__ __forceinline__ void transpose_full_box(const TransposeParams& p, con
         }
     }
     __syncthreads();
-    {
+    if (p.wr_vec4) {
+        // 128-bit stores along the output run: a lane gathers 4 consecutive output cells (and
+        // their status bytes) from the tile and writes them with one store each
+        const RunGeom r = run_geom(p.wr[0], p.runs_out, 4);
+        const bool simple = p.wr[0].by == p.wr[0].b;
+        const uint32_t ss = p.wr[0].s_stride;
+        for (uint32_t pass = warp; pass < r.passes; pass += 8) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint32_t run, pos;
+                if (slot_cell(r, p.runs_out, pass, u * 32 + lane, run, pos)) {
+                    const uint2 t = s_wr[run];
+                    const uint32_t g = t.x + pos * 4;
+                    uint32_t so[4];
+                    if (simple) {
+                        so[0] = t.y + pos * 4 * ss;
+                        so[1] = so[0] + ss; so[2] = so[1] + ss; so[3] = so[2] + ss;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) so[k] = t.y + run_spos(p.wr[0], pos * 4 + k);
+                    }
+                    st_stream4(dst + g, make_float4(s_val[so[0]], s_val[so[1]], s_val[so[2]], s_val[so[3]]));
+                    if (STATUS)
+                        *reinterpret_cast<uint32_t*>(st_dst + g) = (uint32_t)s_st[so[0]] | ((uint32_t)s_st[so[1]] << 8) |
+                                                                   ((uint32_t)s_st[so[2]] << 16) | ((uint32_t)s_st[so[3]] << 24);
+                }
+            }
+        }
+    } else {
         const RunGeom r = run_geom(p.wr[0], p.runs_out);
         const uint32_t gs = p.wr[0].g_stride;
         for (uint32_t pass = warp; pass < r.passes; pass += 8) {
@@ -848,6 +877,15 @@ inline TransposePlan transpose_plan(const std::vector<GDim>& dims_in) {
             // part of the run itself (then its stride is covered by the run's contiguity)
             bool in_run = b[i] > 1 && dims[i].stride < p.rd[0].b;
             if (!in_run) p.rd_vec4 = 0;
+        }
+    // 128-bit stores along the output run: same conditions on the destination side (the run may
+    // be a compound one, its shared-memory positions are resolved cell by cell)
+    static const bool wr_vec_knob = [] { const char* e = getenv("OLAP_BOX_WR_VEC4"); return !e || atoi(e) != 0; }();
+    p.wr_vec4 = wr_vec_knob && p.wr[0].g_stride == 1 && p.wr[0].b % 4 == 0;
+    for (int i = 0; i < k; ++i)
+        if (dst_stride[i] != 1 && (dst_stride[i] % 4 != 0)) {
+            bool in_run = b[i] > 1 && dst_stride[i] < p.wr[0].b;
+            if (!in_run) p.wr_vec4 = 0;
         }
     p.n_axes = k;
     // grid slots in traversal order (the LAST slot varies fastest): boxes that are neighbours in

@@ -837,6 +837,12 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
     for (int d = 0; d < ndim; ++d) {
         if (old_len[d] > 0x7fffffffLL || new_len[d] > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "olap_drill_up: dimension %d longer than 2^31-1", d);
         bool identity = old_len[d] == new_len[d];
+        if (!maps[d]) {
+            // no map: the dimension is untouched, or every item rolls up to the single new item
+            if (!identity && new_len[d] != 1) return fail(OLAP_E_INVALID, "olap_drill_up: dimension %d changes length without a map", d);
+            if (!identity) changed.push_back(d);
+            continue;
+        }
         for (int64_t i = 0; i < old_len[d]; ++i) {
             const int32_t m = maps[d][i];
             if (m < 0 || m >= new_len[d]) return fail(OLAP_E_INVALID, "olap_drill_up: map of dimension %d sends item %lld to %d, outside [0, %lld)", d, (long long)i, m, (long long)new_len[d]);
@@ -867,7 +873,9 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
             for (int q = d + 1; q < ndim; ++q) I *= old_len[q];
             const int64_t C = ndim ? old_len[d] : 1, P = ndim ? new_len[d] : 1;
             static const int32_t zero = 0;
-            const Csr csr = build_csr(ndim ? maps[d] : &zero, C, P, true);
+            std::vector<int32_t> implied;
+            if (ndim && !maps[d] && P != 1) { implied.resize(C); std::iota(implied.begin(), implied.end(), 0); }  // plain copy
+            const Csr csr = build_csr(!ndim ? &zero : (maps[d] ? maps[d] : implied.data()), C, P, true);
             // the CSR depends only on the map: keep it on the device across calls (a cube is
             // usually drilled the same way many times); measure descriptors change every call
             // (new output planes) and travel in the kernel parameters when they fit
@@ -918,7 +926,12 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
                 p.new_len[d] = new_len[d];
                 p.old_stride[d] = stride;
                 stride *= old_len[d];
-                const Csr csr = build_csr(maps[d], old_len[d], new_len[d]);
+                std::vector<int32_t> implied;
+                if (!maps[d]) {  // untouched (identity) or rolled up to one item (zeros)
+                    implied.assign(old_len[d], 0);
+                    if (old_len[d] == new_len[d]) std::iota(implied.begin(), implied.end(), 0);
+                }
+                const Csr csr = build_csr(maps[d] ? maps[d] : implied.data(), old_len[d], new_len[d]);
                 o_ps[d] = t.add(csr.pstart.data(), csr.pstart.size() * 4);
                 o_ch[d] = t.add(csr.children.data(), csr.children.size() * 4);
             }

@@ -593,10 +593,15 @@ class Cube:
             merged = int(np.prod(lens[a:b]))
             old_len = lens[:a] + [merged] + lens[b:]
             new_len = lens[:a] + [1] + lens[b:]
-            maps = [np.arange(n, dtype=np.int32) for n in old_len]
-            maps[a] = np.zeros(merged, np.int32)
+            # None = "unchanged", or "everything to the single new item" for the merged axis
+            # (include/olap_gpu.h: no table is built or checked); other stores get real maps
+            if getattr(cls, "IMPLIED_MAPS", False):
+                maps = [None] * len(old_len)
+            else:
+                maps = [np.arange(n, dtype=np.int32) for n in old_len]
+                maps[a] = np.zeros(merged, np.int32)
             if stores:
-                stores = cls.drillUp_lowered(stores, old_len, new_len, maps, methods)
+                stores = cls.drillUp_lowered_batch(stores, old_len, new_len, maps, methods)
             lens = lens[:a] + lens[b:]
         out = Cube([d for d in self.dimensions if d.id not in remove], cls)
         out.storedMeasures = dict(zip(ids, stores))

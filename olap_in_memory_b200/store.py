@@ -44,6 +44,7 @@ class GpuStore:
     #: allocate a status byte per cell next to the Float32 cells (README.md:698-721)
     WITH_STATUS = True
     FUSED_ROLLUPS = True  # Cube may present a run of removed dimensions as one merged axis (cube.py)
+    IMPLIED_MAPS = True   # drillUp_lowered accepts None for unchanged / rolled-to-one dimensions
 
     def __init__(self, size, type="float32", defaultValue=math.nan, *, _handle=None, with_status=None,
                  uninitialised=False):
@@ -270,6 +271,8 @@ class GpuStore:
         )
         del alive
         return GpuStore._finish(out, n)
+
+    drillUp_lowered_batch = drillUp_lowered  # the name Cube._remove_fused calls (FUSED_ROLLUPS)
 
     @staticmethod
     def drillDown_many(stores, oldDimensions, newDimensions, methods, distributions=None):
