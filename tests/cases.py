@@ -216,7 +216,9 @@ def reorder_cases(seed=3):
                        # two disjoint 4-aligned axis groups: the pair transpose, ragged tiles included
                        ([100, 104], [1, 0]), ([332, 100], [1, 0]), ([12, 32, 32, 44], [3, 2, 1, 0]),
                        ([52, 7, 92], [2, 1, 0]), ([44, 4, 25, 8], [3, 2, 1, 0]), ([20, 12, 10, 10, 10], [4, 3, 1, 2, 0]),
-                       ([72, 200, 12], [2, 0, 1]), ([8, 8, 8, 8, 8], [2, 4, 0, 3, 1])):
+                       ([72, 200, 12], [2, 0, 1]), ([8, 8, 8, 8, 8], [2, 4, 0, 3, 1]),
+                       # 200-cell runs on both sides: the 2-CTA cluster tile (distributed shared memory), ragged too
+                       ([24, 16, 10, 10, 10], [4, 3, 2, 1, 0]), ([28, 12, 6, 10, 10], [4, 3, 2, 1, 0]), ([400, 408], [1, 0])):
         for default in (0.0, math.nan):
             n = int(np.prod(dims))
             yield dict(op="reorder", old_len=list(dims), new_to_old=list(perm), default=default,

@@ -49,6 +49,7 @@ static int check_perm(const std::vector<int64_t>& len, const std::vector<int>& p
 // Run transpose_pair_kernel's own phase code on the CPU (PairHostMem) and compare with the
 // plain permutation: checks the planner's tables, the grid order, ragged tiles and the 4x4
 // micro-tile addressing without a GPU.  Returns -1 when the pair planner declines the shape.
+static int n_pair2 = 0;
 static int emulate_pair(const std::vector<int64_t>& len, const std::vector<int>& perm) {
     const int k = (int)len.size();
     std::vector<int64_t> stride(k), out_len(k), out_stride(k);
@@ -72,11 +73,13 @@ static int emulate_pair(const std::vector<int64_t>& len, const std::vector<int>&
     uint8_t* st_in = reinterpret_cast<uint8_t*>(sti.data());
     uint8_t* st_out = reinterpret_cast<uint8_t*>(sto.data());
     for (int64_t i = 0; i < N; ++i) { in[i] = (float)i; out[i] = -1.0f; st_in[i] = (uint8_t)(i * 7 + 3); }
-    std::vector<float4> smem(plan.smem / 16 + 1);
-    unsigned char* sm = reinterpret_cast<unsigned char*>(smem.data());
-    float* s_val = reinterpret_cast<float*>(sm);
-    uint8_t* s_st = sm + p.st_offset;
-    uint32_t* s_src_row = reinterpret_cast<uint32_t*>(sm + p.tab_offset);
+    const uint32_t split = p.split;
+    if (split == 2) ++n_pair2;
+    std::vector<float4> smem0(plan.smem / 16 + 1), smem1(plan.smem / 16 + 1);
+    unsigned char* sm[2] = {reinterpret_cast<unsigned char*>(smem0.data()), reinterpret_cast<unsigned char*>(smem1.data())};
+    float* s_val_of[2] = {reinterpret_cast<float*>(sm[0]), reinterpret_cast<float*>(sm[1])};
+    uint8_t* s_st_of[2] = {sm[0] + p.st_offset, sm[1] + p.st_offset};
+    uint32_t* s_src_row = reinterpret_cast<uint32_t*>(sm[0] + p.tab_offset);
     uint32_t* s_dst_row = s_src_row + p.B;
     for (uint32_t i = 0; i < p.B; ++i) s_src_row[i] = p.src_row[i];
     for (uint32_t i = 0; i < p.A; ++i) s_dst_row[i] = p.dst_row[i];
@@ -85,6 +88,25 @@ static int emulate_pair(const std::vector<int64_t>& len, const std::vector<int>&
         uint32_t a_eff, b_eff;
         pair_decode(p, (uint32_t)box, sb, db, a_eff, b_eff);
         if (a_eff % 4 || b_eff % 4 || sb % 4 || db % 4) { printf("pair alignment\n"); return 1; }
+        if (split == 2) {
+            const uint32_t mt_cta = p.nIg * p.nJqLoc, nm = (mt_cta + kPairThreads - 1) / kPairThreads;
+            const uint32_t threads = ((mt_cta + nm - 1) / nm + 31) / 32 * 32;
+            if (threads > (uint32_t)kPairThreads || nm > 3) { printf("pair2 threads\n"); return 1; }
+            for (uint32_t rank = 0; rank < 2; ++rank)
+                for (uint32_t tid = 0; tid < threads; ++tid)
+                    for (uint32_t q = 0; q < nm; ++q) {
+                        PairRegs2 r;
+                        pair2_load<true, PairHostMem>(p, rank, tid + q * threads, in + sb, st_in + sb, s_src_row, a_eff >> 2, b_eff >> 2, r);
+                        pair2_stash<true>(p, r, s_val_of[0], s_val_of[1], s_st_of[0], s_st_of[1]);
+                    }
+            for (uint32_t rank = 0; rank < 2; ++rank)
+                for (uint32_t tid = 0; tid < threads; ++tid)
+                    pair2_phase2<true, PairHostMem>(p, rank, tid, out + db, st_out + db, s_val_of[rank], s_st_of[rank], s_dst_row,
+                                                    a_eff, b_eff >> 2, threads);
+            continue;
+        }
+        float* s_val = s_val_of[0];
+        uint8_t* s_st = s_st_of[0];
         const uint32_t n_mt = p.nIg * p.nJq, nm = (n_mt + kPairThreads - 1) / kPairThreads;
         const uint32_t threads = ((n_mt + nm - 1) / nm + 31) / 32 * 32;
         if (threads > (uint32_t)kPairThreads) { printf("pair threads\n"); return 1; }
@@ -126,7 +148,7 @@ int main() {
                 ++n;
             } while (std::next_permutation(perm.begin(), perm.end()) && ++count < 130);
         }
-        printf("pair transposes emulated: %d\n", n_pair);
+        printf("pair transposes emulated: %d (of which 2-CTA cluster tiles: %d)\n", n_pair, n_pair2);
         if (n_pair < 20) { printf("pair planner declined almost everything\n"); ++bad; }
     }
     const std::vector<std::vector<int64_t>> shapes = {

@@ -317,3 +317,24 @@ def test_shared_status_plane_layout():
     assert outs[2].data_f32().reshape(3, 8).tolist() == (3 * x[1::2]).tolist()
     st = np.asarray(outs[1].status).reshape(3, 8)
     assert st[0, 5] == 3 and (np.delete(st.ravel(), 5) == 2).all()
+
+
+def test_cluster_transpose(monkeypatch):
+    """OLAP_PAIR_CLUSTER=1: the 2-CTA cluster / distributed-shared-memory variant of the pair
+    transpose (off by default, see kernels_pair.cuh) stays bit-exact, ragged tiles included."""
+    G = _gpu()
+    monkeypatch.setenv("OLAP_PAIR_CLUSTER", "1")
+    rng = np.random.default_rng(5)
+    for dims, perm in (([24, 16, 10, 10, 10], [4, 3, 2, 1, 0]), ([28, 12, 6, 10, 10], [4, 3, 2, 1, 0]),
+                       ([400, 408], [1, 0]), ([20, 20, 20, 10, 10, 10], [5, 4, 3, 2, 1, 0])):
+        n = int(np.prod(dims))
+        data = rng.integers(1, 1000, n).astype(np.float32)
+        data[rng.random(n) < 0.3] = 0.0
+        s = G(n, "float32", 0)
+        s.set_data_f32(data)
+        out = G.reorder_lowered([s], dims, perm)[0]
+        want = data.reshape(dims).transpose(perm).reshape(-1)
+        assert np.array_equal(out.data_f32(), want)
+        st = out.status
+        if st is not None:
+            assert np.array_equal(np.asarray(st), np.where(want != 0, 2, 1))
