@@ -26,13 +26,14 @@ struct UpLongParams {
     UpMeasure meas_inline[kInlineMeasures];
     const int32_t* pstart;    // [P+1]
     const int32_t* children;  // CSR (unused when RANGE)
-    const int32_t* seg_ptr;   // [(S_row+1) * P]
+    const int32_t* seg_ptr;   // RANGE: [(S_row+1) * P] CSR positions; else [S_row * (P+1)] positions in the segment's own list
+    const uint16_t* perm16;   // !RANGE: [S_row * Cs] cells of every segment (offset from its first child), grouped by parent, ascending
     int64_t O;
     int32_t C, P, I;
     int32_t Cs, S_row, T, SS;  // children per segment, segments per row, segments per CTA, CTAs per row
     int32_t row_out;           // P * I
     FastDiv div_i, div_ss;
-    uint32_t buf_stride, st_offset, bar_offset, state_offset, merge_offset;  // dynamic shared memory layout (bytes)
+    uint32_t buf_stride, st_offset, perm_offset, bar_offset, state_offset, merge_offset;  // dynamic shared memory layout (bytes)
     int32_t G, logG;
     unsigned char* scratch;    // SS > 1: per measure [O*SS*row_out] 16-byte lane states, then as many status bytes
     int64_t scratch_stride;    // bytes per measure
@@ -42,14 +43,15 @@ struct LongDecision {
     bool use = false;
     int32_t Cs = 0, S_row = 0, T = 0, SS = 0, G = 1;
     size_t smem = 0;
-    uint32_t buf_stride = 0, st_offset = 0, bar_offset = 0, state_offset = 0, merge_offset = 0;
+    uint32_t buf_stride = 0, st_offset = 0, perm_offset = 0, bar_offset = 0, state_offset = 0, merge_offset = 0;
     int64_t scratch_stride = 0;
 };
 
 constexpr int kLongStateBytes = 16;
 
 // Called after tile_plan declined: rows too long for one tile, inner run short.
-inline LongDecision long_plan(int64_t O, int64_t C, int64_t P, int64_t I, bool any_status, int n_meas, int sm_count) {
+inline LongDecision long_plan(int64_t O, int64_t C, int64_t P, int64_t I, bool any_status, int n_meas, int sm_count,
+                              bool contiguous) {
     LongDecision d;
     static const int force = [] { const char* e = getenv("OLAP_LONG"); return e ? atoi(e) : -1; }();
     if (force == 0) return d;
@@ -60,13 +62,15 @@ inline LongDecision long_plan(int64_t O, int64_t C, int64_t P, int64_t I, bool a
     const int64_t per_cell = any_status ? 5 : 4;
     static const int64_t budget = [] { const char* e = getenv("OLAP_LONG_KB"); return (int64_t)(e ? atoi(e) : 32) * 1024; }();
     // children per segment: Cs*I cells fill the budget (one of TWO staging buffers) and are a multiple of 16 cells
-    int64_t Cs = std::max<int64_t>(1, budget / (per_cell * I));
-    const int64_t unit = 16 / std::gcd<int64_t, int64_t>(I, 16);  // Cs % unit == 0  =>  (Cs*I) % 16 == 0
+    const int64_t per_child = per_cell * I + (contiguous ? 0 : 2);
+    int64_t Cs = std::max<int64_t>(1, budget / per_child);
+    int64_t unit = 16 / std::gcd<int64_t, int64_t>(I, 16);  // Cs % unit == 0  =>  (Cs*I) % 16 == 0
+    if (!contiguous) unit = std::lcm<int64_t, int64_t>(unit, 8);    // ... and the 2-byte cell list of a segment is a 16-byte multiple
     Cs = std::max(unit, Cs / unit * unit);
-    if (Cs * I * per_cell > 64 * 1024) return d;
+    if (Cs * per_child > 64 * 1024 || (!contiguous && Cs * I > 65535)) return d;
     Cs = std::min<int64_t>(Cs, ceil_div(C, unit) * unit);
     const int64_t S_row = ceil_div(C, Cs);
-    if ((S_row + 1) * P > (int64_t)(8 << 20)) return d;  // seg_ptr table
+    if ((S_row + 1) * (P + 1) > (int64_t)(8 << 20)) return d;  // seg_ptr table
     // CTAs per row: fill the chip a few times over
     const int64_t target = (int64_t)sm_count * 8;
     int64_t SS = std::min<int64_t>(S_row, std::max<int64_t>(1, ceil_div(target, std::max<int64_t>(1, O * n_meas))));
@@ -75,8 +79,9 @@ inline LongDecision long_plan(int64_t O, int64_t C, int64_t P, int64_t I, bool a
     if (O * SS > 0x7fffffffLL) return d;
     d.Cs = (int32_t)Cs; d.S_row = (int32_t)S_row; d.T = (int32_t)T; d.SS = (int32_t)SS;
     const size_t cells = (size_t)Cs * I;
-    d.buf_stride = (uint32_t)(cells * per_cell);  // cells % 16 == 0: every buffer 16-byte aligned
     d.st_offset = (uint32_t)(cells * 4);          // inside a buffer
+    d.perm_offset = (uint32_t)(cells * per_cell); // cells % 16 == 0: 16-byte aligned
+    d.buf_stride = d.perm_offset + (uint32_t)(contiguous ? 0 : Cs * 2);
     d.bar_offset = 2 * d.buf_stride;
     d.state_offset = d.bar_offset + 16;
     d.merge_offset = d.state_offset + (uint32_t)(((size_t)row_out * (kLongStateBytes + 1) + 15) & ~(size_t)15);
@@ -95,11 +100,13 @@ inline LongDecision long_plan(int64_t O, int64_t C, int64_t P, int64_t I, bool a
 
 template <int METHOD, bool NANDEF, bool RANGE, bool STATUS>
 __device__ __forceinline__ void up_long_segment(const UpLongParams& p, const float* s_val, const uint8_t* s_st,
-                                                int32_t s, int32_t c0, Lane<METHOD, NANDEF>* s_state, uint8_t* s_stacc,
-                                                unsigned char* s_merge, int32_t pre_k0, int32_t pre_k1) {
+                                                const uint16_t* s_perm, int32_t s, int32_t c0,
+                                                Lane<METHOD, NANDEF>* s_state, uint8_t* s_stacc, unsigned char* s_merge,
+                                                int32_t pre_k0, int32_t pre_k1) {
     typedef Lane<METHOD, NANDEF> L;
-    const int32_t* lo = p.seg_ptr + (size_t)s * p.P;
-    const int32_t* hi = lo + p.P;
+    // RANGE: CSR positions == child indices; else positions in the segment's staged cell list
+    const int32_t* lo = RANGE ? p.seg_ptr + (size_t)s * p.P : p.seg_ptr + (size_t)s * (p.P + 1);
+    const int32_t* hi = RANGE ? lo + p.P : lo + 1;
     if (p.G > 1) {
         L* s_lane = reinterpret_cast<L*>(s_merge);
         uint8_t* s_stm = s_merge + 256 * kLongStateBytes;
@@ -142,7 +149,7 @@ __device__ __forceinline__ void up_long_segment(const UpLongParams& p, const flo
             }
 #pragma unroll 4
             for (int32_t k = ks; k < ke; ++k) {
-                const uint32_t c = (RANGE ? (uint32_t)k : (uint32_t)p.children[k]) - (uint32_t)c0;
+                const uint32_t c = RANGE ? (uint32_t)k - (uint32_t)c0 : (uint32_t)s_perm[k];
                 const uint32_t idx = c * (uint32_t)p.I + i;
                 lane.step(s_val[idx]);
                 if (STATUS) st |= s_st[idx];
@@ -176,7 +183,7 @@ __device__ __forceinline__ void up_long_segment(const UpLongParams& p, const flo
         uint32_t st = 0;
 #pragma unroll 4
         for (int32_t k = k0; k < k1; ++k) {
-            const uint32_t c = (RANGE ? (uint32_t)k : (uint32_t)p.children[k]) - (uint32_t)c0;
+            const uint32_t c = RANGE ? (uint32_t)k - (uint32_t)c0 : (uint32_t)s_perm[k];
             const uint32_t idx = c * (uint32_t)p.I + i;
             lane.step(s_val[idx]);
             if (STATUS) st |= s_st[idx];
@@ -232,10 +239,12 @@ __device__ __forceinline__ void up_long_body(const UpLongParams& p, const UpMeas
         const uint8_t* g_st = STATUS ? m.st_in + start : nullptr;
         const uint32_t bulk_v = (start & 3) == 0 ? ((n_cells * 4u) & ~15u) : 0u;
         const uint32_t bulk_s = (STATUS && (start & 15) == 0) ? (n_cells & ~15u) : 0u;
+        const uint32_t bulk_p = RANGE ? 0u : (uint32_t)p.Cs * 2u;  // the list is padded to whole segments
         if (threadIdx.x == 0) {
-            mbar_expect_tx(bar + b, bulk_v + bulk_s);
+            mbar_expect_tx(bar + b, bulk_v + bulk_s + bulk_p);
             if (bulk_v) bulk_g2s(s_val, g_val, bulk_v, bar + b);
             if (bulk_s) bulk_g2s(s_st, g_st, bulk_s, bar + b);
+            if (bulk_p) bulk_g2s(smem + b * p.buf_stride + p.perm_offset, p.perm16 + (size_t)s * p.Cs, bulk_p, bar + b);
         }
         for (uint32_t q = (bulk_v >> 2) + threadIdx.x; q < n_cells; q += blockDim.x) s_val[q] = ld_stream1(g_val + q);
         if (STATUS)
@@ -252,16 +261,17 @@ __device__ __forceinline__ void up_long_body(const UpLongParams& p, const UpMeas
             const int j = threadIdx.x >> p.logG;
             if (j < p.row_out) {
                 const uint32_t pi = p.div_i.div((uint32_t)j);
-                pre_k0 = __ldg(p.seg_ptr + (size_t)s * p.P + pi);
-                pre_k1 = __ldg(p.seg_ptr + (size_t)(s + 1) * p.P + pi);
+                pre_k0 = __ldg(p.seg_ptr + (RANGE ? (size_t)s * p.P + pi : (size_t)s * (p.P + 1) + pi));
+                pre_k1 = __ldg(p.seg_ptr + (RANGE ? (size_t)(s + 1) * p.P + pi : (size_t)s * (p.P + 1) + pi + 1));
             }
         }
         mbar_wait(bar + b, parity[b]);
         parity[b] ^= 1u;
         __syncthreads();
         up_long_segment<METHOD, NANDEF, RANGE, STATUS>(p, reinterpret_cast<const float*>(smem + b * p.buf_stride),
-                                                       smem + b * p.buf_stride + p.st_offset, s, s * p.Cs, s_state,
-                                                       s_stacc, s_merge, pre_k0, pre_k1);
+                                                       smem + b * p.buf_stride + p.st_offset,
+                                                       reinterpret_cast<const uint16_t*>(smem + b * p.buf_stride + p.perm_offset),
+                                                       s, s * p.Cs, s_state, s_stacc, s_merge, pre_k0, pre_k1);
         __syncthreads();  // buffer b and the chunk states are free again
     }
     if (p.SS == 1) {
@@ -368,25 +378,46 @@ __global__ void __launch_bounds__(kLongMergeThreads) drillup_long_merge_kernel(c
 #undef OLAP_LONG_MERGE
 }
 
-// seg_ptr[s * P + p] = first position k in parent p's (ascending) child list with child >= s * Cs
-inline std::vector<int32_t> long_seg_table(const std::vector<int32_t>& pstart, const std::vector<int32_t>& children,
-                                           bool contiguous, int64_t C, int64_t P, const LongDecision& d) {
-    std::vector<int32_t> tab((size_t)(d.S_row + 1) * P);
-    for (int64_t s = 0; s <= d.S_row; ++s) {
-        const int64_t bound = std::min<int64_t>(C, s * (int64_t)d.Cs);
-        for (int64_t q = 0; q < P; ++q) {
-            const int32_t k0 = pstart[q], k1 = pstart[q + 1];
-            int32_t k;
-            if (contiguous) k = (int32_t)std::min<int64_t>(k1, std::max<int64_t>(k0, bound));
-            else k = (int32_t)(std::lower_bound(children.begin() + k0, children.begin() + k1, (int32_t)bound) - children.begin());
-            tab[(size_t)s * P + q] = k;
+// Contiguous map: seg_ptr[s * P + p] = first CSR position k of parent p with child >= s * Cs.
+// Any other map: seg_ptr[s * (P+1) + p] = where parent p starts in segment s's own cell list
+// (entry P = its length), and perm16[s * Cs + q] = the q-th cell of that list as an offset from
+// the segment's first child: parents in order, children ascending within a parent.
+struct LongTables {
+    std::vector<int32_t> seg_ptr;
+    std::vector<uint16_t> perm16;
+};
+inline LongTables long_seg_table(const std::vector<int32_t>& pstart, const std::vector<int32_t>& children,
+                                 bool contiguous, int64_t C, int64_t P, const LongDecision& d) {
+    LongTables t;
+    if (contiguous) {
+        t.seg_ptr.resize((size_t)(d.S_row + 1) * P);
+        for (int64_t s = 0; s <= d.S_row; ++s) {
+            const int64_t bound = std::min<int64_t>(C, s * (int64_t)d.Cs);
+            for (int64_t q = 0; q < P; ++q)
+                t.seg_ptr[(size_t)s * P + q] = (int32_t)std::min<int64_t>(pstart[q + 1], std::max<int64_t>(pstart[q], bound));
         }
+        return t;
     }
-    return tab;
+    t.seg_ptr.assign((size_t)d.S_row * (P + 1), 0);
+    t.perm16.assign((size_t)d.S_row * d.Cs, 0);
+    std::vector<int32_t> cursor(pstart.begin(), pstart.end() - 1);  // next unread CSR position per parent
+    for (int64_t s = 0; s < d.S_row; ++s) {
+        const int64_t c0 = s * (int64_t)d.Cs, c1 = std::min<int64_t>(C, c0 + d.Cs);
+        int32_t q = 0;
+        for (int64_t par = 0; par < P; ++par) {
+            t.seg_ptr[(size_t)s * (P + 1) + par] = q;
+            int32_t k = cursor[par];
+            while (k < pstart[par + 1] && children[k] < c1) t.perm16[(size_t)c0 + q++] = (uint16_t)(children[k++] - c0);
+            cursor[par] = k;
+        }
+        t.seg_ptr[(size_t)s * (P + 1) + P] = q;
+    }
+    return t;
 }
 
 inline int launch_up_long(const UpMeasure* d_meas, const UpMeasure* h_meas, int n, bool contiguous,
-                          const int32_t* d_pstart, const int32_t* d_children, const int32_t* d_seg_ptr, int64_t O,
+                          const int32_t* d_pstart, const int32_t* d_children, const int32_t* d_seg_ptr,
+                          const uint16_t* d_perm16, int64_t O,
                           int64_t C, int64_t P, int64_t I, const LongDecision& d, unsigned char* d_scratch) {
     UpLongParams p{};
     p.meas = d_meas;
@@ -394,12 +425,13 @@ inline int launch_up_long(const UpMeasure* d_meas, const UpMeasure* h_meas, int 
     p.pstart = d_pstart;
     p.children = d_children;
     p.seg_ptr = d_seg_ptr;
+    p.perm16 = d_perm16;
     p.O = O; p.C = (int32_t)C; p.P = (int32_t)P; p.I = (int32_t)I;
     p.Cs = d.Cs; p.S_row = d.S_row; p.T = d.T; p.SS = d.SS;
     p.row_out = (int32_t)(P * I);
     p.div_i = FastDiv((uint32_t)I);
     p.div_ss = FastDiv((uint32_t)d.SS);
-    p.buf_stride = d.buf_stride; p.st_offset = d.st_offset; p.bar_offset = d.bar_offset; p.state_offset = d.state_offset; p.merge_offset = d.merge_offset;
+    p.buf_stride = d.buf_stride; p.st_offset = d.st_offset; p.perm_offset = d.perm_offset; p.bar_offset = d.bar_offset; p.state_offset = d.state_offset; p.merge_offset = d.merge_offset;
     p.G = d.G;
     p.logG = 0;
     while ((1 << p.logG) < d.G) ++p.logG;

@@ -883,15 +883,16 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
             for (int k = 0; k < n; ++k) any_status |= meas[k].st_in != nullptr;
             const TileDecision tile = tile_plan(O, C, P, I, any_status);
             LongDecision lng;
-            if (!tile.use) lng = long_plan(O, C, P, I, any_status, n, g.sm_count);
+            if (!tile.use) lng = long_plan(O, C, P, I, any_status, n, g.sm_count, csr.contiguous);
             TablePack stat;
             const size_t o_ps = stat.add(csr.pstart.data(), csr.pstart.size() * 4);
             // a contiguous map needs no child list on the device (children[k] == k)
             const size_t o_ch = csr.contiguous ? 0 : stat.add(csr.children.data(), csr.children.size() * 4);
-            size_t o_seg = 0;
+            size_t o_seg = 0, o_perm = 0;
             if (lng.use) {
-                const std::vector<int32_t> seg = long_seg_table(csr.pstart, csr.children, csr.contiguous, C, P, lng);
-                o_seg = stat.add(seg.data(), seg.size() * 4);
+                const LongTables lt = long_seg_table(csr.pstart, csr.children, csr.contiguous, C, P, lng);
+                o_seg = stat.add(lt.seg_ptr.data(), lt.seg_ptr.size() * 4);
+                if (!lt.perm16.empty()) o_perm = stat.add(lt.perm16.data(), lt.perm16.size() * 2);
             }
             const char* d_stat = nullptr;
             OLAP_TRY(cached_tables(stat, &d_stat));
@@ -908,7 +909,8 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
                 void* scratch = nullptr;
                 if (lng.SS > 1) OLAP_TRY(dev_alloc(&scratch, (size_t)lng.scratch_stride * n));
                 OLAP_TRY(launch_up_long(d_meas, meas.data(), n, csr.contiguous, d_ps, d_ch,
-                                        reinterpret_cast<const int32_t*>(d_stat + o_seg), O, C, P, I, lng,
+                                        reinterpret_cast<const int32_t*>(d_stat + o_seg),
+                                        csr.contiguous ? nullptr : reinterpret_cast<const uint16_t*>(d_stat + o_perm), O, C, P, I, lng,
                                         static_cast<unsigned char*>(scratch)));
                 if (scratch) OLAP_TRY(dev_free(scratch));
             } else {
