@@ -207,6 +207,36 @@ def main():
     expr2 = getParser().parse("a || b * 2 - isNaN(c)")
     run(f"eval/a||b*2-isNaN(c) -> store [{nI}]",
         lambda: GpuStore.evaluate_to_store(expr2, ["a", "b", "c"], ins, {}), 4 * 3 * nI + (4 + S) * nI, nI)
+    # ---- cube-to-cube load (N2) and sparse export / import (N3) ----------------------------
+    dl = [int(1000 * sc) if sc < 1 else 1000, 100, 100, 10]
+    nl = int(np.prod(dl))
+    his = store(nl, 0.0, fill=0.5)
+    mine = GpuStore(nl * 2, "float32", 0.0)  # twice the items on the outer axis
+    to_mine = [np.arange(0, 2 * dl[0], 2, dtype=np.int32)] + [ident(d) for d in dl[1:]]
+
+    def timed_host(name, fn, algo_bytes, cells):
+        if only and not any(name.startswith(o) for o in only):
+            return
+        import time
+
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(args.reps):
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        t = float(np.median(ts))
+        row = {"op": name, "path": lib.olap_last_op_path().decode(), "ms": round(t, 4), "GBs": round(algo_bytes / (t * 1e-3) / 1e9, 1),
+               "frac": round(algo_bytes / (t * 1e-3) / 1e9 / peak, 3), "cells_per_s": cells / (t * 1e-3), "timing": "host wall-clock, synchronous call"}
+        results.append(row)
+        print(json.dumps(row), flush=True)
+
+    timed_host(f"load/scatter every-other outer item {dl} -> x2", lambda: mine.load_lowered(his, [2 * dl[0]] + dl[1:], dl, to_mine),
+               B * 2 * nl, nl)
+    timed_host(f"sparse/export fill 0.5 [{nl}] (12 B per set cell to the host)", lambda: his.export_sparse(), B * nl + 12 * (nl // 2), nl)
+    del his, mine
     if not only or "total" in only:
         import time
 

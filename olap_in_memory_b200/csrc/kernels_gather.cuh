@@ -358,4 +358,69 @@ __global__ void __launch_bounds__(256) load_scatter_kernel(const __grid_constant
     }
 }
 
+// Same scatter with 32-bit index math and, when the innermost axis of the other store lands
+// as one contiguous run in mine (his item j -> my item m0 + j), VEC cells per thread: one
+// decode per vector, 128-bit loads and stores.
+struct ScatterVecParams {
+    const float* src;
+    float* dst;
+    const uint8_t* st_src;
+    uint8_t* st_dst;
+    int dst_nan_default;
+    int nd;                         // outer axes (tables)
+    uint32_t len[OLAP_MAX_DIMS];
+    FastDiv div[OLAP_MAX_DIMS];
+    const int64_t* tbl[OLAP_MAX_DIMS];
+    uint32_t IV;                    // vectors per inner run
+    FastDiv div_iv;
+    int64_t inner_off;              // my offset of his first inner item
+    uint32_t n_vec;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) load_scatter_vec_kernel(const __grid_constant__ ScatterVecParams p) {
+    const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+    if (t >= p.n_vec) return;
+    uint32_t rest = p.div_iv.div(t);
+    int64_t off = p.inner_off + (int64_t)(t - rest * p.IV) * VEC;
+    bool drop = false;
+    for (int d = p.nd - 1; d >= 0; --d) {
+        const uint32_t q = p.div[d].div(rest);
+        const int64_t o = p.tbl[d][rest - q * p.len[d]];
+        rest = q;
+        drop |= o < 0;
+        off += o;
+    }
+    if (drop) return;
+    const int64_t s0 = (int64_t)t * VEC;
+    float v[VEC];
+    if (VEC == 4) {
+        const float4 x = ld_stream4(p.src + s0);
+        v[0] = x.x; v[1 % VEC] = x.y; v[2 % VEC] = x.z; v[3 % VEC] = x.w;
+    } else {
+        v[0] = ld_stream1(p.src + s0);
+    }
+    uint32_t sb = 0;
+    if (p.st_dst && p.st_src) {
+        if (VEC == 4) sb = ld_stream_u32(p.st_src + s0);
+        else sb = p.st_src[s0];
+    }
+    uint32_t so = 0;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        v[e] = canon_store(v[e], p.dst_nan_default);
+        const bool set = present_f(v[e], p.dst_nan_default);
+        uint32_t sx = set ? (uint32_t)OLAP_STATUS_SET : (uint32_t)OLAP_STATUS_UNSET;
+        if (p.st_src && set) sx = (sb >> (8 * e)) & 0xffu;  // "status flags are copied between cubes" README.md:704
+        so |= sx << (8 * e);
+    }
+    if (VEC == 4) {
+        st_stream4(p.dst + off, make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]));
+        if (p.st_dst) *reinterpret_cast<uint32_t*>(p.st_dst + off) = so;
+    } else {
+        p.dst[off] = v[0];
+        if (p.st_dst) p.st_dst[off] = (uint8_t)so;
+    }
+}
+
 }  // namespace olap

@@ -1380,6 +1380,56 @@ int olap_load(olap_store* dst, const olap_store* src, int ndim, const int64_t* m
     if (my_size != dst->size || his_size != src->size) return fail(OLAP_E_INVALID, "olap_load: dimensions do not match the stores");
     OLAP_TRY(ensure_ctx());
     begin_op();
+    bool fast = false;
+    if (his_size && my_size && ndim >= 1 && his_size < ((int64_t)1 << 31)) {
+        // innermost axis: his item j -> my item m0 + j ?  then runs stay contiguous
+        const int L = ndim - 1;
+        bool linear = his_len[L] > 0;
+        for (int64_t j = 0; j < his_len[L] && linear; ++j) linear = his_to_mine[L][j] >= 0 && his_to_mine[L][j] == his_to_mine[L][0] + (int32_t)j;
+        if (linear && his_to_mine[L][0] + his_len[L] > my_len[L]) return fail(OLAP_E_INVALID, "olap_load: item index outside [0, %lld)", (long long)my_len[L]);
+        const int64_t I = linear ? his_len[L] : 1;
+        const int nd = linear ? ndim - 1 : ndim;
+        const int VEC = (linear && I % 4 == 0 && his_to_mine[L][0] % 4 == 0 && my_len[L] % 4 == 0) ? 4 : 1;
+        bool ok = true;
+        for (int d = 0; d < nd; ++d) ok &= his_len[d] <= 0x7fffffffLL;
+        if (ok) {
+            ScatterVecParams p{};
+            TablePack t;
+            std::vector<size_t> offs(nd);
+            int64_t stride = linear ? my_len[L] : 1;
+            for (int d = nd - 1; d >= 0; --d) {
+                std::vector<int64_t> tbl(his_len[d]);
+                for (int64_t j = 0; j < his_len[d]; ++j) {
+                    const int32_t m = his_to_mine[d][j];
+                    if (m >= my_len[d]) return fail(OLAP_E_INVALID, "olap_load: item index %d outside [0, %lld)", m, (long long)my_len[d]);
+                    tbl[j] = m < 0 ? INT64_MIN / 32 : (int64_t)m * stride;
+                }
+                offs[d] = t.add(tbl.data(), tbl.size() * 8);
+                p.len[d] = (uint32_t)his_len[d];
+                p.div[d] = FastDiv((uint32_t)his_len[d]);
+                stride *= my_len[d];
+            }
+            OLAP_TRY(t.upload());
+            for (int d = 0; d < nd; ++d) p.tbl[d] = t.ptr<int64_t>(offs[d]);
+            p.src = src->values; p.dst = dst->values;
+            p.st_src = src->status; p.st_dst = dst->status;
+            p.dst_nan_default = dst->default_kind;
+            p.nd = nd;
+            p.IV = (uint32_t)(I / VEC);
+            p.div_iv = FastDiv(p.IV);
+            p.inner_off = linear ? his_to_mine[L][0] : 0;
+            p.n_vec = (uint32_t)(his_size / VEC);
+            const int64_t gx = ceil_div((int64_t)p.n_vec, 256);
+            KERNELS_BEGIN();
+            if (VEC == 4) load_scatter_vec_kernel<4><<<(unsigned)gx, 256, 0, g.stream>>>(p);
+            else load_scatter_vec_kernel<1><<<(unsigned)gx, 256, 0, g.stream>>>(p);
+            LAUNCHED();
+            OLAP_TRY(t.release());
+            fast = true;
+            end_op(VEC == 4 ? "load/scatter-vec4" : "load/scatter-rows");
+        }
+    }
+    if (fast) return finish_op();
     if (his_size && my_size) {
         ScatterParams p{};
         TablePack t;

@@ -189,6 +189,12 @@ def dice_cases(seed=2):
         ([8, 4], {0: 0}),             # empty result
         ([8, 4], {1: 1}),
         ([1, 9, 12], {1: 9}),
+        # the innermost axis alone is diced: whole source rows staged (dice_inner_kernel), ragged last CTA
+        ([5000, 10], {1: 5}),
+        ([37, 41, 9], {2: 4}),
+        ([3001, 7], {1: 6}),
+        ([6, 5, 300], {2: 299}),
+        ([40, 6, 11], {1: 1, 2: 3}),   # a sliced middle axis in front of the diced innermost one
     ]
     for dims, cut in shapes:
         for default in (0.0, math.nan):
@@ -244,6 +250,28 @@ def load_cases(seed=4):
                     pool = list(range(mine)) + [None] * max(0, his - mine + 1)
                     picked = rng.permutation(len(pool))[:his]
                     his_to_mine.append([pool[i] for i in picked])
+                yield dict(op="load", my_len=my_len, his_len=his_len, his_to_mine=his_to_mine,
+                           my_default=my_default, his_default=his_default,
+                           my_data=make_data(rng, int(np.prod(my_len)), my_default, 0.8, "int"),
+                           his_data=make_data(rng, int(np.prod(his_len)), his_default, 0.6, "int"))
+
+
+def load_linear_cases(seed=8):
+    """The other store's innermost axis lands as one contiguous run in mine (his item j -> my
+    item m0 + j): the vectorised scatter (128-bit when everything is 4-aligned, else rows)."""
+    rng = np.random.default_rng(seed)
+    for my_len, his_len, m0 in (([6, 12], [3, 8], 4), ([5, 7, 10], [4, 7, 6], 2), ([8, 16], [8, 16], 0),
+                                ([9, 40, 24], [12, 33, 20], 4), ([50], [30], 8)):
+        for my_default in (0.0, math.nan):
+            for his_default in (0.0, math.nan):
+                his_to_mine = []
+                for d, (mine, his) in enumerate(zip(my_len, his_len)):
+                    if d == len(my_len) - 1:
+                        his_to_mine.append([m0 + j for j in range(his)])
+                    else:
+                        pool = list(range(mine)) + [None] * max(0, his - mine + 1)
+                        picked = rng.permutation(len(pool))[:his]
+                        his_to_mine.append([pool[i] for i in picked])
                 yield dict(op="load", my_len=my_len, his_len=his_len, his_to_mine=his_to_mine,
                            my_default=my_default, his_default=his_default,
                            my_data=make_data(rng, int(np.prod(my_len)), my_default, 0.8, "int"),

@@ -20,7 +20,7 @@ n = 0
 for with_status in (True, False):
     GpuStore.WITH_STATUS = with_status
     for case in itertools.chain((c for c, _ in golden_io.load()), cases.drillup_cases(), cases.drillup_long_cases(), cases.drilldown_cases(),
-                                cases.dice_cases(), cases.reorder_cases(), cases.load_cases()):
+                                cases.dice_cases(), cases.reorder_cases(), cases.load_cases(), cases.load_linear_cases()):
         cases.run_case(case, GpuStore)
         n += 1
 gc.collect()

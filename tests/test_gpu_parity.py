@@ -16,7 +16,7 @@ from oracle.store_oracle import OracleStore
 pytestmark = pytest.mark.gpu
 
 ALL = list(itertools.chain(cases.drillup_cases(), cases.drillup_long_cases(), cases.drilldown_cases(), cases.dice_cases(),
-                           cases.reorder_cases(), cases.load_cases()))
+                           cases.reorder_cases(), cases.load_cases(), cases.load_linear_cases()))
 
 
 def _gpu():
@@ -338,3 +338,40 @@ def test_cluster_transpose(monkeypatch):
         st = out.status
         if st is not None:
             assert np.array_equal(np.asarray(st), np.where(want != 0, 2, 1))
+
+
+def test_reorder_fuzz_against_numpy():
+    """reorder is a pure permutation: random shapes / permutations (4-aligned and not, so that
+    the pair transpose, the box transpose and the vector gather all get hit, ragged tiles
+    included), two measures per call, against numpy.transpose — values and status bytes."""
+    from olap_in_memory_b200 import _native as N
+
+    G = _gpu()
+    rng = np.random.default_rng(11)
+    paths = {}
+    for trial in range(70):
+        nd = int(rng.integers(2, 6))
+        if trial % 2:
+            dims = [int(rng.choice([4, 8, 12, 20, 36, 44, 100, 104, 200])) for _ in range(nd)]
+        else:
+            dims = [int(rng.integers(2, 60)) for _ in range(nd)]
+        while int(np.prod(dims)) > 3_000_000:
+            dims[int(np.argmax(dims))] //= 2
+        perm = [int(x) for x in rng.permutation(nd)]
+        n = int(np.prod(dims))
+        stores, datas = [], []
+        for _ in range(2):
+            data = rng.integers(1, 1000, n).astype(np.float32)
+            data[rng.random(n) < 0.25] = 0.0
+            s = G(n, "float32", 0)
+            s.set_data_f32(data)
+            stores.append(s)
+            datas.append(data)
+        outs = G.reorder_lowered(stores, dims, perm)
+        path = N.lib().olap_last_op_path().decode()
+        paths[path] = paths.get(path, 0) + 1
+        for data, out in zip(datas, outs):
+            want = data.reshape(dims).transpose(perm).reshape(-1)
+            assert np.array_equal(out.data_f32(), want), (dims, perm, path)
+            assert np.array_equal(np.asarray(out.status), np.where(want != 0, 2, 1)), (dims, perm, path)
+    assert paths.get("reorder/pair-transpose", 0) >= 5 and paths.get("reorder/box-transpose", 0) >= 5, paths

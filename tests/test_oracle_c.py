@@ -11,7 +11,7 @@ from oracle.c_oracle import COracleStore
 from oracle.store_oracle import OracleStore
 
 ALL = list(itertools.chain(cases.drillup_cases(), cases.drilldown_cases(), cases.dice_cases(),
-                           cases.reorder_cases(), cases.load_cases()))
+                           cases.reorder_cases(), cases.load_cases(), cases.load_linear_cases()))
 
 
 def _same_f64(a, b):
