@@ -39,10 +39,17 @@ def main():
     except Exception:
         pass
     rows = []
+    # generic axis of a multiple of 4 items (128-bit accesses); at 1e8 cells also an odd one
+    # (the scalar variant of the same kernel), so that both are on record
+    shapes = []
     for target in (1e6, 1e7, 1e8, 1e9, 1e10):
         if target > args.max:
             break
-        g = max(1, int(round(target / 3652)))
+        g4 = max(4, int(round(target / 3652 / 4)) * 4)
+        shapes.append(g4)
+        if target == 1e8:
+            shapes.append(g4 + 1)
+    for g in shapes:
         dims = [TimeDimension("time", "day", "2010-01-01", "2019-12-31"),
                 GenericDimension("g", "root", [str(i) for i in range(g)])]
         cube = Cube(dims)
@@ -64,6 +71,7 @@ def main():
         def step():
             rolled = cube.drillUp("time", "month")
             ms = lib.olap_last_op_ms()
+            step.path = lib.olap_last_op_path().decode()
             outs = [rolled.evaluateToStore(f"c{k}_f") for k in range(len(FORMULAS))]
             return ms, outs
 
@@ -79,7 +87,8 @@ def main():
             del outs
         k_ms, w_ms = float(np.median(kernel_ms)), float(np.median(wall))
         algo = 5 * len(METHODS) * (n + 120 * g)
-        row = {"cells": n, "measures": len(METHODS), "computed": len(FORMULAS), "drillup_kernel_ms": round(k_ms, 4),
+        row = {"cells": n, "shape": [3652, g], "inner_run": "multiple of 4" if g % 4 == 0 else ("even" if g % 2 == 0 else "odd"),
+               "path": getattr(step, "path", ""), "measures": len(METHODS), "computed": len(FORMULAS), "drillup_kernel_ms": round(k_ms, 4),
                "step_wall_ms": round(w_ms, 3), "measure_cells_per_s_kernel": len(METHODS) * n / (k_ms * 1e-3),
                "measure_cells_per_s_step": len(METHODS) * n / (w_ms * 1e-3),
                "GBs": round(algo / (k_ms * 1e-3) / 1e9, 1), "frac": round(algo / (k_ms * 1e-3) / 1e9 / peak, 3)}

@@ -251,8 +251,10 @@ class GpuStore:
     @staticmethod
     def drillUp_many(stores, oldDimensions, newDimensions, methods):
         """in-memory.js:265-334; maps come from the OLD dimensions (270-274)."""
+        # an untouched dimension needs no map (include/olap_gpu.h: NULL = unchanged): nothing to
+        # build, upload or check for it, however many items it has
         maps = [
-            oldDimensions[i].getGroupIndexFromRootIndexMap(new_dim.rootAttribute)
+            None if new_dim is oldDimensions[i] else oldDimensions[i].getGroupIndexFromRootIndexMap(new_dim.rootAttribute)
             for i, new_dim in enumerate(newDimensions)
         ]
         return GpuStore.drillUp_lowered(stores, _lens(oldDimensions), _lens(newDimensions), maps, methods)
