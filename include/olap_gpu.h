@@ -126,6 +126,25 @@ int olap_store_create_batch(int n, int64_t size, const int* types, const int* de
 int olap_store_destroy(olap_store* s);
 /* `.clone()` in-memory.js:66-73 */
 int olap_store_clone(const olap_store* s, olap_store** out);
+
+/* ---- peer memory (sharded cubes, SURVEY.md §8e: "each rank pulls/pushes its slice through
+ * peer-mapped pointers") -------------------------------------------------------------------
+ * olap_peer_alloc: device memory that another process of the box can map; `handle64` receives
+ * the 64-byte CUDA IPC handle to send to the peers.  olap_peer_open maps a peer's buffer.
+ * olap_store_wrap: a store over memory the library does not own (destroy leaves it alone). */
+int olap_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int olap_peer_open(const unsigned char* handle64, void** ptr);
+int olap_peer_close(void* ptr);
+int olap_peer_free(void* ptr);
+int olap_store_wrap(void* values, void* status, int64_t size, int type, int default_kind, olap_store** out);
+/* drillUp (in-memory.js:265-334) of the OUTERMOST axis, [c_rows, inner] -> [p_rows, inner], where
+ * output row r of store k is written to row_values[k * p_rows + r] (and its status bytes to
+ * row_status[k * p_rows + r]; NULL when the stores carry no status plane) instead of a new
+ * store: with peer pointers, the partial rollup of a sharded dimension lands directly in the
+ * owning rank's receive buffer — rollup and exchange in ONE kernel over NVLink. */
+int olap_drill_up_rows(olap_store* const* src, int n, const int* methods, int64_t c_rows, int64_t p_rows,
+                       int64_t inner, const int32_t* row_map, float* const* row_values,
+                       uint8_t* const* row_status);
 int64_t olap_store_size(const olap_store* s);        /* `.size` in-memory.js:18-20 */
 int64_t olap_store_byte_length(const olap_store* s); /* `.byteLength` in-memory.js:8-16 */
 int olap_store_type(const olap_store* s);

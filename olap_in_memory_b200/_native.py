@@ -64,6 +64,13 @@ SIGNATURES = {
     "olap_store_create_batch": (C.c_int, [C.c_int, C.c_int64, p_int, p_int, C.c_int, C.c_int, pp_store]),
     "olap_store_destroy": (C.c_int, [p_store]),
     "olap_store_clone": (C.c_int, [p_store, pp_store]),
+    "olap_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    "olap_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "olap_peer_close": (C.c_int, [C.c_void_p]),
+    "olap_peer_free": (C.c_int, [C.c_void_p]),
+    "olap_store_wrap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, pp_store]),
+    "olap_drill_up_rows": (C.c_int, [pp_store, C.c_int, p_int, C.c_int64, C.c_int64, C.c_int64, p_i32,
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "olap_store_size": (C.c_int64, [p_store]),
     "olap_store_byte_length": (C.c_int64, [p_store]),
     "olap_store_type": (C.c_int, [p_store]),

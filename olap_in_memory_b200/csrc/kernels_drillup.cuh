@@ -320,6 +320,11 @@ struct UpMidParams {
     uint32_t row_vecs;    // P * IV
     uint32_t blocks_per_row;
     int n_measures;
+    // optional (O == 1): output row pi of measure k does not go to meas[k].out but to
+    // row_out[k * P + pi] (and row_st[...]) — e.g. straight into the receive buffer of the
+    // rank that owns the row, through a peer-mapped pointer (olap_drill_up_rows)
+    float* const* row_out;
+    uint8_t* const* row_st;
 };
 
 template <int VEC>
@@ -433,7 +438,12 @@ __global__ void __launch_bounds__(256) drillup_mid_kernel(const __grid_constant_
     if (o >= p.O || j >= p.row_vecs) return;
     const uint32_t pi = p.div_iv.div(j);
     const uint32_t iv = j - pi * p.IV;
-    const UpMeasure m = p.meas ? p.meas[blockIdx.y] : p.meas_inline[blockIdx.y];
+    UpMeasure m = p.meas ? p.meas[blockIdx.y] : p.meas_inline[blockIdx.y];
+    if (p.row_out) {  // rebase so that  out + pi * I_total + inner  lands in the row's own buffer
+        const size_t slot = (size_t)blockIdx.y * p.P + pi;
+        m.out = p.row_out[slot] - (int64_t)pi * p.I_total;
+        if (m.st_in) m.st_out = p.row_st[slot] - (int64_t)pi * p.I_total;
+    }
     const bool status = m.st_in != nullptr;
     if (m.nan_default) {
         if (status) up_mid_dispatch<true, VEC, RANGE, true, U>(p, m, o, pi, iv);

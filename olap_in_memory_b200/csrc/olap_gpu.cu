@@ -121,7 +121,7 @@ int alloc_batch(int n, int64_t size, const int* types, const int* default_kinds,
 
 // bytes of the guard (and of the alignment padding before it) that no longer hold 0xA5
 static void check_guards(const olap_store* s) {
-    if (!g_guard || !g.ready) return;
+    if (!g_guard || !g.ready || !s->arena) return;  // wrapped stores (olap_store_wrap) carry no guard regions
     auto check = [&](const char* plane, size_t used) {
         const size_t span = pad256(used) + kGuardBytes - used;
         std::vector<unsigned char> host(span);
@@ -294,7 +294,8 @@ static uint32_t next_pow2(uint32_t v) {
 }
 
 static int launch_up_mid(const UpMeasure* d_meas, const UpMeasure* h_meas, int n, const Csr& csr,
-                         const int32_t* d_pstart, const int32_t* d_children, int64_t O, int64_t C, int64_t P, int64_t I) {
+                         const int32_t* d_pstart, const int32_t* d_children, int64_t O, int64_t C, int64_t P, int64_t I,
+                         float* const* d_row_out = nullptr, uint8_t* const* d_row_st = nullptr) {
     const int VEC = (I % 4 == 0) ? 4 : (I % 2 == 0 ? 2 : 1);
     const int64_t IV_total = I / VEC;
     // chunk the inner run so that one row of output vectors fits 32-bit math
@@ -318,6 +319,8 @@ static int launch_up_mid(const UpMeasure* d_meas, const UpMeasure* h_meas, int n
         p.div_iv = FastDiv((uint32_t)iv_n);
         p.row_vecs = (uint32_t)(P * iv_n);
         p.n_measures = n;
+        p.row_out = d_row_out;
+        p.row_st = d_row_st;
         // too few output vectors to fill the chip and long child lists: split each parent's
         // children over G thread rows (drillup_split_kernel)
         static const int split_knob = [] { const char* e = getenv("OLAP_SPLIT"); return e ? atoi(e) : -1; }();
@@ -327,6 +330,7 @@ static int launch_up_mid(const UpMeasure* d_meas, const UpMeasure* h_meas, int n
         int G = 1;
         while (G < 32 && threads * G * 4 <= want_threads && avg_children >= 8 * G) G *= 2;
         if (split_knob >= 0) G = split_knob;
+        if (d_row_out) G = 1;  // row pointer tables: plain mid kernel only
         if (G >= 2 && O * ceil_div(p.row_vecs, 32) <= 0x7fffffffLL) {
             p.blocks_per_row = (uint32_t)ceil_div(p.row_vecs, 32);
             const size_t smem = (size_t)G * 32 * VEC * 16 + (size_t)G * 32 * 4;
@@ -1460,6 +1464,104 @@ int olap_load(olap_store* dst, const olap_store* src, int ndim, const int64_t* m
         OLAP_TRY(t.release());
     }
     end_op("load/scatter");
+    return finish_op();
+}
+
+// ---- peer memory and the fused rollup + exchange (sharded cubes) --------------------------
+// Buffers that other processes of the box can map (cudaMalloc + CUDA IPC; the stream-ordered
+// pool cannot be exported), stores that wrap such memory, and a drillUp of the OUTERMOST axis
+// that writes every output row to a caller-given pointer: with peer-mapped pointers each rank
+// stores its partial rollup of a sharded dimension STRAIGHT into the receive buffer of the
+// rank that owns the row, over NVLink, from inside the rollup kernel — no partial plane in
+// local HBM, no separate all-to-all.
+int olap_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64) {
+    if (!ptr || !handle64) return fail(OLAP_E_INVALID, "olap_peer_alloc: null argument");
+    OLAP_TRY(ensure_ctx());
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    OLAP_CUDA(cudaMalloc(ptr, bytes ? bytes : 256));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*ptr);
+        *ptr = nullptr;
+        return fail(OLAP_E_CUDA, "olap_peer_alloc: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle64, &h, 64);
+    return OLAP_OK;
+}
+
+int olap_peer_open(const unsigned char* handle64, void** ptr) {
+    if (!ptr || !handle64) return fail(OLAP_E_INVALID, "olap_peer_open: null argument");
+    OLAP_TRY(ensure_ctx());
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    OLAP_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return OLAP_OK;
+}
+
+int olap_peer_close(void* ptr) {
+    if (!ptr) return OLAP_OK;
+    OLAP_CUDA(cudaIpcCloseMemHandle(ptr));
+    return OLAP_OK;
+}
+
+int olap_peer_free(void* ptr) {
+    if (!ptr) return OLAP_OK;
+    OLAP_CUDA(cudaFree(ptr));
+    return OLAP_OK;
+}
+
+int olap_store_wrap(void* values, void* status, int64_t size, int type, int default_kind, olap_store** out) {
+    if (!values || !out || size < 0) return fail(OLAP_E_INVALID, "olap_store_wrap: invalid argument");
+    OLAP_TRY(check_type_default(type, default_kind));
+    olap_store* s = new olap_store();
+    s->size = size;
+    s->type = type;
+    s->default_kind = default_kind;
+    s->values = static_cast<float*>(values);
+    s->status = static_cast<uint8_t*>(status);
+    s->arena = nullptr;  // not owned: olap_store_destroy leaves the memory alone
+    *out = s;
+    return OLAP_OK;
+}
+
+int olap_drill_up_rows(olap_store* const* src, int n, const int* methods, int64_t c_rows, int64_t p_rows, int64_t inner,
+                       const int32_t* row_map, float* const* row_values, uint8_t* const* row_status) {
+    int64_t size = 0;
+    OLAP_TRY(check_batch(src, n, "olap_drill_up_rows", &size));
+    if (!methods || !row_map || !row_values) return fail(OLAP_E_INVALID, "olap_drill_up_rows: null argument");
+    if (c_rows <= 0 || p_rows <= 0 || inner <= 0 || c_rows > 0x7fffffffLL || p_rows > 0x7fffffffLL)
+        return fail(OLAP_E_INVALID, "olap_drill_up_rows: invalid shape");
+    if (c_rows * inner != size) return fail(OLAP_E_INVALID, "olap_drill_up_rows: shape describes %lld cells, store has %lld", (long long)(c_rows * inner), (long long)size);
+    for (int k = 0; k < n; ++k)
+        if (methods[k] < OLAP_SUM || methods[k] > OLAP_COUNT) return fail(OLAP_E_INVALID, "Unsupported aggregation method: %d", methods[k]);
+    for (int64_t i = 0; i < c_rows; ++i)
+        if (row_map[i] < 0 || row_map[i] >= p_rows) return fail(OLAP_E_INVALID, "olap_drill_up_rows: row %lld maps to %d, outside [0, %lld)", (long long)i, row_map[i], (long long)p_rows);
+    bool any_status = false;
+    for (int k = 0; k < n; ++k) any_status |= src[k]->status != nullptr;
+    if (any_status && !row_status) return fail(OLAP_E_INVALID, "olap_drill_up_rows: stores carry a status plane but no status rows were given");
+    OLAP_TRY(ensure_ctx());
+    begin_op();
+    std::vector<UpMeasure> meas(n);
+    for (int k = 0; k < n; ++k) {
+        const uint8_t* si = row_status ? st_in_of(src, k) : nullptr;
+        // out / st_out are placeholders (non-null where a plane exists): the kernel rebases them per row
+        meas[k] = UpMeasure{src[k]->values, const_cast<float*>(src[k]->values), si, si ? const_cast<uint8_t*>(si) : nullptr,
+                            methods[k], src[k]->default_kind};
+    }
+    const Csr csr = build_csr(row_map, c_rows, p_rows);
+    TablePack t;
+    const size_t o_meas = t.add(meas.data(), sizeof(UpMeasure) * n);
+    const size_t o_ps = t.add(csr.pstart.data(), csr.pstart.size() * 4);
+    const size_t o_ch = t.add(csr.children.data(), csr.children.size() * 4);
+    const size_t o_rv = t.add(row_values, sizeof(float*) * (size_t)n * p_rows);
+    std::vector<uint8_t*> no_status((size_t)n * p_rows, nullptr);
+    const size_t o_rs = t.add(row_status ? (const void*)row_status : (const void*)no_status.data(), sizeof(uint8_t*) * (size_t)n * p_rows);
+    OLAP_TRY(t.upload());
+    OLAP_TRY(launch_up_mid(t.ptr<UpMeasure>(o_meas), meas.data(), n, csr, t.ptr<int32_t>(o_ps), t.ptr<int32_t>(o_ch), 1, c_rows,
+                           p_rows, inner, t.ptr<float*>(o_rv), t.ptr<uint8_t*>(o_rs)));
+    OLAP_TRY(t.release());
+    end_op("drillup/mid-rows-p2p");
     return finish_op();
 }
 

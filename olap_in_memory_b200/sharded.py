@@ -20,6 +20,8 @@ torch.distributed is plumbing: NCCL moves the planes (zero-copy views of the dev
 stores, olap_in_memory_b200/interop.py); every arithmetic step is a store call."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from .cube import Cube  # noqa: F401  (re-exported for convenience)
@@ -43,6 +45,45 @@ def _prod(xs):
 
 def _is_device_store(store):
     return hasattr(store, "_h")
+
+
+# OLAP_SHARDED_P2P=0: rollups of a sharded dimension go through NCCL all-to-all (partial planes
+# in local HBM, then one exchange per plane).  Default on GPUs: ONE kernel per call computes the
+# partial rollup and stores every output row straight into the receive buffer of the rank that
+# owns it, through peer-mapped pointers over NVLink (olap_drill_up_rows).
+P2P_EXCHANGE = os.environ.get("OLAP_SHARDED_P2P", "1") != "0"
+
+
+class _PeerBuffers:
+    """Receive buffers that every rank of the group has mapped (CUDA IPC), cached by size."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, comm, nbytes):
+        import ctypes as C
+
+        from . import _native as N
+
+        key = (id(comm.group), int(nbytes))
+        hit = cls._cache.get(key)
+        if hit is not None:
+            return hit
+        mine = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        N.check(N.lib().olap_peer_alloc(int(nbytes), C.byref(mine), handle))
+        handles = [None] * comm.world
+        comm.dist.all_gather_object(handles, handle.raw, group=comm.group)
+        ptrs = []
+        for r, h in enumerate(handles):
+            if r == comm.rank:
+                ptrs.append(mine.value)
+                continue
+            p = C.c_void_p()
+            N.check(N.lib().olap_peer_open(C.create_string_buffer(h, 64), C.byref(p)))
+            ptrs.append(p.value)
+        cls._cache[key] = ptrs
+        return ptrs
 
 
 class _Comm:
@@ -305,6 +346,9 @@ class ShardedCube:
             else:
                 plan.append((m, method, "plain"))
         stores = [self.storedMeasures[m] for m, _, _ in plan]
+        if P2P_EXCHANGE and self.comm.on and _is_device_store(stores[0]):
+            received = self._partials_into_peers(stores, [meth for _, meth, _ in plan], row_map, out_bounds, new_rows_total)
+            return self._combine(out, plan, ids, methods, received, my_out_rows)
         partials = self._partials(stores, old_len, new_len, maps, [meth for _, meth, _ in plan])
 
         # 2. one all-to-all per plane: rank r receives the W partials of ITS output rows
@@ -321,7 +365,11 @@ class ShardedCube:
         self._exchange_all(partials, received, in_splits, out_splits)
         del partials
 
-        # 3. ordered combine of the W partials: a drillUp over the rank axis
+        return self._combine(out, plan, ids, methods, received, my_out_rows)
+
+    def _combine(self, out, plan, ids, methods, received, my_out_rows):
+        """3. ordered combine of the W partials: a drillUp over the rank axis."""
+        W = self.world
         comb_old = [W, my_out_rows] + self.inner_lens
         comb_new = [1, my_out_rows] + self.inner_lens
         comb_maps = [np.zeros(W, dtype=np.int32)] + [np.arange(n, dtype=np.int32) for n in comb_old[1:]]
@@ -337,6 +385,64 @@ class ShardedCube:
                 out.storedMeasures[m] = combined[k]
                 k += 1
         return out
+
+    def _partials_into_peers(self, stores, part_methods, row_map, out_bounds, new_rows_total):
+        """1 + 2 fused: the partial rollup of my rows, every output row written by the kernel
+        into the receive buffer of its owner (slot = my rank), over NVLink.  Returns my receive
+        planes wrapped as stores [W, my_out_rows, inner...]."""
+        import ctypes as C
+
+        import torch
+
+        from . import _native as N
+        from .store import _method_code
+
+        W, me, inner = self.world, self.rank, self.inner
+        K = len(stores)
+        rows_of = [out_bounds[r + 1] - out_bounds[r] for r in range(W)]
+        with_status = bool(N.lib().olap_store_status_ptr(stores[0]._h))
+        r_max = max(rows_of)
+        pad = lambda b: (b + 255) // 256 * 256  # every plane starts on a 256-byte boundary, like a store's own planes
+        plane_v, plane_s = pad(W * r_max * inner * 4), pad(W * r_max * inner)
+        nbytes = K * plane_v + (K * plane_s if with_status else 0) + 256
+        # nobody may still be combining the previous contents of these buffers
+        self.comm.dist.barrier(group=self.comm.group)
+        bases = _PeerBuffers.get(self.comm, nbytes)
+
+        def val_ptr(r, k, src_rank):  # plane k of rank r's buffer, slot of the sending rank
+            return bases[r] + k * plane_v + src_rank * rows_of[r] * inner * 4
+
+        def st_ptr(r, k, src_rank):
+            return bases[r] + K * plane_v + k * plane_s + src_rank * rows_of[r] * inner
+
+        owner = np.searchsorted(np.asarray(out_bounds[1:]), np.arange(new_rows_total), side="right")
+        row_vals = (C.c_void_p * (K * new_rows_total))()
+        row_sts = (C.c_void_p * (K * new_rows_total))() if with_status else None
+        for k in range(K):
+            for j in range(new_rows_total):
+                r = int(owner[j])
+                local = j - out_bounds[r]
+                row_vals[k * new_rows_total + j] = val_ptr(r, k, me) + local * inner * 4
+                if with_status:
+                    row_sts[k * new_rows_total + j] = st_ptr(r, k, me) + local * inner
+        codes = [_method_code(m) for m in part_methods]
+        rows_local = self.rows_local
+        N.check(N.lib().olap_drill_up_rows(N.store_array([s._h for s in stores]), K, N.int_array(codes), rows_local,
+                                           new_rows_total, inner, np.ascontiguousarray(row_map, dtype=np.int32).ctypes.data_as(N.p_i32),
+                                           row_vals, row_sts))
+        torch.cuda.synchronize()
+        # every rank has finished storing into every buffer
+        self.comm.dist.barrier(group=self.comm.group)
+        received = []
+        my_rows = rows_of[me]
+        for k, src_store in enumerate(stores):
+            h = C.c_void_p()
+            N.check(N.lib().olap_store_wrap(C.c_void_p(val_ptr(me, k, 0)), C.c_void_p(st_ptr(me, k, 0)) if with_status else None,
+                                            W * my_rows * inner, N.TYPES[src_store._type],
+                                            N.DEFAULT_NAN if src_store._defaultValue != src_store._defaultValue else N.DEFAULT_ZERO,
+                                            C.byref(h)))
+            received.append(self._store_cls._wrap(h.value))
+        return received
 
     def _partials(self, stores, old_len, new_len, maps, methods):
         if _is_device_store(stores[0]):
