@@ -73,8 +73,8 @@ def main():
     for label, fn, n_out in (
         (f"inner {last}->all (shard-local)", lambda: cube.drillUp(last, "all"), n_total // 10),
         (f"mid {mid}->parity (shard-local)", lambda: cube.drillUp(mid, "parity"), n_total // 5),
-        ("sharded dim0->all (all_to_all + combine)", lambda: cube.drillUp("dim0", "all"), n_total // 10),
-        ("sharded dim0->parity (all_to_all + combine)", lambda: cube.drillUp("dim0", "parity"), n_total // 5),
+        ("sharded dim0->all (exchange + combine)", lambda: cube.drillUp("dim0", "all"), n_total // 10),
+        ("sharded dim0->parity (exchange + combine)", lambda: cube.drillUp("dim0", "parity"), n_total // 5),
     ):
         ms = timed(fn)
         row = {"op": label, "n_gpus": world, "cells_in": n_total, "measures": measures, "ms": round(ms, 3),
@@ -84,6 +84,9 @@ def main():
             # average travels as (sum, count): 4 planes for 3 measures
             planes = 4
             # every rank holds a partial of the FULL output and sends (W-1)/W of it
+            from olap_in_memory_b200 import sharded as _sh
+
+            row["exchange"] = "peer stores from the rollup kernel" if _sh.P2P_EXCHANGE else "NCCL all-to-all per plane"
             row["nvlink_bytes_sent_per_gpu"] = 5 * planes * n_out * (world - 1) // world
             row["nvlink_GBs_per_gpu"] = round(row["nvlink_bytes_sent_per_gpu"] / (ms * 1e-3) / 1e9, 1)
         rows.append(row)
