@@ -1530,7 +1530,9 @@ int olap_drill_up_rows(olap_store* const* src, int n, const int* methods, int64_
     int64_t size = 0;
     OLAP_TRY(check_batch(src, n, "olap_drill_up_rows", &size));
     if (!methods || !row_map || !row_values) return fail(OLAP_E_INVALID, "olap_drill_up_rows: null argument");
-    if (c_rows <= 0 || p_rows <= 0 || inner <= 0 || c_rows > 0x7fffffffLL || p_rows > 0x7fffffffLL)
+    // c_rows == 0 is legal: a rank that holds no row of the sharded axis still fills its slot of
+    // every receive buffer with "unset" (the combine step reads all W slots)
+    if (c_rows < 0 || p_rows <= 0 || inner <= 0 || c_rows > 0x7fffffffLL || p_rows > 0x7fffffffLL)
         return fail(OLAP_E_INVALID, "olap_drill_up_rows: invalid shape");
     if (c_rows * inner != size) return fail(OLAP_E_INVALID, "olap_drill_up_rows: shape describes %lld cells, store has %lld", (long long)(c_rows * inner), (long long)size);
     for (int k = 0; k < n; ++k)

@@ -416,20 +416,28 @@ class ShardedCube:
             return bases[r] + K * plane_v + k * plane_s + src_rank * rows_of[r] * inner
 
         owner = np.searchsorted(np.asarray(out_bounds[1:]), np.arange(new_rows_total), side="right")
+        # The kernel walks the output rows in table order.  Every rank starts with the rows of
+        # its RIGHT neighbour and ends with its own, so at any moment the W ranks store to W
+        # different receivers (rows in plain order would make everybody hit rank 0 first, then
+        # rank 1, ...: one NVLink ingress at a time — measured on 8 B200: 76.7 ms for the 1e10-cell
+        # cube against 60 ms for NCCL).  Position q of the table holds output row order[q].
+        order = sorted(range(new_rows_total), key=lambda j: ((int(owner[j]) - me - 1) % W, j))
+        position = np.empty(new_rows_total, dtype=np.int32)
+        position[np.asarray(order, dtype=np.int64)] = np.arange(new_rows_total, dtype=np.int32)
         row_vals = (C.c_void_p * (K * new_rows_total))()
         row_sts = (C.c_void_p * (K * new_rows_total))() if with_status else None
         for k in range(K):
-            for j in range(new_rows_total):
+            for q, j in enumerate(order):
                 r = int(owner[j])
                 local = j - out_bounds[r]
-                row_vals[k * new_rows_total + j] = val_ptr(r, k, me) + local * inner * 4
+                row_vals[k * new_rows_total + q] = val_ptr(r, k, me) + local * inner * 4
                 if with_status:
-                    row_sts[k * new_rows_total + j] = st_ptr(r, k, me) + local * inner
+                    row_sts[k * new_rows_total + q] = st_ptr(r, k, me) + local * inner
         codes = [_method_code(m) for m in part_methods]
         rows_local = self.rows_local
+        permuted_map = np.ascontiguousarray(position[np.asarray(row_map, dtype=np.int64)], dtype=np.int32)
         N.check(N.lib().olap_drill_up_rows(N.store_array([s._h for s in stores]), K, N.int_array(codes), rows_local,
-                                           new_rows_total, inner, np.ascontiguousarray(row_map, dtype=np.int32).ctypes.data_as(N.p_i32),
-                                           row_vals, row_sts))
+                                           new_rows_total, inner, permuted_map.ctypes.data_as(N.p_i32), row_vals, row_sts))
         torch.cuda.synchronize()
         # every rank has finished storing into every buffer
         self.comm.dist.barrier(group=self.comm.group)
