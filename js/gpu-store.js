@@ -48,6 +48,26 @@ class GpuStore {
     return new Map(Array.from(keys, (k, i) => [Number(k), values[i]]));
   }
 
+  serialize() {                      // in-memory.js:75-101, same record, cells from the device compaction
+    const { toBuffer } = require('olap-in-memory/src/serialization');
+    const { keys, values } = native.exportSparse(this._h);   // BigInt64Array, Float32Array
+    const Typed = { int32: Int32Array, uint32: Uint32Array, float32: Float32Array, float64: Float64Array }[this._type];
+    return toBuffer({
+      size: this._size,
+      type: this._type,
+      defaultValue: this._defaultValue,
+      indexes: Uint32Array.from(keys, Number),
+      dataBuffer: Typed.from(values),
+    });
+  }
+  static deserialize(buffer) {       // in-memory.js:103-116
+    const { fromBuffer } = require('olap-in-memory/src/serialization');
+    const data = fromBuffer(buffer);
+    const store = new GpuStore(data.size, data.type, data.defaultValue);
+    native.importSparse(store._h, BigInt64Array.from(data.indexes, BigInt), Float32Array.from(data.dataBuffer));
+    return store;
+  }
+
   getValue(index) { return native.getValue(this._h, index); }
   setValue(index, value) { native.setValue(this._h, index, value ?? this._defaultValue); }
   fill(value) { native.fill(this._h, value); }

@@ -703,6 +703,47 @@ class Cube:
         return out
 
 
+    # ---------------------------------------------------------- serialization
+    def serialize(self):
+        """cube.js:1135-1151, byte-compatible with the reference's wire format."""
+        from .serialization import toBuffer
+
+        return toBuffer({
+            "dimensions": [dim.serialize() for dim in self.dimensions],
+            "storedMeasuresKeys": list(self.storedMeasures.keys()),
+            "storedMeasures": [store.serialize() for store in self.storedMeasures.values()],
+            "storedMeasuresRules": self.storedMeasuresRules,
+            "computedMeasures": {m: e.toString() for m, e in self.computedMeasures.items()},
+        })
+
+    def serializeToBase64String(self):  # cube.js:1153-1155
+        import base64
+
+        return base64.b64encode(self.serialize()).decode("ascii")
+
+    @classmethod
+    def deserialize(cls, buffer, store_cls=None):
+        """cube.js:1157-1179.  Every store is rebuilt with the cube's own cell count (the
+        wire format keeps only a Float32 of it, serialization.js:71-74)."""
+        from .dimension import DimensionFactory
+        from .serialization import fromBuffer
+
+        data = fromBuffer(buffer)
+        cube = cls([DimensionFactory.deserialize(d) for d in data["dimensions"]], store_cls)
+        cube.storedMeasuresRules = data["storedMeasuresRules"]
+        for key, blob in zip(data["storedMeasuresKeys"], data["storedMeasures"]):
+            cube.storedMeasures[key] = cube._store_cls.deserialize(blob, cube.storeSize)
+        parser = getParser()
+        cube.computedMeasures = {m: parser.parse(text) for m, text in data["computedMeasures"].items()}
+        return cube
+
+    @classmethod
+    def deserializeFromBase64String(cls, serializedBase64, store_cls=None):  # cube.js:1181-1185
+        import base64
+
+        return cls.deserialize(base64.b64decode(serializedBase64), store_cls)
+
+
 class _PerMeasure(list):
     """Marks an argument that holds one value per stored measure."""
 

@@ -16,6 +16,9 @@ class CatchAll(AbstractDimension):
     def attributes(self):
         raise NotImplementedError("Unsupported")
 
+    def serialize(self):  # catch-all.js:16-18
+        raise NotImplementedError("Unsupported")
+
     def getItems(self, _attribute=None):
         return ["_total"]
 

@@ -40,6 +40,31 @@ class GenericDimension(AbstractDimension):
     def attributes(self):
         return list(self._rootIdxToGroupIdx.keys())
 
+    @staticmethod
+    def deserialize(buffer):  # generic.js:47-60
+        from ..serialization import fromBuffer
+
+        data = fromBuffer(buffer)
+        dim = GenericDimension(data["id"], data["rootAttribute"], data["attributeItems"][data["rootAttribute"]],
+                               data["label"])
+        dim._items.update(data["attributeItems"])
+        dim._itemToLabel.update(data["attributeLabels"])
+        dim._rootIdxToGroupIdx.update({k: np.asarray(v, dtype=np.int32) for k, v in data["attributeMappings"].items()})
+        return dim
+
+    def serialize(self):  # generic.js:62-72
+        from ..serialization import toBuffer
+
+        return toBuffer({
+            "id": self.id,
+            "label": self.label,
+            "rootAttribute": self._rootAttribute,
+            "rootItems": self._items[self._rootAttribute],
+            "attributeItems": self._items,
+            "attributeLabels": self._itemToLabel,
+            "attributeMappings": {k: np.asarray(v).astype(np.uint32) for k, v in self._rootIdxToGroupIdx.items()},
+        })
+
     def addAttribute(self, baseAttr, newAttr, baseToNew, newToNewLabel=None):
         """Derive attribute `newAttr` from `baseAttr` through `baseToNew`
         (dict or callable).  Nothing is modified if the mapping raises."""

@@ -25,6 +25,24 @@ class TimeDimension(AbstractDimension):
     def attributes(self):
         return [self._rootAttribute, *TimeSlot.upperSlots[self._rootAttribute]]
 
+    @staticmethod
+    def deserialize(buffer):  # time.js:28-37
+        from ..serialization import fromBuffer
+
+        data = fromBuffer(buffer)
+        return TimeDimension(data["id"], data["rootAttribute"], data["start"], data["end"], data["label"])
+
+    def serialize(self):  # time.js:39-47
+        from ..serialization import toBuffer
+
+        return toBuffer({
+            "id": self.id,
+            "label": self.label,
+            "rootAttribute": self.rootAttribute,
+            "start": self._start.value,
+            "end": self._end.value,
+        })
+
     def getItems(self, attribute=None):
         if self._start.value > self._end.value:
             return []

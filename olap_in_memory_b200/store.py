@@ -146,6 +146,32 @@ class GpuStore:
         values = np.ascontiguousarray(values, dtype=np.float32)
         N.check(N.lib().olap_store_import_sparse(self._h, keys.ctypes.data, values.ctypes.data, keys.size))
 
+    def serialize(self):
+        """in-memory.js:75-101: {size, type, defaultValue, indexes: Uint32Array, dataBuffer} in the
+        reference's wire format; the set cells leave the device through the ordered stream
+        compaction (keys ascending: the Map order of a store filled by `set data`)."""
+        from .serialization import store_to_buffer
+
+        keys, values = self.export_sparse()
+        return store_to_buffer(self._size, self._type, self._defaultValue, keys, values)
+
+    @classmethod
+    def deserialize(cls, buffer, size=None):
+        """in-memory.js:103-116.  The wire format carries `size` as a Float32
+        (serialization.js:71-74); `size`, when given, is the caller's exact cell count and must
+        round to the transmitted one."""
+        from .serialization import store_from_buffer
+
+        wire_size, type, default, keys, values = store_from_buffer(buffer)
+        if size is None:
+            size = wire_size
+        elif int(np.float32(size)) != wire_size:
+            raise N.OlapValueError(f"value length is invalid: {size} !== {wire_size}")
+        store = cls(size, type, default)
+        if keys.size:
+            store.import_sparse(keys, values)
+        return store
+
     def clone(self):  # in-memory.js:66-73
         out = C.c_void_p()
         N.check(N.lib().olap_store_clone(self._h, C.byref(out)))

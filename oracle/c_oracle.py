@@ -134,6 +134,22 @@ class COracleStore:
     def fill(self, value):
         lib().ostore_fill(self._h, float(value))
 
+    def serialize(self):  # in-memory.js:75-101 (Map order)
+        from olap_in_memory_b200.serialization import store_to_buffer
+
+        keys, vals = self.entries()
+        return store_to_buffer(self._size, self._type, self._defaultValue, keys, vals)
+
+    @classmethod
+    def deserialize(cls, buffer, size=None):  # in-memory.js:103-116
+        from olap_in_memory_b200.serialization import store_from_buffer
+
+        wire_size, type, default, keys, values = store_from_buffer(buffer)
+        store = cls(wire_size if size is None else size, type, default)
+        for k, v in zip(keys.tolist(), values.tolist()):
+            store.setValue(k, v)
+        return store
+
     def clone(self):
         return self._wrap(lib().ostore_clone(self._h))
 

@@ -111,6 +111,21 @@ class OracleStore:
         0x2 when the cell is set, 0x1 when it is not."""
         return [0x2 if i in self._dataMap else 0x1 for i in range(self._size)]
 
+    def serialize(self):  # in-memory.js:75-101 (keys in Map order)
+        from olap_in_memory_b200.serialization import store_to_buffer
+
+        return store_to_buffer(self._size, self._type, self._defaultValue, list(self._dataMap.keys()),
+                               list(self._dataMap.values()))
+
+    @classmethod
+    def deserialize(cls, buffer, size=None):  # in-memory.js:103-116: no presence filter
+        from olap_in_memory_b200.serialization import store_from_buffer
+
+        wire_size, type, default, keys, values = store_from_buffer(buffer)
+        store = cls(wire_size if size is None else size, type, default)
+        store._dataMap = dict(zip(keys.tolist(), values.tolist()))
+        return store
+
     def clone(self):  # in-memory.js:66-73
         return OracleStore(self._size, self._type, self._defaultValue, self._dataMap)
 

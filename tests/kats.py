@@ -424,4 +424,39 @@ def kat_compose_intersection(S):  # cube-to-cube.js:6-48
     check(new.getNestedArray("antennas"), [[1, 2], [4, 8], [16, 32]])
 
 
+# ---------------------------------------------------------- cube-serialize.js
+def kat_serialize_cube_round_trip(S):  # cube-serialize.js:30-52
+    items = [str(i) for i in range(50)]
+    cube = Cube(
+        [
+            GenericDimension("dim1", "root", items),
+            GenericDimension("dim2", "root", items),
+            TimeDimension("time", "month", "2010-01", "2011-01"),
+        ],
+        S,
+    )
+    cube.createStoredMeasure("main", {}, "float32", 0)
+    cube.setData("main", [30] * (len(items) * len(items) * 13))
+    buffer = cube.serialize()
+    new = Cube.deserialize(buffer, S)
+    check(new.getNestedObject("main"), cube.getNestedObject("main"))
+    # the same bytes again: the format is canonical for a store filled by setData
+    assert new.serialize() == buffer
+    assert Cube.deserializeFromBase64String(cube.serializeToBase64String(), S).serialize() == buffer
+
+
+def kat_serialize_test_cube(S):  # the shared fixture through the wire: attributes, rules, formula, sparse cells
+    cube = create_test_cube(S)
+    cube.setSingleData("antennas", {"location": "toledo", "period": "winter"}, 0)  # an unset cell
+    new = Cube.deserialize(cube.serialize(), S)
+    assert new.dimensionIds == ["location", "period"]
+    assert new.getDimension("location").attributes == cube.getDimension("location").attributes
+    assert new.storedMeasuresRules == cube.storedMeasuresRules
+    check(new.getNestedArray("antennas"), [[1, 2], [4, 0], [16, 32]])
+    check(sorted(new.getStatusMap("antennas").keys()), [0, 1, 2, 4, 5])
+    check(new.getNestedArray("router_by_antennas"), cube.getNestedArray("router_by_antennas"))
+    check(new.drillUp("location", "continent").getNestedArray("routers"), [[7, 11], [16, 32]])
+    assert new.storedMeasures["antennas"]._type == "uint32"
+
+
 ALL_KATS = [v for k, v in sorted(globals().items()) if k.startswith("kat_")]
