@@ -517,20 +517,35 @@ class ShardedCube:
         return out
 
     def dice(self, dimensionId, attribute, items, reorder=False):
-        """Dice of a dimension inside the shard (shard-local)."""
+        """Dice: a shard-local gather, whichever dimension is diced (no communication)."""
         idx = self.getDimensionIndex(dimensionId)
-        if idx < self.prefix:
-            raise NotImplementedError("dice on a sharded dimension re-partitions rows; not in this round (SURVEY §8e)")
         old_dim = self.dimensions[idx]
         new_dim = old_dim.dice(attribute, items, reorder)
         if new_dim is old_dim:
             return self
         new_dims = list(self.dimensions)
         new_dims[idx] = new_dim
-        out = self._derive(new_dims, self.row_bounds)
         old_idx = old_dim.getItemsToIdx()
+        kept = np.asarray([old_idx[i] for i in new_dim.getItems()], dtype=np.int32)
         keep = [np.arange(n, dtype=np.int32) for n in self._local_lens()]
-        keep[1 + idx - self.prefix] = np.asarray([old_idx[i] for i in new_dim.getItems()], dtype=np.int32)
+        if idx < self.prefix:
+            # Dice of a sharded dimension: whole rows are dropped where they live, nothing moves
+            # (SURVEY.md §8e "drop/reassign whole rows; rebalance optional").  Kept rows stay in
+            # ascending order, so every rank's survivors are one contiguous range of the new row
+            # numbering; the shard sizes may become uneven.
+            if kept.size > 1 and np.any(np.diff(kept) <= 0):
+                raise NotImplementedError("dice(reorder=True) that permutes a sharded dimension moves rows between ranks")
+            old_prefix_lens = [d.numItems for d in self.dimensions[: self.prefix]]
+            survives = np.zeros(old_prefix_lens[idx], dtype=bool)
+            survives[kept] = True
+            coord = (np.arange(self.rows_total, dtype=np.int64) // _prod(old_prefix_lens[idx + 1:])) % old_prefix_lens[idx]
+            row_kept = survives[coord]
+            before = np.concatenate([[0], np.cumsum(row_kept)])
+            out = self._derive(new_dims, [int(before[b]) for b in self.row_bounds])
+            keep[0] = np.flatnonzero(row_kept[self.row0:self.row1]).astype(np.int32)
+        else:
+            out = self._derive(new_dims, self.row_bounds)
+            keep[1 + idx - self.prefix] = kept
         ids = list(self.storedMeasures)
         if ids:
             res = self._call("dice_lowered", [self.storedMeasures[m] for m in ids], self._local_lens(), keep)
@@ -538,21 +553,43 @@ class ShardedCube:
         return out
 
     def drillDown(self, dimensionId, attribute):
-        """drillDown of a dimension inside the shard (shard-local)."""
+        """drillDown: shard-local whichever dimension is drilled (every child row is produced by
+        the rank that holds its parent row; no communication)."""
         idx = self.getDimensionIndex(dimensionId)
-        if idx < self.prefix:
-            raise NotImplementedError("drillDown of a sharded dimension re-partitions rows; not in this round")
         old_dim = self.dimensions[idx]
         if old_dim.rootAttribute == attribute:
             return self
         new_dim = old_dim.drillDown(attribute)
         new_dims = list(self.dimensions)
         new_dims[idx] = new_dim
-        out = self._derive(new_dims, self.row_bounds)
+        child_to_parent = np.asarray(new_dim.getGroupIndexFromRootIndexMap(old_dim.rootAttribute), np.int32)
         old_len = self._local_lens()
-        new_len = [self.rows_local] + [d.numItems for d in new_dims[self.prefix:]]
-        maps = [np.arange(n, dtype=np.int32) for n in new_len]
-        maps[1 + idx - self.prefix] = np.asarray(new_dim.getGroupIndexFromRootIndexMap(old_dim.rootAttribute), np.int32)
+        if idx < self.prefix:
+            # new global row -> old global row; the rows whose parent I hold must form one
+            # contiguous range of the new numbering, rank after rank (true when the drilled
+            # dimension is the outermost one, or when the shard bounds fall on its boundaries)
+            old_prefix_lens = [d.numItems for d in self.dimensions[: self.prefix]]
+            new_prefix_lens = [d.numItems for d in new_dims[: self.prefix]]
+            below = _prod(old_prefix_lens[idx + 1:])
+            new_rows = np.arange(_prod(new_prefix_lens), dtype=np.int64)
+            outer, rest = np.divmod(new_rows, new_prefix_lens[idx] * below)
+            coord, low = np.divmod(rest, below)
+            old_row = (outer * old_prefix_lens[idx] + child_to_parent[coord]) * below + low
+            owner = np.searchsorted(np.asarray(self.row_bounds[1:]), old_row, side="right")
+            if owner.size > 1 and np.any(np.diff(owner) < 0):
+                raise NotImplementedError("drillDown of a sharded dimension whose shard bounds cut through it "
+                                          "re-partitions rows; shard on that dimension alone (prefix=1) or align the bounds")
+            new_bounds = [int(b) for b in np.searchsorted(owner, np.arange(self.world + 1), side="left")]
+            out = self._derive(new_dims, new_bounds)
+            mine = old_row[new_bounds[self.rank]:new_bounds[self.rank + 1]] - self.row0
+            new_len = [int(mine.size)] + self.inner_lens
+            maps = [np.arange(n, dtype=np.int32) for n in new_len]
+            maps[0] = mine.astype(np.int32)
+        else:
+            out = self._derive(new_dims, self.row_bounds)
+            new_len = [self.rows_local] + [d.numItems for d in new_dims[self.prefix:]]
+            maps = [np.arange(n, dtype=np.int32) for n in new_len]
+            maps[1 + idx - self.prefix] = child_to_parent
         ids = list(self.storedMeasures)
         methods = [self.storedMeasuresRules[m].get(dimensionId) or "sum" for m in ids]
         if ids:
