@@ -702,7 +702,6 @@ class Cube:
         out.computedMeasures.update(otherCube.computedMeasures)
         return out
 
-
     # ---------------------------------------------------------- serialization
     def serialize(self):
         """cube.js:1135-1151, byte-compatible with the reference's wire format."""
