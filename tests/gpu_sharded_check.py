@@ -14,7 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from test_sharded_gloo import METHODS, _collect, _dims, _fill  # noqa: E402
+from test_sharded_gloo import (METHODS, _collect, _dims, _fill, _time_first_collect, _time_first_dims,  # noqa: E402
+                               _time_first_fill)
 
 
 def main():
@@ -68,6 +69,21 @@ def main():
                 failures += 1
                 if rank == 0:
                     print("MISMATCH tiny", default, m)
+    # drillDown (and a dice, and a rollup back) of the sharded time dimension
+    for prefix in (1, 2):
+        sc, rc = ShardedCube(_time_first_dims(), prefix=prefix), Cube(_time_first_dims(), OracleStore)
+        try:
+            got = _time_first_collect(sc, _time_first_fill(sc, 0.0))
+        except NotImplementedError:
+            if prefix == 2 and (8 * 7) % world:  # bounds cut through a quarter: refused, by design
+                continue
+            raise
+        want = _time_first_collect(rc, _time_first_fill(rc, 0.0))
+        for key in want:
+            if not np.allclose(got[key], want[key], rtol=1e-6, atol=0, equal_nan=True):
+                failures += 1
+                if rank == 0:
+                    print("MISMATCH time-first", prefix, key, np.asarray(got[key]).ravel()[:8], np.asarray(want[key]).ravel()[:8])
     t = torch.tensor([failures], device="cuda")
     dist.all_reduce(t)
     if rank == 0:
