@@ -21,6 +21,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ndims", type=int, default=9)  # 10^9 cells
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--only", default="", help="run only the operations whose label contains this text")
+    ap.add_argument("--exchange", default="", choices=("", "p2p", "nccl", "both"),
+                    help="exchange mode(s) of the sharded rollups (default: the library's own default)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -70,12 +73,9 @@ def main():
     rows = []
     last = f"dim{args.ndims - 1}"
     mid = f"dim{args.ndims // 2}"
-    for label, fn, n_out in (
-        (f"inner {last}->all (shard-local)", lambda: cube.drillUp(last, "all"), n_total // 10),
-        (f"mid {mid}->parity (shard-local)", lambda: cube.drillUp(mid, "parity"), n_total // 5),
-        ("sharded dim0->all (exchange + combine)", lambda: cube.drillUp("dim0", "all"), n_total // 10),
-        ("sharded dim0->parity (exchange + combine)", lambda: cube.drillUp("dim0", "parity"), n_total // 5),
-    ):
+    from olap_in_memory_b200 import sharded as _sh
+
+    def emit(label, fn, n_out):
         ms = timed(fn)
         row = {"op": label, "n_gpus": world, "cells_in": n_total, "measures": measures, "ms": round(ms, 3),
                "measure_cells_per_s": measures * n_total / (ms * 1e-3),
@@ -84,14 +84,28 @@ def main():
             # average travels as (sum, count): 4 planes for 3 measures
             planes = 4
             # every rank holds a partial of the FULL output and sends (W-1)/W of it
-            from olap_in_memory_b200 import sharded as _sh
-
             row["exchange"] = "peer stores from the rollup kernel" if _sh.P2P_EXCHANGE else "NCCL all-to-all per plane"
             row["nvlink_bytes_sent_per_gpu"] = 5 * planes * n_out * (world - 1) // world
             row["nvlink_GBs_per_gpu"] = round(row["nvlink_bytes_sent_per_gpu"] / (ms * 1e-3) / 1e9, 1)
         rows.append(row)
         if rank == 0:
             print(json.dumps(row), flush=True)
+
+    for label, fn, n_out in (
+        (f"inner {last}->all (shard-local)", lambda: cube.drillUp(last, "all"), n_total // 10),
+        (f"mid {mid}->parity (shard-local)", lambda: cube.drillUp(mid, "parity"), n_total // 5),
+        ("sharded dim0->all (exchange + combine)", lambda: cube.drillUp("dim0", "all"), n_total // 10),
+        ("sharded dim0->parity (exchange + combine)", lambda: cube.drillUp("dim0", "parity"), n_total // 5),
+    ):
+        if args.only and args.only not in label:
+            continue
+        modes = [None]
+        if "sharded" in label and world > 1 and args.exchange:
+            modes = {"p2p": [True], "nccl": [False], "both": [True, False]}[args.exchange]
+        for mode in modes:
+            if mode is not None:
+                _sh.P2P_EXCHANGE = mode
+            emit(label, fn, n_out)
     if world > 1:
         dist.destroy_process_group()
 
