@@ -106,3 +106,56 @@ def test_dimension_records():  # generic.js:47-72, time.js:28-47, factory.js:5-1
     assert data == {"id": "time", "label": "Time", "rootAttribute": "month", "start": "2010-01-01", "end": "2011-01-31"}
     new = DimensionFactory.deserialize(time.serialize())
     assert isinstance(new, TimeDimension) and new.getItems() == time.getItems() and new.serialize() == time.serialize()
+
+
+# ---- property tests: every value the format can carry survives the wire, records stay 4-byte aligned ----
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_f32 = st.floats(width=32, allow_nan=False)
+_leaf = st.one_of(
+    st.none(), st.booleans(), _f32, st.text(max_size=12), st.binary(max_size=9),
+    st.lists(st.integers(-2**31, 2**31 - 1), max_size=5).map(lambda v: np.asarray(v, dtype=np.int32)),
+    st.lists(_f32, max_size=5).map(lambda v: np.asarray(v, dtype=np.float32)),
+    st.lists(st.floats(allow_nan=False), max_size=5).map(lambda v: np.asarray(v, dtype=np.float64)),
+)
+_tree = st.recursive(_leaf, lambda kids: st.one_of(st.lists(kids, max_size=4), st.dictionaries(st.text(max_size=6), kids, max_size=4)),
+                     max_leaves=12)
+
+
+def _same(a, b):
+    if isinstance(a, np.ndarray):
+        return isinstance(b, np.ndarray) and a.dtype == b.dtype and a.tolist() == b.tolist()
+    if isinstance(a, dict):
+        return isinstance(b, dict) and set(a) == set(b) and all(_same(a[k], b[k]) for k in a)
+    if isinstance(a, list):
+        return isinstance(b, list) and len(a) == len(b) and all(_same(x, y) for x, y in zip(a, b))
+    return type(a) is type(b) and a == b
+
+
+@settings(max_examples=200, deadline=None)
+@given(_tree)
+def test_any_tree_round_trips(tree):
+    buf = toBuffer(tree)
+    assert len(buf) % 4 == 0  # every record keeps the Uint32Array views of fromBuffer aligned (serialization.js:91-92)
+    back = fromBuffer(buf)
+    assert _same(tree, back), (tree, back)
+    # keys come back in JavaScript's enumeration order; from there on the bytes are a fixed point
+    assert toBuffer(fromBuffer(toBuffer(back))) == toBuffer(back)
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.integers(0, 200).flatmap(lambda n: st.tuples(
+    st.just(n), st.sampled_from(["float32", "int32", "uint32", "float64"]), st.sampled_from([0.0, math.nan]),
+    st.lists(st.integers(0, max(n - 1, 0)), unique=True, max_size=n), st.randoms(use_true_random=False))))
+def test_oracle_store_round_trips_in_map_order(args):
+    from oracle.store_oracle import OracleStore
+
+    n, type_, default, keys, rnd = args
+    store = OracleStore(n, type_, default)
+    for k in keys:  # insertion order = Map order, not ascending
+        store.setValue(k, float(rnd.randint(1, 1000)))
+    back = OracleStore.deserialize(store.serialize())
+    assert (back._size, back._type) == (n, type_)
+    assert list(back._dataMap.items()) == list(store._dataMap.items())
+    assert (back._defaultValue != back._defaultValue) == (default != default)
+    assert back.serialize() == store.serialize()
