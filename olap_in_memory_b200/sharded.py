@@ -602,5 +602,79 @@ class ShardedCube:
         return out
 
 
+    def reorderDimensions(self, dimensionIds):
+        """Axis permutation (cube.js:757-783).  Permutations of the dimensions inside the shard
+        are shard-local.  With the cube sharded on its outermost dimension alone (prefix = 1),
+        a permutation that brings ANOTHER dimension to the front re-partitions the cells on
+        that dimension: one local transpose, one all-to-all, a row gather and one more local
+        transpose."""
+        dimensionIds = list(dimensionIds)
+        if dimensionIds == self.dimensionIds:
+            return self
+        perm = [self.getDimensionIndex(i) for i in dimensionIds]  # new position -> old position
+        if sorted(perm) != list(range(len(self.dimensions))):
+            raise ValueError("Invalid dimensions provided")
+        new_dims = [self.dimensions[j] for j in perm]
+        ids = list(self.storedMeasures)
+        stores = [self.storedMeasures[m] for m in ids]
+        lens = [d.numItems for d in self.dimensions]
+        if perm[: self.prefix] == list(range(self.prefix)):
+            out = self._derive(new_dims, self.row_bounds)
+            if stores:
+                order = [0] + [1 + j - self.prefix for j in perm[self.prefix:]]
+                out.storedMeasures = dict(zip(ids, self._reorder(stores, self._local_lens(), order)))
+            return out
+        if self.prefix != 1:
+            raise NotImplementedError("reorder that moves a sharded dimension needs the cube sharded on its "
+                                      "outermost dimension alone (prefix=1)")
+        W, k = self.world, perm[0]
+        new_bounds = split_rows(lens[k], W)
+        out = self._derive(new_dims, new_bounds)
+        if not stores:
+            return out
+        others = [j for j in perm[1:] if j != 0]  # old positions, in their new order, without the two sharded axes
+        other_lens = [lens[j] for j in others]
+        O = _prod(other_lens)
+        my_k = new_bounds[self.rank + 1] - new_bounds[self.rank]
+        src_rows = [self.row_bounds[r + 1] - self.row_bounds[r] for r in range(W)]
+        # 1. local transpose to [Dk, my rows of D0, others]: the cells for rank r are one contiguous run
+        sent = self._reorder(stores, [self.rows_local] + lens[1:], [k, 0] + others)
+        # 2. all-to-all: from rank s I receive the block [my Dk items, s's rows of D0, others]
+        in_splits = [(new_bounds[r + 1] - new_bounds[r]) * self.rows_local * O for r in range(W)]
+        out_splits = [my_k * src_rows[r] * O for r in range(W)]
+        if W == 1:
+            received = sent
+        else:
+            received = [self._empty_like(s, sum(out_splits)) for s in stores]
+            self._exchange_all(sent, received, in_splits, out_splits)
+        del sent
+        # 3. rows (k, d0) of the W received blocks -> one block [my Dk items, D0, others]
+        d0_total = lens[0]
+        block_start = np.concatenate([[0], np.cumsum([my_k * r for r in src_rows])])
+        owner = np.searchsorted(np.asarray(self.row_bounds[1:]), np.arange(d0_total), side="right")
+        d0_local = np.arange(d0_total) - np.asarray(self.row_bounds)[owner]
+        rows = (block_start[owner][None, :] + np.arange(my_k)[:, None] * np.asarray(src_rows)[owner][None, :]
+                + d0_local[None, :]).reshape(-1).astype(np.int32)
+        if my_k * d0_total * O == 0:
+            out.storedMeasures = {m: self._empty_like(s, 0) for m, s in zip(ids, stores)}
+            return out
+        gathered = self._call("dice_lowered", received, [my_k * d0_total, O], [rows, np.arange(O, dtype=np.int32)])
+        del received
+        # 4. local transpose to the requested order
+        final = [0] + [1 if j == 0 else 2 + others.index(j) for j in perm[1:]]
+        if final != list(range(len(final))):
+            gathered = self._reorder(gathered, [my_k, d0_total] + other_lens, final)
+        out.storedMeasures = dict(zip(ids, gathered))
+        return out
+
+    def _reorder(self, stores, old_len, new_to_old):
+        if _prod(old_len) == 0:
+            return [self._empty_like(s, 0) for s in stores]
+        return self._call("reorder_lowered", stores, old_len, new_to_old)
+
+    def _empty_like(self, store, size):
+        return self._store_cls(size, store._type, store._defaultValue)
+
+
 class _Per(list):
     """One value per store (methods)."""
