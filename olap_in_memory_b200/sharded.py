@@ -178,6 +178,7 @@ class ShardedCube:
         self.row0, self.row1 = self.row_bounds[self.rank], self.row_bounds[self.rank + 1]
         self.storedMeasures = {}
         self.storedMeasuresRules = {}
+        self.computedMeasures = {}
 
     # ------------------------------------------------------------------ basics
     @property
@@ -206,6 +207,37 @@ class ShardedCube:
         self.storedMeasures[measureId] = self._store_cls(self.localSize, type, defaultValue)
         self.storedMeasuresRules[measureId] = {} if rules is None else rules
 
+    def createComputedMeasure(self, measureId, formula):
+        """cube.js:95-125.  Evaluation is shard-local (one fused kernel over my rows); an
+        `x__total` variable is the whole-cube total: local totals + one all-reduce."""
+        import re
+
+        from .parser import getParser
+
+        if measureId in self.storedMeasures or measureId in self.computedMeasures:
+            raise ValueError(f"This measure already exists {measureId}")
+        for other, expr in self.computedMeasures.items():  # formulas may use computed measures: inline them (cube.js:107-121)
+            pattern = re.compile(rf"\b{re.escape(other)}\b")
+            if pattern.search(formula):
+                formula = pattern.sub(f"({expr.toString()})", formula)
+        expression = getParser().parse(formula)
+        known = set(self.storedMeasures) | {f"{m}__total" for m in self.storedMeasures}
+        unknown = [v for v in expression.variables() if v not in known]
+        if unknown:
+            raise ValueError(f"Unknown measure(s): {','.join(unknown)}")
+        self.computedMeasures[measureId] = expression
+
+    def _evaluate_local(self, measureId):
+        expression = self.computedMeasures[measureId]
+        names = expression.variables()
+        cell_names = [n for n in names if "__total" not in n]
+        # every rank takes part in the all-reduce, whether it holds rows or not
+        totals = {n: self.getTotal(n.replace("__total", "")) for n in names if "__total" in n}
+        if self.localSize == 0:
+            return np.empty(0, dtype=np.float64)
+        stores = [self.storedMeasures[n] for n in cell_names]
+        return np.asarray(self._store_cls.evaluate(expression, cell_names, stores, totals, self.localSize), dtype=np.float64)
+
     def setLocalData(self, measureId, values):
         """Cells of MY rows, row-major (length rows_local * inner)."""
         self._set(self.storedMeasures[measureId], values)
@@ -216,6 +248,8 @@ class ShardedCube:
         self.setLocalData(measureId, values[self.row0 * self.inner: self.row1 * self.inner])
 
     def getLocalData(self, measureId):
+        if measureId in self.computedMeasures:
+            return self._evaluate_local(measureId)
         return self._get(self.storedMeasures[measureId])
 
     def getData(self, measureId):
@@ -249,6 +283,7 @@ class ShardedCube:
     def _derive(self, dimensions, row_bounds=None):
         out = ShardedCube(dimensions, self.prefix, self._store_cls, self.comm.group, row_bounds)
         out.storedMeasuresRules = dict(self.storedMeasuresRules)
+        out.computedMeasures = dict(self.computedMeasures)  # formulas follow the cube through every transform (cube.js:1010-1011)
         return out
 
     # ----------------------------------------------------------- lowered store calls
