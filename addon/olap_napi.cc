@@ -12,15 +12,22 @@
 
 #include "../include/olap_gpu.h"
 
-#define NAPI_OK(call) \
-    if ((call) != napi_ok) { napi_throw_error(env, nullptr, "N-API call failed: " #call); return nullptr; }
+#define NAPI_OK(call)                                                      \
+    do {                                                                   \
+        if ((call) != napi_ok) {                                           \
+            napi_throw_error(env, nullptr, "N-API call failed: " #call);   \
+            return nullptr;                                                \
+        }                                                                  \
+    } while (0)
 
 static napi_value throw_last(napi_env env) {
     napi_throw_error(env, nullptr, olap_last_error());
     return nullptr;
 }
-#define OLAP_CALL(expr) \
-    if ((expr) != OLAP_OK) return throw_last(env)
+#define OLAP_CALL(expr)                                \
+    do {                                               \
+        if ((expr) != OLAP_OK) return throw_last(env); \
+    } while (0)
 
 static void finalize_store(napi_env env, void* data, void*) {
     olap_store* s = static_cast<olap_store*>(data);
@@ -122,8 +129,11 @@ static napi_value Upload(napi_env env, napi_callback_info info) {
     size_t len;
     void* data;
     NAPI_OK(napi_get_typedarray_info(env, a.v[1], &t, &len, &data, nullptr, nullptr));
-    if (t == napi_float32_array) OLAP_CALL(olap_store_upload_f32(unwrap(env, a.v[0]), static_cast<float*>(data), (int64_t)len));
-    else OLAP_CALL(olap_store_upload_f64(unwrap(env, a.v[0]), static_cast<double*>(data), (int64_t)len));
+    if (t == napi_float32_array) {
+        OLAP_CALL(olap_store_upload_f32(unwrap(env, a.v[0]), static_cast<float*>(data), (int64_t)len));
+    } else {
+        OLAP_CALL(olap_store_upload_f64(unwrap(env, a.v[0]), static_cast<double*>(data), (int64_t)len));
+    }
     return nullptr;
 }
 
@@ -134,8 +144,11 @@ static napi_value Download(napi_env env, napi_callback_info info) {
     size_t len;
     void* data;
     NAPI_OK(napi_get_typedarray_info(env, a.v[1], &t, &len, &data, nullptr, nullptr));
-    if (t == napi_float32_array) OLAP_CALL(olap_store_download_f32(unwrap(env, a.v[0]), static_cast<float*>(data), (int64_t)len));
-    else OLAP_CALL(olap_store_download_f64(unwrap(env, a.v[0]), static_cast<double*>(data), (int64_t)len));
+    if (t == napi_float32_array) {
+        OLAP_CALL(olap_store_download_f32(unwrap(env, a.v[0]), static_cast<float*>(data), (int64_t)len));
+    } else {
+        OLAP_CALL(olap_store_download_f64(unwrap(env, a.v[0]), static_cast<double*>(data), (int64_t)len));
+    }
     return nullptr;
 }
 
@@ -190,9 +203,200 @@ static napi_value Total(napi_env env, napi_callback_info info) {
     return out;
 }
 
-// drillDown, load, eval, presence, exportSparse, setValue(s), fill, clone follow the same
-// pattern (unpack -> one olap_* call -> wrap) and are omitted from this excerpt only for
-// length; INTEGRATION.md lists the full table of bindings.
+// Float64Array[] (entries may be null) -> const double* const*, with the lengths
+static void f64_list(napi_env env, napi_value arr, std::vector<const double*>& ptrs, std::vector<int64_t>& lens) {
+    uint32_t n = 0;
+    napi_get_array_length(env, arr, &n);
+    ptrs.assign(n, nullptr);
+    lens.assign(n, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        napi_value e;
+        napi_get_element(env, arr, i, &e);
+        bool typed = false;
+        napi_is_typedarray(env, e, &typed);
+        if (!typed) continue;  // null: no distribution for this store
+        napi_typedarray_type t;
+        size_t len;
+        void* data;
+        napi_get_typedarray_info(env, e, &t, &len, &data, nullptr, nullptr);
+        ptrs[i] = static_cast<const double*>(data);
+        lens[i] = (int64_t)len;
+    }
+}
+
+// drillDown(stores[], methods Int32Array, oldLen[], newLen[], maps Int32Array[], dist (Float64Array|null)[]) -> stores[]
+static napi_value DrillDown(napi_env env, napi_callback_info info) {
+    GET_ARGS();
+    auto src = store_list(env, a.v[0]);
+    napi_typedarray_type t;
+    size_t len;
+    void* mdata;
+    NAPI_OK(napi_get_typedarray_info(env, a.v[1], &t, &len, &mdata, nullptr, nullptr));
+    auto old_len = int64_list(env, a.v[2]), new_len = int64_list(env, a.v[3]);
+    auto maps = map_list(env, a.v[4]);
+    std::vector<const double*> dist;
+    std::vector<int64_t> dist_len;
+    f64_list(env, a.v[5], dist, dist_len);
+    dist.resize(src.size(), nullptr);
+    dist_len.resize(src.size(), 0);
+    std::vector<olap_store*> out(src.size());
+    OLAP_CALL(olap_drill_down(src.data(), (int)src.size(), static_cast<const int*>(mdata), (int)old_len.size(),
+                              old_len.data(), new_len.data(), maps.data(), dist.data(), dist_len.data(), out.data()));
+    return store_array_out(env, out);
+}
+
+// load(dst, src, myLen[], hisLen[], hisToMine Int32Array[])
+static napi_value Load(napi_env env, napi_callback_info info) {
+    GET_ARGS();
+    auto my_len = int64_list(env, a.v[2]), his_len = int64_list(env, a.v[3]);
+    auto maps = map_list(env, a.v[4]);
+    OLAP_CALL(olap_load(unwrap(env, a.v[0]), unwrap(env, a.v[1]), (int)my_len.size(), my_len.data(), his_len.data(), maps.data()));
+    return nullptr;
+}
+
+// clone(store) -> external
+static napi_value Clone(napi_env env, napi_callback_info info) {
+    GET_ARGS();
+    olap_store* s = nullptr;
+    OLAP_CALL(olap_store_clone(unwrap(env, a.v[0]), &s));
+    return wrap_store(env, s);
+}
+
+// getValue(store, index) -> number
+static napi_value GetValue(napi_env env, napi_callback_info info) {
+    GET_ARGS();
+    int64_t index;
+    napi_get_value_int64(env, a.v[1], &index);
+    double v;
+    OLAP_CALL(olap_store_get_value(unwrap(env, a.v[0]), index, &v));
+    napi_value out;
+    NAPI_OK(napi_create_double(env, v, &out));
+    return out;
+}
+
+// setValue(store, index, value)
+static napi_value SetValue(napi_env env, napi_callback_info info) {
+    GET_ARGS();
+    int64_t index;
+    double v;
+    napi_get_value_int64(env, a.v[1], &index);
+    napi_get_value_double(env, a.v[2], &v);
+    OLAP_CALL(olap_store_set_value(unwrap(env, a.v[0]), index, v));
+    return nullptr;
+}
+
+// setValues(store, indexes BigInt64Array, values Float64Array): batched point updates
+static napi_value SetValues(napi_env env, napi_callback_info info) {
+    GET_ARGS();
+    napi_typedarray_type t;
+    size_t n, nv;
+    void *idx, *val;
+    NAPI_OK(napi_get_typedarray_info(env, a.v[1], &t, &n, &idx, nullptr, nullptr));
+    NAPI_OK(napi_get_typedarray_info(env, a.v[2], &t, &nv, &val, nullptr, nullptr));
+    OLAP_CALL(olap_store_set_values(unwrap(env, a.v[0]), static_cast<const int64_t*>(idx), static_cast<const double*>(val),
+                                    (int64_t)(n < nv ? n : nv)));
+    return nullptr;
+}
+
+// fill(store, value)
+static napi_value Fill(napi_env env, napi_callback_info info) {
+    GET_ARGS();
+    double v;
+    napi_get_value_double(env, a.v[1], &v);
+    OLAP_CALL(olap_store_fill(unwrap(env, a.v[0]), v));
+    return nullptr;
+}
+
+// presence(store, Uint8Array) / status(store, Uint8Array)
+static napi_value Presence(napi_env env, napi_callback_info info) {
+    GET_ARGS();
+    napi_typedarray_type t;
+    size_t len;
+    void* data;
+    NAPI_OK(napi_get_typedarray_info(env, a.v[1], &t, &len, &data, nullptr, nullptr));
+    OLAP_CALL(olap_store_presence(unwrap(env, a.v[0]), static_cast<uint8_t*>(data), (int64_t)len));
+    return nullptr;
+}
+static napi_value Status(napi_env env, napi_callback_info info) {
+    GET_ARGS();
+    napi_typedarray_type t;
+    size_t len;
+    void* data;
+    NAPI_OK(napi_get_typedarray_info(env, a.v[1], &t, &len, &data, nullptr, nullptr));
+    OLAP_CALL(olap_store_status(unwrap(env, a.v[0]), static_cast<uint8_t*>(data), (int64_t)len));
+    return nullptr;
+}
+
+// exportSparse(store) -> { keys: BigInt64Array, values: Float32Array }   (keys ascending)
+static napi_value ExportSparse(napi_env env, napi_callback_info info) {
+    GET_ARGS();
+    olap_store* s = unwrap(env, a.v[0]);
+    int64_t count = 0;
+    OLAP_CALL(olap_store_count_present(s, &count));
+    napi_value kbuf, vbuf, keys, values, out;
+    void *kdata, *vdata;
+    NAPI_OK(napi_create_arraybuffer(env, (size_t)count * 8, &kdata, &kbuf));
+    NAPI_OK(napi_create_arraybuffer(env, (size_t)count * 4, &vdata, &vbuf));
+    OLAP_CALL(olap_store_export_sparse(s, count, static_cast<int64_t*>(kdata), static_cast<float*>(vdata), &count));
+    NAPI_OK(napi_create_typedarray(env, napi_bigint64_array, (size_t)count, kbuf, 0, &keys));
+    NAPI_OK(napi_create_typedarray(env, napi_float32_array, (size_t)count, vbuf, 0, &values));
+    NAPI_OK(napi_create_object(env, &out));
+    NAPI_OK(napi_set_named_property(env, out, "keys", keys));
+    NAPI_OK(napi_set_named_property(env, out, "values", values));
+    return out;
+}
+
+// importSparse(store, keys BigInt64Array, values Float32Array)
+static napi_value ImportSparse(napi_env env, napi_callback_info info) {
+    GET_ARGS();
+    napi_typedarray_type t;
+    size_t n, nv;
+    void *keys, *values;
+    NAPI_OK(napi_get_typedarray_info(env, a.v[1], &t, &n, &keys, nullptr, nullptr));
+    NAPI_OK(napi_get_typedarray_info(env, a.v[2], &t, &nv, &values, nullptr, nullptr));
+    OLAP_CALL(olap_store_import_sparse(unwrap(env, a.v[0]), static_cast<const int64_t*>(keys), static_cast<const float*>(values),
+                                       (int64_t)(n < nv ? n : nv)));
+    return nullptr;
+}
+
+// evaluate(program string, stores[], totals Float64Array, out Float64Array)  — Cube.getData(computedId)
+static napi_value Evaluate(napi_env env, napi_callback_info info) {
+    GET_ARGS();
+    size_t plen = 0;
+    NAPI_OK(napi_get_value_string_utf8(env, a.v[0], nullptr, 0, &plen));
+    std::vector<char> program(plen + 1);
+    NAPI_OK(napi_get_value_string_utf8(env, a.v[0], program.data(), program.size(), &plen));
+    auto src = store_list(env, a.v[1]);
+    napi_typedarray_type t;
+    size_t nt, n;
+    void *totals, *out;
+    NAPI_OK(napi_get_typedarray_info(env, a.v[2], &t, &nt, &totals, nullptr, nullptr));
+    NAPI_OK(napi_get_typedarray_info(env, a.v[3], &t, &n, &out, nullptr, nullptr));
+    OLAP_CALL(olap_eval(program.data(), src.data(), (int)src.size(), static_cast<const double*>(totals), (int)nt,
+                        static_cast<double*>(out), 0, 0, nullptr));
+    return nullptr;
+}
+
+// evaluateToStore(program string, stores[], totals Float64Array, type, defaultKind) -> external  — copyToStoredMeasure
+static napi_value EvaluateToStore(napi_env env, napi_callback_info info) {
+    GET_ARGS();
+    size_t plen = 0;
+    NAPI_OK(napi_get_value_string_utf8(env, a.v[0], nullptr, 0, &plen));
+    std::vector<char> program(plen + 1);
+    NAPI_OK(napi_get_value_string_utf8(env, a.v[0], program.data(), program.size(), &plen));
+    auto src = store_list(env, a.v[1]);
+    napi_typedarray_type t;
+    size_t nt;
+    void* totals;
+    NAPI_OK(napi_get_typedarray_info(env, a.v[2], &t, &nt, &totals, nullptr, nullptr));
+    int32_t type, kind;
+    napi_get_value_int32(env, a.v[3], &type);
+    napi_get_value_int32(env, a.v[4], &kind);
+    olap_store* s = nullptr;
+    OLAP_CALL(olap_eval(program.data(), src.data(), (int)src.size(), static_cast<const double*>(totals), (int)nt, nullptr, type,
+                        kind, &s));
+    return wrap_store(env, s);
+}
 
 static napi_value Init(napi_env env, napi_value exports) {
     const napi_property_descriptor props[] = {
@@ -203,6 +407,19 @@ static napi_value Init(napi_env env, napi_value exports) {
         {"dice", nullptr, Dice, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"reorder", nullptr, Reorder, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"total", nullptr, Total, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"drillDown", nullptr, DrillDown, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"load", nullptr, Load, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"clone", nullptr, Clone, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"getValue", nullptr, GetValue, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"setValue", nullptr, SetValue, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"setValues", nullptr, SetValues, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"fill", nullptr, Fill, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"presence", nullptr, Presence, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"status", nullptr, Status, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"exportSparse", nullptr, ExportSparse, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"importSparse", nullptr, ImportSparse, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"evaluate", nullptr, Evaluate, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"evaluateToStore", nullptr, EvaluateToStore, nullptr, nullptr, nullptr, napi_default, nullptr},
     };
     napi_define_properties(env, exports, sizeof props / sizeof props[0], props);
     if (olap_init(0) != OLAP_OK) return throw_last(env);  // no CPU fallback: fail at require() time

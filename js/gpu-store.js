@@ -5,7 +5,7 @@
 //   becomes          const InMemoryStore = require('olap-gpu-store/js/gpu-store');
 // Everything else in cube.js stays as it is: the class below has the members Cube uses
 // (constructor, byteLength, size, total, data, getValue, setValue, fill, clone, load,
-// reorder, dice, drillUp, drillDown, _type, _defaultValue, _dataMap).  It lowers
+// reorder, dice, drillUp, drillDown, serialize, deserialize, _type, _defaultValue, _dataMap).  It lowers
 // dimension objects to Int32Array maps — exactly the arrays the reference already builds
 // (generic.js:243-247, time.js:182-197) — and calls the N-API addon (addon/olap_napi.cc).
 const native = require('../addon/build/Release/olap_gpu.node');
@@ -13,6 +13,38 @@ const native = require('../addon/build/Release/olap_gpu.node');
 const TYPES = { int32: 0, uint32: 1, float32: 2, float64: 3 };
 const METHODS = { sum: 0, average: 1, highest: 2, lowest: 3, first: 4, last: 5, product: 6 };
 const lens = (dims) => dims.map((d) => d.numItems);
+
+// expr-eval keeps a parsed Expression as a postfix token list already (`expression.tokens`:
+// INUMBER / IVAR / IOP1 / IOP2 / IOP3 / IFUNCALL / IEXPR instructions); this rewrites it into the
+// text olap_eval() takes (include/olap_gpu.h).  A function call arrives as IVAR(name), the
+// arguments, then IFUNCALL(argc); the lazy branches of `a ? b : c` arrive as IEXPR token lists.
+function toPostfix(tokens, slots) {
+  const stack = [];
+  const number = (v) => (Number.isNaN(v) ? '#nan' : v === Infinity ? '#inf' : v === -Infinity ? '#-inf' : `#${v}`);
+  for (const t of tokens) {
+    if (t.type === 'INUMBER') stack.push({ text: number(t.value) });
+    else if (t.type === 'IVAR') stack.push(t.value in slots ? { text: slots[t.value] } : { fn: t.value });
+    else if (t.type === 'IEXPR') stack.push({ text: toPostfix(t.value, slots) });
+    else if (t.type === 'IOP1') {
+      const a = stack.pop();
+      stack.push({ text: t.value === '-' ? `${a.text} neg` : t.value === '+' ? a.text : `${a.text} call:${t.value}:1` });
+    } else if (t.type === 'IOP2') {
+      const b = stack.pop();
+      const a = stack.pop();
+      stack.push({ text: `${a.text} ${b.text} ${t.value}` });
+    } else if (t.type === 'IOP3') {
+      const c = stack.pop();
+      const b = stack.pop();
+      const a = stack.pop();
+      stack.push({ text: `${a.text} ${b.text} ${c.text} ?:` });
+    } else if (t.type === 'IFUNCALL') {
+      const args = stack.splice(stack.length - t.value, t.value);
+      const f = stack.pop();
+      stack.push({ text: `${args.map((x) => x.text).join(' ')} call:${f.fn}:${t.value}`.trim() });
+    } else throw new Error(`Unsupported formula instruction: ${t.type}`);
+  }
+  return stack.pop().text;
+}
 
 class GpuStore {
   constructor(size, type = 'float32', defaultValue = Number.NaN, handle = undefined) {
@@ -109,6 +141,20 @@ class GpuStore {
       return Int32Array.from(hd.getItems(), (item) => mine[item] ?? -1);
     });
     native.load(this._h, other._h, lens(myDims), lens(hisDims), maps);
+  }
+
+  // Computed measures (cube.js:331-363): ONE fused kernel instead of a per-cell tree walk.
+  // A patched Cube.getData(computedId) calls
+  //   GpuStore.evaluate(expression, cellNames, cellNames.map((n) => this.storedMeasures[n]), totals, this.storeSize)
+  // in place of the loop at cube.js:353-360 (same arguments the Python host passes, store.py).
+  static evaluate(expression, cellNames, stores, totals, size) {
+    const totalNames = Object.keys(totals);
+    const slots = {};
+    cellNames.forEach((n, k) => { slots[n] = `v${k}`; });
+    totalNames.forEach((n, k) => { slots[n] = `t${k}`; });
+    const out = new Float64Array(size);
+    native.evaluate(toPostfix(expression.tokens, slots), stores.map((s) => s._h), Float64Array.from(totalNames, (n) => totals[n]), out);
+    return Array.from(out);
   }
 
   // Batched forms used by a patched Cube to serve all measures with one launch.

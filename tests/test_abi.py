@@ -61,3 +61,25 @@ def test_host_side_argument_errors_use_reference_texts():
         _default_kind(1)
     with pytest.raises(ValueError, match="Unsupported aggregation method: median"):
         _method_code("median")
+
+
+def test_napi_shim_type_checks_against_the_header():
+    """addon/olap_napi.cc cannot be built here (no Node.js headers), but it can be type-checked:
+    a stub node_api.h with the published N-API signatures (addon/stub/) lets g++ verify every
+    olap_* call of the shim against include/olap_gpu.h, and that every `native.<name>` the JS
+    facade uses is a property the shim defines."""
+    import re
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    proc = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "addon", "stub"),
+                           os.path.join(root, "addon", "olap_napi.cc")], capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    shim = open(os.path.join(root, "addon", "olap_napi.cc")).read()
+    defined = set(re.findall(r'\{"(\w+)", nullptr, \w+, nullptr', shim))
+    used = set(re.findall(r"native\.(\w+)", open(os.path.join(root, "js", "gpu-store.js")).read()))
+    assert used <= defined, sorted(used - defined)
