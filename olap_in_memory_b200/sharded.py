@@ -316,7 +316,22 @@ class ShardedCube:
         group_map = np.asarray(old_dim.getGroupIndexFromRootIndexMap(new_dim.rootAttribute), dtype=np.int32)
         if idx >= self.prefix:
             return self._drill_up_local(new_dims, idx, group_map, ids, methods)
+        if _prod(d.numItems for d in new_dims[: self.prefix]) < self.world and self.prefix < len(self.dimensions):
+            # fewer output rows than ranks: shard the result on the next dimension as well
+            # (SURVEY.md §8e "leaving the result sharded on the next axis") instead of piling
+            # it up on the first ranks
+            return self._deepened().drillUp(dimensionId, attribute)
         return self._drill_up_sharded(new_dims, idx, group_map, ids, methods)
+
+    def _deepened(self):
+        """The same cells, seen as a cube sharded on one more leading dimension: every row
+        becomes numItems rows and the bounds scale with it.  Nothing moves."""
+        n = self.dimensions[self.prefix].numItems
+        out = ShardedCube(self.dimensions, self.prefix + 1, self._store_cls, self.comm.group, [b * n for b in self.row_bounds])
+        out.storedMeasures = dict(self.storedMeasures)
+        out.storedMeasuresRules = dict(self.storedMeasuresRules)
+        out.computedMeasures = dict(self.computedMeasures)
+        return out
 
     def _drill_up_local(self, new_dims, idx, group_map, ids, methods):
         """The drilled dimension lies inside my shard: no communication."""

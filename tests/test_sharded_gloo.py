@@ -237,6 +237,13 @@ def _reorder_collect(cube, sharded_prefix=None):
                 out[(order, "diced", m)] = np.asarray(moved.dice("product", "sku", ["p1", "p4"]).getData(m), dtype=np.float64)
                 out[(order, "back", m)] = np.asarray(moved.reorderDimensions(["region", "product", "time"]).getData(m),
                                                      dtype=np.float64)
+    # a rollup of the sharded dimension that leaves fewer rows than ranks shards the result on the next dimension too
+    if sharded_prefix == 1:
+        rolled = cube.drillUp("region", "all")
+        assert rolled.prefix == 2 and rolled.rows_total == 5
+        sizes = np.diff(rolled.row_bounds)
+        assert sizes.max() - sizes.min() <= 1 and sizes.sum() == 5, rolled.row_bounds
+        assert cube.drillUp("region", "country").prefix == (1 if cube.world <= 2 else 2)
     # computed measures: shard-local evaluation, `__total` through one all-reduce, formulas carried through transforms
     cube.createComputedMeasure("ratio", "(m_sum + m_highest) / m_lowest")
     cube.createComputedMeasure("share", "m_sum / m_sum__total + ratio")
