@@ -569,8 +569,46 @@ class ShardedCube:
     def dice(self, dimensionId, attribute, items, reorder=False):
         """Dice: a shard-local gather, whichever dimension is diced (no communication)."""
         idx = self.getDimensionIndex(dimensionId)
+        return self._dice_to(idx, self.dimensions[idx].dice(attribute, items, reorder))
+
+    def diceRange(self, dimensionId, attribute, start, end):  # cube.js:809-832
+        idx = self.getDimensionIndex(dimensionId)
+        return self._dice_to(idx, self.dimensions[idx].diceRange(attribute, start, end))
+
+    def removeDimension(self, dimensionId):
+        """cube.js:950-964: roll the dimension up to 'all' with each measure's rule, then forget
+        it.  Forgetting a one-item dimension changes no cell and no shard bound."""
+        idx = self.getDimensionIndex(dimensionId)
+        if len(self.dimensions) == 1:
+            raise NotImplementedError("removing the only dimension of a sharded cube leaves one cell: use getTotal")
+        rolled = self.drillUp(dimensionId, "all")
+        if idx < rolled.prefix and rolled.prefix == 1:
+            rolled = rolled._deepened()
+        dims = [d for d in rolled.dimensions if d.id != dimensionId]
+        out = ShardedCube(dims, rolled.prefix - (1 if idx < rolled.prefix else 0), self._store_cls, self.comm.group,
+                          list(rolled.row_bounds))
+        out.storedMeasures = dict(rolled.storedMeasures)
+        out.computedMeasures = dict(self.computedMeasures)
+        out.storedMeasuresRules = {m: {k: v for k, v in rules.items() if k != dimensionId}
+                                   for m, rules in self.storedMeasuresRules.items()}
+        return out
+
+    def removeDimensions(self, dimensionIds):  # cube.js:899-908
+        cube = self
+        for dimensionId in dimensionIds:
+            cube = cube.removeDimension(dimensionId)
+        return cube
+
+    def keepDimensions(self, dimensionIds):  # cube.js:890-897
+        return self.removeDimensions([d for d in self.dimensionIds if d not in dimensionIds])
+
+    def slice(self, dimensionId, attribute, value):  # cube.js:799-807
+        if self.getDimensionIndex(dimensionId) == -1:
+            raise ValueError(f"slice: no such dimension: {dimensionId}")
+        return self.dice(dimensionId, attribute, [value]).removeDimension(dimensionId)
+
+    def _dice_to(self, idx, new_dim):
         old_dim = self.dimensions[idx]
-        new_dim = old_dim.dice(attribute, items, reorder)
         if new_dim is old_dim:
             return self
         new_dims = list(self.dimensions)
