@@ -159,3 +159,39 @@ def test_oracle_store_round_trips_in_map_order(args):
     assert list(back._dataMap.items()) == list(store._dataMap.items())
     assert (back._defaultValue != back._defaultValue) == (default != default)
     assert back.serialize() == store.serialize()
+
+
+def _golden_b64():
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "serialized_test_cube.b64")) as f:
+        return f.read().strip()
+
+
+def _check_golden_cube(store_cls):
+    from olap_in_memory_b200 import Cube
+
+    cube = Cube.deserializeFromBase64String(_golden_b64(), store_cls)
+    assert cube.dimensionIds == ["location", "period"] and cube.storedMeasureIds == ["antennas", "routers"]
+    assert cube.getDimension("location").attributes == ["all", "city", "country", "continent", "citySize"]
+    assert cube.getNestedArray("antennas") == [[1, 2], [4, 0], [16, 32]]
+    assert cube.getNestedArray("routers") == [[3, 2], [4, 9], [16, 32]]
+    assert cube.drillUp("location", "continent").getNestedArray("antennas") == [[5, 2], [16, 32]]
+    assert cube.computedMeasureIds == ["router_by_antennas"]
+    # ascending keys = the Map order of this fixture: the device store and the oracles emit the same bytes
+    assert cube.serializeToBase64String() == _golden_b64()
+
+
+def test_golden_serialized_cube_on_the_oracles():  # tests/golden/make_serialized.py
+    from oracle.c_oracle import COracleStore
+    from oracle.store_oracle import OracleStore
+
+    _check_golden_cube(OracleStore)
+    _check_golden_cube(COracleStore)
+
+
+@pytest.mark.gpu
+def test_golden_serialized_cube_on_the_device():
+    from olap_in_memory_b200.store import GpuStore
+
+    _check_golden_cube(GpuStore)
