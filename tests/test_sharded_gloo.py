@@ -348,3 +348,104 @@ def test_reorder_inside_the_shard_is_local():
         sharded.reorderDimensions(["b", "a", "c", "d"])
     with pytest.raises(ValueError):
         sharded.reorderDimensions(["a", "b", "c", "c"])
+
+
+# ---- random operation sequences: the sharded cube must track ONE cube step by step -------------------
+def _fuzz_dims(rng):
+    from olap_in_memory_b200 import GenericDimension, TimeDimension
+
+    region = GenericDimension("region", "city", [f"c{i}" for i in range(7)])
+    region.addAttribute("city", "country", lambda c: "even" if int(c[1:]) % 2 == 0 else "odd")
+    product = GenericDimension("product", "sku", [f"p{i}" for i in range(5)])
+    product.addAttribute("sku", "family", lambda p: f"f{int(p[1:]) // 2}")
+    dims = [region, product, TimeDimension("time", "month", "2010-01", "2010-12")]
+    order = rng.permutation(3)
+    return [dims[i] for i in order]
+
+
+def _fuzz_op(rng, cube):
+    """One random transform as (method name, args), chosen from the cube's current dimensions."""
+    dims = cube.dimensions
+    dim = dims[int(rng.integers(len(dims)))]
+    kind = rng.choice(["drillUp", "dice", "reorder", "remove", "drillDown", "drillUp", "dice"])
+    if kind == "drillUp":
+        choices = [a for a in dim.attributes if a != dim.rootAttribute]
+        if choices:
+            return "drillUp", (dim.id, str(rng.choice(choices)))
+    if kind == "dice" and dim.numItems > 1:
+        items = dim.getItems()
+        if dim.id == "time":
+            lo = int(rng.integers(len(items)))
+            hi = int(rng.integers(lo, len(items)))
+            return "diceRange", (dim.id, dim.rootAttribute, items[lo], items[hi])
+        keep = [it for it in items if rng.random() < 0.6] or [items[0]]
+        return "dice", (dim.id, dim.rootAttribute, keep)
+    if kind == "reorder" and len(dims) > 1:
+        return "reorderDimensions", ([dims[i].id for i in rng.permutation(len(dims))],)
+    if kind == "remove" and len(dims) > 1:
+        return "removeDimension", (dim.id,)
+    time = next((d for d in dims if d.id == "time"), None)
+    if time is not None and time.rootAttribute in ("quarter", "semester", "year"):
+        return "drillDown", ("time", "month")
+    return "reorderDimensions", ([d.id for d in dims],)  # no-op
+
+
+def _fuzz_worker(rank, world, port, queue):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from olap_in_memory_b200 import Cube
+        from olap_in_memory_b200.sharded import ShardedCube
+        from oracle.store_oracle import OracleStore
+
+        log = []
+        for seed in range(int(os.environ.get("OLAP_FUZZ_SEEDS", "24"))):
+            rng = np.random.default_rng(100 + seed)  # the same stream on every rank
+            prefix = 1 + seed % 2
+            default = math.nan if seed % 3 == 0 else 0.0
+            dims = _fuzz_dims(rng)
+            sharded, single = ShardedCube(dims, prefix=prefix, store_cls=OracleStore), Cube(dims, OracleStore)
+            values = rng.integers(1, 100, 7 * 5 * 12).astype(np.float64)
+            values[rng.random(values.size) < 0.3] = default
+            for cube in (sharded, single):
+                for m, rule in (("m_sum", "sum"), ("m_high", "highest")):
+                    cube.createStoredMeasure(m, {"region": rule, "product": rule, "time": rule}, "float32", default)
+                    cube.setData(m, values.tolist())
+            for step in range(7):
+                name, args = _fuzz_op(rng, single)
+                try:
+                    moved = getattr(sharded, name)(*args)
+                except NotImplementedError:
+                    log.append((seed, step, name, "refused"))
+                    continue
+                sharded, single = moved, getattr(single, name)(*args)
+                assert sharded.dimensionIds == single.dimensionIds, (seed, step, name, args)
+                for m in ("m_sum", "m_high"):
+                    got, want = np.asarray(sharded.getData(m), np.float64), np.asarray(single.getData(m), np.float64)
+                    ok = got.shape == want.shape and np.allclose(got, want, rtol=1e-12, atol=0, equal_nan=True)
+                    log.append((seed, step, name, "ok" if ok else f"MISMATCH {m} {args} prefix={sharded.prefix} bounds={sharded.row_bounds}"))
+        if rank == 0:
+            queue.put(log)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_random_operation_sequences_on_three_ranks():
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fuzz_worker, args=(r, 3, port, queue)) for r in range(3)]
+    for p in procs:
+        p.start()
+    log = queue.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    bad = [entry for entry in log if entry[3] not in ("ok", "refused")]
+    print(f"fuzz: {len(log)} checks, {sum(1 for e in log if e[3] == 'refused')} refused, ops {sorted({e[2] for e in log})}")
+    assert not bad, bad[:5]
+    assert sum(1 for entry in log if entry[3] == "ok") >= 60, len(log)
+    assert {entry[2] for entry in log if entry[3] == "ok"} >= {"drillUp", "dice", "diceRange", "reorderDimensions", "removeDimension"}
