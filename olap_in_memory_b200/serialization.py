@@ -47,7 +47,7 @@ def _u32(*values):
 def _js_key_order(keys):
     """Object.entries order: canonical array indexes (0 .. 2^32-2) ascending, then strings."""
     def index_of(k):
-        if isinstance(k, str) and k.isdigit() and (k == "0" or k[0] != "0") and int(k) < 4294967295:
+        if isinstance(k, str) and k.isascii() and k.isdigit() and (k == "0" or k[0] != "0") and int(k) < 4294967295:
             return int(k)
         return None
 

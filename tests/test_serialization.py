@@ -53,6 +53,7 @@ def test_strings_arrays_objects_byte_for_byte():
     assert toBuffer({"ab": 1}) == u32(5) + u32(3, 1) + u32(len(entry)) + entry
     # Object.entries: array-index keys first, ascending; then insertion order
     assert list(fromBuffer(toBuffer({"b": 1, "10": 2, "a": 3, "2": 4, "01": 5})).keys()) == ["2", "10", "b", "a", "01"]
+    assert list(fromBuffer(toBuffer({"b": 1, "\u00b9": 2, "7": 3})).keys()) == ["7", "b", "\u00b9"]  # only ASCII digits form an index
 
 
 def test_reference_round_trip():  # test/cube-serialize.js:7-27
