@@ -133,7 +133,7 @@ def _same(a, b):
     return type(a) is type(b) and a == b
 
 
-@settings(max_examples=200, deadline=None)
+@settings(max_examples=300, deadline=None, derandomize=True)
 @given(_tree)
 def test_any_tree_round_trips(tree):
     buf = toBuffer(tree)
@@ -144,7 +144,7 @@ def test_any_tree_round_trips(tree):
     assert toBuffer(fromBuffer(toBuffer(back))) == toBuffer(back)
 
 
-@settings(max_examples=100, deadline=None)
+@settings(max_examples=150, deadline=None, derandomize=True)
 @given(st.integers(0, 200).flatmap(lambda n: st.tuples(
     st.just(n), st.sampled_from(["float32", "int32", "uint32", "float64"]), st.sampled_from([0.0, math.nan]),
     st.lists(st.integers(0, max(n - 1, 0)), unique=True, max_size=n), st.randoms(use_true_random=False))))
