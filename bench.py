@@ -17,9 +17,14 @@ measure `(m_sum + m_avg) / m_max` is evaluated on the result by the JIT-fused ke
             plain-C restatement of src/store/in-memory.js) on the host cores, on a
             bounded sample of the same workload.
 
-Launch:  python bench.py [--gpus N --steps K --warmup W] ; for N > 1 under torchrun,
-one rank per GPU, each rank holding its own config-2 cube (weak scaling: the path
-shards on an outer axis with no data-path collective)."""
+Launch:  python bench.py [--gpus N --steps K --warmup W].  N = 1 runs config 2 (the
+configuration the metric is quoted on).  For N > 1, under torchrun with one rank per GPU,
+the step is config 4 of BASELINE.json: ONE univac-style cube (10 dimensions x 10 items =
+1e10 cells, 3 stored measures) sharded by rows of (dim0, dim1) across the N ranks — strong
+scaling, fixed total cells — and a step rolls up an inner dimension (dim9 -> all, shard-local,
+HBM-bound) AND the sharded dimension (dim0 -> all: every rank computes its own output rows,
+reading the child rows out of its peers' stores over NVLink inside the rollup kernel).  A
+sharded-vs-single-cube parity guard runs on the devices before anything is timed."""
 from __future__ import annotations
 
 import argparse
@@ -38,6 +43,8 @@ if ROOT not in sys.path:
 TIME_START, TIME_END = "2010-01-01", "2019-12-31"
 GENERIC = 32
 METHODS = ("sum", "average", "highest")
+SHARDED_METHODS = ("sum", "average", "highest")  # rules of the three measures of the N > 1 cube, on every dimension
+NVLINK_GBS = 770.0  # B200_PROFILING.md: measured peer copy per direction per GPU (900 nominal)
 FORMULA = "(m_sum + m_avg) / m_max"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
@@ -149,17 +156,78 @@ def cpu_port_run(steps, warmup, threads, inner):
     return cells / dt, dt * 1e3, sample
 
 
+REFERENCE_THREADS = 16  # fixed, so that BENCH and SCALE boxes (16 / 32 host threads) time the same baseline
+
+
+def cpu_port_run_univac(steps, warmup, threads, ndims=6):
+    """The reference's algorithm on the N > 1 workload: each thread owns a univac-style sub-cube
+    (ndims dimensions x 10 items) x 3 measures and rolls up its innermost dimension and dim0."""
+    from oracle.c_oracle import COracleStore
+
+    lens = [10] * ndims
+    n = 10 ** ndims
+    ident = [np.arange(10, dtype=np.int32) for _ in lens]
+    zeros = np.zeros(10, dtype=np.int32)
+    stores = []
+    for t in range(threads):
+        per = []
+        for m, _ in enumerate(SHARDED_METHODS):
+            st = COracleStore(n, "float32", 0.0)
+            st.set_data_f32(synth(np.empty(n, np.float32), 1 + t, m))
+            per.append(st)
+        stores.append(per)
+
+    def work(t):
+        for st, method in zip(stores[t], SHARDED_METHODS):
+            st.drillUp_lowered(lens, lens[:-1] + [1], ident[:-1] + [zeros], method)
+            st.drillUp_lowered(lens, [1] + lens[1:], [zeros] + ident[1:], method)
+
+    def one_step():
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    cells = 2 * threads * len(SHARDED_METHODS) * n
+    sample = (f"drillUp dim{ndims - 1}->all and dim0->all of a [10]^{ndims} = {n}-cell cube x {len(SHARDED_METHODS)} measures "
+              f"({'/'.join(SHARDED_METHODS)}) per thread, {threads} independent sub-cubes, C port of in-memory.js:265-334 "
+              f"(ordered hash map)")
+    return cells / dt, dt * 1e3, sample
+
+
 def run_reference(args, rank):
+    """The reference's own algorithm (C port of in-memory.js, oracle/) on the host cores, on a
+    bounded SAMPLE of this arm's workload — the sample, not the full config, is what
+    `config.workload` names.  Warm-up as asked (at least one step, so that first-touch page
+    faults stay out of the timed region); the thread count is fixed and printed."""
     if rank != 0:
         return
-    threads = max(1, min(os.cpu_count() or 1, 32))
-    value, ms, sample = cpu_port_run(max(1, args.steps), max(0, min(args.warmup, 1)), threads, 512)
+    threads = max(1, min(os.cpu_count() or 1, REFERENCE_THREADS))
+    warmup = max(1, args.warmup)
+    steps = max(1, args.steps)
+    if args.gpus > 1:
+        value, ms, sample = cpu_port_run_univac(steps, warmup, threads)
+        config = sharded_config(args.gpus)
+    else:
+        value, ms, sample = cpu_port_run(steps, warmup, threads, 512)
+        config = workload_config()
+    config = dict(config)
+    config["full_workload"] = config["workload"]
+    config["workload"] = "SAMPLE of the arm's workload (the reference keeps cells in a JS Map capped at 2^24 entries): " + sample
     line = {
         "impl": "reference", "metric": "drillUp input measure-cells/s", "value": value, "unit": "cells/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(),
-        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads, "kind": "port", "sample": sample},
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config,
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads, "kind": "port", "sample": sample,
+                         "host_threads_available": os.cpu_count()},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -171,7 +239,20 @@ def workload_config():
                         "measures (time rules sum/average/highest) + 1 computed measure; drillUp time day->month "
                         "-> 3932160 cells; per-measure status plane (5 B/cell)",
             "cells_in": 3652 * GENERIC ** 3, "cells_out": 120 * GENERIC ** 3, "measures": 3, "computed": FORMULA,
-            "l2": "inputs (2.4 GB) exceed the 126 MB L2, no flush needed", "sharding": "one config-2 cube per GPU"}
+            "l2": "inputs (2.4 GB) exceed the 126 MB L2, no flush needed", "sharding": "single GPU"}
+
+
+def sharded_config(world, ndims=None):
+    ndims = ndims or int(os.environ.get("OLAP_BENCH_NDIMS", "10"))
+    n = 10 ** ndims
+    return {"workload": f"config 4: univac-style cube of {ndims} dimensions x 10 items = {n} cells, 3 stored float32 measures "
+                        f"(rules {'/'.join(SHARDED_METHODS)} on every dimension), per-measure status plane (5 B/cell), ONE cube "
+                        f"sharded by rows of (dim0, dim1) across {world} GPUs; a step = drillUp dim{ndims - 1}->all (shard-local) + "
+                        f"drillUp dim0->all (the sharded dimension: peer-memory pull over NVLink inside the rollup kernel)",
+            "cells_in": n, "measures": 3, "ops_per_step": 2, "ndims": ndims,
+            "l2": "per-GPU inputs exceed the 126 MB L2, no flush needed",
+            "sharding": f"strong scaling: fixed {n}-cell cube, rows of (dim0, dim1) split over {world} ranks",
+            "note": "N = 1 runs config 2 (the metric's own configuration); compare the N = 2, 4, 8 lines with one another"}
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -336,6 +417,289 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------ GPU arm, N > 1: one sharded cube
+def univac_dims(ndims):
+    from olap_in_memory_b200 import GenericDimension
+
+    dims = []
+    for k in range(ndims):
+        d = GenericDimension(f"dim{k}", "root", [str(i) for i in range(10)])
+        d.addAttribute("root", "parity", lambda item: "even" if int(item) % 2 == 0 else "odd")
+        dims.append(d)
+    return dims
+
+
+def sharded_parity_guard(dist, rank, world):
+    """Hardware parity proof of the multi-GPU path, run before anything is timed: small sharded
+    cubes against ONE single-GPU cube of the same data (itself held bit-equal to the CPU oracle by
+    tests/).  Pull exchange: bit-exact, every method, both defaults, mixed-sign data whose float32
+    partial sums would cancel badly; NCCL exchange: rel 1e-6 (float32 partials); plus the paths
+    that had only ever run over gloo: prefix-deepening rollups, the re-partitioning
+    reorderDimensions, sharded computed measures.  Returns a summary for the JSON line."""
+    import math
+
+    from olap_in_memory_b200 import Cube
+    from olap_in_memory_b200 import sharded as SH
+    from olap_in_memory_b200.sharded import ShardedCube
+
+    rules = ("sum", "average", "highest", "lowest", "first", "last")
+    nd = 6
+    n = 10 ** nd
+    mismatches, cases, timed_path_mismatches = [], 0, 0
+    default_mode = SH.EXCHANGE
+
+    def same_bits(a, b):
+        a = np.asarray(a, dtype=np.float64).astype(np.float32)
+        b = np.asarray(b, dtype=np.float64).astype(np.float32)
+        return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+    for default in (0.0, math.nan):
+        for kind in ("uniform", "sparse mixed-sign"):
+            rng = np.random.default_rng(17)
+            sc, ref = ShardedCube(univac_dims(nd), prefix=2), Cube(univac_dims(nd))
+            for m, rule in enumerate(rules):
+                if kind == "uniform":
+                    data = rng.uniform(1.0, 1000.0, n).astype(np.float32)
+                else:
+                    data = (rng.uniform(-1e6, 1e6, n) * rng.choice([1.0, 1e-6], n)).astype(np.float32)
+                    data[rng.random(n) < 0.4] = default
+                for c in (sc, ref):
+                    c.createStoredMeasure(f"m_{rule}", {f"dim{k}": rule for k in range(nd)}, "float32", default)
+                    c.setData(f"m_{rule}", data)
+            for c in (sc, ref):
+                c.createComputedMeasure("ratio", "(m_sum + m_average) / m_highest")
+            ops = [("dim0", "all"), ("dim0", "parity"), ("dim1", "all"), (f"dim{nd - 1}", "all")]
+            for mode in ("pull", "nccl"):
+                SH.EXCHANGE = mode
+                for dim, attr in ops:
+                    a, b = sc.drillUp(dim, attr), ref.drillUp(dim, attr)
+                    for rule in rules:
+                        got, want = a.getData(f"m_{rule}"), b.getData(f"m_{rule}")
+                        cases += 1
+                        if mode == "pull" or dim not in ("dim0", "dim1"):
+                            ok = same_bits(got, want)
+                        elif kind != "uniform" and rule in ("sum", "average"):
+                            continue  # float32 partials under cancellation: outside the NCCL path's stated tolerance
+                        else:
+                            ok = np.allclose(got, np.asarray(want, dtype=np.float64), rtol=1e-6, atol=0, equal_nan=True)
+                        if not ok:
+                            mismatches.append(f"{mode} default={default} {kind} drillUp({dim},{attr}) m_{rule}")
+                            timed_path_mismatches += mode == default_mode and (dim, attr) in (("dim0", "all"), (f"dim{nd - 1}", "all"))
+                    if mode == "pull" and attr == "all":
+                        cases += 1
+                        if not np.allclose(a.getData("ratio"), np.asarray(b.getData("ratio"), dtype=np.float64), rtol=1e-6, atol=0, equal_nan=True):
+                            mismatches.append(f"computed measure after drillUp({dim},{attr}) default={default} {kind}")
+            SH.EXCHANGE = default_mode
+            # the re-partitioning reorder (cube.js:757-783) on a prefix-1 cube, then a rollup of the new sharded axis
+            if kind == "uniform":
+                s1 = ShardedCube(univac_dims(nd), prefix=1)
+                for rule in ("sum", "first"):
+                    s1.createStoredMeasure(f"m_{rule}", {f"dim{k}": rule for k in range(nd)}, "float32", default)
+                    s1.setData(f"m_{rule}", np.asarray(ref.getData(f"m_{rule}"), dtype=np.float32))
+                order = ["dim2", "dim0", "dim4", "dim1", "dim3"]
+                try:
+                    ra, rb = s1.reorderDimensions(order), ref.reorderDimensions(order)
+                    for rule in ("sum", "first"):
+                        cases += 2
+                        if not same_bits(ra.getData(f"m_{rule}"), rb.getData(f"m_{rule}")):
+                            mismatches.append(f"reorderDimensions m_{rule} default={default}")
+                        if not same_bits(ra.drillUp("dim2", "all").getData(f"m_{rule}"), rb.drillUp("dim2", "all").getData(f"m_{rule}")):
+                            mismatches.append(f"reorderDimensions then drillUp(dim2,all) m_{rule} default={default}")
+                except Exception as exc:  # reported, not fatal: not on the timed path
+                    mismatches.append(f"reorderDimensions raised {type(exc).__name__}: {exc}")
+    import torch
+
+    t = torch.tensor([len(mismatches), timed_path_mismatches], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"cases": cases, "mismatches": int(t[0].item()), "first_mismatches": mismatches[:5], "timed_path_mismatches": int(t[1].item()),
+            "what": "small sharded cubes vs ONE single-GPU cube on the same data: pull exchange bit-exact (6 methods, 0 / NaN default, "
+                    "mixed-sign sparse data), NCCL exchange rel 1e-6, deepened prefixes, re-partitioning reorder, computed measures"}
+
+
+def run_sharded(args, rank, world, local_rank):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from olap_in_memory_b200 import _native as N
+    from olap_in_memory_b200 import interop
+    from olap_in_memory_b200 import sharded as SH
+    from olap_in_memory_b200.sharded import ShardedCube, _pull_tables
+
+    torch.cuda.set_device(local_rank)
+    N.init(local_rank)
+    lib = N.lib()
+    stream = torch.cuda.Stream()
+    N.check(lib.olap_set_stream(stream.cuda_stream))
+    guard = sharded_parity_guard(dist, rank, world)
+    assert guard["timed_path_mismatches"] == 0, f"bench: the sharded rollups do not match the single-GPU cube: {guard}"
+
+    cfg = sharded_config(world)
+    ndims = cfg["ndims"]
+    dims = univac_dims(ndims)
+    cube = ShardedCube(dims, prefix=2)
+    names = ["m_sum", "m_avg", "m_max"]
+    with torch.cuda.stream(stream):
+        for name, rule in zip(names, SHARDED_METHODS):
+            cube.createStoredMeasure(name, {d.id: rule for d in dims}, "float32", 0)
+            interop.values_tensor(cube.storedMeasures[name]).uniform_(1.0, 1000.0)
+            st = interop.status_tensor(cube.storedMeasures[name])
+            if st is not None:
+                st.fill_(2)
+    torch.cuda.synchronize()
+    n_total, n_local, measures = cube.storeSize, cube.localSize, len(names)
+    last = f"dim{ndims - 1}"
+
+    def op_inner():
+        return cube.drillUp(last, "all")
+
+    def op_outer():
+        return cube.drillUp("dim0", "all")
+
+    def step_device():
+        return op_inner(), op_outer()
+
+    clocks = Clocks(local_rank)
+    clocks.start()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        timed.launches = lib.olap_kernel_launches()
+        clocks.busy.set()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+        barrier()
+        clocks.busy.clear()
+        timed.launches = lib.olap_kernel_launches() - timed.launches
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def max_over_ranks(x):
+        t = torch.tensor([float(x)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # full-size property before timing: a sum rollup preserves the grand total
+    total_before = cube.getTotal("m_sum")
+    rolled = op_outer()
+    total_after = rolled.getTotal("m_sum")
+    assert abs(total_after - total_before) <= 1e-6 * abs(total_before), "bench: dim0 -> all lost cells"
+    deep = rolled.prefix
+    out_bounds = list(rolled.row_bounds)
+    del rolled
+
+    N.check(lib.olap_set_async(1))
+    ms_value = timed(step_device, args.steps, args.warmup)
+    launches = timed.launches
+    N.check(lib.olap_set_async(0))
+    ms_inner = timed(op_inner, max(3, min(args.steps, 10)), 1)
+    ms_outer = timed(op_outer, max(3, min(args.steps, 10)), 1)
+    # kernel-only brackets (CUDA events inside the library, on its stream)
+    k_inner, k_outer = [], []
+    for _ in range(3):
+        op_inner()
+        k_inner.append(lib.olap_last_op_ms())
+        path_inner = lib.olap_last_op_path().decode()
+        op_outer()
+        k_outer.append(lib.olap_last_op_ms())
+        path_outer = lib.olap_last_op_path().decode()
+    k_inner_ms, k_outer_ms = max_over_ranks(np.mean(k_inner)), max_over_ranks(np.mean(k_outer))
+
+    # bytes that cross NVLink into this GPU during dim0 -> all: the remote children of my output rows
+    view = cube
+    while view.prefix < deep:
+        view = view._deepened()
+    full_map = view._row_map(0, np.zeros(10, dtype=np.int32), [1] + [10] * (deep - 1), all_rows=True)
+    _, child_rank, _ = _pull_tables(full_map, view.row_bounds, out_bounds[rank], out_bounds[rank + 1])
+    bytes_per_row = 5 * measures * view.inner
+    nvlink_in = max_over_ranks(int((child_rank != rank).sum()) * bytes_per_row)
+    pulled = SH.EXCHANGE == "pull" and path_outer == "drillup/pull-peers"
+
+    # ---- e2e: host buffers -> sharded cube -> both rollups -> host
+    def pinned(n_floats):
+        p = C.c_void_p()
+        N.check(lib.olap_host_alloc(max(1, n_floats) * 4, C.byref(p)))
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(max(1, n_floats),)), p
+
+    host_in, keep_in = pinned(n_local)
+    block = synth(np.empty(min(n_local, 1 << 24), np.float32), 1 + rank, 0)
+    for lo in range(0, n_local, block.size):
+        hi = min(n_local, lo + block.size)
+        host_in[lo:hi] = block[: hi - lo]
+    a, b = step_device()
+    out_cells = max(next(iter(a.storedMeasures.values())).size, next(iter(b.storedMeasures.values())).size)
+    d2h_local = measures * (next(iter(a.storedMeasures.values())).size + next(iter(b.storedMeasures.values())).size) * 4
+    del a, b
+    host_out, keep_out = pinned(out_cells)
+
+    def step_e2e():
+        for name in names:
+            cube.setLocalData(name, host_in[:n_local])
+        a, b = step_device()
+        for res in (a, b):
+            for name in names:
+                st = res.storedMeasures[name]
+                N.check(lib.olap_store_download_f32(st._h, host_out.ctypes.data, st.size))
+        return float(host_out[0])
+
+    ms_e2e = timed(step_e2e, max(1, min(args.steps, 2)), 1)
+    clk = clocks.summary()
+    t = torch.tensor([float(d2h_local)], device="cuda")
+    dist.all_reduce(t)
+    d2h_total = int(t.item())
+
+    peak, peak_src = FALLBACK_HBM_GBS, "fallback"
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        peak_src = "measured"
+    except Exception:
+        pass
+    cells_per_step = 2 * measures * n_total
+    value = cells_per_step / (ms_value * 1e-3)
+    inner_bytes = 5 * measures * (n_local + n_local // 10)
+    nv_gbs = nvlink_in / (k_outer_ms * 1e-3) / 1e9
+    if rank == 0:
+        line = {
+            "metric": "drillUp input measure-cells/s", "value": value, "unit": "cells/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_value, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "e2e": {"value": cells_per_step / (ms_e2e * 1e-3), "unit": "cells/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": measures * n_total * 4, "d2h_bytes_per_step": d2h_total,
+                    "note": "every rank uploads its shard of the 3 measures from one pinned host buffer, runs both rollups, downloads the 6 result planes"},
+            "gpu_launches": int(launches), "clocks": clk,
+            "roofline": {"bound": "nvlink", "achieved": nv_gbs, "peak": NVLINK_GBS, "unit": "GB/s", "frac": nv_gbs / NVLINK_GBS,
+                         "traffic": None, "kernel": path_outer, "kernel_ms": k_outer_ms, "algorithmic_bytes": nvlink_in,
+                         "peak_source": "B200_PROFILING.md measured peer copy per direction per GPU",
+                         "what": "bytes the busiest GPU reads from its peers during drillUp dim0 -> all (remote children of its "
+                                 "output rows x 5 B x 3 measures) / kernel time, max over ranks"},
+            "sharded": {
+                "exchange": SH.EXCHANGE, "pulled_over_peer_memory": pulled, "prefix_after_rollup": deep,
+                "rows_per_rank_out": [out_bounds[r + 1] - out_bounds[r] for r in range(world)],
+                "inner_rollup": {"op": f"drillUp {last}->all (shard-local)", "ms": ms_inner, "kernel_ms": k_inner_ms, "kernel": path_inner,
+                                 "hbm_GBs_per_gpu": inner_bytes / (k_inner_ms * 1e-3) / 1e9,
+                                 "hbm_frac": inner_bytes / (k_inner_ms * 1e-3) / 1e9 / peak, "hbm_peak": peak, "peak_source": peak_src},
+                "sharded_rollup": {"op": "drillUp dim0->all (sharded dimension)", "ms": ms_outer, "kernel_ms": k_outer_ms, "kernel": path_outer,
+                                   "nvlink_bytes_in_per_gpu": nvlink_in, "nvlink_GBs_per_gpu": nv_gbs, "nvlink_frac_of_770": nv_gbs / NVLINK_GBS,
+                                   "bound_ms": nvlink_in / (NVLINK_GBS * 1e9) * 1e3},
+                "parity_guard": guard,
+            },
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -358,7 +722,10 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        if world > 1:
+            run_sharded(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -22,8 +22,8 @@ def main():
     ap.add_argument("--ndims", type=int, default=9)  # 10^9 cells
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--only", default="", help="run only the operations whose label contains this text")
-    ap.add_argument("--exchange", default="", choices=("", "p2p", "nccl", "both"),
-                    help="exchange mode(s) of the sharded rollups (default: the library's own default)")
+    ap.add_argument("--exchange", default="", help="comma-separated exchange modes of the sharded rollups to time "
+                    "(pull, push, nccl; default: the library's own default)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -84,9 +84,12 @@ def main():
             # average travels as (sum, count): 4 planes for 3 measures
             planes = 4
             # every rank holds a partial of the FULL output and sends (W-1)/W of it
-            row["exchange"] = "peer stores from the rollup kernel" if _sh.P2P_EXCHANGE else "NCCL all-to-all per plane"
-            row["nvlink_bytes_sent_per_gpu"] = 5 * planes * n_out * (world - 1) // world
-            row["nvlink_GBs_per_gpu"] = round(row["nvlink_bytes_sent_per_gpu"] / (ms * 1e-3) / 1e9, 1)
+            row["exchange"] = _sh.EXCHANGE
+            if _sh.EXCHANGE == "pull":  # every rank reads (W-1)/W of the children of its output rows, 3 measures x 5 B
+                row["nvlink_bytes_per_gpu"] = 5 * measures * (n_total // world) * (world - 1) // world
+            else:
+                row["nvlink_bytes_per_gpu"] = 5 * planes * n_out * (world - 1) // world
+            row["nvlink_GBs_per_gpu"] = round(row["nvlink_bytes_per_gpu"] / (ms * 1e-3) / 1e9, 1)
         rows.append(row)
         if rank == 0:
             print(json.dumps(row), flush=True)
@@ -101,10 +104,10 @@ def main():
             continue
         modes = [None]
         if "sharded" in label and world > 1 and args.exchange:
-            modes = {"p2p": [True], "nccl": [False], "both": [True, False]}[args.exchange]
+            modes = args.exchange.split(",")
         for mode in modes:
             if mode is not None:
-                _sh.P2P_EXCHANGE = mode
+                _sh.EXCHANGE = mode
             emit(label, fn, n_out)
     if world > 1:
         dist.destroy_process_group()

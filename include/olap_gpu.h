@@ -118,6 +118,10 @@ int olap_host_free(void* p);
  * fill the planes with the default — only for a store whose every cell is about to be
  * overwritten (receive buffers of the multi-GPU exchange). */
 #define OLAP_CREATE_UNINITIALISED 2
+/* bit 2 (OLAP_CREATE_SHAREABLE): the store lives in memory that the other processes of the box can
+ * map (cudaMalloc + CUDA IPC instead of the stream-ordered pool): the local shard of a sharded
+ * cube.  Results of transforms of a shareable store are shareable too. */
+#define OLAP_CREATE_SHAREABLE 4
 int olap_store_create(int64_t size, int type, int default_kind, int with_status, olap_store** out);
 /* n stores of equal size carved from one allocation (a cube's stored measures).
  * shared_status != 0: one status plane shared by all n stores. */
@@ -145,6 +149,25 @@ int olap_store_wrap(void* values, void* status, int64_t size, int type, int defa
 int olap_drill_up_rows(olap_store* const* src, int n, const int* methods, int64_t c_rows, int64_t p_rows,
                        int64_t inner, const int32_t* row_map, float* const* row_values,
                        uint8_t* const* row_status);
+/* Pull model of the same rollup (the default on GPUs).  olap_store_ipc_export: the 64-byte CUDA IPC
+ * handle of the block a SHAREABLE store lives in, and the byte offsets of its values / status plane
+ * (-1: none) inside that block, to be sent to the peers.  olap_peer_map: map a peer's block (cached
+ * by handle; a block recycled by its owner keeps its handle).  olap_peer_unmap_all closes them.
+ * olap_drill_up_pull: drillUp (in-memory.js:265-334) of the sharded row axis where the rank that
+ * OWNS output rows reads their child rows out of the ranks that hold them: output row j (of
+ * out_rows, `inner` cells each) aggregates child rows row_start[j] .. row_start[j+1]-1 of the child
+ * tables, in that order (ascending global row = the reference's iteration order); child c is row
+ * child_row[c] of rank child_rank[c], whose store k starts at base_values[k * n_ranks + rank] (an
+ * address valid in THIS process: local, or peer-mapped) and holds rank_rows[rank] rows.  `like`
+ * gives type / default / status layout of the n results.  One kernel; cells cross NVLink once;
+ * bit-equal to the unsharded olap_drill_up for every method. */
+int olap_store_ipc_export(const olap_store* s, unsigned char* handle64, int64_t* values_offset, int64_t* status_offset);
+int olap_peer_map(const unsigned char* handle64, void** ptr);
+int olap_peer_unmap_all(void);
+int olap_drill_up_pull(olap_store* const* like, int n, const int* methods, int64_t out_rows, int64_t inner,
+                       const int32_t* row_start, const int32_t* child_rank, const int64_t* child_row, int n_ranks,
+                       const int64_t* rank_rows, const void* const* base_values, const void* const* base_status,
+                       olap_store** out);
 int64_t olap_store_size(const olap_store* s);        /* `.size` in-memory.js:18-20 */
 int64_t olap_store_byte_length(const olap_store* s); /* `.byteLength` in-memory.js:8-16 */
 int olap_store_type(const olap_store* s);

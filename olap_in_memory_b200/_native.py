@@ -12,7 +12,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libolapgpu.so")
+# OLAP_LIB: another build of the same ABI (A/B timing of older commits, tools/ab_drillup.sh); symbols
+# such a build lacks are skipped, calling them raises AttributeError
+LIB_PATH = os.environ.get("OLAP_LIB") or os.path.join(_HERE, "libolapgpu.so")
 
 OK = 0
 E_INVALID, E_CUDA, E_NOMEM, E_UNSUPPORTED = -1, -2, -3, -4
@@ -71,6 +73,11 @@ SIGNATURES = {
     "olap_store_wrap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, pp_store]),
     "olap_drill_up_rows": (C.c_int, [pp_store, C.c_int, p_int, C.c_int64, C.c_int64, C.c_int64, p_i32,
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "olap_store_ipc_export": (C.c_int, [p_store, C.c_char_p, p_i64, p_i64]),
+    "olap_peer_map": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "olap_peer_unmap_all": (C.c_int, []),
+    "olap_drill_up_pull": (C.c_int, [pp_store, C.c_int, p_int, C.c_int64, C.c_int64, p_i32, p_i32, p_i64, C.c_int, p_i64,
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), pp_store]),
     "olap_store_size": (C.c_int64, [p_store]),
     "olap_store_byte_length": (C.c_int64, [p_store]),
     "olap_store_type": (C.c_int, [p_store]),
@@ -110,6 +117,8 @@ def load_library(path: str = LIB_PATH):
         )
     lib = C.CDLL(path)
     for name, (restype, argtypes) in SIGNATURES.items():
+        if os.environ.get("OLAP_LIB") and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)
         fn.restype = restype
         fn.argtypes = argtypes

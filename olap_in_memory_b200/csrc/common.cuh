@@ -71,6 +71,10 @@ struct Arena {
     void* base = nullptr;
     size_t bytes = 0;
     std::atomic<int> refs{0};
+    // shareable: the block comes from cudaMalloc (CUDA IPC cannot export the stream-ordered pool), so
+    // that the other ranks of a sharded cube can map it and read its cells over NVLink
+    // (olap_store_ipc_export / olap_drill_up_pull).  Freed blocks are recycled by size.
+    bool shareable = false;
 };
 
 }  // namespace olap
@@ -89,7 +93,7 @@ namespace olap {
 // Allocate `n` stores of `size` cells in one arena.  Layout (contiguous):
 //   values[0][size] ... values[n-1][size]  |  status planes (n, 1 or 0), each padded to 256 B.
 int alloc_batch(int n, int64_t size, const int* types, const int* default_kinds, bool with_status,
-                bool shared_status, olap_store** out);
+                bool shared_status, olap_store** out, bool shareable = false);
 
 // Small host->device table upload through pinned staging (async on the stream).
 // Tables of one call are packed into a single device buffer.

@@ -6,6 +6,8 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <array>
+#include <map>
 #include <numeric>
 
 #include "common.cuh"
@@ -16,6 +18,7 @@
 #include "kernels_pair.cuh"
 #include "kernels_tile.cuh"
 #include "kernels_long.cuh"
+#include "kernels_pull.cuh"
 
 namespace olap {
 
@@ -92,17 +95,50 @@ static const bool g_guard = [] { const char* e = getenv("OLAP_GUARD"); return e 
 static std::atomic<int64_t> g_guard_violations{0};
 constexpr size_t kGuardBytes = 256;
 
+// Shareable blocks (cudaMalloc, exportable through CUDA IPC) are recycled by exact size: a sharded
+// cube re-creates result stores of the same sizes query after query, and a recycled block keeps its
+// IPC handle, so the mappings the peers hold stay valid.  All library work runs on one stream, so
+// handing a freed block to a later call is stream-ordered by construction.
+static std::multimap<size_t, void*> g_share_free;
+static int share_alloc(void** p, size_t bytes) {
+    if (bytes == 0) bytes = 256;
+    auto it = g_share_free.find(bytes);
+    if (it != g_share_free.end()) {
+        *p = it->second;
+        g_share_free.erase(it);
+        return OLAP_OK;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) {  // give the cached blocks back and try again
+        cudaGetLastError();
+        for (auto& kv : g_share_free) cudaFree(kv.second);
+        g_share_free.clear();
+        e = cudaMalloc(p, bytes);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *p = nullptr;
+        return fail(e == cudaErrorMemoryAllocation ? OLAP_E_NOMEM : OLAP_E_CUDA,
+                    "device allocation of %zu shareable bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return OLAP_OK;
+}
+static void share_free(void* p, size_t bytes) {
+    if (p) g_share_free.emplace(bytes ? bytes : 256, p);
+}
+
 int alloc_batch(int n, int64_t size, const int* types, const int* default_kinds, bool with_status,
-                bool shared_status, olap_store** out) {
+                bool shared_status, olap_store** out, bool shareable) {
     const size_t guard = g_guard ? kGuardBytes : 0;
     const size_t vplane = pad256((size_t)size * sizeof(float)) + guard;
     const size_t splane = with_status ? pad256((size_t)size) + guard : 0;
     const int n_status = with_status ? (shared_status ? 1 : n) : 0;
     const size_t bytes = vplane * n + splane * n_status;
     Arena* arena = new Arena();
-    int rc = dev_alloc(&arena->base, bytes);
+    int rc = shareable ? share_alloc(&arena->base, bytes) : dev_alloc(&arena->base, bytes);
     if (rc != OLAP_OK) { delete arena; return rc; }
     arena->bytes = bytes;
+    arena->shareable = shareable;
     arena->refs = n;
     char* base = static_cast<char*>(arena->base);
     if (g_guard && bytes) cudaMemsetAsync(base, 0xA5, bytes, g.stream);
@@ -241,7 +277,9 @@ static int alloc_like(olap_store* const* src, int n, int64_t new_size, olap_stor
         with_status &= src[k]->status != nullptr;
         shared &= src[k]->status == src[0]->status;
     }
-    return alloc_batch(n, new_size, types, defaults, with_status, with_status && shared, out);
+    // results of a shareable store stay shareable: the next query may be a rollup of the sharded axis
+    const bool shareable = src[0]->arena && src[0]->arena->shareable;
+    return alloc_batch(n, new_size, types, defaults, with_status, with_status && shared, out, shareable);
 }
 
 static int fill_default(olap_store* s) {
@@ -557,8 +595,9 @@ int olap_store_create_batch(int n, int64_t size, const int* types, const int* de
     if (size < 0) return fail(OLAP_E_INVALID, "olap_store_create_batch: negative size");
     for (int k = 0; k < n; ++k) OLAP_TRY(check_type_default(types[k], default_kinds[k]));
     OLAP_TRY(ensure_ctx());
-    OLAP_TRY(alloc_batch(n, size, types, default_kinds, (with_status & 1) != 0, shared_status != 0, out));
-    if (with_status & 2) return finish_op();  // OLAP_CREATE_UNINITIALISED: the caller overwrites every cell
+    OLAP_TRY(alloc_batch(n, size, types, default_kinds, (with_status & 1) != 0, shared_status != 0, out,
+                         (with_status & OLAP_CREATE_SHAREABLE) != 0));
+    if (with_status & OLAP_CREATE_UNINITIALISED) return finish_op();  // OLAP_CREATE_UNINITIALISED: the caller overwrites every cell
     for (int k = 0; k < n; ++k) {
         olap_store tmp = *out[k];
         tmp.status = st_out_of(out, k);
@@ -579,7 +618,8 @@ int olap_store_destroy(olap_store* s) {
     Arena* a = s->arena;
     delete s;
     if (a && --a->refs == 0) {
-        if (g.ready) cudaFreeAsync(a->base, g.stream);
+        if (a->shareable) share_free(a->base, a->bytes);
+        else if (g.ready) cudaFreeAsync(a->base, g.stream);
         delete a;
     }
     return OLAP_OK;
@@ -588,7 +628,8 @@ int olap_store_destroy(olap_store* s) {
 int olap_store_clone(const olap_store* s, olap_store** out) {
     if (!s || !out) return fail(OLAP_E_INVALID, "olap_store_clone: null argument");
     OLAP_TRY(ensure_ctx());
-    OLAP_TRY(alloc_batch(1, s->size, &s->type, &s->default_kind, s->status != nullptr, false, out));
+    OLAP_TRY(alloc_batch(1, s->size, &s->type, &s->default_kind, s->status != nullptr, false, out,
+                         s->arena && s->arena->shareable));
     if (s->size) {
         OLAP_CUDA(cudaMemcpyAsync((*out)->values, s->values, (size_t)s->size * 4, cudaMemcpyDeviceToDevice, g.stream));
         if (s->status) OLAP_CUDA(cudaMemcpyAsync((*out)->status, s->status, (size_t)s->size, cudaMemcpyDeviceToDevice, g.stream));
@@ -1567,6 +1608,156 @@ int olap_drill_up_rows(olap_store* const* src, int n, const int* methods, int64_
     return finish_op();
 }
 
+// ---- pull model: stores that peers can map, and the rollup that reads them ------------------
+int olap_store_ipc_export(const olap_store* s, unsigned char* handle64, int64_t* values_offset, int64_t* status_offset) {
+    if (!s || !handle64 || !values_offset || !status_offset) return fail(OLAP_E_INVALID, "olap_store_ipc_export: null argument");
+    if (!s->arena || !s->arena->shareable)
+        return fail(OLAP_E_UNSUPPORTED, "olap_store_ipc_export: the store was not created with OLAP_CREATE_SHAREABLE");
+    OLAP_TRY(ensure_ctx());
+    cudaIpcMemHandle_t h;
+    OLAP_CUDA(cudaIpcGetMemHandle(&h, s->arena->base));
+    memcpy(handle64, &h, 64);
+    *values_offset = reinterpret_cast<const char*>(s->values) - static_cast<const char*>(s->arena->base);
+    *status_offset = s->status ? reinterpret_cast<const char*>(s->status) - static_cast<const char*>(s->arena->base) : -1;
+    return OLAP_OK;
+}
+
+// Mappings of peers' blocks, by IPC handle.  A recycled block keeps its handle, so a sharded cube
+// that is queried repeatedly opens each peer block once.  Least recently used mappings are closed
+// beyond kPeerMapCap entries (their blocks may have been freed by the owner since).
+namespace {
+struct PeerMapping { void* ptr; uint64_t stamp; };
+std::map<std::array<unsigned char, 64>, PeerMapping> g_peer_maps;
+uint64_t g_peer_clock = 0;
+constexpr size_t kPeerMapCap = 512;
+}  // namespace
+
+int olap_peer_map(const unsigned char* handle64, void** ptr) {
+    if (!ptr || !handle64) return fail(OLAP_E_INVALID, "olap_peer_map: null argument");
+    OLAP_TRY(ensure_ctx());
+    std::array<unsigned char, 64> key;
+    memcpy(key.data(), handle64, 64);
+    auto it = g_peer_maps.find(key);
+    if (it != g_peer_maps.end()) {
+        it->second.stamp = ++g_peer_clock;
+        *ptr = it->second.ptr;
+        return OLAP_OK;
+    }
+    if (g_peer_maps.size() >= kPeerMapCap) {
+        auto victim = g_peer_maps.begin();
+        for (auto q = g_peer_maps.begin(); q != g_peer_maps.end(); ++q)
+            if (q->second.stamp < victim->second.stamp) victim = q;
+        OLAP_CUDA(cudaStreamSynchronize(g.stream));  // no kernel may still be reading it
+        cudaIpcCloseMemHandle(victim->second.ptr);
+        g_peer_maps.erase(victim);
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    OLAP_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    g_peer_maps[key] = PeerMapping{*ptr, ++g_peer_clock};
+    return OLAP_OK;
+}
+
+int olap_peer_unmap_all(void) {
+    if (!g.ready) return OLAP_OK;
+    OLAP_CUDA(cudaStreamSynchronize(g.stream));
+    for (auto& kv : g_peer_maps) cudaIpcCloseMemHandle(kv.second.ptr);
+    g_peer_maps.clear();
+    return OLAP_OK;
+}
+
+int olap_drill_up_pull(olap_store* const* like, int n, const int* methods, int64_t out_rows, int64_t inner,
+                       const int32_t* row_start, const int32_t* child_rank, const int64_t* child_row, int n_ranks,
+                       const int64_t* rank_rows, const void* const* base_values, const void* const* base_status,
+                       olap_store** out) {
+    int64_t like_size = 0;
+    OLAP_TRY(check_batch(like, n, "olap_drill_up_pull", &like_size));
+    if (!methods || !row_start || !rank_rows || !base_values || !out) return fail(OLAP_E_INVALID, "olap_drill_up_pull: null argument");
+    if (out_rows < 0 || inner <= 0 || n_ranks < 1) return fail(OLAP_E_INVALID, "olap_drill_up_pull: invalid shape");
+    for (int k = 0; k < n; ++k)
+        if (methods[k] < OLAP_SUM || methods[k] > OLAP_COUNT) return fail(OLAP_E_INVALID, "Unsupported aggregation method: %d", methods[k]);
+    int64_t new_size = 0;
+    if (mul_overflow(out_rows, inner, &new_size)) return fail(OLAP_E_INVALID, "olap_drill_up_pull: cube size overflows int64");
+    if (out_rows > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "olap_drill_up_pull: more than 2^31-1 output rows");
+    if (row_start[0] != 0) return fail(OLAP_E_INVALID, "olap_drill_up_pull: row_start[0] must be 0");
+    for (int64_t j = 0; j < out_rows; ++j)
+        if (row_start[j + 1] < row_start[j]) return fail(OLAP_E_INVALID, "olap_drill_up_pull: row_start is not ascending");
+    const int64_t nc = row_start[out_rows];
+    if (nc && (!child_rank || !child_row)) return fail(OLAP_E_INVALID, "olap_drill_up_pull: null child tables");
+    std::vector<int64_t> child_off((size_t)nc);
+    for (int64_t c = 0; c < nc; ++c) {
+        const int32_t r = child_rank[c];
+        if (r < 0 || r >= n_ranks) return fail(OLAP_E_INVALID, "olap_drill_up_pull: child %lld lives on rank %d, outside [0, %d)", (long long)c, r, n_ranks);
+        if (child_row[c] < 0 || child_row[c] >= rank_rows[r])
+            return fail(OLAP_E_INVALID, "olap_drill_up_pull: child %lld is row %lld of rank %d, which holds %lld rows", (long long)c, (long long)child_row[c], r, (long long)rank_rows[r]);
+        child_off[c] = child_row[c] * inner;
+    }
+    bool any_status = false;
+    for (int k = 0; k < n; ++k) any_status |= like[k]->status != nullptr;
+    if (any_status && !base_status) return fail(OLAP_E_INVALID, "olap_drill_up_pull: stores carry a status plane but no status bases were given");
+    for (int k = 0; k < n; ++k)
+        for (int r = 0; r < n_ranks; ++r) {
+            // a rank without rows is never dereferenced; every other base must be a real address
+            if (rank_rows[r] && !base_values[(size_t)k * n_ranks + r]) return fail(OLAP_E_INVALID, "olap_drill_up_pull: null base of store %d on rank %d", k, r);
+        }
+    OLAP_TRY(ensure_ctx());
+    OLAP_TRY(alloc_like(like, n, new_size, out));
+    begin_op();
+    if (new_size) {
+        std::vector<PullMeasure> meas(n);
+        std::vector<const void*> bs((size_t)n * n_ranks, nullptr);
+        for (int k = 0; k < n; ++k) {
+            // a status plane shared by several measures is read and written by the first of them only
+            const bool own_status = out[k]->status && st_in_of(like, k) && st_out_of(out, k);
+            meas[k] = PullMeasure{out[k]->values, own_status ? out[k]->status : nullptr, methods[k], like[k]->default_kind};
+            if (own_status)
+                for (int r = 0; r < n_ranks; ++r) bs[(size_t)k * n_ranks + r] = base_status[(size_t)k * n_ranks + r];
+        }
+        TablePack t;
+        const size_t o_meas = t.add(meas.data(), sizeof(PullMeasure) * n);
+        const size_t o_rs = t.add(row_start, sizeof(int32_t) * (size_t)(out_rows + 1));
+        const size_t o_cr = t.add(child_rank, sizeof(int32_t) * (size_t)nc);
+        const size_t o_co = t.add(child_off.data(), sizeof(int64_t) * (size_t)nc);
+        const size_t o_bv = t.add(base_values, sizeof(void*) * (size_t)n * n_ranks);
+        const size_t o_bs = t.add(bs.data(), sizeof(void*) * (size_t)n * n_ranks);
+        OLAP_TRY(t.upload());
+        // 128-bit path: every row of every rank must start on a 16-byte boundary
+        bool vec4 = inner % 4 == 0;
+        for (size_t q = 0; q < (size_t)n * n_ranks && vec4; ++q) {
+            vec4 &= (reinterpret_cast<uintptr_t>(base_values[q]) & 15) == 0;
+            vec4 &= (reinterpret_cast<uintptr_t>(bs[q]) & 3) == 0;
+        }
+        UpPullParams p{};
+        p.meas = t.ptr<PullMeasure>(o_meas);
+        p.row_start = t.ptr<int32_t>(o_rs);
+        p.child_rank = t.ptr<int32_t>(o_cr);
+        p.child_off = t.ptr<int64_t>(o_co);
+        p.base_v = t.ptr<const float*>(o_bv);
+        p.base_s = t.ptr<const uint8_t*>(o_bs);
+        p.n_ranks = n_ranks;
+        p.rows = out_rows;
+        p.inner = inner;
+        p.IV = vec4 ? inner / 4 : inner;
+        const uint32_t bx = (uint32_t)std::min<int64_t>(256, next_pow2((uint32_t)std::min<int64_t>(p.IV, 256)));
+        const uint32_t by = 256 / bx;
+        const int64_t gx = ceil_div(p.IV, bx);
+        if (gx > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "olap_drill_up_pull: inner run too long");
+        const int64_t rows_per_launch = (int64_t)65535 * by;
+        KERNELS_BEGIN();
+        for (int64_t r0 = 0; r0 < out_rows; r0 += rows_per_launch) {
+            p.row0 = r0;
+            const int64_t gy = ceil_div(std::min(rows_per_launch, out_rows - r0), by);
+            dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)n), block(bx, by);
+            if (vec4) drillup_pull_kernel<4><<<grid, block, 0, g.stream>>>(p);
+            else drillup_pull_kernel<1><<<grid, block, 0, g.stream>>>(p);
+            LAUNCHED();
+        }
+        OLAP_TRY(t.release());
+    }
+    end_op("drillup/pull-peers");
+    return finish_op();
+}
+
 // ---- computed measures --------------------------------------------------------------------
 int olap_eval(const char* program, olap_store* const* inputs, int n_inputs, const double* totals, int n_totals,
               double* out_host_f64, int out_type, int out_default_kind, olap_store** out_store) {
@@ -1588,7 +1779,8 @@ int olap_eval(const char* program, olap_store* const* inputs, int n_inputs, cons
         OLAP_TRY(check_type_default(out_type, out_default_kind));
         bool with_status = true;
         for (int q = 0; q < n_inputs; ++q) with_status &= inputs[q]->status != nullptr;
-        OLAP_TRY(alloc_batch(1, size, &out_type, &out_default_kind, with_status, false, &result));
+        OLAP_TRY(alloc_batch(1, size, &out_type, &out_default_kind, with_status, false, &result,
+                             inputs[0]->arena && inputs[0]->arena->shareable));
         out32 = result->values;
         st_out = result->status;
     } else if (size) {

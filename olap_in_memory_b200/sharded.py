@@ -47,11 +47,39 @@ def _is_device_store(store):
     return hasattr(store, "_h")
 
 
-# OLAP_SHARDED_P2P=0: rollups of a sharded dimension go through NCCL all-to-all (partial planes
-# in local HBM, then one exchange per plane).  Default on GPUs: ONE kernel per call computes the
-# partial rollup and stores every output row straight into the receive buffer of the rank that
-# owns it, through peer-mapped pointers over NVLink (olap_drill_up_rows).
-P2P_EXCHANGE = os.environ.get("OLAP_SHARDED_P2P", "1") != "0"
+# How a rollup of a sharded dimension moves its cells between GPUs (OLAP_SHARDED_EXCHANGE):
+#   "pull" (default on GPUs): the rank that owns an output row reads its child rows straight out of
+#          the peers' stores through CUDA-IPC-mapped pointers, inside ONE rollup kernel
+#          (olap_drill_up_pull): no partial planes, no receive buffers, no combine pass, and the
+#          result is bit-equal to the unsharded rollup (same accumulation order).
+#   "push": ONE kernel per call computes the partial rollup of the local rows and stores every
+#          output row into the receive buffer of the rank that owns it (olap_drill_up_rows), then an
+#          ordered combine of the W partials.
+#   "nccl": partial planes in local HBM, one NCCL all-to-all per plane, ordered combine (also the
+#          path of the gloo / CPU tests).
+EXCHANGE = os.environ.get("OLAP_SHARDED_EXCHANGE", "nccl" if os.environ.get("OLAP_SHARDED_P2P", "1") == "0" else "pull")
+# a rollup whose output rows would be spread unevenly (10 rows over 8 ranks: 2,2,1,1,1,1,1,1) is
+# computed on a deeper row axis when the imbalance exceeds this factor
+MAX_IMBALANCE = 1.1
+
+
+def _pull_tables(full_map, in_bounds, j0, j1):
+    """Child tables of olap_drill_up_pull for the rank that owns output rows j0..j1-1.
+
+    full_map[i] = output row of global input row i (all ranks' rows); in_bounds = row bounds of the
+    input shards.  Returns (row_start, child_rank, child_row): output row j0 + j aggregates the
+    children row_start[j] .. row_start[j+1]-1, listed in ascending global input row (the
+    reference's iteration order); child c is local row child_row[c] of rank
+    child_rank[c]."""
+    full_map = np.asarray(full_map, dtype=np.int64)
+    bounds = np.asarray(in_bounds, dtype=np.int64)
+    mine = np.flatnonzero((full_map >= j0) & (full_map < j1))  # ascending global rows
+    parents = full_map[mine] - j0
+    order = np.argsort(parents, kind="stable")  # by output row, global row order kept inside a row
+    rows, parents = mine[order], parents[order]
+    row_start = np.searchsorted(parents, np.arange(j1 - j0 + 1, dtype=np.int64), side="left").astype(np.int32)
+    rank = np.searchsorted(bounds[1:], rows, side="right")
+    return row_start, rank.astype(np.int32), (rows - bounds[rank]).astype(np.int64)
 
 
 def _peer_row_tables(bases, out_bounds, me, K, inner, plane_v, plane_s, with_status):
@@ -97,7 +125,9 @@ class _PeerBuffers:
 
         from . import _native as N
 
-        key = (id(comm.group), int(nbytes))
+        # the membership of the group, not id(group): ids are reused after garbage collection
+        group = comm.group if comm.group is not None else comm.dist.group.WORLD
+        key = (tuple(comm.dist.get_process_group_ranks(group)), int(nbytes))
         hit = cls._cache.get(key)
         if hit is not None:
             return hit
@@ -236,7 +266,12 @@ class ShardedCube:
         return -1
 
     def createStoredMeasure(self, measureId, rules=None, type="float32", defaultValue=0):
-        self.storedMeasures[measureId] = self._store_cls(self.localSize, type, defaultValue)
+        if getattr(self._store_cls, "SHAREABLE_SHARDS", False):
+            # device stores of a sharded cube live in memory the peers can map (pull exchange)
+            store = self._store_cls(self.localSize, type, defaultValue, shareable=True)
+        else:
+            store = self._store_cls(self.localSize, type, defaultValue)
+        self.storedMeasures[measureId] = store
         self.storedMeasuresRules[measureId] = {} if rules is None else rules
 
     def createComputedMeasure(self, measureId, formula):
@@ -348,21 +383,33 @@ class ShardedCube:
         group_map = np.asarray(old_dim.getGroupIndexFromRootIndexMap(new_dim.rootAttribute), dtype=np.int32)
         if idx >= self.prefix:
             return self._drill_up_local(new_dims, idx, group_map, ids, methods)
-        if _prod(d.numItems for d in new_dims[: self.prefix]) < self.world and self.prefix < len(self.dimensions):
-            # fewer output rows than ranks: shard the result on the next dimension as well
-            # (SURVEY.md §8e "leaving the result sharded on the next axis") instead of piling
-            # it up on the first ranks
+        new_rows = _prod(d.numItems for d in new_dims[: self.prefix])
+        heaviest = -(-new_rows // self.world) * self.world  # rows of the busiest rank x ranks
+        deeper = self.prefix < len(self.dimensions)
+        uneven = heaviest > MAX_IMBALANCE * new_rows and deeper and self.inner // self.dimensions[self.prefix].numItems >= 256
+        if deeper and (new_rows < self.world or uneven):
+            # fewer output rows than ranks, or rows that do not spread evenly (10 rows over 8 ranks:
+            # the two ranks with 2 rows would take twice as long as the others): shard the result
+            # on the next dimension as well (SURVEY.md §8e "leaving the result sharded on the next
+            # axis").  Nothing moves: the same cells are read as more, shorter rows.
             return self._deepened().drillUp(dimensionId, attribute)
         return self._drill_up_sharded(new_dims, idx, group_map, ids, methods)
 
     def _deepened(self):
         """The same cells, seen as a cube sharded on one more leading dimension: every row
         becomes numItems rows and the bounds scale with it.  Nothing moves."""
+        key = tuple(id(s) for s in self.storedMeasures.values())
+        hit = getattr(self, "_deep", None)
+        if hit is not None and hit[0] == key:  # the same view again: its peer mappings are still good
+            hit[1].storedMeasuresRules = dict(self.storedMeasuresRules)
+            hit[1].computedMeasures = dict(self.computedMeasures)
+            return hit[1]
         n = self.dimensions[self.prefix].numItems
         out = ShardedCube(self.dimensions, self.prefix + 1, self._store_cls, self.comm.group, [b * n for b in self.row_bounds])
         out.storedMeasures = dict(self.storedMeasures)
         out.storedMeasuresRules = dict(self.storedMeasuresRules)
         out.computedMeasures = dict(self.computedMeasures)
+        self._deep = (key, out)
         return out
 
     def _drill_up_local(self, new_dims, idx, group_map, ids, methods):
@@ -378,10 +425,10 @@ class ShardedCube:
             out.storedMeasures = dict(zip(ids, results))
         return out
 
-    def _row_map(self, idx, group_map, new_prefix_lens):
-        """my local row -> global row of the drilled cube"""
+    def _row_map(self, idx, group_map, new_prefix_lens, all_rows=False):
+        """my local row (or, with all_rows, every global row) -> global row of the drilled cube"""
         old_prefix_lens = [d.numItems for d in self.dimensions[: self.prefix]]
-        rows = np.arange(self.row0, self.row1, dtype=np.int64)
+        rows = np.arange(0 if all_rows else self.row0, self.rows_total if all_rows else self.row1, dtype=np.int64)
         coords = []
         rest = rows
         for n in reversed(old_prefix_lens):
@@ -392,7 +439,7 @@ class ShardedCube:
         new_row = np.zeros_like(rows)
         for c, n in zip(coords, new_prefix_lens):
             new_row = new_row * n + c
-        return new_row.astype(np.int32)
+        return new_row if all_rows else new_row.astype(np.int32)
 
     def _drill_up_sharded(self, new_dims, idx, group_map, ids, methods):
         """The drilled dimension is (part of) the sharded row axis."""
@@ -412,6 +459,10 @@ class ShardedCube:
                                  maps, _Per(methods))
             out.storedMeasures = dict(zip(ids, results))
             return out
+        if EXCHANGE == "pull" and self.comm.on and all(_is_device_store(self.storedMeasures[m]) for m in ids):
+            pulled = self._drill_up_pull(out, new_prefix_lens, idx, group_map, ids, methods, out_bounds)
+            if pulled is not None:
+                return pulled
         my_out_rows = out_bounds[self.rank + 1] - out_bounds[self.rank]
         row_map = self._row_map(idx, group_map, new_prefix_lens)
         old_len = self._local_lens()
@@ -428,7 +479,7 @@ class ShardedCube:
             else:
                 plan.append((m, method, "plain"))
         stores = [self.storedMeasures[m] for m, _, _ in plan]
-        if P2P_EXCHANGE and self.comm.on and _is_device_store(stores[0]):
+        if EXCHANGE in ("pull", "push") and self.comm.on and _is_device_store(stores[0]):
             received = self._partials_into_peers(stores, [meth for _, meth, _ in plan], row_map, out_bounds, new_rows_total)
             return self._combine(out, plan, ids, methods, received, my_out_rows)
         partials = self._partials(stores, old_len, new_len, maps, [meth for _, meth, _ in plan])
@@ -448,6 +499,93 @@ class ShardedCube:
         del partials
 
         return self._combine(out, plan, ids, methods, received, my_out_rows)
+
+    # ------------------------------------------------------------------ pull exchange
+    def _peer_views(self, stores):
+        """Addresses, in MY address space, of every rank's planes of these stores: two lists
+        [K][W] (values, status; None without a plane).  Handles travel once per set of stores (one
+        all_gather of ~100 bytes per store) and are remembered on the cube; mappings are cached
+        by the library (a recycled block keeps its handle).  None when a store of some rank cannot
+        be exported (not created shareable)."""
+        key = tuple(s._h for s in stores)
+        hit = self._pull_cache.get(key) if hasattr(self, "_pull_cache") else None
+        if hit is not None:
+            return hit
+        import ctypes as C
+
+        from . import _native as N
+
+        try:
+            mine = [s.ipc_export() for s in stores]
+        except N.OlapError:
+            mine = None
+        everyone = [None] * self.world
+        self.comm.dist.all_gather_object(everyone, mine, group=self.comm.group)
+        if any(e is None for e in everyone):
+            return None
+        lib = N.lib()
+        base_v = [[0] * self.world for _ in stores]
+        base_s = [[0] * self.world for _ in stores]
+        opened = {}
+        for r, exported in enumerate(everyone):
+            for k, (handle, v_off, s_off) in enumerate(exported):
+                if r == self.rank:
+                    base_v[k][r] = lib.olap_store_values_ptr(stores[k]._h)
+                    base_s[k][r] = lib.olap_store_status_ptr(stores[k]._h) or 0
+                    continue
+                if handle not in opened:
+                    p = C.c_void_p()
+                    N.check(lib.olap_peer_map(handle, C.byref(p)))
+                    opened[handle] = p.value
+                base_v[k][r] = opened[handle] + v_off
+                base_s[k][r] = opened[handle] + s_off if s_off >= 0 else 0
+        if not hasattr(self, "_pull_cache"):
+            self._pull_cache = {}
+        self._pull_cache[key] = (base_v, base_s)
+        return base_v, base_s
+
+    def _drill_up_pull(self, out, new_prefix_lens, idx, group_map, ids, methods, out_bounds):
+        """Rollup of a sharded dimension, pull model: I compute MY output rows, reading their child
+        rows out of the ranks that hold them (peer-mapped loads over NVLink inside the rollup
+        kernel).  Children are walked in ascending global row order, so every method — first /
+        last, the double sums, `average` — gives the bits of the unsharded rollup."""
+        import ctypes as C
+
+        from . import _native as N
+        from .store import _method_code
+
+        stores = [self.storedMeasures[m] for m in ids]
+        views = self._peer_views(stores)
+        if views is None:
+            return None
+        base_v, base_s = views
+        W, K = self.world, len(stores)
+        j0, j1 = out_bounds[self.rank], out_bounds[self.rank + 1]
+        key = (idx, group_map.tobytes(), tuple(self.row_bounds), j0, j1)
+        tables = self._pull_tables_cache.get(key) if hasattr(self, "_pull_tables_cache") else None
+        if tables is None:
+            full_map = self._row_map(idx, group_map, new_prefix_lens, all_rows=True)
+            tables = _pull_tables(full_map, self.row_bounds, j0, j1)
+            self._pull_tables_cache = {key: tables}
+        row_start, child_rank, child_row = tables
+        lib = N.lib()
+        with_status = bool(lib.olap_store_status_ptr(stores[0]._h))
+        flat_v = (C.c_void_p * (K * W))(*[base_v[k][r] or None for k in range(K) for r in range(W)])
+        flat_s = (C.c_void_p * (K * W))(*[base_s[k][r] or None for k in range(K) for r in range(W)]) if with_status else None
+        rank_rows = N.i64_array([self.row_bounds[r + 1] - self.row_bounds[r] for r in range(W)])
+        results = (C.c_void_p * K)()
+        # every rank's stores are complete (their producing kernels have finished) before anyone reads them
+        N.check(lib.olap_sync())
+        self.comm.dist.barrier(group=self.comm.group)
+        N.check(lib.olap_drill_up_pull(N.store_array([s._h for s in stores]), K, N.int_array([_method_code(m) for m in methods]),
+                                       j1 - j0, self.inner, row_start.ctypes.data_as(N.p_i32),
+                                       child_rank.ctypes.data_as(N.p_i32), child_row.ctypes.data_as(N.p_i64), W, rank_rows,
+                                       flat_v, flat_s, results))
+        # nobody frees or overwrites a store while a peer may still be reading it
+        N.check(lib.olap_sync())
+        self.comm.dist.barrier(group=self.comm.group)
+        out.storedMeasures = {m: self._store_cls._wrap(results[k]) for k, m in enumerate(ids)}
+        return out
 
     def _combine(self, out, plan, ids, methods, received, my_out_rows):
         """3. ordered combine of the W partials: a drillUp over the rank axis."""
@@ -487,7 +625,9 @@ class ShardedCube:
         pad = lambda b: (b + 255) // 256 * 256  # every plane starts on a 256-byte boundary, like a store's own planes
         plane_v, plane_s = pad(W * r_max * inner * 4), pad(W * r_max * inner)
         nbytes = K * plane_v + (K * plane_s if with_status else 0) + 256
-        # nobody may still be combining the previous contents of these buffers
+        # nobody may still be combining the previous contents of these buffers (the barrier orders
+        # host threads only: drain the library's own stream first, whatever the async mode)
+        N.check(N.lib().olap_sync())
         self.comm.dist.barrier(group=self.comm.group)
         bases = _PeerBuffers.get(self.comm, nbytes)
 
@@ -505,6 +645,7 @@ class ShardedCube:
         permuted_map = np.ascontiguousarray(position[np.asarray(row_map, dtype=np.int64)], dtype=np.int32)
         N.check(N.lib().olap_drill_up_rows(N.store_array([s._h for s in stores]), K, N.int_array(codes), rows_local,
                                            new_rows_total, inner, permuted_map.ctypes.data_as(N.p_i32), row_vals, row_sts))
+        N.check(N.lib().olap_sync())
         torch.cuda.synchronize()
         # every rank has finished storing into every buffer
         self.comm.dist.barrier(group=self.comm.group)

@@ -45,9 +45,10 @@ class GpuStore:
     WITH_STATUS = True
     FUSED_ROLLUPS = True  # Cube may present a run of removed dimensions as one merged axis (cube.py)
     IMPLIED_MAPS = True   # drillUp_lowered accepts None for unchanged / rolled-to-one dimensions
+    SHAREABLE_SHARDS = True  # ShardedCube creates its local shards in memory the peers can map (CUDA IPC)
 
     def __init__(self, size, type="float32", defaultValue=math.nan, *, _handle=None, with_status=None,
-                 uninitialised=False):
+                 uninitialised=False, shareable=False):
         if _handle is not None:
             self._h = _handle
         else:
@@ -56,7 +57,8 @@ class GpuStore:
                 raise N.OlapValueError("Invalid type")  # in-memory.js:59-60
             out = C.c_void_p()
             status = self.WITH_STATUS if with_status is None else with_status
-            flags = int(bool(status)) | (2 if uninitialised else 0)  # OLAP_CREATE_UNINITIALISED
+            # OLAP_CREATE_UNINITIALISED = 2, OLAP_CREATE_SHAREABLE = 4 (peers of a sharded cube can map it)
+            flags = int(bool(status)) | (2 if uninitialised else 0) | (4 if shareable else 0)
             N.check(N.lib().olap_store_create(int(size), N.TYPES[type], kind, flags, C.byref(out)))
             self._h = out.value
         lib = N.lib()
@@ -171,6 +173,13 @@ class GpuStore:
         if keys.size:
             store.import_sparse(keys, values)
         return store
+
+    def ipc_export(self):
+        """(64-byte CUDA IPC handle, values offset, status offset or -1) of a shareable store."""
+        handle = C.create_string_buffer(64)
+        v_off, s_off = C.c_int64(), C.c_int64()
+        N.check(N.lib().olap_store_ipc_export(self._h, handle, C.byref(v_off), C.byref(s_off)))
+        return handle.raw, v_off.value, s_off.value
 
     def clone(self):  # in-memory.js:66-73
         out = C.c_void_p()
