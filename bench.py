@@ -469,22 +469,23 @@ def sharded_parity_guard(dist, rank, world):
             for c in (sc, ref):
                 c.createComputedMeasure("ratio", "(m_sum + m_average) / m_highest")
             ops = [("dim0", "all"), ("dim0", "parity"), ("dim1", "all"), (f"dim{nd - 1}", "all")]
-            for mode in ("pull", "nccl"):
+            for mode in ("pull", "pull2", "nccl"):
                 SH.EXCHANGE = mode
                 for dim, attr in ops:
                     a, b = sc.drillUp(dim, attr), ref.drillUp(dim, attr)
+                    exchanged = dim in ("dim0", "dim1")
                     for rule in rules:
                         got, want = a.getData(f"m_{rule}"), b.getData(f"m_{rule}")
                         cases += 1
-                        if mode == "pull" or dim not in ("dim0", "dim1"):
-                            ok = same_bits(got, want)
-                        elif kind != "uniform" and rule in ("sum", "average"):
-                            continue  # float32 partials under cancellation: outside the NCCL path's stated tolerance
+                        if mode == "pull" or not exchanged or rule not in ("sum", "average"):
+                            ok = same_bits(got, want)  # pull reads the children themselves; order-only rules are exact in every mode
+                        elif kind != "uniform":
+                            continue  # float32 partial sums under cancellation: outside the stated tolerance of pull2 / nccl
                         else:
                             ok = np.allclose(got, np.asarray(want, dtype=np.float64), rtol=1e-6, atol=0, equal_nan=True)
                         if not ok:
                             mismatches.append(f"{mode} default={default} {kind} drillUp({dim},{attr}) m_{rule}")
-                            timed_path_mismatches += mode == default_mode and (dim, attr) in (("dim0", "all"), (f"dim{nd - 1}", "all"))
+                            timed_path_mismatches += (dim, attr) in (("dim0", "all"), (f"dim{nd - 1}", "all"))
                     if mode == "pull" and attr == "all":
                         cases += 1
                         if not np.allclose(a.getData("ratio"), np.asarray(b.getData("ratio"), dtype=np.float64), rtol=1e-6, atol=0, equal_nan=True):
@@ -496,7 +497,7 @@ def sharded_parity_guard(dist, rank, world):
                 for rule in ("sum", "first"):
                     s1.createStoredMeasure(f"m_{rule}", {f"dim{k}": rule for k in range(nd)}, "float32", default)
                     s1.setData(f"m_{rule}", np.asarray(ref.getData(f"m_{rule}"), dtype=np.float32))
-                order = ["dim2", "dim0", "dim4", "dim1", "dim3"]
+                order = ["dim2", "dim0"] + [f"dim{k}" for k in range(nd - 1, 0, -1) if k != 2]
                 try:
                     ra, rb = s1.reorderDimensions(order), ref.reorderDimensions(order)
                     for rule in ("sum", "first"):
@@ -525,7 +526,7 @@ def run_sharded(args, rank, world, local_rank):
     from olap_in_memory_b200 import _native as N
     from olap_in_memory_b200 import interop
     from olap_in_memory_b200 import sharded as SH
-    from olap_in_memory_b200.sharded import ShardedCube, _pull_tables
+    from olap_in_memory_b200.sharded import ShardedCube, _exchange_costs
 
     torch.cuda.set_device(local_rank)
     N.init(local_rank)
@@ -598,6 +599,7 @@ def run_sharded(args, rank, world, local_rank):
     assert abs(total_after - total_before) <= 1e-6 * abs(total_before), "bench: dim0 -> all lost cells"
     deep = rolled.prefix
     out_bounds = list(rolled.row_bounds)
+    exchange = getattr(rolled, "last_exchange", SH.EXCHANGE)
     del rolled
 
     N.check(lib.olap_set_async(1))
@@ -612,9 +614,10 @@ def run_sharded(args, rank, world, local_rank):
         op_inner()
         k_inner.append(lib.olap_last_op_ms())
         path_inner = lib.olap_last_op_path().decode()
-        op_outer()
-        k_outer.append(lib.olap_last_op_ms())
-        path_outer = lib.olap_last_op_path().decode()
+        res = op_outer()
+        k_outer.append(getattr(res, "last_pull_ms", None) or lib.olap_last_op_ms())  # the pull kernel itself
+        path_outer = "drillup/pull-peers" if getattr(res, "last_pull_ms", None) else lib.olap_last_op_path().decode()
+        del res
     k_inner_ms, k_outer_ms = max_over_ranks(np.mean(k_inner)), max_over_ranks(np.mean(k_outer))
 
     # bytes that cross NVLink into this GPU during dim0 -> all: the remote children of my output rows
@@ -622,10 +625,10 @@ def run_sharded(args, rank, world, local_rank):
     while view.prefix < deep:
         view = view._deepened()
     full_map = view._row_map(0, np.zeros(10, dtype=np.int32), [1] + [10] * (deep - 1), all_rows=True)
-    _, child_rank, _ = _pull_tables(full_map, view.row_bounds, out_bounds[rank], out_bounds[rank + 1])
-    bytes_per_row = 5 * measures * view.inner
-    nvlink_in = max_over_ranks(int((child_rank != rank).sum()) * bytes_per_row)
-    pulled = SH.EXCHANGE == "pull" and path_outer == "drillup/pull-peers"
+    direct_rows, partial_rows, _, _, _ = _exchange_costs(full_map, view.row_bounds, out_bounds)
+    planes = measures + sum(1 for m in SHARDED_METHODS if m == "average")  # `average` partials travel as (sum, count)
+    nvlink_in = float(direct_rows * 5 * measures * view.inner if exchange == "pull" else partial_rows * 5 * planes * view.inner)
+    pulled = path_outer == "drillup/pull-peers" or exchange == "pull2"
 
     # ---- e2e: host buffers -> sharded cube -> both rollups -> host
     def pinned(n_floats):
@@ -682,10 +685,11 @@ def run_sharded(args, rank, world, local_rank):
             "roofline": {"bound": "nvlink", "achieved": nv_gbs, "peak": NVLINK_GBS, "unit": "GB/s", "frac": nv_gbs / NVLINK_GBS,
                          "traffic": None, "kernel": path_outer, "kernel_ms": k_outer_ms, "algorithmic_bytes": nvlink_in,
                          "peak_source": "B200_PROFILING.md measured peer copy per direction per GPU",
-                         "what": "bytes the busiest GPU reads from its peers during drillUp dim0 -> all (remote children of its "
-                                 "output rows x 5 B x 3 measures) / kernel time, max over ranks"},
+                         "what": "bytes the busiest GPU reads from its peers during drillUp dim0 -> all (pull: the remote children of its "
+                                 "output rows x 5 B x 3 measures; pull2: the peers' partial rows x 5 B x 4 planes) / device time of the "
+                                 "pull kernel, max over ranks"},
             "sharded": {
-                "exchange": SH.EXCHANGE, "pulled_over_peer_memory": pulled, "prefix_after_rollup": deep,
+                "exchange": exchange, "exchange_setting": SH.EXCHANGE, "pulled_over_peer_memory": pulled, "prefix_after_rollup": deep,
                 "rows_per_rank_out": [out_bounds[r + 1] - out_bounds[r] for r in range(world)],
                 "inner_rollup": {"op": f"drillUp {last}->all (shard-local)", "ms": ms_inner, "kernel_ms": k_inner_ms, "kernel": path_inner,
                                  "hbm_GBs_per_gpu": inner_bytes / (k_inner_ms * 1e-3) / 1e9,

@@ -168,6 +168,9 @@ int olap_drill_up_pull(olap_store* const* like, int n, const int* methods, int64
                        const int32_t* row_start, const int32_t* child_rank, const int64_t* child_row, int n_ranks,
                        const int64_t* rank_rows, const void* const* base_values, const void* const* base_status,
                        olap_store** out);
+/* dst's status plane := src's (same size; a no-op when either store has none).  Finishes the
+ * `average` of a sharded rollup: the quotient sum / count keeps the merged flags of the sums. */
+int olap_store_copy_status(olap_store* dst, const olap_store* src);
 int64_t olap_store_size(const olap_store* s);        /* `.size` in-memory.js:18-20 */
 int64_t olap_store_byte_length(const olap_store* s); /* `.byteLength` in-memory.js:8-16 */
 int olap_store_type(const olap_store* s);

@@ -78,6 +78,7 @@ SIGNATURES = {
     "olap_peer_unmap_all": (C.c_int, []),
     "olap_drill_up_pull": (C.c_int, [pp_store, C.c_int, p_int, C.c_int64, C.c_int64, p_i32, p_i32, p_i64, C.c_int, p_i64,
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), pp_store]),
+    "olap_store_copy_status": (C.c_int, [p_store, p_store]),
     "olap_store_size": (C.c_int64, [p_store]),
     "olap_store_byte_length": (C.c_int64, [p_store]),
     "olap_store_type": (C.c_int, [p_store]),

@@ -103,6 +103,10 @@ struct TablePack {
     size_t add(const void* data, size_t bytes);  // returns offset, 16-byte aligned
     int upload();
     int release();
+    TablePack() = default;
+    TablePack(const TablePack&) = delete;
+    TablePack& operator=(const TablePack&) = delete;
+    ~TablePack() { if (dev) dev_free(dev); }  // error returns between upload() and release() (stream-ordered free)
     template <typename T>
     T* ptr(size_t off) const { return reinterpret_cast<T*>(static_cast<char*>(dev) + off); }
 };

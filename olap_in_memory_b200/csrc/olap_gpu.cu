@@ -100,8 +100,11 @@ constexpr size_t kGuardBytes = 256;
 // IPC handle, so the mappings the peers hold stay valid.  All library work runs on one stream, so
 // handing a freed block to a later call is stream-ordered by construction.
 static std::multimap<size_t, void*> g_share_free;
+// cudaMalloc carves small requests out of shared 2 MiB slabs, and an IPC handle names the slab:
+// every exported block gets whole slabs of its own, so that handle <-> block is one to one
+static size_t share_round(size_t bytes) { return std::max<size_t>(1, (bytes + (2u << 20) - 1) >> 21) << 21; }
 static int share_alloc(void** p, size_t bytes) {
-    if (bytes == 0) bytes = 256;
+    bytes = share_round(bytes);
     auto it = g_share_free.find(bytes);
     if (it != g_share_free.end()) {
         *p = it->second;
@@ -124,7 +127,7 @@ static int share_alloc(void** p, size_t bytes) {
     return OLAP_OK;
 }
 static void share_free(void* p, size_t bytes) {
-    if (p) g_share_free.emplace(bytes ? bytes : 256, p);
+    if (p) g_share_free.emplace(share_round(bytes), p);
 }
 
 int alloc_batch(int n, int64_t size, const int* types, const int* default_kinds, bool with_status,
@@ -236,6 +239,7 @@ static int cached_tables(const TablePack& pack, const char** dev_out) {
     victim->host = pack.host;
     victim->stamp = clock;
     *dev_out = static_cast<const char*>(up.dev);
+    up.dev = nullptr;  // the cache owns it now
     return OLAP_OK;
 }
 
@@ -282,6 +286,22 @@ static int alloc_like(olap_store* const* src, int n, int64_t new_size, olap_stor
     return alloc_batch(n, new_size, types, defaults, with_status, with_status && shared, out, shareable);
 }
 
+// Result stores of a call in flight: destroyed (and the caller's out[] cleared) on every early
+// return; `done()` hands them over on success.
+struct OutGuard {
+    olap_store** out;
+    int n;
+    OutGuard(olap_store** o, int count) : out(o), n(count) {}
+    ~OutGuard() {
+        if (!out) return;
+        for (int k = 0; k < n; ++k) { olap_store_destroy(out[k]); out[k] = nullptr; }
+    }
+    int done(int rc) {
+        if (rc == OLAP_OK) out = nullptr;
+        return rc;
+    }
+};
+
 static int fill_default(olap_store* s) {
     if (s->size == 0) return OLAP_OK;
     fill_kernel<<<grid_for(s->size, kStoreThreads), kStoreThreads, 0, g.stream>>>(
@@ -291,11 +311,6 @@ static int fill_default(olap_store* s) {
 }
 
 // status planes that several stores share must be written by one of them only
-static const uint8_t* st_in_of(olap_store* const* src, int k) {
-    for (int q = 0; q < k; ++q)
-        if (src[q]->status == src[k]->status) return nullptr;
-    return src[k]->status;
-}
 static uint8_t* st_out_of(olap_store** out, int k) {
     for (int q = 0; q < k; ++q)
         if (out[q]->status == out[k]->status) return nullptr;
@@ -597,13 +612,14 @@ int olap_store_create_batch(int n, int64_t size, const int* types, const int* de
     OLAP_TRY(ensure_ctx());
     OLAP_TRY(alloc_batch(n, size, types, default_kinds, (with_status & 1) != 0, shared_status != 0, out,
                          (with_status & OLAP_CREATE_SHAREABLE) != 0));
-    if (with_status & OLAP_CREATE_UNINITIALISED) return finish_op();  // OLAP_CREATE_UNINITIALISED: the caller overwrites every cell
+    OutGuard guard(out, n);
+    if (with_status & OLAP_CREATE_UNINITIALISED) return guard.done(finish_op());  // the caller overwrites every cell
     for (int k = 0; k < n; ++k) {
         olap_store tmp = *out[k];
         tmp.status = st_out_of(out, k);
         OLAP_TRY(fill_default(&tmp));
     }
-    return finish_op();
+    return guard.done(finish_op());
 }
 
 int olap_store_create(int64_t size, int type, int default_kind, int with_status, olap_store** out) {
@@ -630,10 +646,20 @@ int olap_store_clone(const olap_store* s, olap_store** out) {
     OLAP_TRY(ensure_ctx());
     OLAP_TRY(alloc_batch(1, s->size, &s->type, &s->default_kind, s->status != nullptr, false, out,
                          s->arena && s->arena->shareable));
+    OutGuard guard(out, 1);
     if (s->size) {
         OLAP_CUDA(cudaMemcpyAsync((*out)->values, s->values, (size_t)s->size * 4, cudaMemcpyDeviceToDevice, g.stream));
         if (s->status) OLAP_CUDA(cudaMemcpyAsync((*out)->status, s->status, (size_t)s->size, cudaMemcpyDeviceToDevice, g.stream));
     }
+    return guard.done(finish_op());
+}
+
+int olap_store_copy_status(olap_store* dst, const olap_store* src) {
+    if (!dst || !src) return fail(OLAP_E_INVALID, "olap_store_copy_status: null store");
+    if (dst->size != src->size) return fail(OLAP_E_INVALID, "value length is invalid: %lld !== %lld", (long long)dst->size, (long long)src->size);
+    OLAP_TRY(ensure_ctx());
+    if (dst->status && src->status && dst->size)
+        OLAP_CUDA(cudaMemcpyAsync(dst->status, src->status, (size_t)dst->size, cudaMemcpyDeviceToDevice, g.stream));
     return finish_op();
 }
 
@@ -897,6 +923,7 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
     }
     OLAP_TRY(ensure_ctx());
     OLAP_TRY(alloc_like(src, n, new_size, out));
+    OutGuard guard(out, n);
     begin_op();
     const char* path = "drillup/empty";
     if (new_size == 0) {
@@ -905,9 +932,13 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
         for (int k = 0; k < n; ++k) { olap_store t = *out[k]; t.status = st_out_of(out, k); OLAP_TRY(fill_default(&t)); }
     } else {
         std::vector<UpMeasure> meas(n);
-        for (int k = 0; k < n; ++k)
-            meas[k] = UpMeasure{src[k]->values, out[k]->values, out[k]->status ? st_in_of(src, k) : nullptr,
-                                st_in_of(src, k) ? st_out_of(out, k) : nullptr, methods[k], src[k]->default_kind};
+        for (int k = 0; k < n; ++k) {
+            // a status plane shared by the RESULTS is written by the first of them only; results with
+            // planes of their own each merge their source's plane, even when one source store is
+            // passed twice (sum and count of a sharded `average`)
+            uint8_t* so = out[k]->status && src[k]->status ? st_out_of(out, k) : nullptr;
+            meas[k] = UpMeasure{src[k]->values, out[k]->values, so ? src[k]->status : nullptr, so, methods[k], src[k]->default_kind};
+        }
         TablePack t;
         const size_t o_meas = t.add(meas.data(), sizeof(UpMeasure) * n);
         if (changed.size() <= 1) {
@@ -994,7 +1025,7 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
         OLAP_TRY(t.release());
     }
     end_op(path);
-    return finish_op();
+    return guard.done(finish_op());
 }
 
 // ---- gather family ----------------------------------------------------------------------
@@ -1167,8 +1198,8 @@ static std::vector<GatherMeasure> gather_measures(olap_store* const* src, olap_s
         GatherMeasure m{};
         m.in = src[k]->values;
         m.out = out[k]->values;
-        m.st_in = out[k]->status ? st_in_of(src, k) : nullptr;
-        m.st_out = m.st_in ? st_out_of(out, k) : nullptr;
+        m.st_out = out[k]->status && src[k]->status ? st_out_of(out, k) : nullptr;
+        m.st_in = m.st_out ? src[k]->status : nullptr;
         m.nan_default = src[k]->default_kind;
         m.int_rounding = src[k]->type == OLAP_INT32 || src[k]->type == OLAP_UINT32;
         m.method_is_sum = 1;
@@ -1209,6 +1240,7 @@ int olap_dice(olap_store* const* src, int n, int ndim, const int64_t* old_len, c
     }
     OLAP_TRY(ensure_ctx());
     OLAP_TRY(alloc_like(src, n, new_size, out));
+    OutGuard guard(out, n);
     begin_op();
     const char* path = "dice/empty";
     if (new_size) {
@@ -1216,7 +1248,7 @@ int olap_dice(olap_store* const* src, int n, int ndim, const int64_t* old_len, c
         OLAP_TRY(run_gather(G_COPY, src, n, dims, new_size, old_size, meas, nullptr, &path));
     }
     end_op(path);
-    return finish_op();
+    return guard.done(finish_op());
 }
 
 int olap_reorder(olap_store* const* src, int n, int ndim, const int64_t* old_len, const int32_t* new_to_old,
@@ -1242,6 +1274,7 @@ int olap_reorder(olap_store* const* src, int n, int ndim, const int64_t* old_len
     }
     OLAP_TRY(ensure_ctx());
     OLAP_TRY(alloc_like(src, n, size, out));
+    OutGuard guard(out, n);
     begin_op();
     const char* path = "reorder/empty";
     if (size) {
@@ -1272,7 +1305,7 @@ int olap_reorder(olap_store* const* src, int n, int ndim, const int64_t* old_len
         }
     }
     end_op(path);
-    return finish_op();
+    return guard.done(finish_op());
 }
 
 int olap_drill_down(olap_store* const* src, int n, const int* methods, int ndim, const int64_t* old_len,
@@ -1322,6 +1355,7 @@ int olap_drill_down(olap_store* const* src, int n, const int* methods, int ndim,
     if (any_dist && (old_size == 0 || new_size % old_size != 0)) return fail(OLAP_E_INVALID, "olap_drill_down: distributions need newSize to be a multiple of oldSize");
     OLAP_TRY(ensure_ctx());
     OLAP_TRY(alloc_like(src, n, new_size, out));
+    OutGuard guard(out, n);
     begin_op();
     const char* path = "drilldown/empty";
     int rc = OLAP_OK;
@@ -1340,8 +1374,8 @@ int olap_drill_down(olap_store* const* src, int n, const int* methods, int ndim,
         for (int k = 0; k < n; ++k) {
             const bool is_int = src[k]->type == OLAP_INT32 || src[k]->type == OLAP_UINT32;
             const bool is_sum = methods ? methods[k] == OLAP_SUM : true;
-            const uint8_t* si = out[k]->status ? st_in_of(src, k) : nullptr;
-            dm[k] = DownMeasure{src[k]->values, out[k]->values, si, si ? st_out_of(out, k) : nullptr,
+            uint8_t* so = out[k]->status && src[k]->status ? st_out_of(out, k) : nullptr;
+            dm[k] = DownMeasure{src[k]->values, out[k]->values, so ? src[k]->status : nullptr, so,
                                 src[k]->default_kind, !is_sum ? 1 : (is_int ? 2 : 0)};
         }
         TablePack t;
@@ -1366,8 +1400,8 @@ int olap_drill_down(olap_store* const* src, int n, const int* methods, int ndim,
         for (int k = 0; k < n; ++k) {
             const bool is_int = src[k]->type == OLAP_INT32 || src[k]->type == OLAP_UINT32;
             const bool is_sum = methods ? methods[k] == OLAP_SUM : true;
-            const uint8_t* si = out[k]->status ? st_in_of(src, k) : nullptr;
-            dm[k] = DownMeasure{src[k]->values, out[k]->values, si, si ? st_out_of(out, k) : nullptr,
+            uint8_t* so = out[k]->status && src[k]->status ? st_out_of(out, k) : nullptr;
+            dm[k] = DownMeasure{src[k]->values, out[k]->values, so ? src[k]->status : nullptr, so,
                                 src[k]->default_kind, !is_sum ? 1 : (is_int ? 2 : 0)};
         }
         TablePack t;
@@ -1408,11 +1442,8 @@ int olap_drill_down(olap_store* const* src, int n, const int* methods, int ndim,
         if (any_dist) OLAP_TRY(dpack.release());
     }
     end_op(path);
-    if (rc != OLAP_OK) {
-        for (int k = 0; k < n; ++k) { olap_store_destroy(out[k]); out[k] = nullptr; }
-        return rc;
-    }
-    return finish_op();
+    if (rc != OLAP_OK) return rc;  // the guard destroys the results
+    return guard.done(finish_op());
 }
 
 int olap_load(olap_store* dst, const olap_store* src, int ndim, const int64_t* my_len, const int64_t* his_len,
@@ -1519,7 +1550,7 @@ int olap_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64) {
     if (!ptr || !handle64) return fail(OLAP_E_INVALID, "olap_peer_alloc: null argument");
     OLAP_TRY(ensure_ctx());
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    OLAP_CUDA(cudaMalloc(ptr, bytes ? bytes : 256));
+    OLAP_CUDA(cudaMalloc(ptr, share_round(bytes)));
     cudaIpcMemHandle_t h;
     cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
     if (e != cudaSuccess) {
@@ -1587,7 +1618,7 @@ int olap_drill_up_rows(olap_store* const* src, int n, const int* methods, int64_
     begin_op();
     std::vector<UpMeasure> meas(n);
     for (int k = 0; k < n; ++k) {
-        const uint8_t* si = row_status ? st_in_of(src, k) : nullptr;
+        const uint8_t* si = row_status ? src[k]->status : nullptr;  // every row buffer is written, shared source plane or not
         // out / st_out are placeholders (non-null where a plane exists): the kernel rebases them per row
         meas[k] = UpMeasure{src[k]->values, const_cast<float*>(src[k]->values), si, si ? const_cast<uint8_t*>(si) : nullptr,
                             methods[k], src[k]->default_kind};
@@ -1702,13 +1733,14 @@ int olap_drill_up_pull(olap_store* const* like, int n, const int* methods, int64
         }
     OLAP_TRY(ensure_ctx());
     OLAP_TRY(alloc_like(like, n, new_size, out));
+    OutGuard guard(out, n);
     begin_op();
     if (new_size) {
         std::vector<PullMeasure> meas(n);
         std::vector<const void*> bs((size_t)n * n_ranks, nullptr);
         for (int k = 0; k < n; ++k) {
             // a status plane shared by several measures is read and written by the first of them only
-            const bool own_status = out[k]->status && st_in_of(like, k) && st_out_of(out, k);
+            const bool own_status = out[k]->status && like[k]->status && st_out_of(out, k);
             meas[k] = PullMeasure{out[k]->values, own_status ? out[k]->status : nullptr, methods[k], like[k]->default_kind};
             if (own_status)
                 for (int r = 0; r < n_ranks; ++r) bs[(size_t)k * n_ranks + r] = base_status[(size_t)k * n_ranks + r];
@@ -1755,7 +1787,7 @@ int olap_drill_up_pull(olap_store* const* like, int n, const int* methods, int64
         OLAP_TRY(t.release());
     }
     end_op("drillup/pull-peers");
-    return finish_op();
+    return guard.done(finish_op());
 }
 
 // ---- computed measures --------------------------------------------------------------------
@@ -1804,6 +1836,8 @@ int olap_eval(const char* program, olap_store* const* inputs, int n_inputs, cons
         if (cr != CUDA_SUCCESS) {
             const char* msg = "?";
             jit_api().GetErrorString(cr, &msg);
+            olap_store_destroy(result);
+            dev_free(out64);
             return fail(OLAP_E_CUDA, "launching the formula kernel failed: %s", msg);
         }
         LAUNCHED();

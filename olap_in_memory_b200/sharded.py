@@ -57,7 +57,14 @@ def _is_device_store(store):
 #          ordered combine of the W partials.
 #   "nccl": partial planes in local HBM, one NCCL all-to-all per plane, ordered combine (also the
 #          path of the gloo / CPU tests).
-EXCHANGE = os.environ.get("OLAP_SHARDED_EXCHANGE", "nccl" if os.environ.get("OLAP_SHARDED_P2P", "1") == "0" else "pull")
+#   "pull2": shard-local partial rollup into compact partial stores first, then the pull kernel
+#          combines the W partials in rank order (= ascending row order).  Moves (W-1)/W of the
+#          OUTPUT instead of (W-1)/W of my share of the INPUT: cheaper when every rank holds many
+#          children of each parent (few ranks, long dimension); float32 partials (rel 1e-6).
+#   "auto" (default): "pull" or "pull2", whichever the byte count says is faster (_exchange_costs).
+EXCHANGE = os.environ.get("OLAP_SHARDED_EXCHANGE", "nccl" if os.environ.get("OLAP_SHARDED_P2P", "1") == "0" else "auto")
+# planning figures of the cost model (GB/s): peer reads with both directions busy, local HBM
+PLAN_NVLINK_GBS, PLAN_HBM_GBS = 600.0, 6000.0
 # a rollup whose output rows would be spread unevenly (10 rows over 8 ranks: 2,2,1,1,1,1,1,1) is
 # computed on a deeper row axis when the imbalance exceeds this factor
 MAX_IMBALANCE = 1.1
@@ -112,6 +119,44 @@ def _peer_row_tables(bases, out_bounds, me, K, inner, plane_v, plane_s, with_sta
     if with_status:
         row_status = ((base + np.uint64(K * plane_v) + cell0.astype(np.uint64))[None, :] + k * np.uint64(plane_s)).reshape(-1)
     return position, row_values.reshape(-1), row_status
+
+
+def _exchange_costs(full_map, in_bounds, out_bounds):
+    """Rows that cross NVLink into the busiest rank for the two pull variants, and what the two-phase
+    variant costs locally.  Pure function of the row map and the shard bounds, so every rank takes
+    the same decision without talking.  Returns (direct_remote_rows, partial_remote_rows,
+    partial_rows_max, local_rows_max, touched) with touched[s] = sorted output rows rank s holds
+    children of."""
+    full_map = np.asarray(full_map, dtype=np.int64)
+    ib, ob = np.asarray(in_bounds, dtype=np.int64), np.asarray(out_bounds, dtype=np.int64)
+    W = len(ib) - 1
+    owner_in = np.searchsorted(ib[1:], np.arange(full_map.size), side="right")
+    owner_out = np.searchsorted(ob[1:], full_map, side="right")
+    direct = np.bincount(owner_out[owner_in != owner_out], minlength=W)
+    touched = [np.unique(full_map[ib[s]:ib[s + 1]]) for s in range(W)]
+    partial = np.zeros(W, dtype=np.int64)
+    for s in range(W):
+        dest = np.searchsorted(ob[1:], touched[s], side="right")
+        cnt = np.bincount(dest, minlength=W)
+        cnt[s] = 0
+        partial += cnt
+    return int(direct.max(initial=0)), int(partial.max(initial=0)), max((t.size for t in touched), default=0), int(np.diff(ib).max(initial=0)), touched
+
+
+def _pull2_tables(touched, j0, j1):
+    """Child tables of the second phase of "pull2" for the rank that owns output rows j0..j1-1:
+    output row j combines the partial row of every rank that holds children of j, in ascending
+    rank order; rank r's partial of j is row index(j in touched[r]) of its compact partial store."""
+    ranks, rows, parents = [], [], []
+    for r, t in enumerate(touched):
+        lo, hi = np.searchsorted(t, [j0, j1])
+        parents.append(np.asarray(t[lo:hi], dtype=np.int64) - j0)
+        rows.append(np.arange(lo, hi, dtype=np.int64))
+        ranks.append(np.full(hi - lo, r, dtype=np.int32))
+    parents, rows, ranks = np.concatenate(parents), np.concatenate(rows), np.concatenate(ranks)
+    order = np.argsort(parents, kind="stable")  # by output row; rank order kept inside a row
+    row_start = np.searchsorted(parents[order], np.arange(j1 - j0 + 1, dtype=np.int64), side="left").astype(np.int32)
+    return row_start, np.ascontiguousarray(ranks[order]), np.ascontiguousarray(rows[order])
 
 
 class _PeerBuffers:
@@ -459,10 +504,26 @@ class ShardedCube:
                                  maps, _Per(methods))
             out.storedMeasures = dict(zip(ids, results))
             return out
-        if EXCHANGE == "pull" and self.comm.on and all(_is_device_store(self.storedMeasures[m]) for m in ids):
-            pulled = self._drill_up_pull(out, new_prefix_lens, idx, group_map, ids, methods, out_bounds)
+        mode = EXCHANGE
+        if mode in ("auto", "pull", "pull2") and self.comm.on and all(_is_device_store(self.storedMeasures[m]) for m in ids):
+            full_map = self._row_map(idx, group_map, new_prefix_lens, all_rows=True)
+            touched = None
+            if mode != "pull":
+                direct, partial, partial_rows, local_rows, touched = _exchange_costs(full_map, self.row_bounds, out_bounds)
+                planes = len(ids) + sum(1 for m in methods if m == "average")
+                t_direct = direct * len(ids) / PLAN_NVLINK_GBS
+                t_two = (local_rows * len(ids) + 2 * partial_rows * planes) / PLAN_HBM_GBS + partial * planes / PLAN_NVLINK_GBS
+                if mode == "auto":
+                    mode = "pull" if t_direct <= t_two else "pull2"
+            if mode == "pull":
+                pulled = self._drill_up_pull(out, full_map, idx, group_map, ids, methods, out_bounds)
+            else:
+                pulled = self._drill_up_pull2(out, full_map, touched, ids, methods, out_bounds)
             if pulled is not None:
+                out.last_exchange = mode
                 return pulled
+            mode = "push"
+        out.last_exchange = mode
         my_out_rows = out_bounds[self.rank + 1] - out_bounds[self.rank]
         row_map = self._row_map(idx, group_map, new_prefix_lens)
         old_len = self._local_lens()
@@ -479,7 +540,7 @@ class ShardedCube:
             else:
                 plan.append((m, method, "plain"))
         stores = [self.storedMeasures[m] for m, _, _ in plan]
-        if EXCHANGE in ("pull", "push") and self.comm.on and _is_device_store(stores[0]):
+        if mode != "nccl" and self.comm.on and _is_device_store(stores[0]):
             received = self._partials_into_peers(stores, [meth for _, meth, _ in plan], row_map, out_bounds, new_rows_total)
             return self._combine(out, plan, ids, methods, received, my_out_rows)
         partials = self._partials(stores, old_len, new_len, maps, [meth for _, meth, _ in plan])
@@ -501,14 +562,14 @@ class ShardedCube:
         return self._combine(out, plan, ids, methods, received, my_out_rows)
 
     # ------------------------------------------------------------------ pull exchange
-    def _peer_views(self, stores):
+    def _peer_views(self, stores, remember=True):
         """Addresses, in MY address space, of every rank's planes of these stores: two lists
         [K][W] (values, status; None without a plane).  Handles travel once per set of stores (one
         all_gather of ~100 bytes per store) and are remembered on the cube; mappings are cached
         by the library (a recycled block keeps its handle).  None when a store of some rank cannot
         be exported (not created shareable)."""
         key = tuple(s._h for s in stores)
-        hit = self._pull_cache.get(key) if hasattr(self, "_pull_cache") else None
+        hit = self._pull_cache.get(key) if remember and hasattr(self, "_pull_cache") else None
         if hit is not None:
             return hit
         import ctypes as C
@@ -539,12 +600,13 @@ class ShardedCube:
                     opened[handle] = p.value
                 base_v[k][r] = opened[handle] + v_off
                 base_s[k][r] = opened[handle] + s_off if s_off >= 0 else 0
-        if not hasattr(self, "_pull_cache"):
-            self._pull_cache = {}
-        self._pull_cache[key] = (base_v, base_s)
+        if remember:  # the stores of the cube itself: their handles stay valid as long as the cube holds them
+            if not hasattr(self, "_pull_cache"):
+                self._pull_cache = {}
+            self._pull_cache[key] = (base_v, base_s)
         return base_v, base_s
 
-    def _drill_up_pull(self, out, new_prefix_lens, idx, group_map, ids, methods, out_bounds):
+    def _drill_up_pull(self, out, full_map, idx, group_map, ids, methods, out_bounds):
         """Rollup of a sharded dimension, pull model: I compute MY output rows, reading their child
         rows out of the ranks that hold them (peer-mapped loads over NVLink inside the rollup
         kernel).  Children are walked in ascending global row order, so every method — first /
@@ -564,27 +626,82 @@ class ShardedCube:
         key = (idx, group_map.tobytes(), tuple(self.row_bounds), j0, j1)
         tables = self._pull_tables_cache.get(key) if hasattr(self, "_pull_tables_cache") else None
         if tables is None:
-            full_map = self._row_map(idx, group_map, new_prefix_lens, all_rows=True)
             tables = _pull_tables(full_map, self.row_bounds, j0, j1)
             self._pull_tables_cache = {key: tables}
+        rank_rows = [self.row_bounds[r + 1] - self.row_bounds[r] for r in range(W)]
+        results = self._pull_call(stores, methods, views, tables, rank_rows, j1 - j0)
+        out.last_pull_ms = self.last_pull_ms
+        out.storedMeasures = {m: self._store_cls._wrap(results[k]) for k, m in enumerate(ids)}
+        return out
+
+    def _pull_call(self, stores, methods, views, tables, rank_rows, out_rows):
+        """olap_drill_up_pull between two barriers: every rank's source stores are complete before
+        anyone reads them, and nobody frees or overwrites one while a peer may still be reading."""
+        import ctypes as C
+
+        from . import _native as N
+        from .store import _method_code
+
+        base_v, base_s = views
         row_start, child_rank, child_row = tables
+        W, K = self.world, len(stores)
         lib = N.lib()
         with_status = bool(lib.olap_store_status_ptr(stores[0]._h))
         flat_v = (C.c_void_p * (K * W))(*[base_v[k][r] or None for k in range(K) for r in range(W)])
         flat_s = (C.c_void_p * (K * W))(*[base_s[k][r] or None for k in range(K) for r in range(W)]) if with_status else None
-        rank_rows = N.i64_array([self.row_bounds[r + 1] - self.row_bounds[r] for r in range(W)])
+        rank_rows = N.i64_array(rank_rows)
         results = (C.c_void_p * K)()
         # every rank's stores are complete (their producing kernels have finished) before anyone reads them
         N.check(lib.olap_sync())
         self.comm.dist.barrier(group=self.comm.group)
         N.check(lib.olap_drill_up_pull(N.store_array([s._h for s in stores]), K, N.int_array([_method_code(m) for m in methods]),
-                                       j1 - j0, self.inner, row_start.ctypes.data_as(N.p_i32),
+                                       out_rows, self.inner, row_start.ctypes.data_as(N.p_i32),
                                        child_rank.ctypes.data_as(N.p_i32), child_row.ctypes.data_as(N.p_i64), W, rank_rows,
                                        flat_v, flat_s, results))
         # nobody frees or overwrites a store while a peer may still be reading it
         N.check(lib.olap_sync())
+        self.last_pull_ms = lib.olap_last_op_ms()  # device time of the pull kernel on this rank (profiling aid)
         self.comm.dist.barrier(group=self.comm.group)
-        out.storedMeasures = {m: self._store_cls._wrap(results[k]) for k, m in enumerate(ids)}
+        return results
+
+    def _drill_up_pull2(self, out, full_map, touched, ids, methods, out_bounds):
+        """Two-phase pull: (1) shard-local partial rollup of my rows into ONE compact partial row per
+        output row I hold children of (`average` as a sum and a count plane); (2) the pull kernel
+        combines, for each of MY output rows, the partial rows of the ranks that have one, in rank
+        order — ranks hold contiguous ascending row ranges, so that is ascending row order and
+        first / last stay exact; sums of float32 partials (rel 1e-6)."""
+        me, W = self.rank, self.world
+        if touched is None:
+            touched = _exchange_costs(full_map, self.row_bounds, out_bounds)[4]
+        plan = []
+        for m, method in zip(ids, methods):
+            if method == "average":
+                plan += [(m, "sum", "sum"), (m, "__count", "sum")]
+            else:
+                plan.append((m, method, method))
+        stores = [self.storedMeasures[m] for m, _, _ in plan]
+        mine = touched[me]
+        local_map = np.searchsorted(mine, full_map[self.row0:self.row1]).astype(np.int32)
+        maps = [local_map] + [None] * len(self.inner_lens)
+        partials = self._store_cls.drillUp_lowered(stores, self._local_lens(), [int(mine.size)] + self.inner_lens, maps,
+                                                   [meth for _, meth, _ in plan])
+        views = self._peer_views(partials, remember=False)
+        if views is None:
+            return None
+        j0, j1 = out_bounds[me], out_bounds[me + 1]
+        tables = _pull2_tables(touched, j0, j1)
+        results = self._pull_call(partials, [comb for _, _, comb in plan], views, tables, [int(t.size) for t in touched], j1 - j0)
+        del partials
+        out.last_pull_ms = self.last_pull_ms
+        combined = [self._store_cls._wrap(h) for h in results]
+        k = 0
+        for m, method in zip(ids, methods):
+            if method == "average":
+                out.storedMeasures[m] = self._divide(combined[k], combined[k + 1])
+                k += 2
+            else:
+                out.storedMeasures[m] = combined[k]
+                k += 1
         return out
 
     def _combine(self, out, plan, ids, methods, received, my_out_rows):
@@ -717,8 +834,14 @@ class ShardedCube:
         if _is_device_store(sums):
             # `c ? s / c : default` as the postfix program of olap_eval (one fused kernel)
             default = "#nan" if sums._defaultValue != sums._defaultValue else "#0.0"
-            return self._store_cls.eval_program(f"v1 v0 v1 / {default} ?:", [sums, counts], [], sums._type,
-                                                sums._defaultValue)
+            out = self._store_cls.eval_program(f"v1 v0 v1 / {default} ?:", [sums, counts], [], sums._type,
+                                               sums._defaultValue)
+            # the quotient keeps the merged status flags of the sums (the unsharded `average` ORs its
+            # children's flags exactly like `sum` does); the formula kernel alone would derive SET / UNSET
+            from . import _native as N
+
+            N.check(N.lib().olap_store_copy_status(out._h, sums._h))
+            return out
         out = type(sums)(sums.size, sums._type, sums._defaultValue)
         s, c = sums.data, counts.data
         out.data = [sv / cv if (cv == cv and cv != 0) else sums._defaultValue for sv, cv in zip(s, c)]
