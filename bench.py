@@ -485,7 +485,7 @@ def sharded_parity_guard(dist, rank, world):
                             ok = np.allclose(got, np.asarray(want, dtype=np.float64), rtol=1e-6, atol=0, equal_nan=True)
                         if not ok:
                             mismatches.append(f"{mode} default={default} {kind} drillUp({dim},{attr}) m_{rule}")
-                            timed_path_mismatches += (dim, attr) in (("dim0", "all"), (f"dim{nd - 1}", "all"))
+                            timed_path_mismatches += mode == default_mode and (dim, attr) in (("dim0", "all"), (f"dim{nd - 1}", "all"))
                     if mode == "pull" and attr == "all":
                         cases += 1
                         if not np.allclose(a.getData("ratio"), np.asarray(b.getData("ratio"), dtype=np.float64), rtol=1e-6, atol=0, equal_nan=True):
@@ -504,7 +504,7 @@ def sharded_parity_guard(dist, rank, world):
                         cases += 2
                         if not same_bits(ra.getData(f"m_{rule}"), rb.getData(f"m_{rule}")):
                             mismatches.append(f"reorderDimensions m_{rule} default={default}")
-                        if not same_bits(ra.drillUp("dim2", "all").getData(f"m_{rule}"), rb.drillUp("dim2", "all").getData(f"m_{rule}")):
+                        if not same_bits(ra.drillUp("dim2", "all").getData(f"m_{rule}"), rb.drillUp("dim2", "all").getData(f"m_{rule}")):  # default exchange: pull
                             mismatches.append(f"reorderDimensions then drillUp(dim2,all) m_{rule} default={default}")
                 except Exception as exc:  # reported, not fatal: not on the timed path
                     mismatches.append(f"reorderDimensions raised {type(exc).__name__}: {exc}")
@@ -600,6 +600,7 @@ def run_sharded(args, rank, world, local_rank):
     deep = rolled.prefix
     out_bounds = list(rolled.row_bounds)
     exchange = getattr(rolled, "last_exchange", SH.EXCHANGE)
+    exchange_setting = SH.EXCHANGE
     del rolled
 
     N.check(lib.olap_set_async(1))
@@ -620,6 +621,20 @@ def run_sharded(args, rank, world, local_rank):
         del res
     k_inner_ms, k_outer_ms = max_over_ranks(np.mean(k_inner)), max_over_ranks(np.mean(k_outer))
 
+    # the partial-based exchange modes on the same rollup (opt-in: float32 partials, rel 1e-6), a few repetitions each
+    alternatives = {}
+    free_b = torch.tensor([float(torch.cuda.mem_get_info()[0])], device="cuda")
+    dist.all_reduce(free_b, op=dist.ReduceOp.MIN)
+    room = float(free_b.item()) > 2 * 5 * 4 * (n_total // 10) + (8 << 30)  # partial planes + receive buffers, every rank
+    for mode in ("pull2", "push", "nccl"):
+        if mode == exchange or not room or os.environ.get("OLAP_BENCH_ALTERNATIVES", "1") == "0":
+            continue
+        SH.EXCHANGE = mode
+        try:
+            alternatives[mode] = timed(op_outer, 3, 1)
+        except Exception as exc:  # an alternative that cannot run here (memory for receive buffers) is reported, not fatal
+            alternatives[mode] = f"{type(exc).__name__}: {exc}"[:200]
+        SH.EXCHANGE = exchange_setting
     # bytes that cross NVLink into this GPU during dim0 -> all: the remote children of my output rows
     view = cube
     while view.prefix < deep:
@@ -689,7 +704,8 @@ def run_sharded(args, rank, world, local_rank):
                                  "output rows x 5 B x 3 measures; pull2: the peers' partial rows x 5 B x 4 planes) / device time of the "
                                  "pull kernel, max over ranks"},
             "sharded": {
-                "exchange": exchange, "exchange_setting": SH.EXCHANGE, "pulled_over_peer_memory": pulled, "prefix_after_rollup": deep,
+                "exchange": exchange, "exchange_setting": exchange_setting,
+                "alternative_exchanges_ms": alternatives, "pulled_over_peer_memory": pulled, "prefix_after_rollup": deep,
                 "rows_per_rank_out": [out_bounds[r + 1] - out_bounds[r] for r in range(world)],
                 "inner_rollup": {"op": f"drillUp {last}->all (shard-local)", "ms": ms_inner, "kernel_ms": k_inner_ms, "kernel": path_inner,
                                  "hbm_GBs_per_gpu": inner_bytes / (k_inner_ms * 1e-3) / 1e9,

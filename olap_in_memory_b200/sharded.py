@@ -61,8 +61,13 @@ def _is_device_store(store):
 #          combines the W partials in rank order (= ascending row order).  Moves (W-1)/W of the
 #          OUTPUT instead of (W-1)/W of my share of the INPUT: cheaper when every rank holds many
 #          children of each parent (few ranks, long dimension); float32 partials (rel 1e-6).
-#   "auto" (default): "pull" or "pull2", whichever the byte count says is faster (_exchange_costs).
-EXCHANGE = os.environ.get("OLAP_SHARDED_EXCHANGE", "nccl" if os.environ.get("OLAP_SHARDED_P2P", "1") == "0" else "auto")
+#   "auto": "pull" or "pull2", whichever the byte count says is faster (_exchange_costs).
+# The default is "pull": parity first — it is the only mode whose sums are the unsharded cube's bits
+# (the others add float32-rounded partials: rel 1e-6 on same-sign data, not bounded under
+# cancellation).  With fewer ranks than children per parent (2 GPUs, a 10-item dimension) the
+# partial-based modes move fewer bytes: 2 x B200, 1e10 cells x 3 measures, dim0 -> all: pull 63 ms,
+# pull2 47 ms, push 33 ms, nccl 53 ms.
+EXCHANGE = os.environ.get("OLAP_SHARDED_EXCHANGE", "nccl" if os.environ.get("OLAP_SHARDED_P2P", "1") == "0" else "pull")
 # planning figures of the cost model (GB/s): peer reads with both directions busy, local HBM
 PLAN_NVLINK_GBS, PLAN_HBM_GBS = 600.0, 6000.0
 # a rollup whose output rows would be spread unevenly (10 rows over 8 ranks: 2,2,1,1,1,1,1,1) is

@@ -4,7 +4,7 @@
 # timed with HEAD's bench_ops.py through OLAP_LIB.  Runs on the GPU box through gpurun.
 set -u
 o=gpurun_out
-for lib in build/ab/*/libolapgpu.so olap_in_memory_b200/libolapgpu.so; do
+for lib in ${AB_LIBS:-build/ab/*/libolapgpu.so} olap_in_memory_b200/libolapgpu.so; do
   tag=$(basename $(dirname $lib))
   OLAP_LIB=$PWD/$lib timeout 300 python bench_ops.py --only drillup/time-outer --reps 7 --out $o/ab_$tag.json > $o/ab_$tag.log 2>&1
   echo "== $tag"; python - <<PY

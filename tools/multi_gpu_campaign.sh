@@ -14,7 +14,7 @@ run() { # run N cmd...
   timeout ${TMO:-600} python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port "$@"
 }
 for n in $ns; do
-  for mode in pull push nccl; do
+  for mode in ${CHECK_MODES:-pull pull2 push nccl}; do
     OLAP_SHARDED_EXCHANGE=$mode run $n tests/gpu_sharded_check.py > $o/shard_check_${tag}_n${n}_$mode.log 2>&1
     echo "check n=$n $mode: $(grep gpu_sharded_check $o/shard_check_${tag}_n${n}_$mode.log | tail -1)"
   done
