@@ -447,6 +447,7 @@ def sharded_parity_guard(dist, rank, world):
     n = 10 ** nd
     mismatches, cases, timed_path_mismatches = [], 0, 0
     default_mode = SH.EXCHANGE
+    min_deep, SH.MIN_DEEP_INNER = SH.MIN_DEEP_INNER, 64  # let the small cubes take the balance-driven deepening too
 
     def same_bits(a, b):
         a = np.asarray(a, dtype=np.float64).astype(np.float32)
@@ -510,6 +511,7 @@ def sharded_parity_guard(dist, rank, world):
                     mismatches.append(f"reorderDimensions raised {type(exc).__name__}: {exc}")
     import torch
 
+    SH.MIN_DEEP_INNER = min_deep
     t = torch.tensor([len(mismatches), timed_path_mismatches], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return {"cases": cases, "mismatches": int(t[0].item()), "first_mismatches": mismatches[:5], "timed_path_mismatches": int(t[1].item()),

@@ -381,8 +381,45 @@ __device__ __forceinline__ void up_mid_body(const UpMidParams& p, const UpMeasur
     Lane<METHOD, NANDEF> lane[VEC];
     uint32_t st = 0;
 
+#ifdef OLAP_UP_PIPE
+    // Software pipeline: two half-batches of H children; the loads of the next half are already in
+    // flight while the current half is folded, so a thread never drops to zero outstanding loads at a
+    // batch boundary.  Slots past the last child hold the unset value (every lane skips it) — no tail.
+    constexpr int H = U / 2;
+    const float unset = NANDEF ? canon_nan() : 0.0f;
+    auto fetch = [&](Cells<VEC>(&c)[H], int32_t kk) {
+#pragma unroll
+        for (int u = 0; u < H; ++u) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) c[u].v[e] = unset;
+            c[u].st = 0;
+            if (kk + u < k1) {
+                const int64_t child = RANGE ? (int64_t)(kk + u) : (int64_t)p.children[kk + u];
+                c[u] = load_cells<VEC, STATUS>(src, st_src, child * stride);
+            }
+        }
+    };
+    auto fold = [&](const Cells<VEC>(&c)[H]) {
+#pragma unroll
+        for (int u = 0; u < H; ++u) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) lane[e].step(c[u].v[e]);
+            st |= c[u].st;
+        }
+    };
+    Cells<VEC> ca[H], cb[H];
+    fetch(ca, k0);
+    for (int32_t kk = k0; kk < k1; kk += 2 * H) {
+        fetch(cb, kk + H);
+        fold(ca);
+        fetch(ca, kk + 2 * H);
+        fold(cb);
+    }
+    int32_t k = k1;
+#else
     // U children in flight per thread
     int32_t k = k0;
+#endif
     for (; k + U <= k1; k += U) {
         Cells<VEC> c[U];
 #pragma unroll

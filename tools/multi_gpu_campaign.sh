@@ -14,12 +14,13 @@ run() { # run N cmd...
   timeout ${TMO:-600} python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port "$@"
 }
 for n in $ns; do
-  for mode in ${CHECK_MODES:-pull pull2 push nccl}; do
+  for mode in ${CHECK_MODES-pull pull2 push nccl}; do
     OLAP_SHARDED_EXCHANGE=$mode run $n tests/gpu_sharded_check.py > $o/shard_check_${tag}_n${n}_$mode.log 2>&1
     echo "check n=$n $mode: $(grep gpu_sharded_check $o/shard_check_${tag}_n${n}_$mode.log | tail -1)"
   done
 done
 for n in $ns; do
+  [ -n "${NOBENCH:-}" ] && continue
   if [ -n "${SMALL:-}" ]; then
     OLAP_BENCH_NDIMS=$SMALL run $n bench.py --gpus $n --steps 5 --warmup 3 > $o/bench_${tag}_n${n}_small.json 2> $o/bench_${tag}_n${n}_small.err
     echo "bench small n=$n: $(cut -c1-400 $o/bench_${tag}_n${n}_small.json)"; tail -3 $o/bench_${tag}_n${n}_small.err
