@@ -381,45 +381,8 @@ __device__ __forceinline__ void up_mid_body(const UpMidParams& p, const UpMeasur
     Lane<METHOD, NANDEF> lane[VEC];
     uint32_t st = 0;
 
-#ifdef OLAP_UP_PIPE
-    // Software pipeline: two half-batches of H children; the loads of the next half are already in
-    // flight while the current half is folded, so a thread never drops to zero outstanding loads at a
-    // batch boundary.  Slots past the last child hold the unset value (every lane skips it) — no tail.
-    constexpr int H = U / 2;
-    const float unset = NANDEF ? canon_nan() : 0.0f;
-    auto fetch = [&](Cells<VEC>(&c)[H], int32_t kk) {
-#pragma unroll
-        for (int u = 0; u < H; ++u) {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) c[u].v[e] = unset;
-            c[u].st = 0;
-            if (kk + u < k1) {
-                const int64_t child = RANGE ? (int64_t)(kk + u) : (int64_t)p.children[kk + u];
-                c[u] = load_cells<VEC, STATUS>(src, st_src, child * stride);
-            }
-        }
-    };
-    auto fold = [&](const Cells<VEC>(&c)[H]) {
-#pragma unroll
-        for (int u = 0; u < H; ++u) {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) lane[e].step(c[u].v[e]);
-            st |= c[u].st;
-        }
-    };
-    Cells<VEC> ca[H], cb[H];
-    fetch(ca, k0);
-    for (int32_t kk = k0; kk < k1; kk += 2 * H) {
-        fetch(cb, kk + H);
-        fold(ca);
-        fetch(ca, kk + 2 * H);
-        fold(cb);
-    }
-    int32_t k = k1;
-#else
     // U children in flight per thread
     int32_t k = k0;
-#endif
     for (; k + U <= k1; k += U) {
         Cells<VEC> c[U];
 #pragma unroll
@@ -466,8 +429,16 @@ __device__ __forceinline__ void up_mid_dispatch(const UpMidParams& p, const UpMe
     }
 }
 
+// The second launch bound matters: without it ptxas aims for <= 64 registers, cannot keep the U child
+// vectors of a batch live, and interleaves the loads with the double adds of the sum / average lanes
+// (SASS: LDG x4, DADD x3, LDG, DADD x6, ...): 4-5 loads in flight instead of 2U, and builds that differ
+// in unrelated code land on different allocations (48 / 58 / 60 registers: 0.52 - 0.85 of peak on
+// day -> year).  With "3 CTAs per SM" (<= 80 registers) every batch is LDG x 2U, then the adds.
+#ifndef OLAP_MID_MINB
+#define OLAP_MID_MINB 3
+#endif
 template <int VEC, bool RANGE, int U>
-__global__ void __launch_bounds__(256) drillup_mid_kernel(const __grid_constant__ UpMidParams p) {
+__global__ void __launch_bounds__(256, U == 8 ? OLAP_MID_MINB : 4) drillup_mid_kernel(const __grid_constant__ UpMidParams p) {
     const uint32_t brow = blockIdx.x / p.blocks_per_row;  // uniform per block
     const uint32_t bcol = blockIdx.x - brow * p.blocks_per_row;
     const int64_t o = (int64_t)brow * blockDim.y + threadIdx.y;

@@ -126,7 +126,7 @@ __device__ __forceinline__ void up_pull_dispatch(const UpPullParams& p, const Pu
 // grid = (column blocks of a row, row blocks, measures), block = (bx, by): thread (tx, ty) owns output
 // vector iv = blockIdx.x * bx + tx of row  row0 + blockIdx.y * by + ty.
 template <int VEC>
-__global__ void __launch_bounds__(256) drillup_pull_kernel(const __grid_constant__ UpPullParams p) {
+__global__ void __launch_bounds__(256, 2) drillup_pull_kernel(const __grid_constant__ UpPullParams p) {
     const int64_t row = p.row0 + (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
     const int64_t iv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= p.rows || iv >= p.IV) return;
