@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(256, U == 8 ? OLAP_MID_MINB : 4) drillup_mid_k
 // reduces the g-th contiguous chunk of the parent's children (same coalesced 128-bit loads
 // as kernel A), lane states meet in shared memory and row 0 folds them IN CHUNK ORDER, so
 // first/last stay exact and the double sums only change their association.
-template <int METHOD, bool NANDEF, int VEC, bool RANGE, bool STATUS>
+template <int METHOD, bool NANDEF, int VEC, bool RANGE, bool STATUS, int U>
 __device__ __forceinline__ void up_split_body(const UpMidParams& p, const UpMeasure& m, int64_t o, uint32_t pi,
                                               uint32_t iv, bool live, unsigned char* smem_raw) {
     typedef Lane<METHOD, NANDEF> L;
@@ -485,7 +485,6 @@ __device__ __forceinline__ void up_split_body(const UpMidParams& p, const UpMeas
         const int32_t ks = min(k1, k0 + g * per), ke = min(k1, ks + per);
         const float* src = m.in + o * p.in_row + inner;
         const uint8_t* st_src = STATUS ? m.st_in + o * p.in_row + inner : nullptr;
-        constexpr int U = 4;
         int32_t k = ks;
         for (; k + U <= ke; k += U) {
             Cells<VEC> c[U];
@@ -530,24 +529,27 @@ __device__ __forceinline__ void up_split_body(const UpMidParams& p, const UpMeas
     if (STATUS) store_status<VEC>(m.st_out + out_off, k0 == k1 ? unset_status<VEC>() : st);
 }
 
-template <bool NANDEF, int VEC, bool RANGE, bool STATUS>
+template <bool NANDEF, int VEC, bool RANGE, bool STATUS, int U>
 __device__ __forceinline__ void up_split_dispatch(const UpMidParams& p, const UpMeasure& m, int64_t o, uint32_t pi,
                                                   uint32_t iv, bool live, unsigned char* smem_raw) {
     switch (m.method) {
-        case OLAP_SUM: up_split_body<OLAP_SUM, NANDEF, VEC, RANGE, STATUS>(p, m, o, pi, iv, live, smem_raw); break;
-        case OLAP_AVERAGE: up_split_body<OLAP_AVERAGE, NANDEF, VEC, RANGE, STATUS>(p, m, o, pi, iv, live, smem_raw); break;
-        case OLAP_HIGHEST: up_split_body<OLAP_HIGHEST, NANDEF, VEC, RANGE, STATUS>(p, m, o, pi, iv, live, smem_raw); break;
-        case OLAP_LOWEST: up_split_body<OLAP_LOWEST, NANDEF, VEC, RANGE, STATUS>(p, m, o, pi, iv, live, smem_raw); break;
-        case OLAP_FIRST: up_split_body<OLAP_FIRST, NANDEF, VEC, RANGE, STATUS>(p, m, o, pi, iv, live, smem_raw); break;
-        case OLAP_LAST: up_split_body<OLAP_LAST, NANDEF, VEC, RANGE, STATUS>(p, m, o, pi, iv, live, smem_raw); break;
-        case OLAP_COUNT: up_split_body<OLAP_COUNT, NANDEF, VEC, RANGE, STATUS>(p, m, o, pi, iv, live, smem_raw); break;
-        default: up_split_body<OLAP_PRODUCT, NANDEF, VEC, RANGE, STATUS>(p, m, o, pi, iv, live, smem_raw); break;
+        case OLAP_SUM: up_split_body<OLAP_SUM, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv, live, smem_raw); break;
+        case OLAP_AVERAGE: up_split_body<OLAP_AVERAGE, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv, live, smem_raw); break;
+        case OLAP_HIGHEST: up_split_body<OLAP_HIGHEST, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv, live, smem_raw); break;
+        case OLAP_LOWEST: up_split_body<OLAP_LOWEST, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv, live, smem_raw); break;
+        case OLAP_FIRST: up_split_body<OLAP_FIRST, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv, live, smem_raw); break;
+        case OLAP_LAST: up_split_body<OLAP_LAST, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv, live, smem_raw); break;
+        case OLAP_COUNT: up_split_body<OLAP_COUNT, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv, live, smem_raw); break;
+        default: up_split_body<OLAP_PRODUCT, NANDEF, VEC, RANGE, STATUS, U>(p, m, o, pi, iv, live, smem_raw); break;
     }
 }
 
-// blockDim = (32, G); one outer row per block row: blockIdx.x = o * blocks_per_row + column block
-template <int VEC, bool RANGE>
-__global__ void __launch_bounds__(1024) drillup_split_kernel(const __grid_constant__ UpMidParams p) {
+// blockDim = (32, G); one outer row per block row: blockIdx.x = o * blocks_per_row + column block.
+// WIDE (G <= 8, 256 threads): 8 children in flight per thread under the register budget of the mid
+// kernel (3 CTAs per SM); otherwise G <= 32 thread rows with 4 children in flight each.
+template <int VEC, bool RANGE, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? 256 : 1024, WIDE ? 3 : 1) drillup_split_kernel(const __grid_constant__ UpMidParams p) {
+    constexpr int U = WIDE ? 8 : 4;
     extern __shared__ __align__(16) unsigned char smem_split[];
     const uint32_t brow = blockIdx.x / p.blocks_per_row;
     const uint32_t bcol = blockIdx.x - brow * p.blocks_per_row;
@@ -559,11 +561,11 @@ __global__ void __launch_bounds__(1024) drillup_split_kernel(const __grid_consta
     const UpMeasure m = p.meas ? p.meas[blockIdx.y] : p.meas_inline[blockIdx.y];
     const bool status = m.st_in != nullptr;
     if (m.nan_default) {
-        if (status) up_split_dispatch<true, VEC, RANGE, true>(p, m, o, pi, iv, live, smem_split);
-        else up_split_dispatch<true, VEC, RANGE, false>(p, m, o, pi, iv, live, smem_split);
+        if (status) up_split_dispatch<true, VEC, RANGE, true, U>(p, m, o, pi, iv, live, smem_split);
+        else up_split_dispatch<true, VEC, RANGE, false, U>(p, m, o, pi, iv, live, smem_split);
     } else {
-        if (status) up_split_dispatch<false, VEC, RANGE, true>(p, m, o, pi, iv, live, smem_split);
-        else up_split_dispatch<false, VEC, RANGE, false>(p, m, o, pi, iv, live, smem_split);
+        if (status) up_split_dispatch<false, VEC, RANGE, true, U>(p, m, o, pi, iv, live, smem_split);
+        else up_split_dispatch<false, VEC, RANGE, false, U>(p, m, o, pi, iv, live, smem_split);
     }
 }
 
@@ -664,7 +666,9 @@ struct DownMidParams {
     uint32_t blocks_per_row;
 };
 
-template <int VEC, bool RANGE, bool STATUS>
+// KIND is the measure's kind (0: float sum, 1: copy, 2: integer spreading), a template parameter so
+// that the float / copy loops are a bare address step + two stores per child and stay unrolled.
+template <int VEC, bool RANGE, bool STATUS, int KIND>
 __device__ __forceinline__ void down_mid_body(const DownMidParams& p, const DownMeasure& m, int64_t o, uint32_t pi,
                                               uint32_t iv) {
     const int32_t k0 = p.pstart[pi], k1 = p.pstart[pi + 1];
@@ -673,55 +677,66 @@ __device__ __forceinline__ void down_mid_body(const DownMidParams& p, const Down
     const int64_t in_off = o * p.in_row + (int64_t)pi * p.I_total + inner;
     const Cells<VEC> c = load_cells<VEC, STATUS>(m.in, m.st_in, in_off);
     const int nan_default = m.nan_default;
-    const uint32_t n = (uint32_t)(k1 - k0);
-    const double dn = (double)n;
+    const double dn = (double)(uint32_t)(k1 - k0);
     float r[VEC];
     bool truthy[VEC];
-    double base[VEC], step[VEC];
+    double base[VEC], step[VEC], prev[VEC];
     uint32_t st_ok = 0;
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
         const float x = c.v[e];
         truthy[e] = x != 0.0f && x == x;  // `if (!oldValue) continue` (in-memory.js:386-387)
-        if (m.kind == 0) r[e] = canon_store((float)((double)x / dn), nan_default);
-        else if (m.kind == 1) r[e] = x;
+        if (KIND == 0) r[e] = canon_store((float)((double)x / dn), nan_default);
+        else if (KIND == 1) r[e] = x;
         else {
             const double q = (double)x / dn;
             base[e] = floor(q);
             step[e] = fma(-trunc(q), dn, (double)x) / dn;  // (v % n) / n
+            prev[e] = floor(-step[e]);                     // floor((k - 1) * step) at k = 0
             r[e] = 0.0f;
         }
         if (!truthy[e]) r[e] = default_of(nan_default);
         const uint32_t sb = STATUS ? ((c.st >> (8 * e)) & 0xffu) : 0u;
-        const bool ok = truthy[e] && (m.kind == 2 || present_f(r[e], nan_default));
+        const bool ok = truthy[e] && (KIND == 2 || present_f(r[e], nan_default));
         st_ok |= (ok ? ((sb | OLAP_STATUS_INTERPOLATED) & 0xffu) : (uint32_t)OLAP_STATUS_UNSET) << (8 * e);
     }
     float* dst = m.out + o * p.out_row + inner;
     uint8_t* st_dst = STATUS ? m.st_out + o * p.out_row + inner : nullptr;
+    if (KIND != 2) {
+        // every child receives the same vector: nothing but stores
+        int32_t k = k0;
+#pragma unroll 4
+        for (; k < k1; ++k) {
+            const int64_t off = (RANGE ? (int64_t)k : (int64_t)p.children[k]) * p.I_total;
+            store_cells<VEC>(dst + off, r);
+            if (STATUS) store_status<VEC>(st_dst + off, st_ok);
+        }
+    } else
     for (int32_t k = k0; k < k1; ++k) {
-        const int64_t child = RANGE ? (int64_t)k : (int64_t)p.children[k];
-        const int64_t off = child * p.I_total;
-        uint32_t st = st_ok;
-        if (m.kind == 2) {
-            const double kk = (double)(k - k0);
-            st = 0;
+        const int64_t off = (RANGE ? (int64_t)k : (int64_t)p.children[k]) * p.I_total;
+        const double kk = (double)(k - k0);
+        uint32_t st = 0;
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                const bool last_is_same = floor(kk * step[e]) == floor((kk - 1.0) * step[e]);
-                const float val = canon_store((float)(last_is_same ? base[e] : base[e] + 1.0), nan_default);
-                r[e] = truthy[e] ? val : default_of(nan_default);
-                const uint32_t sb = STATUS ? ((c.st >> (8 * e)) & 0xffu) : 0u;
-                const bool ok = truthy[e] && present_f(val, nan_default);
-                st |= (ok ? ((sb | OLAP_STATUS_INTERPOLATED) & 0xffu) : (uint32_t)OLAP_STATUS_UNSET) << (8 * e);
-            }
+        for (int e = 0; e < VEC; ++e) {
+            // floor(k * step) !== floor((k - 1) * step) (in-memory.js:409-416); the previous floor is carried along
+            const double cur = floor(kk * step[e]);
+            const bool last_is_same = cur == prev[e];
+            prev[e] = cur;
+            const float val = canon_store((float)(last_is_same ? base[e] : base[e] + 1.0), nan_default);
+            r[e] = truthy[e] ? val : default_of(nan_default);
+            const uint32_t sb = STATUS ? ((c.st >> (8 * e)) & 0xffu) : 0u;
+            const bool ok = truthy[e] && present_f(val, nan_default);
+            st |= (ok ? ((sb | OLAP_STATUS_INTERPOLATED) & 0xffu) : (uint32_t)OLAP_STATUS_UNSET) << (8 * e);
         }
         store_cells<VEC>(dst + off, r);
         if (STATUS) store_status<VEC>(st_dst + off, st);
     }
 }
 
-template <int VEC, bool RANGE>
-__global__ void __launch_bounds__(256) drilldown_mid_kernel(const __grid_constant__ DownMidParams p) {
+// KIND >= 0: every measure of the call has that kind (the common case: its loop alone decides the
+// register count — 8 resident CTAs for the float / copy kernels); KIND < 0: kinds differ, dispatch per measure.
+template <int VEC, bool RANGE, int KIND>
+__global__ void __launch_bounds__(256, KIND == 0 || KIND == 1 ? 6 : 4) drilldown_mid_kernel(const __grid_constant__ DownMidParams p) {
     const uint32_t brow = blockIdx.x / p.blocks_per_row;
     const uint32_t bcol = blockIdx.x - brow * p.blocks_per_row;
     const int64_t o = (int64_t)brow * blockDim.y + threadIdx.y;
@@ -730,8 +745,19 @@ __global__ void __launch_bounds__(256) drilldown_mid_kernel(const __grid_constan
     const uint32_t pi = p.div_iv.div(j);
     const uint32_t iv = j - pi * p.IV;
     const DownMeasure m = p.meas[blockIdx.y];
-    if (m.st_in) down_mid_body<VEC, RANGE, true>(p, m, o, pi, iv);
-    else down_mid_body<VEC, RANGE, false>(p, m, o, pi, iv);
+    if (KIND >= 0) {
+        constexpr int K = KIND >= 0 ? KIND : 0;
+        if (m.st_in) down_mid_body<VEC, RANGE, true, K>(p, m, o, pi, iv);
+        else down_mid_body<VEC, RANGE, false, K>(p, m, o, pi, iv);
+    } else if (m.st_in) {
+        if (m.kind == 0) down_mid_body<VEC, RANGE, true, 0>(p, m, o, pi, iv);
+        else if (m.kind == 1) down_mid_body<VEC, RANGE, true, 1>(p, m, o, pi, iv);
+        else down_mid_body<VEC, RANGE, true, 2>(p, m, o, pi, iv);
+    } else {
+        if (m.kind == 0) down_mid_body<VEC, RANGE, false, 0>(p, m, o, pi, iv);
+        else if (m.kind == 1) down_mid_body<VEC, RANGE, false, 1>(p, m, o, pi, iv);
+        else down_mid_body<VEC, RANGE, false, 2>(p, m, o, pi, iv);
+    }
 }
 
 }  // namespace olap
@@ -750,29 +776,36 @@ struct DownInnerParams {
     const int32_t* cnt_of;     // [P] siblings per parent
     int64_t O;
     int32_t P, C;
-    uint32_t RB;               // rows per CTA
-    FastDiv div_c;
-    int vec4;                  // C % 4 == 0: 128-bit stores
+    uint32_t I;                // cells of the untouched inner run (1: the drilled axis is the innermost one)
+    uint32_t RB;               // rows (outer indices) per CTA
+    FastDiv div_i, div_pi, div_ci;  // by I, P * I, C * I
+    int vec4;                  // I % 4 == 0 (or I == 1 and C % 4 == 0): 128-bit stores
 };
 
-// Everything that depends only on the PARENT (value / n, integer base and step, status) is
-// computed once per parent while staging; a child cell then costs two shared-memory reads.
-template <bool STATUS>
+// A CTA owns RB consecutive outer indices: their RB * P * I parent cells are staged once, and
+// everything that depends only on the PARENT cell (value / n, integer base and step, status) is
+// computed while staging; the CTA then emits its RB * C * I output cells in memory order, every
+// thread 4 consecutive cells with one 128-bit store.  The output span of a CTA is contiguous and
+// written front to back: full sectors, one sequential write stream per CTA — which is what a short
+// inner run (I = 100: 400-byte runs per child with the parent-driven kernel) needs.
+template <bool STATUS, bool I1>
 __device__ __forceinline__ void down_inner_body(const DownInnerParams& p, const DownMeasure& m, unsigned char* smem) {
-    const uint32_t n_par = p.RB * (uint32_t)p.P;
-    double* s_step = reinterpret_cast<double*>(smem);                 // [RB * P]  integer spreading only
-    float* s_res = reinterpret_cast<float*>(s_step + n_par);          // [RB * P]  child value (or floor(v/n))
+    const uint32_t PI = I1 ? (uint32_t)p.P : (uint32_t)p.P * p.I, CI = I1 ? (uint32_t)p.C : (uint32_t)p.C * p.I;
+    const uint32_t n_par = p.RB * PI;
+    double* s_step = reinterpret_cast<double*>(smem);                 // [RB * P * I]  integer spreading only
+    float* s_res = reinterpret_cast<float*>(s_step + n_par);          // [RB * P * I]  child value (or floor(v/n))
     int32_t* s_parent = reinterpret_cast<int32_t*>(s_res + n_par);    // [C]
     int32_t* s_rank = s_parent + p.C;                                 // [C]
-    uint8_t* s_st = reinterpret_cast<uint8_t*>(s_rank + p.C);         // [RB * P]  child status
-    uint8_t* s_truthy = s_st + n_par;                                 // [RB * P]
+    uint8_t* s_st = reinterpret_cast<uint8_t*>(s_rank + p.C);         // [RB * P * I]  child status
+    uint8_t* s_truthy = s_st + n_par;                                 // [RB * P * I]
     const int64_t row0 = (int64_t)blockIdx.x * p.RB;
     const uint32_t rows = (uint32_t)min((int64_t)p.RB, p.O - row0);
     const int nan_default = m.nan_default;
-    for (uint32_t i = threadIdx.x; i < rows * (uint32_t)p.P; i += blockDim.x) {
-        const float x = m.in[row0 * p.P + i];
-        const uint32_t sb = STATUS ? m.st_in[row0 * p.P + i] : 0u;
-        const uint32_t par = i % (uint32_t)p.P;
+    for (uint32_t i = threadIdx.x; i < rows * PI; i += blockDim.x) {
+        const float x = m.in[row0 * PI + i];
+        const uint32_t sb = STATUS ? m.st_in[row0 * PI + i] : 0u;
+        const uint32_t in_row = i - p.div_pi.div(i) * PI;
+        const uint32_t par = I1 ? in_row : p.div_i.div(in_row);
         const double dn = (double)p.cnt_of[par];
         const bool truthy = x != 0.0f && x == x;  // `if (!oldValue) continue` (in-memory.js:386-387)
         float r;
@@ -793,15 +826,15 @@ __device__ __forceinline__ void down_inner_body(const DownInnerParams& p, const 
         s_rank[c] = p.rank_of[c];
     }
     __syncthreads();
-    const uint32_t cells = rows * (uint32_t)p.C;
-    float* out = m.out + row0 * p.C;
-    uint8_t* st_out = STATUS ? m.st_out + row0 * p.C : nullptr;
-    auto cell = [&](uint32_t r, uint32_t c, uint32_t& so) {
-        const uint32_t i = r * (uint32_t)p.P + (uint32_t)s_parent[c];
-        float v = s_res[i];
-        so = s_st[i];
-        if (m.kind == 2 && s_truthy[i]) {
-            const double k = (double)s_rank[c], step = s_step[i];
+    const uint32_t cells = rows * CI;
+    float* out = m.out + row0 * CI;
+    uint8_t* st_out = STATUS ? m.st_out + row0 * CI : nullptr;
+    // cell `src` of the staged parents as seen by child `c` (rank among its siblings: s_rank[c])
+    auto cell = [&](uint32_t src, uint32_t c, uint32_t& so) {
+        float v = s_res[src];
+        so = s_st[src];
+        if (m.kind == 2 && s_truthy[src]) {
+            const double k = (double)s_rank[c], step = s_step[src];
             const bool last_is_same = floor(k * step) == floor((k - 1.0) * step);
             v = canon_store(last_is_same ? v : v + 1.0f, nan_default);
             if (STATUS && !present_f(v, nan_default)) so = OLAP_STATUS_UNSET;
@@ -810,34 +843,58 @@ __device__ __forceinline__ void down_inner_body(const DownInnerParams& p, const 
     };
     if (p.vec4) {
         for (uint32_t t = threadIdx.x * 4; t < cells; t += blockDim.x * 4) {
-            const uint32_t r = p.div_c.div(t);
-            const uint32_t c0 = t - r * (uint32_t)p.C;  // C % 4 == 0: the 4 cells share the row
+            const uint32_t r = p.div_ci.div(t);
+            const uint32_t w = t - r * CI;
             float v[4];
             uint32_t st = 0;
+            if (I1) {  // C % 4 == 0: four consecutive children of one row
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                uint32_t so;
-                v[e] = cell(r, c0 + e, so);
-                st |= so << (8 * e);
+                for (int e = 0; e < 4; ++e) {
+                    uint32_t so;
+                    v[e] = cell(r * PI + (uint32_t)s_parent[w + e], w + e, so);
+                    st |= so << (8 * e);
+                }
+            } else {         // I % 4 == 0: four consecutive inner cells of one child
+                const uint32_t c = p.div_i.div(w), i = w - c * p.I;
+                const uint32_t src = r * PI + (uint32_t)s_parent[c] * p.I + i;
+                if (m.kind != 2) {
+                    const float4 q = *reinterpret_cast<const float4*>(s_res + src);
+                    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                    st = *reinterpret_cast<const uint32_t*>(s_st + src);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        uint32_t so;
+                        v[e] = cell(src + e, c, so);
+                        st |= so << (8 * e);
+                    }
+                }
             }
             st_stream4(out + t, make_float4(v[0], v[1], v[2], v[3]));
             if (STATUS) *reinterpret_cast<uint32_t*>(st_out + t) = st;
         }
     } else {
         for (uint32_t t = threadIdx.x; t < cells; t += blockDim.x) {
-            const uint32_t r = p.div_c.div(t);
+            const uint32_t r = p.div_ci.div(t);
+            const uint32_t w = t - r * CI;
+            const uint32_t c = I1 ? w : p.div_i.div(w), i = I1 ? 0u : w - c * p.I;
             uint32_t so;
-            out[t] = cell(r, t - r * (uint32_t)p.C, so);
+            out[t] = cell(r * PI + (I1 ? (uint32_t)s_parent[c] : (uint32_t)s_parent[c] * p.I + i), c, so);
             if (STATUS) st_out[t] = (uint8_t)so;
         }
     }
 }
 
-__global__ void __launch_bounds__(256) drilldown_inner_kernel(const __grid_constant__ DownInnerParams p) {
+__global__ void __launch_bounds__(256, 4) drilldown_inner_kernel(const __grid_constant__ DownInnerParams p) {
     extern __shared__ __align__(16) unsigned char smem_di[];
     const DownMeasure m = p.meas[blockIdx.y];
-    if (m.st_in) down_inner_body<true>(p, m, smem_di);
-    else down_inner_body<false>(p, m, smem_di);
+    if (p.I == 1) {
+        if (m.st_in) down_inner_body<true, true>(p, m, smem_di);
+        else down_inner_body<false, true>(p, m, smem_di);
+    } else {
+        if (m.st_in) down_inner_body<true, false>(p, m, smem_di);
+        else down_inner_body<false, false>(p, m, smem_di);
+    }
 }
 
 }  // namespace olap

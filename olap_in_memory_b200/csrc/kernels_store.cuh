@@ -90,7 +90,7 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long x)
 // `get total`: double sum of the set cells, plus their count.  Per-block partials are
 // written to scratch and folded by the last block (threadfence + ticket), which keeps
 // the result deterministic for a given grid.
-__global__ void __launch_bounds__(kStoreThreads) total_kernel(const float* __restrict__ v, int64_t n, int nan_default,
+__global__ void __launch_bounds__(kStoreThreads, 4) total_kernel(const float* __restrict__ v, int64_t n, int nan_default,
                                                               double* __restrict__ partial_sum,
                                                               unsigned long long* __restrict__ partial_cnt,
                                                               unsigned int* __restrict__ ticket,
@@ -99,10 +99,31 @@ __global__ void __launch_bounds__(kStoreThreads) total_kernel(const float* __res
     __shared__ double s_sum[kStoreThreads / 32];
     __shared__ unsigned long long s_cnt[kStoreThreads / 32];
     __shared__ bool s_last;
-    double acc = 0.0;
-    unsigned long long cnt = 0;
+    // U vectors in flight per thread, one accumulator per vector slot (independent add chains),
+    // presence folded into the arithmetic (an unset cell adds 0.0 and counts 0)
+    constexpr int U = 4;
+    double accs[U] = {0.0, 0.0, 0.0, 0.0};
+    uint32_t cnts[U] = {0u, 0u, 0u, 0u};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
-    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    for (; i + (U - 1) * stride + 4 <= n; i += U * stride) {
+        float4 t[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) t[u] = ld_stream4(v + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float e[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool set = present_f(e[k], nan_default);
+                accs[u] += set ? (double)e[k] : 0.0;
+                cnts[u] += set ? 1u : 0u;
+            }
+        }
+    }
+    double acc = (accs[0] + accs[1]) + (accs[2] + accs[3]);
+    unsigned long long cnt = (unsigned long long)cnts[0] + cnts[1] + cnts[2] + cnts[3];
+    for (; i < n; i += stride) {
         float e[4];
         int m = 4;
         if (i + 4 <= n) {

@@ -393,12 +393,15 @@ static int launch_up_mid(const UpMeasure* d_meas, const UpMeasure* h_meas, int n
     do {                                                                                                   \
         static bool attr = false;                                                                          \
         if (!attr) {                                                                                       \
-            OLAP_CUDA(cudaFuncSetAttribute(drillup_split_kernel<V, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            OLAP_CUDA(cudaFuncSetAttribute(drillup_split_kernel<V, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            32 * 32 * 4 * 16 + 32 * 32 * 4));                               \
             attr = true;                                                                                   \
         }                                                                                                  \
-        drillup_split_kernel<V, R><<<grid, block, smem, g.stream>>>(p);                                    \
+        if (wide) drillup_split_kernel<V, R, true><<<grid, block, smem, g.stream>>>(p);                    \
+        else drillup_split_kernel<V, R, false><<<grid, block, smem, g.stream>>>(p);                        \
     } while (0)
+            static const int wide_knob = [] { const char* e = getenv("OLAP_SPLIT_WIDE"); return e ? atoi(e) : 1; }();
+            const bool wide = wide_knob && G <= 8;
             if (VEC == 4) { if (csr.contiguous) OLAP_SPLIT_LAUNCH(4, true); else OLAP_SPLIT_LAUNCH(4, false); }
             else if (VEC == 2) { if (csr.contiguous) OLAP_SPLIT_LAUNCH(2, true); else OLAP_SPLIT_LAUNCH(2, false); }
             else { if (csr.contiguous) OLAP_SPLIT_LAUNCH(1, true); else OLAP_SPLIT_LAUNCH(1, false); }
@@ -436,7 +439,7 @@ static int launch_up_mid(const UpMeasure* d_meas, const UpMeasure* h_meas, int n
 }
 
 static int launch_down_mid(const DownMeasure* d_meas, int n, const Csr& csr, const int32_t* d_pstart,
-                           const int32_t* d_children, int64_t O, int64_t P, int64_t C, int64_t I) {
+                           const int32_t* d_children, int64_t O, int64_t P, int64_t C, int64_t I, int kind) {
     const int VEC = (I % 4 == 0) ? 4 : (I % 2 == 0 ? 2 : 1);
     const int64_t IV_total = I / VEC;
     const int64_t max_row = ((int64_t)1 << 30);
@@ -463,33 +466,46 @@ static int launch_down_mid(const DownMeasure* d_meas, int n, const Csr& csr, con
         if (gx > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "drillDown: grid too large (%lld blocks)", (long long)gx);
         dim3 grid((unsigned)gx, (unsigned)n), block(bx, by);
         KERNELS_BEGIN();
-        if (VEC == 4) {
-            if (csr.contiguous) drilldown_mid_kernel<4, true><<<grid, block, 0, g.stream>>>(p);
-            else drilldown_mid_kernel<4, false><<<grid, block, 0, g.stream>>>(p);
-        } else if (VEC == 2) {
-            if (csr.contiguous) drilldown_mid_kernel<2, true><<<grid, block, 0, g.stream>>>(p);
-            else drilldown_mid_kernel<2, false><<<grid, block, 0, g.stream>>>(p);
-        } else {
-            if (csr.contiguous) drilldown_mid_kernel<1, true><<<grid, block, 0, g.stream>>>(p);
-            else drilldown_mid_kernel<1, false><<<grid, block, 0, g.stream>>>(p);
-        }
+#define OLAP_DOWN_K(V, R)                                                                              \
+    do {                                                                                               \
+        if (kind == 0) drilldown_mid_kernel<V, R, 0><<<grid, block, 0, g.stream>>>(p);                 \
+        else if (kind == 1) drilldown_mid_kernel<V, R, 1><<<grid, block, 0, g.stream>>>(p);            \
+        else if (kind == 2) drilldown_mid_kernel<V, R, 2><<<grid, block, 0, g.stream>>>(p);            \
+        else drilldown_mid_kernel<V, R, -1><<<grid, block, 0, g.stream>>>(p);                          \
+    } while (0)
+        if (VEC == 4) { if (csr.contiguous) OLAP_DOWN_K(4, true); else OLAP_DOWN_K(4, false); }
+        else if (VEC == 2) { if (csr.contiguous) OLAP_DOWN_K(2, true); else OLAP_DOWN_K(2, false); }
+        else { if (csr.contiguous) OLAP_DOWN_K(1, true); else OLAP_DOWN_K(1, false); }
+#undef OLAP_DOWN_K
         LAUNCHED();
     }
     return OLAP_OK;
 }
 
+// The block kernel stages P * I parent cells (14 bytes each) of at least one outer index in shared memory.
+// With an inner run behind the drilled axis the integer-spreading measures stay on the parent-driven
+// kernel, which carries floor((k - 1) * step) from child to child (the block kernel would redo both
+// floors per cell: 0.38 against 0.64 of peak).
+static bool down_block_fits(int64_t P, int64_t C, int64_t I, bool any_int = false) {
+    static const int knob = [] { const char* e = getenv("OLAP_DOWN_BLOCK"); return e ? atoi(e) : 1; }();
+    if (I == 1) return C <= 8192 && P <= 8192;
+    return knob && !any_int && P * I <= 8192 && C <= 8192 && C * I < (1 << 28) && I <= 2048;
+}
+
 static int launch_down_inner(const DownMeasure* d_meas, int n, const int32_t* d_parent, const int32_t* d_rank,
-                             const int32_t* d_cnt, int64_t O, int64_t P, int64_t C) {
+                             const int32_t* d_cnt, int64_t O, int64_t P, int64_t C, int64_t I) {
     DownInnerParams p{};
     p.meas = d_meas;
     p.parent_of = d_parent;
     p.rank_of = d_rank;
     p.cnt_of = d_cnt;
-    p.O = O; p.P = (int32_t)P; p.C = (int32_t)C;
-    p.RB = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(O, 8192 / C));
-    if (C % 4 != 0 || ((int64_t)p.RB * C) % 4 != 0) p.vec4 = 0; else p.vec4 = 1;
-    p.div_c = FastDiv((uint32_t)C);
-    const size_t smem = (size_t)p.RB * P * (8 + 4 + 2) + (size_t)C * 8 + 16;
+    p.O = O; p.P = (int32_t)P; p.C = (int32_t)C; p.I = (uint32_t)I;
+    p.RB = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(O, 8192 / (C * I)));
+    p.vec4 = I == 1 ? (C % 4 == 0 && ((int64_t)p.RB * C) % 4 == 0) : (I % 4 == 0);
+    p.div_i = FastDiv((uint32_t)I);
+    p.div_pi = FastDiv((uint32_t)(P * I));
+    p.div_ci = FastDiv((uint32_t)(C * I));
+    const size_t smem = (size_t)p.RB * P * I * (8 + 4 + 1 + 1) + (size_t)C * 8 + 16;
     const int64_t gx = ceil_div(O, p.RB);
     if (gx > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "drillDown: grid too large");
     static bool attr = false;
@@ -1353,6 +1369,9 @@ int olap_drill_down(olap_store* const* src, int n, const int* methods, int ndim,
     bool any_dist = false;
     for (int k = 0; k < n; ++k) any_dist |= dist && dist[k];
     if (any_dist && (old_size == 0 || new_size % old_size != 0)) return fail(OLAP_E_INVALID, "olap_drill_down: distributions need newSize to be a multiple of oldSize");
+    bool any_int_sum = false;
+    for (int k = 0; k < n; ++k)
+        any_int_sum |= (src[k]->type == OLAP_INT32 || src[k]->type == OLAP_UINT32) && (methods ? methods[k] == OLAP_SUM : true);
     OLAP_TRY(ensure_ctx());
     OLAP_TRY(alloc_like(src, n, new_size, out));
     OutGuard guard(out, n);
@@ -1361,7 +1380,7 @@ int olap_drill_down(olap_store* const* src, int n, const int* methods, int ndim,
     int rc = OLAP_OK;
     if (new_size && old_size == 0) {
         for (int k = 0; k < n; ++k) { olap_store t = *out[k]; t.status = st_out_of(out, k); OLAP_TRY(fill_default(&t)); }
-    } else if (new_size && !any_dist && changed.size() == 1 &&
+    } else if (new_size && !any_dist && changed.size() == 1 && !down_block_fits(old_len[changed[0]], new_len[changed[0]], inner_of_changed, any_int_sum) &&
                ((inner_of_changed % 4 == 0 && inner_of_changed >= 32) || (inner_of_changed % 2 == 0 && inner_of_changed >= 64) ||
                 inner_of_changed >= 128)) {
         // one changed dimension with a long inner run: parent-driven kernel
@@ -1384,12 +1403,14 @@ int olap_drill_down(olap_store* const* src, int n, const int* methods, int ndim,
         const size_t o_ch = t.add(csr.children.data(), csr.children.size() * 4);
         OLAP_TRY(t.upload());
         path = inner_of_changed % 4 == 0 ? "drilldown/mid-vec4" : (inner_of_changed % 2 == 0 ? "drilldown/mid-vec2" : "drilldown/mid-scalar");
+        int kind = dm[0].kind;  // the kind all measures share, or -1
+        for (int k = 1; k < n; ++k) if (dm[k].kind != kind) kind = -1;
         OLAP_TRY(launch_down_mid(t.ptr<DownMeasure>(o_meas), n, csr, t.ptr<int32_t>(o_ps), t.ptr<int32_t>(o_ch), O,
-                                 old_len[d], new_len[d], inner_of_changed));
+                                 old_len[d], new_len[d], inner_of_changed, kind));
         OLAP_TRY(t.release());
-    } else if (new_size && !any_dist && changed.size() == 1 && inner_of_changed == 1 && new_len[changed[0]] <= 8192 &&
-               old_len[changed[0]] <= 8192) {
-        // the drilled dimension is the innermost one: row kernel with 128-bit stores
+    } else if (new_size && !any_dist && changed.size() == 1 && down_block_fits(old_len[changed[0]], new_len[changed[0]], inner_of_changed, any_int_sum)) {
+        // the drilled dimension is the innermost one, or the run behind it is short: block kernel,
+        // parents staged in shared memory, output written front to back with 128-bit stores
         const int d = changed[0];
         int64_t O = 1;
         for (int q = 0; q < d; ++q) O *= old_len[q];
@@ -1410,9 +1431,9 @@ int olap_drill_down(olap_store* const* src, int n, const int* methods, int ndim,
         const size_t o_rank = t.add(rank.data(), (size_t)C * 4);
         const size_t o_cnt = t.add(cnt.data(), (size_t)P * 4);
         OLAP_TRY(t.upload());
-        path = "drilldown/inner-rows";
+        path = inner_of_changed == 1 ? "drilldown/inner-rows" : "drilldown/block-rows";
         OLAP_TRY(launch_down_inner(t.ptr<DownMeasure>(o_meas), n, t.ptr<int32_t>(o_par), t.ptr<int32_t>(o_rank),
-                                   t.ptr<int32_t>(o_cnt), O, P, C));
+                                   t.ptr<int32_t>(o_cnt), O, P, C, inner_of_changed));
         OLAP_TRY(t.release());
     } else if (new_size) {
         auto meas = gather_measures(src, out, n);
