@@ -100,7 +100,7 @@ int alloc_batch(int n, int64_t size, const int* types, const int* default_kinds,
 struct TablePack {
     std::vector<char> host;
     void* dev = nullptr;
-    size_t add(const void* data, size_t bytes);  // returns offset, 16-byte aligned
+    size_t add(const void* data, size_t bytes, size_t align = 16);  // returns the offset (aligned; the device base is 256-byte aligned)
     int upload();
     int release();
     TablePack() = default;

@@ -53,12 +53,23 @@ struct PairParams {
     FastDiv div_nJqLoc;
 };
 
+// One (merged) axis of the permutation as the planner sees it — what the tensor-map variant
+// (kernels_tma.cuh) needs to describe the tile to the TMA unit.
+struct PairAxis {
+    int64_t len, box;                // items, items of it inside one tile
+    int64_t src_stride, dst_stride;  // cells
+    int group;                       // 1: part of the input run, 2: part of the output run, 0: extent 1
+    int slot;                        // grid slot (PairParams::len/bsize/... index) of this axis
+};
+
 struct PairPlan {
     bool use = false;
     PairParams p{};
     int64_t n_boxes = 0;
     size_t smem = 0;
     std::vector<uint32_t> src_row, dst_row;
+    std::vector<PairAxis> axes;
+    bool geometry = false;           // A, B, tables, grid and axes are valid (even when `use` is false for lack of shared memory)
 };
 
 // Memory accessors: the device flavour streams through L1; the host flavour lets
@@ -604,6 +615,14 @@ inline PairPlan transpose_pair_plan_for(const std::vector<GDim>& dims_in, int64_
         if (gi.partial && ax == gi.axes.back()) p.in_axis = slot;
         if (go.partial && ax == go.axes.back()) p.out_axis = slot;
     }
+    plan.axes.resize(k);
+    for (int q = 0; q < k; ++q) {
+        const int ax = order[q];
+        int group = 0;
+        if (std::find(gi.axes.begin(), gi.axes.end(), ax) != gi.axes.end()) group = 1;
+        if (std::find(go.axes.begin(), go.axes.end(), ax) != go.axes.end()) group = 2;
+        plan.axes[ax] = PairAxis{dims[ax].len, b[ax], dims[ax].stride, dst_stride[ax], group, k - 1 - q};
+    }
     p.in_mult = (uint32_t)gi.mult;
     p.out_mult = (uint32_t)go.mult;
     if (!gi.partial) p.in_mult = p.A;
@@ -620,6 +639,7 @@ inline PairPlan transpose_pair_plan_for(const std::vector<GDim>& dims_in, int64_
     p.tab_offset = (uint32_t)(p.st_offset + ((cells + 15) & ~(size_t)15));
     plan.smem = p.tab_offset + ((size_t)p.A + p.B) * sizeof(uint32_t);
     const uint32_t mt_per_cta = split == 2 ? p.nIg * p.nJqLoc : p.nIg * p.nJq;
+    plan.geometry = split == 1;
     if (plan.smem > 200 * 1024 || mt_per_cta > 3u * kPairThreads) return plan;
     if (split == 1 && plan.smem > 100 * 1024 && mt_per_cta <= (uint32_t)kPairThreads) return plan;
     plan.use = true;

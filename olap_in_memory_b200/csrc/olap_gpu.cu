@@ -19,6 +19,7 @@
 #include "kernels_tile.cuh"
 #include "kernels_long.cuh"
 #include "kernels_pull.cuh"
+#include "kernels_tma.cuh"
 
 namespace olap {
 
@@ -172,8 +173,8 @@ static void check_guards(const olap_store* s) {
     if (s->status) check(reinterpret_cast<const char*>(s->status), (size_t)s->size);
 }
 
-size_t TablePack::add(const void* data, size_t bytes) {
-    const size_t off = (host.size() + 15) & ~(size_t)15;
+size_t TablePack::add(const void* data, size_t bytes, size_t align) {
+    const size_t off = (host.size() + align - 1) & ~(align - 1);
     host.resize(off + bytes);
     if (bytes) memcpy(host.data() + off, data, bytes);
     return off;
@@ -1295,10 +1296,26 @@ int olap_reorder(olap_store* const* src, int n, int ndim, const int64_t* old_len
     const char* path = "reorder/empty";
     if (size) {
         auto meas = gather_measures(src, out, n);
-        PairPlan pp = transpose_pair_plan(dims);
+        TmaPlan tm = transpose_tma_plan(dims);
+        if (tm.use && !tma_encode_fn()) tm.use = false;  // a driver without cuTensorMapEncodeTiled
+        PairPlan pp;
+        if (!tm.use) pp = transpose_pair_plan(dims);
         TransposePlan tp;
-        if (!pp.use) tp = transpose_plan(dims);
-        if (pp.use) {
+        if (!tm.use && !pp.use) tp = transpose_plan(dims);
+        if (tm.use) {
+            path = "reorder/tma-transpose";
+            std::vector<CUtensorMap> maps;
+            OLAP_TRY(tma_encode_maps(tm, meas, maps));
+            TablePack t;
+            const size_t o_meas = t.add(meas.data(), sizeof(GatherMeasure) * n);
+            const size_t o_src = t.add(tm.pair.src_row.data(), tm.pair.src_row.size() * sizeof(uint32_t));
+            const size_t o_dst = t.add(tm.pair.dst_row.data(), tm.pair.dst_row.size() * sizeof(uint32_t));
+            const size_t o_maps = t.add(maps.data(), maps.size() * sizeof(CUtensorMap), 64);
+            OLAP_TRY(t.upload());
+            OLAP_TRY(launch_transpose_tma(t.ptr<GatherMeasure>(o_meas), t.ptr<uint32_t>(o_src), t.ptr<uint32_t>(o_dst),
+                                          t.ptr<CUtensorMap>(o_maps), n, tm));
+            OLAP_TRY(t.release());
+        } else if (pp.use) {
             path = "reorder/pair-transpose";
             TablePack t;
             const size_t o_meas = t.add(meas.data(), sizeof(GatherMeasure) * n);

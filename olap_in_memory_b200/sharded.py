@@ -356,6 +356,19 @@ class ShardedCube:
         stores = [self.storedMeasures[n] for n in cell_names]
         return np.asarray(self._store_cls.evaluate(expression, cell_names, stores, totals, self.localSize), dtype=np.float64)
 
+    def getLocalStore(self, measureId, type="float32", defaultValue=0):
+        """My rows of a measure as a device store: the stored measure itself, or a computed measure
+        evaluated by one fused kernel over my rows without leaving the device (Cube.evaluateToStore;
+        the device half of copyToStoredMeasure, cube.js:205-215)."""
+        if measureId in self.storedMeasures:
+            return self.storedMeasures[measureId]
+        expression = self.computedMeasures[measureId]
+        names = expression.variables()
+        cell_names = [n for n in names if "__total" not in n]
+        totals = {n: self.getTotal(n.replace("__total", "")) for n in names if "__total" in n}
+        return self._store_cls.evaluate_to_store(expression, cell_names, [self.storedMeasures[n] for n in cell_names], totals,
+                                                 type, defaultValue)
+
     def setLocalData(self, measureId, values):
         """Cells of MY rows, row-major (length rows_local * inner)."""
         self._set(self.storedMeasures[measureId], values)

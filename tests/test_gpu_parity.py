@@ -374,4 +374,44 @@ def test_reorder_fuzz_against_numpy():
             want = data.reshape(dims).transpose(perm).reshape(-1)
             assert np.array_equal(out.data_f32(), want), (dims, perm, path)
             assert np.array_equal(np.asarray(out.status), np.where(want != 0, 2, 1)), (dims, perm, path)
-    assert paths.get("reorder/pair-transpose", 0) >= 5 and paths.get("reorder/box-transpose", 0) >= 5, paths
+    disjoint = paths.get("reorder/pair-transpose", 0) + paths.get("reorder/tma-transpose", 0)
+    assert disjoint >= 5 and paths.get("reorder/box-transpose", 0) >= 5, paths
+
+
+@pytest.mark.parametrize("knobs", [{}, {"OLAP_TMA_OUT": "200"}, {"OLAP_TMA_STAGES": "1", "OLAP_TMA_STORE_STAGES": "1"}])
+def test_tma_transpose(monkeypatch, knobs):
+    """The tensor-map variant of the disjoint-group transpose (kernels_tma.cuh: cp.async.bulk.tensor
+    loads into a ring of shared-memory stages, register transposition, tensor-map stores; status
+    bytes on the side): bit-exact against numpy.transpose, ragged tiles (TMA zero-fill / clipping),
+    merged dimensions, several measures, with and without status plane, a NaN default."""
+    from olap_in_memory_b200 import _native as N
+
+    G = _gpu()
+    monkeypatch.setenv("OLAP_TRANSPOSE_TMA", "1")  # opt-in: measured slower than the pair kernel (profiles/README.md)
+    for key, value in knobs.items():
+        monkeypatch.setenv(key, value)
+    rng = np.random.default_rng(23)
+    hit = 0
+    for dims, perm in (([24, 16, 10, 10, 10], [4, 3, 2, 1, 0]), ([28, 12, 6, 10, 10], [4, 3, 2, 1, 0]),
+                       ([400, 408], [1, 0]), ([20, 20, 20, 10, 10, 10], [5, 4, 3, 2, 1, 0]),
+                       ([36, 52, 44], [2, 1, 0]), ([104, 9, 100], [2, 1, 0]), ([12, 200, 3, 100], [3, 2, 0, 1]),
+                       ([3652, 32, 32], [2, 1, 0]), ([100, 100, 12, 12], [2, 3, 0, 1])):
+        n = int(np.prod(dims))
+        for with_status, default in ((True, 0.0), (False, 0.0), (True, float("nan"))):
+            stores, datas = [], []
+            for _ in range(2):
+                data = rng.integers(1, 1000, n).astype(np.float32)
+                data[rng.random(n) < 0.3] = default
+                s = G(n, "float32", default, with_status=with_status)
+                s.set_data_f32(data)
+                stores.append(s)
+                datas.append(data)
+            outs = G.reorder_lowered(stores, dims, perm)
+            hit += N.lib().olap_last_op_path() == b"reorder/tma-transpose"
+            for data, out in zip(datas, outs):
+                want = data.reshape(dims).transpose(perm).reshape(-1)
+                assert np.array_equal(out.data_f32().view(np.uint32), want.view(np.uint32)), (dims, perm, with_status, default)
+                if with_status:
+                    set_ = want == want if default != default else want != 0
+                    assert np.array_equal(np.asarray(out.status), np.where(set_, 2, 1)), (dims, perm)
+    assert hit >= 12, hit
