@@ -39,9 +39,9 @@ def main():
     dims += [TimeDimension("time", "month", "2010-01", "2010-10")]
     dims += [GenericDimension(name, "root", [f"{name}{i}" for i in range(10)]) for name in ("e", "f")]
     cube = Cube(dims)
-    cube.createStoredMeasure("m", {"time": "sum"}, "float32", 0)
-    interop.values_tensor(cube.storedMeasures["m"]).uniform_(1.0, 1000.0)
-    interop.status_tensor(cube.storedMeasures["m"]).fill_(2)
+    cube.createStoredMeasure("amount", {"time": "sum"}, "float32", 0)
+    interop.values_tensor(cube.storedMeasures["amount"]).uniform_(1.0, 1000.0)
+    interop.status_tensor(cube.storedMeasures["amount"]).fill_(2)
     torch.cuda.synchronize()
     rows = []
 
@@ -65,8 +65,8 @@ def main():
     every_other = [f"a{i}" for i in range(0, 100, 2)]
     diced = timed("dice a -> every other item", lambda: cube.dice("a", "root", every_other), 5 * 2 * (n // 2), n, n // 2)
     rev = timed("reorderDimensions -> reversed", lambda: cube.reorderDimensions(["f", "e", "time", "c", "b", "a"]), 5 * 2 * n, n, n)
-    ref = interop.values_tensor(cube.storedMeasures["m"]).view(100, 100, 100, 10, 10, 10)
-    got = interop.values_tensor(rev.storedMeasures["m"]).view(10, 10, 10, 100, 100, 100)
+    ref = interop.values_tensor(cube.storedMeasures["amount"]).view(100, 100, 100, 10, 10, 10)
+    got = interop.values_tensor(rev.storedMeasures["amount"]).view(10, 10, 10, 100, 100, 100)
     assert torch.equal(got[3, 7, 1, :, 42, 5], ref[5, 42, :, 1, 7, 3]) and torch.equal(got[:, 0, 9, 99, 0, 50], ref[50, 0, 99, 9, 0, :])
     del rev, got, ref
     n_d = diced.storeSize
@@ -75,10 +75,10 @@ def main():
     assert down.storeSize == n_out == 15_200_000_000
     # property at full size: days roll back up to their month (the reference's down-then-up round trip, test/cube-drilling.js:85-140)
     back = down.drillUp("time", "month")
-    a = interop.values_tensor(back.storedMeasures["m"])
-    b = interop.values_tensor(diced.storedMeasures["m"])
+    a = interop.values_tensor(back.storedMeasures["amount"])
+    b = interop.values_tensor(diced.storedMeasures["amount"])
     rel = float(((a - b).abs() / b.abs()).max().item())
-    st = interop.status_tensor(down.storedMeasures["m"])
+    st = interop.status_tensor(down.storedMeasures["amount"])
     flags = torch.unique(st[:: 1000003]).tolist()
     row = {"check": "drillUp(drillDown(x)) == x at 1.52e10 cells", "max_rel_err": rel, "status_flags_seen": flags,
            "roll_back_kernel_ms": round(lib.olap_last_op_ms(), 3)}

@@ -438,7 +438,7 @@ __device__ __forceinline__ void up_mid_dispatch(const UpMidParams& p, const UpMe
 #define OLAP_MID_MINB 3
 #endif
 template <int VEC, bool RANGE, int U>
-__global__ void __launch_bounds__(256, U == 8 ? OLAP_MID_MINB : 4) drillup_mid_kernel(const __grid_constant__ UpMidParams p) {
+__global__ void __launch_bounds__(256, U == 8 ? (VEC == 4 ? OLAP_MID_MINB : 4) : 4) drillup_mid_kernel(const __grid_constant__ UpMidParams p) {
     const uint32_t brow = blockIdx.x / p.blocks_per_row;  // uniform per block
     const uint32_t bcol = blockIdx.x - brow * p.blocks_per_row;
     const int64_t o = (int64_t)brow * blockDim.y + threadIdx.y;

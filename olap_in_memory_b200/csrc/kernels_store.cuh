@@ -37,10 +37,14 @@ __global__ void __launch_bounds__(kStoreThreads) canon_f32_kernel(float* __restr
 }
 
 // `set data` from doubles: Math.fround then canonicalise.
+// `lossy` (nullable): first index (+1) whose double does not survive the Float32 cell — integer stores
+// are expected to hold exact integers (counts above 2^24 would silently change).
 __global__ void __launch_bounds__(kStoreThreads) from_f64_kernel(const double* __restrict__ src, float* __restrict__ v,
-                                                                 uint8_t* __restrict__ st, int64_t n, int nan_default) {
+                                                                 uint8_t* __restrict__ st, int64_t n, int nan_default,
+                                                                 unsigned long long* __restrict__ lossy) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (lossy && src[i] == src[i] && (double)(float)src[i] != src[i]) atomicMin(lossy, (unsigned long long)i + 1);
         const float t = canon_store((float)src[i], nan_default);
         v[i] = t;
         if (st) st[i] = present_f(t, nan_default) ? OLAP_STATUS_SET : OLAP_STATUS_UNSET;
@@ -66,11 +70,13 @@ __global__ void __launch_bounds__(kStoreThreads) fill_kernel(float* __restrict__
 __global__ void __launch_bounds__(kStoreThreads) set_values_kernel(float* __restrict__ v, uint8_t* __restrict__ st,
                                                                    const int64_t* __restrict__ idx,
                                                                    const double* __restrict__ val, int64_t n,
-                                                                   int64_t size, int nan_default) {
+                                                                   int64_t size, int nan_default,
+                                                                   unsigned long long* __restrict__ lossy) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t k = idx[i];
     if (k < 0 || k >= size) return;
+    if (lossy && val[i] == val[i] && (double)(float)val[i] != val[i]) atomicMin(lossy, (unsigned long long)i + 1);
     const float t = canon_store((float)val[i], nan_default);
     v[k] = t;
     if (st) st[k] = present_f(t, nan_default) ? OLAP_STATUS_SET : OLAP_STATUS_UNSET;

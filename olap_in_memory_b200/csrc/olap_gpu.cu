@@ -698,6 +698,20 @@ static int check_len(const olap_store* s, int64_t n) {
     return OLAP_OK;
 }
 
+// Cells are Float32 for every store type.  The reference keeps JS doubles, so an int32 / uint32 store
+// there holds counts above 2^24 exactly; here such a value would silently become a neighbour.  Uploads
+// and setValue(s) of integer stores therefore refuse values that do not survive Math.fround
+// (OLAP_LOSSY_INTS=1 restores the silent rounding).  float64 stores round by declared contract.
+static bool strict_ints(const olap_store* s) {
+    static const bool relaxed = [] { const char* e = getenv("OLAP_LOSSY_INTS"); return e && atoi(e) != 0; }();
+    return !relaxed && (s->type == OLAP_INT32 || s->type == OLAP_UINT32);
+}
+static int lossy_error(const olap_store* s, int64_t index, double value) {
+    return fail(OLAP_E_UNSUPPORTED, "value %.17g at index %lld of an %s store is not representable in its Float32 cell "
+                "(the reference would keep it exact; use a float32 store or set OLAP_LOSSY_INTS=1 to round)", value,
+                (long long)index, s->type == OLAP_INT32 ? "int32" : "uint32");
+}
+
 int olap_store_upload_f32(olap_store* s, const float* host, int64_t n) {
     OLAP_TRY(check_len(s, n));
     OLAP_TRY(ensure_ctx());
@@ -713,13 +727,19 @@ int olap_store_upload_f64(olap_store* s, const double* host, int64_t n) {
     OLAP_TRY(ensure_ctx());
     if (n == 0) return OLAP_OK;
     void* tmp;
-    OLAP_TRY(dev_alloc(&tmp, (size_t)n * 8));
+    OLAP_TRY(dev_alloc(&tmp, (size_t)n * 8 + 8));
     OLAP_CUDA(cudaMemcpyAsync(tmp, host, (size_t)n * 8, cudaMemcpyHostToDevice, g.stream));
-    from_f64_kernel<<<grid_for(n, kStoreThreads), kStoreThreads, 0, g.stream>>>((const double*)tmp, s->values, s->status, n, s->default_kind);
+    // integer stores hold exact integers in the reference (JS doubles): refuse what a Float32 cell would change
+    unsigned long long* lossy = strict_ints(s) ? reinterpret_cast<unsigned long long*>(static_cast<char*>(tmp) + (size_t)n * 8) : nullptr;
+    if (lossy) OLAP_CUDA(cudaMemsetAsync(lossy, 0xff, 8, g.stream));
+    from_f64_kernel<<<grid_for(n, kStoreThreads), kStoreThreads, 0, g.stream>>>((const double*)tmp, s->values, s->status, n, s->default_kind, lossy);
     LAUNCHED();
+    unsigned long long first = ~0ull;
+    if (lossy) OLAP_CUDA(cudaMemcpyAsync(&first, lossy, 8, cudaMemcpyDeviceToHost, g.stream));
     OLAP_TRY(dev_free(tmp));
     // the host buffer is borrowed for the call only
     OLAP_CUDA(cudaStreamSynchronize(g.stream));
+    if (first != ~0ull) return lossy_error(s, (int64_t)first - 1, host[first - 1]);
     return finish_op();
 }
 
@@ -764,12 +784,16 @@ int olap_store_set_values(olap_store* s, const int64_t* indexes, const double* v
     if (!s || (n && (!indexes || !values))) return fail(OLAP_E_INVALID, "olap_store_set_values: null argument");
     OLAP_TRY(ensure_ctx());
     if (n == 0) return OLAP_OK;
+    if (strict_ints(s))  // the values are on the host: check before anything is written
+        for (int64_t i = 0; i < n; ++i)
+            if (values[i] == values[i] && (double)(float)values[i] != values[i] && indexes[i] >= 0 && indexes[i] < s->size)
+                return lossy_error(s, indexes[i], values[i]);
     TablePack t;
     const size_t oi = t.add(indexes, (size_t)n * 8);
     const size_t ov = t.add(values, (size_t)n * 8);
     OLAP_TRY(t.upload());
     set_values_kernel<<<(unsigned)ceil_div(n, kStoreThreads), kStoreThreads, 0, g.stream>>>(
-        s->values, s->status, t.ptr<int64_t>(oi), t.ptr<double>(ov), n, s->size, s->default_kind);
+        s->values, s->status, t.ptr<int64_t>(oi), t.ptr<double>(ov), n, s->size, s->default_kind, nullptr);
     LAUNCHED();
     OLAP_TRY(t.release());
     return finish_op();

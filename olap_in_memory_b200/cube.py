@@ -32,6 +32,18 @@ def _default_store_cls():
     return GpuStore
 
 
+def _to_int32(x):
+    """JS ToInt32: NaN / infinities -> 0, truncation toward zero, wrap modulo 2^32 into [-2^31, 2^31)."""
+    if x != x or x in (float("inf"), float("-inf")):
+        return 0
+    n = int(x) & 0xFFFFFFFF
+    return n - (1 << 32) if n >= (1 << 31) else n
+
+
+def _js_or(a, b):
+    return _to_int32(a) | _to_int32(b)
+
+
 def _check_measure_id(measureId):
     if not _MEASURE_ID.match(measureId):
         raise ValueError(f"Invalid measureId: {measureId}")
@@ -226,11 +238,17 @@ class Cube:
         if measureId in self.storedMeasures:
             return self.storedMeasures[measureId]._dataMap
         if measureId in self.computedMeasures:
+            # cube.js:374-386: union of the stored measures' keys in first-seen order; a key seen before
+            # with a truthy value gets  previous | value  (JS ToInt32 bitwise OR), else the value itself
             result = {}
             for store in self.storedMeasures.values():
                 for key, value in store._dataMap.items():
-                    result[key] = value
-            return dict(sorted(result.items()))
+                    previous = result.get(key)
+                    if previous is not None and previous == previous and previous != 0:
+                        result[key] = _js_or(previous, value)
+                    else:
+                        result[key] = value
+            return result
         raise KeyError(f"getStatusMap: no such measure {measureId}")
 
     def getStatus(self, measureId):

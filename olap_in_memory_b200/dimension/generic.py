@@ -15,7 +15,7 @@ from .abstract import AbstractDimension
 
 
 def _get_or_call(objfun, param):
-    if not objfun:
+    if objfun is None:  # JS `!objfun`: an empty object {} is truthy there (labels become undefined, not the item)
         return param
     if callable(objfun):
         return objfun(param)

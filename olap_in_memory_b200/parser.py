@@ -309,6 +309,10 @@ class _P:
 
 
 def _fmt_num(v):
+    if v != v:
+        return "NaN"
+    if v in (math.inf, -math.inf):  # a literal such as 1e999
+        return "Infinity" if v > 0 else "-Infinity"
     if v == int(v) and abs(v) < 1e15:
         return str(int(v))
     return repr(v)

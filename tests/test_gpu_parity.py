@@ -415,3 +415,23 @@ def test_tma_transpose(monkeypatch, knobs):
                     set_ = want == want if default != default else want != 0
                     assert np.array_equal(np.asarray(out.status), np.where(set_, 2, 1)), (dims, perm)
     assert hit >= 12, hit
+
+
+def test_integer_stores_refuse_values_their_float32_cell_would_change():
+    """the reference keeps JS doubles for every store type; an int32 / uint32 store whose
+    count exceeds 2^24 must not silently come back as a neighbouring integer."""
+    from olap_in_memory_b200 import _native as N
+
+    G = _gpu()
+    s = G(4, "uint32", 0)
+    s.data = [1.0, 16777216.0, 3.0, 0.5]  # exact in Float32 (non-integers are the caller's business, as in JS)
+    assert s.data == [1.0, 16777216.0, 3.0, 0.5]
+    with pytest.raises(N.OlapError, match="16777217 at index 2 of an uint32 store"):
+        s.data = [1.0, 2.0, 16777217.0, 4.0]
+    with pytest.raises(N.OlapError, match="not representable"):
+        s.setValue(1, 16777217.0)
+    with pytest.raises(N.OlapError, match="int32 store"):
+        G(2, "int32", 0).setValues([0, 1], [5.0, -33554433.0])
+    f = G(2, "float64", 0)  # float64 stores round by declared contract
+    f.data = [0.1, 16777217.0]
+    assert f.data == [float(np.float32(0.1)), 16777216.0]
