@@ -371,9 +371,14 @@ inline bool tma_side(const std::vector<PairAxis>& axes, bool input_side, int run
 
 inline TmaPlan transpose_tma_plan(const std::vector<GDim>& dims) {
     TmaPlan plan;
-    static const int knob = [] { const char* e = getenv("OLAP_TRANSPOSE_TMA"); return e ? atoi(e) : 0; }();
-    static const int64_t want_in = [] { const char* e = getenv("OLAP_TMA_IN"); return e ? (int64_t)atoi(e) : (int64_t)0; }();
-    static const int64_t want_out = [] { const char* e = getenv("OLAP_TMA_OUT"); return e ? (int64_t)atoi(e) : (int64_t)0; }();
+    // Opt-in (OLAP_TRANSPOSE_TMA=1): measured SLOWER than the pair kernel on the 6-D reversal of config 3
+    // (1.88 - 2.37 ms against 1.77 ms without status plane, 3.1 - 3.8 ms against 2.36 ms with it) — the time per
+    // tile is set by the SM (TMA unit on 400-byte box rows + the shared-memory transposition), not by load
+    // latency: halving the CTAs doubles the time, deeper rings do not help (profiles/README.md).  The knobs
+    // are read at every call so that a test can switch the path on.
+    auto env_int = [](const char* name) { const char* e = getenv(name); return e ? atoi(e) : 0; };
+    const int knob = env_int("OLAP_TRANSPOSE_TMA");
+    const int64_t want_in = env_int("OLAP_TMA_IN"), want_out = env_int("OLAP_TMA_OUT");
     if (!knob) return plan;
     plan.pair = transpose_pair_plan_for(dims, want_in, want_out);
     if (!plan.pair.geometry) return plan;
@@ -398,8 +403,7 @@ inline TmaPlan transpose_tma_plan(const std::vector<GDim>& dims) {
     const size_t tab_bytes = (((size_t)g.A + g.B) * 4 + 127) & ~(size_t)127;
     const size_t fixed = st_bytes + tab_bytes + 2 * kTmaMaxStages * 8 + 128;
     const size_t budget = 227 * 1024;
-    static const int nst_knob = [] { const char* e = getenv("OLAP_TMA_STAGES"); return e ? atoi(e) : 0; }();
-    static const int ns_knob = [] { const char* e = getenv("OLAP_TMA_STORE_STAGES"); return e ? atoi(e) : 0; }();
+    const int nst_knob = env_int("OLAP_TMA_STAGES"), ns_knob = env_int("OLAP_TMA_STORE_STAGES");
     const size_t stages = (budget - fixed) / p.stage_stride;
     if (stages < 2) return plan;
     p.ns = stages >= 4 ? 2 : 1;
