@@ -93,6 +93,10 @@ int olap_set_stream(void* cuda_stream);
 /* 1: calls return without draining the stream (caller uses olap_sync). */
 int olap_set_async(int enabled);
 int olap_sync(void);
+/* 1: every store created from now on (results of transforms included) is shareable with the other
+ * processes of the box (OLAP_CREATE_SHAREABLE) — what a process holding one shard of a sharded cube
+ * wants: any of its stores may be the source of a peer's pull. */
+int olap_set_shareable(int enabled);
 const char* olap_last_error(void);
 /* Translate a method name ("sum", "average", ...) — in-memory.js:282-296.
  * Unknown names fail with "Unsupported aggregation method: <name>". */

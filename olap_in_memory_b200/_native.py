@@ -54,6 +54,7 @@ SIGNATURES = {
     "olap_set_stream": (C.c_int, [C.c_void_p]),
     "olap_set_async": (C.c_int, [C.c_int]),
     "olap_sync": (C.c_int, []),
+    "olap_set_shareable": (C.c_int, [C.c_int]),
     "olap_last_error": (C.c_char_p, []),
     "olap_method_from_name": (C.c_int, [C.c_char_p, p_int]),
     "olap_kernel_launches": (C.c_int64, []),

@@ -101,6 +101,7 @@ constexpr size_t kGuardBytes = 256;
 // IPC handle, so the mappings the peers hold stay valid.  All library work runs on one stream, so
 // handing a freed block to a later call is stream-ordered by construction.
 static std::multimap<size_t, void*> g_share_free;
+static bool g_share_all = false;  // olap_set_shareable(1): every new store of this process is shareable
 // cudaMalloc carves small requests out of shared 2 MiB slabs, and an IPC handle names the slab:
 // every exported block gets whole slabs of its own, so that handle <-> block is one to one
 static size_t share_round(size_t bytes) { return std::max<size_t>(1, (bytes + (2u << 20) - 1) >> 21) << 21; }
@@ -138,6 +139,7 @@ int alloc_batch(int n, int64_t size, const int* types, const int* default_kinds,
     const size_t splane = with_status ? pad256((size_t)size) + guard : 0;
     const int n_status = with_status ? (shared_status ? 1 : n) : 0;
     const size_t bytes = vplane * n + splane * n_status;
+    shareable |= g_share_all;
     Arena* arena = new Arena();
     int rc = shareable ? share_alloc(&arena->base, bytes) : dev_alloc(&arena->base, bytes);
     if (rc != OLAP_OK) { delete arena; return rc; }
@@ -569,6 +571,11 @@ int olap_set_stream(void* cuda_stream) {
 
 int olap_set_async(int enabled) {
     g.async = enabled != 0;
+    return OLAP_OK;
+}
+
+int olap_set_shareable(int enabled) {
+    g_share_all = enabled != 0;
     return OLAP_OK;
 }
 

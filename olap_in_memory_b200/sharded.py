@@ -284,6 +284,12 @@ class ShardedCube:
         self._store_cls = store_cls
         self.comm = _Comm(group)
         self.rank, self.world = self.comm.rank, self.comm.world
+        if self.world > 1 and getattr(store_cls, "SHAREABLE_SHARDS", False):
+            # this process holds one shard: whatever store it creates from now on (exchange buffers,
+            # results of transforms) may become the source of a peer's pull
+            from . import _native as N
+
+            N.check(N.lib().olap_set_shareable(1))
         self.rows_total = _prod(d.numItems for d in self.dimensions[: self.prefix])
         self.inner_lens = [d.numItems for d in self.dimensions[self.prefix:]]
         self.inner = _prod(self.inner_lens)
@@ -1062,6 +1068,8 @@ class ShardedCube:
         return self._call("reorder_lowered", stores, old_len, new_to_old)
 
     def _empty_like(self, store, size):
+        if getattr(self._store_cls, "SHAREABLE_SHARDS", False):  # a later rollup of the sharded axis may pull from it
+            return self._store_cls(size, store._type, store._defaultValue, shareable=True)
         return self._store_cls(size, store._type, store._defaultValue)
 
 
