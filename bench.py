@@ -381,8 +381,10 @@ def run_ours(args, rank, world, local_rank):
     cells_per_step = measures * n_in
     value = world * cells_per_step / (ms_value * 1e-3)
     e2e_value = world * cells_per_step / (ms_e2e * 1e-3)
-    bytes_per_cell = 5  # float32 cell + status byte, per measure
-    algo_bytes = bytes_per_cell * measures * (n_in + n_out)
+    # float32 cell + status byte per measure; the status plane of a store filled by setData follows from its
+    # values (olap_store_status_derived), so the rollup never reads it: 4 bytes per input cell, 5 per output cell
+    derived = all(cube.storedMeasures[name].status_derived for name in names)
+    algo_bytes = measures * ((4 if derived else 5) * n_in + 5 * n_out)
     achieved = algo_bytes / (up_ms * 1e-3) / 1e9
     peak, peak_src = FALLBACK_HBM_GBS, "fallback"
     try:
@@ -411,6 +413,9 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches), "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": path, "kernel_ms": up_ms, "algorithmic_bytes": algo_bytes,
+                         "bytes_per_cell": {"input": 4 if derived else 5, "output": 5,
+                                            "why": "input status planes are derived from the values (set by setData) and not read" if derived
+                                                   else "value + status byte"},
                          "peak_source": peak_src},
             "cpu_baseline": cpu,
         }
@@ -547,10 +552,9 @@ def run_sharded(args, rank, world, local_rank):
         for name, rule in zip(names, SHARDED_METHODS):
             cube.createStoredMeasure(name, {d.id: rule for d in dims}, "float32", 0)
             interop.values_tensor(cube.storedMeasures[name]).uniform_(1.0, 1000.0)
-            st = interop.status_tensor(cube.storedMeasures[name])
-            if st is not None:
-                st.fill_(2)
     torch.cuda.synchronize()
+    for name in names:  # planes written through raw pointers: canonicalise values, derive the status plane from them
+        cube.storedMeasures[name].canonicalise()
     n_total, n_local, measures = cube.storeSize, cube.localSize, len(names)
     last = f"dim{ndims - 1}"
 
@@ -644,7 +648,9 @@ def run_sharded(args, rank, world, local_rank):
     full_map = view._row_map(0, np.zeros(10, dtype=np.int32), [1] + [10] * (deep - 1), all_rows=True)
     direct_rows, partial_rows, _, _, _ = _exchange_costs(full_map, view.row_bounds, out_bounds)
     planes = measures + sum(1 for m in SHARDED_METHODS if m == "average")  # `average` partials travel as (sum, count)
-    nvlink_in = float(direct_rows * 5 * measures * view.inner if exchange == "pull" else partial_rows * 5 * planes * view.inner)
+    pull_derived = bool(getattr(view, "last_pull_derived", False))  # status planes derived from the values: not read over NVLink
+    cell_bytes = 4 if (exchange == "pull" and pull_derived) else 5
+    nvlink_in = float(direct_rows * cell_bytes * measures * view.inner if exchange == "pull" else partial_rows * 5 * planes * view.inner)
     pulled = path_outer == "drillup/pull-peers" or exchange == "pull2"
 
     # ---- e2e: host buffers -> sharded cube -> both rollups -> host
@@ -713,7 +719,7 @@ def run_sharded(args, rank, world, local_rank):
                                  "hbm_GBs_per_gpu": inner_bytes / (k_inner_ms * 1e-3) / 1e9,
                                  "hbm_frac": inner_bytes / (k_inner_ms * 1e-3) / 1e9 / peak, "hbm_peak": peak, "peak_source": peak_src},
                 "sharded_rollup": {"op": "drillUp dim0->all (sharded dimension)", "ms": ms_outer, "kernel_ms": k_outer_ms, "kernel": path_outer,
-                                   "nvlink_bytes_in_per_gpu": nvlink_in, "nvlink_GBs_per_gpu": nv_gbs, "nvlink_frac_of_770": nv_gbs / NVLINK_GBS,
+                                   "nvlink_bytes_in_per_gpu": nvlink_in, "bytes_per_cell_over_nvlink": cell_bytes, "nvlink_GBs_per_gpu": nv_gbs, "nvlink_frac_of_770": nv_gbs / NVLINK_GBS,
                                    "bound_ms": nvlink_in / (NVLINK_GBS * 1e9) * 1e3},
                 "parity_guard": guard,
             },

@@ -98,6 +98,15 @@ def main():
                 lambda: GpuStore.drillUp_lowered([s], [3652, I], [120, I], [month, ident(I)], [method]),
                 B * (3652 + 120) * I, 3652 * I)
             del s
+    # the same rollup of a store whose status plane follows from its values (what setData leaves behind): the
+    # plane is not read, 4 bytes per input cell + 5 per output cell
+    for method in ("sum", "average", "highest"):
+        s = store(3652 * I, 0.0)
+        s.canonicalise()
+        run(f"drillup/derived-status day->month {method} zero [1,3652,{I}]",
+            lambda: GpuStore.drillUp_lowered([s], [3652, I], [120, I], [month, ident(I)], [method]),
+            (4 * 3652 + B * 120) * I, 3652 * I)
+        del s
     s = store(3652 * I, 0.0, 0.25)
     run(f"drillup/time-outer day->month sum zero fill=0.25 [1,3652,{I}]",
         lambda: GpuStore.drillUp_lowered([s], [3652, I], [120, I], [month, ident(I)], ["sum"]), B * (3652 + 120) * I, 3652 * I)

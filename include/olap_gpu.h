@@ -164,14 +164,17 @@ int olap_drill_up_rows(olap_store* const* src, int n, const int* methods, int64_
  * child_row[c] of rank child_rank[c], whose store k starts at base_values[k * n_ranks + rank] (an
  * address valid in THIS process: local, or peer-mapped) and holds rank_rows[rank] rows.  `like`
  * gives type / default / status layout of the n results.  One kernel; cells cross NVLink once;
- * bit-equal to the unsharded olap_drill_up for every method. */
+ * bit-equal to the unsharded olap_drill_up for every method.  derive_status != 0: the status planes of
+ * ALL source stores on ALL ranks are derived (olap_store_status_derived): they are not read (base_status
+ * may be NULL), the children's status bytes are recomputed from their values — 4 instead of 5 bytes per
+ * cell over NVLink. */
 int olap_store_ipc_export(const olap_store* s, unsigned char* handle64, int64_t* values_offset, int64_t* status_offset);
 int olap_peer_map(const unsigned char* handle64, void** ptr);
 int olap_peer_unmap_all(void);
 int olap_drill_up_pull(olap_store* const* like, int n, const int* methods, int64_t out_rows, int64_t inner,
                        const int32_t* row_start, const int32_t* child_rank, const int64_t* child_row, int n_ranks,
                        const int64_t* rank_rows, const void* const* base_values, const void* const* base_status,
-                       olap_store** out);
+                       int derive_status, olap_store** out);
 /* dst's status plane := src's (same size; a no-op when either store has none).  Finishes the
  * `average` of a sharded rollup: the quotient sum / count keeps the merged flags of the sums. */
 int olap_store_copy_status(olap_store* dst, const olap_store* src);
@@ -180,9 +183,21 @@ int64_t olap_store_byte_length(const olap_store* s); /* `.byteLength` in-memory.
 int olap_store_type(const olap_store* s);
 int olap_store_default_kind(const olap_store* s);
 int olap_store_has_status(const olap_store* s);
-/* raw device pointers (for NCCL / torch interop on the host side) */
-void* olap_store_values_ptr(const olap_store* s);
-void* olap_store_status_ptr(const olap_store* s);
+/* Raw device pointers (for NCCL / torch interop on the host side).  The _ptr forms give MUTABLE access and
+ * make the library forget that the status plane follows from the values (see olap_store_status_derived);
+ * the _cptr forms are for reading only.  olap_store_canonicalise re-derives the status plane from the
+ * values (and canonicalises them: -0 -> +0 under a zero default, any NaN -> the canonical NaN) after the
+ * planes were written through raw pointers. */
+void* olap_store_values_ptr(olap_store* s);
+void* olap_store_status_ptr(olap_store* s);
+const void* olap_store_values_cptr(const olap_store* s);
+const void* olap_store_status_cptr(const olap_store* s);
+int olap_store_canonicalise(olap_store* s);
+/* 1 when every status byte of the store equals  set ? OLAP_STATUS_SET : OLAP_STATUS_UNSET  by construction
+ * (after create / upload / fill / sparse import / eval, and through dice, reorder, clone; not after
+ * drillUp, drillDown, load from a store that is not, for planes shared by several stores, wrapped memory
+ * or once a mutable raw pointer was handed out).  drillUp of such a store never reads its status plane. */
+int olap_store_status_derived(const olap_store* s);
 
 /* ---- data boundary -------------------------------------------------------- */
 /* `set data` in-memory.js:39-46.  n != size fails with

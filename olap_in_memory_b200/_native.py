@@ -78,7 +78,7 @@ SIGNATURES = {
     "olap_peer_map": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "olap_peer_unmap_all": (C.c_int, []),
     "olap_drill_up_pull": (C.c_int, [pp_store, C.c_int, p_int, C.c_int64, C.c_int64, p_i32, p_i32, p_i64, C.c_int, p_i64,
-                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), pp_store]),
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, pp_store]),
     "olap_store_copy_status": (C.c_int, [p_store, p_store]),
     "olap_store_size": (C.c_int64, [p_store]),
     "olap_store_byte_length": (C.c_int64, [p_store]),
@@ -87,6 +87,10 @@ SIGNATURES = {
     "olap_store_has_status": (C.c_int, [p_store]),
     "olap_store_values_ptr": (C.c_void_p, [p_store]),
     "olap_store_status_ptr": (C.c_void_p, [p_store]),
+    "olap_store_values_cptr": (C.c_void_p, [p_store]),
+    "olap_store_status_cptr": (C.c_void_p, [p_store]),
+    "olap_store_canonicalise": (C.c_int, [p_store]),
+    "olap_store_status_derived": (C.c_int, [p_store]),
     "olap_store_upload_f32": (C.c_int, [p_store, C.c_void_p, C.c_int64]),
     "olap_store_upload_f64": (C.c_int, [p_store, C.c_void_p, C.c_int64]),
     "olap_store_download_f32": (C.c_int, [p_store, C.c_void_p, C.c_int64]),

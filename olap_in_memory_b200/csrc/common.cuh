@@ -86,6 +86,13 @@ struct olap_store {
     float* values = nullptr;
     uint8_t* status = nullptr;  // optional plane (may be shared with sibling stores)
     olap::Arena* arena = nullptr;
+    // The status plane says nothing the values do not: every cell holds  set ? SET : UNSET.  True after
+    // create / upload / fill / sparse import / eval and through dice, reorder and clone; false after
+    // drillUp (OR-merged flags), drillDown (INTERPOLATED), for planes shared by several stores, wrapped
+    // memory, and as soon as a raw plane pointer is handed out.  Kernels that load the values anyway
+    // (drillUp) then never read the plane: 4 instead of 5 bytes per input cell.
+    bool derived = false;
+    bool shared_plane = false;
 };
 
 namespace olap {

@@ -27,7 +27,14 @@ struct UpMeasure {
     uint8_t* st_out;       // nullable
     int method;
     int nan_default;
+    // st_in == nullptr but st_out != nullptr: the source's status plane holds nothing its values do not
+    // say (status == set ? SET : UNSET in every cell, olap_store::derived): the kernel derives the
+    // children's status bytes from the values it loads anyway and never reads the plane
+    int derive = 0;
 };
+
+// status handling of a kernel body: no plane, load the plane, derive it from the values
+enum { ST_NONE = 0, ST_LOAD = 1, ST_DERIVE = 2 };
 
 // ---- per-lane accumulator -------------------------------------------------
 // `has` mirrors "newStore._dataMap.has(newIdx)" (in-memory.js:311): after every
@@ -333,21 +340,32 @@ struct Cells {
     uint32_t st;
 };
 
-template <int VEC, bool STATUS>
+// SET / UNSET bytes of VEC cells from their values (the status of a store whose plane is `derived`)
+template <int VEC, bool NANDEF>
+__device__ __forceinline__ uint32_t derived_status(const float (&v)[VEC]) {
+    uint32_t st = 0;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e)
+        st |= (present_f(v[e], NANDEF) ? (uint32_t)OLAP_STATUS_SET : (uint32_t)OLAP_STATUS_UNSET) << (8 * e);
+    return st;
+}
+
+template <int VEC, int STATUS, bool NANDEF = false>
 __device__ __forceinline__ Cells<VEC> load_cells(const float* src, const uint8_t* st_src, int64_t off) {
     Cells<VEC> c;
     if (VEC == 4) {
         const float4 t = ld_stream4(src + off);
         c.v[0] = t.x; c.v[1 % VEC] = t.y; c.v[2 % VEC] = t.z; c.v[3 % VEC] = t.w;
-        c.st = STATUS ? ld_stream_u32(st_src + off) : 0u;
+        c.st = STATUS == ST_LOAD ? ld_stream_u32(st_src + off) : 0u;
     } else if (VEC == 2) {
         const float2 t = ld_stream2(src + off);
         c.v[0] = t.x; c.v[1 % VEC] = t.y;
-        c.st = STATUS ? ld_stream_u16(st_src + off) : 0u;
+        c.st = STATUS == ST_LOAD ? ld_stream_u16(st_src + off) : 0u;
     } else {
         c.v[0] = ld_stream1(src + off);
-        c.st = STATUS ? (uint32_t)st_src[off] : 0u;
+        c.st = STATUS == ST_LOAD ? (uint32_t)st_src[off] : 0u;
     }
+    if (STATUS == ST_DERIVE) c.st = derived_status<VEC, NANDEF>(c.v);
     return c;
 }
 
@@ -369,13 +387,13 @@ __device__ __forceinline__ uint32_t unset_status() {  // OLAP_STATUS_UNSET in ea
     return VEC == 4 ? 0x01010101u : (VEC == 2 ? 0x0101u : 0x01u);
 }
 
-template <int METHOD, bool NANDEF, int VEC, bool RANGE, bool STATUS, int U>
+template <int METHOD, bool NANDEF, int VEC, bool RANGE, int STATUS, int U>
 __device__ __forceinline__ void up_mid_body(const UpMidParams& p, const UpMeasure& m, int64_t o, uint32_t pi,
                                             uint32_t iv) {
     const int32_t k0 = p.pstart[pi], k1 = p.pstart[pi + 1];
     const int64_t inner = p.i_base + (int64_t)iv * VEC;
     const float* src = m.in + o * p.in_row + inner;
-    const uint8_t* st_src = STATUS ? m.st_in + o * p.in_row + inner : nullptr;
+    const uint8_t* st_src = STATUS == ST_LOAD ? m.st_in + o * p.in_row + inner : nullptr;
     const int64_t stride = p.I_total;
 
     Lane<METHOD, NANDEF> lane[VEC];
@@ -388,7 +406,7 @@ __device__ __forceinline__ void up_mid_body(const UpMidParams& p, const UpMeasur
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t child = RANGE ? (int64_t)(k + u) : (int64_t)p.children[k + u];
-            c[u] = load_cells<VEC, STATUS>(src, st_src, child * stride);
+            c[u] = load_cells<VEC, STATUS, NANDEF>(src, st_src, child * stride);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -399,7 +417,7 @@ __device__ __forceinline__ void up_mid_body(const UpMidParams& p, const UpMeasur
     }
     for (; k < k1; ++k) {
         const int64_t child = RANGE ? (int64_t)k : (int64_t)p.children[k];
-        const Cells<VEC> c = load_cells<VEC, STATUS>(src, st_src, child * stride);
+        const Cells<VEC> c = load_cells<VEC, STATUS, NANDEF>(src, st_src, child * stride);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) lane[e].step(c.v[e]);
         st |= c.st;
@@ -414,7 +432,7 @@ __device__ __forceinline__ void up_mid_body(const UpMidParams& p, const UpMeasur
     if (STATUS) store_status<VEC>(m.st_out + out_off, k0 == k1 ? unset_status<VEC>() : st);  // no child: not set
 }
 
-template <bool NANDEF, int VEC, bool RANGE, bool STATUS, int U>
+template <bool NANDEF, int VEC, bool RANGE, int STATUS, int U>
 __device__ __forceinline__ void up_mid_dispatch(const UpMidParams& p, const UpMeasure& m, int64_t o, uint32_t pi,
                                                 uint32_t iv) {
     switch (m.method) {
@@ -450,15 +468,17 @@ __global__ void __launch_bounds__(256, U == 8 ? (VEC == 4 ? OLAP_MID_MINB : 4) :
     if (p.row_out) {  // rebase so that  out + pi * I_total + inner  lands in the row's own buffer
         const size_t slot = (size_t)blockIdx.y * p.P + pi;
         m.out = p.row_out[slot] - (int64_t)pi * p.I_total;
-        if (m.st_in) m.st_out = p.row_st[slot] - (int64_t)pi * p.I_total;
+        if (m.st_in || m.derive) m.st_out = p.row_st[slot] - (int64_t)pi * p.I_total;
     }
-    const bool status = m.st_in != nullptr;
+    const int status = m.st_in ? ST_LOAD : (m.derive ? ST_DERIVE : ST_NONE);
     if (m.nan_default) {
-        if (status) up_mid_dispatch<true, VEC, RANGE, true, U>(p, m, o, pi, iv);
-        else up_mid_dispatch<true, VEC, RANGE, false, U>(p, m, o, pi, iv);
+        if (status == ST_LOAD) up_mid_dispatch<true, VEC, RANGE, ST_LOAD, U>(p, m, o, pi, iv);
+        else if (status == ST_DERIVE) up_mid_dispatch<true, VEC, RANGE, ST_DERIVE, U>(p, m, o, pi, iv);
+        else up_mid_dispatch<true, VEC, RANGE, ST_NONE, U>(p, m, o, pi, iv);
     } else {
-        if (status) up_mid_dispatch<false, VEC, RANGE, true, U>(p, m, o, pi, iv);
-        else up_mid_dispatch<false, VEC, RANGE, false, U>(p, m, o, pi, iv);
+        if (status == ST_LOAD) up_mid_dispatch<false, VEC, RANGE, ST_LOAD, U>(p, m, o, pi, iv);
+        else if (status == ST_DERIVE) up_mid_dispatch<false, VEC, RANGE, ST_DERIVE, U>(p, m, o, pi, iv);
+        else up_mid_dispatch<false, VEC, RANGE, ST_NONE, U>(p, m, o, pi, iv);
     }
 }
 
@@ -467,7 +487,7 @@ __global__ void __launch_bounds__(256, U == 8 ? (VEC == 4 ? OLAP_MID_MINB : 4) :
 // reduces the g-th contiguous chunk of the parent's children (same coalesced 128-bit loads
 // as kernel A), lane states meet in shared memory and row 0 folds them IN CHUNK ORDER, so
 // first/last stay exact and the double sums only change their association.
-template <int METHOD, bool NANDEF, int VEC, bool RANGE, bool STATUS, int U>
+template <int METHOD, bool NANDEF, int VEC, bool RANGE, int STATUS, int U>
 __device__ __forceinline__ void up_split_body(const UpMidParams& p, const UpMeasure& m, int64_t o, uint32_t pi,
                                               uint32_t iv, bool live, unsigned char* smem_raw) {
     typedef Lane<METHOD, NANDEF> L;
@@ -484,14 +504,14 @@ __device__ __forceinline__ void up_split_body(const UpMidParams& p, const UpMeas
         const int32_t per = (k1 - k0 + G - 1) / G;
         const int32_t ks = min(k1, k0 + g * per), ke = min(k1, ks + per);
         const float* src = m.in + o * p.in_row + inner;
-        const uint8_t* st_src = STATUS ? m.st_in + o * p.in_row + inner : nullptr;
+        const uint8_t* st_src = STATUS == ST_LOAD ? m.st_in + o * p.in_row + inner : nullptr;
         int32_t k = ks;
         for (; k + U <= ke; k += U) {
             Cells<VEC> c[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int64_t child = RANGE ? (int64_t)(k + u) : (int64_t)p.children[k + u];
-                c[u] = load_cells<VEC, STATUS>(src, st_src, child * p.I_total);
+                c[u] = load_cells<VEC, STATUS, NANDEF>(src, st_src, child * p.I_total);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -502,7 +522,7 @@ __device__ __forceinline__ void up_split_body(const UpMidParams& p, const UpMeas
         }
         for (; k < ke; ++k) {
             const int64_t child = RANGE ? (int64_t)k : (int64_t)p.children[k];
-            const Cells<VEC> c = load_cells<VEC, STATUS>(src, st_src, child * p.I_total);
+            const Cells<VEC> c = load_cells<VEC, STATUS, NANDEF>(src, st_src, child * p.I_total);
 #pragma unroll
             for (int e = 0; e < VEC; ++e) lane[e].step(c.v[e]);
             st |= c.st;
@@ -529,7 +549,7 @@ __device__ __forceinline__ void up_split_body(const UpMidParams& p, const UpMeas
     if (STATUS) store_status<VEC>(m.st_out + out_off, k0 == k1 ? unset_status<VEC>() : st);
 }
 
-template <bool NANDEF, int VEC, bool RANGE, bool STATUS, int U>
+template <bool NANDEF, int VEC, bool RANGE, int STATUS, int U>
 __device__ __forceinline__ void up_split_dispatch(const UpMidParams& p, const UpMeasure& m, int64_t o, uint32_t pi,
                                                   uint32_t iv, bool live, unsigned char* smem_raw) {
     switch (m.method) {
@@ -559,13 +579,15 @@ __global__ void __launch_bounds__(WIDE ? 256 : 1024, WIDE ? 3 : 1) drillup_split
     const uint32_t pi = live ? p.div_iv.div(j) : 0u;
     const uint32_t iv = live ? j - pi * p.IV : 0u;
     const UpMeasure m = p.meas ? p.meas[blockIdx.y] : p.meas_inline[blockIdx.y];
-    const bool status = m.st_in != nullptr;
+    const int status = m.st_in ? ST_LOAD : (m.derive ? ST_DERIVE : ST_NONE);
     if (m.nan_default) {
-        if (status) up_split_dispatch<true, VEC, RANGE, true, U>(p, m, o, pi, iv, live, smem_split);
-        else up_split_dispatch<true, VEC, RANGE, false, U>(p, m, o, pi, iv, live, smem_split);
+        if (status == ST_LOAD) up_split_dispatch<true, VEC, RANGE, ST_LOAD, U>(p, m, o, pi, iv, live, smem_split);
+        else if (status == ST_DERIVE) up_split_dispatch<true, VEC, RANGE, ST_DERIVE, U>(p, m, o, pi, iv, live, smem_split);
+        else up_split_dispatch<true, VEC, RANGE, ST_NONE, U>(p, m, o, pi, iv, live, smem_split);
     } else {
-        if (status) up_split_dispatch<false, VEC, RANGE, true, U>(p, m, o, pi, iv, live, smem_split);
-        else up_split_dispatch<false, VEC, RANGE, false, U>(p, m, o, pi, iv, live, smem_split);
+        if (status == ST_LOAD) up_split_dispatch<false, VEC, RANGE, ST_LOAD, U>(p, m, o, pi, iv, live, smem_split);
+        else if (status == ST_DERIVE) up_split_dispatch<false, VEC, RANGE, ST_DERIVE, U>(p, m, o, pi, iv, live, smem_split);
+        else up_split_dispatch<false, VEC, RANGE, ST_NONE, U>(p, m, o, pi, iv, live, smem_split);
     }
 }
 

@@ -23,6 +23,7 @@ struct PullMeasure {
     uint8_t* st_out;  // nullable: no status plane, or a plane another measure of the call writes
     int method;
     int nan_default;
+    int derive;       // the sources' status planes are derived (olap_store::derived): never read, recomputed from the values
 };
 
 struct UpPullParams {
@@ -63,7 +64,7 @@ __device__ __noinline__ float exact_redo_pull(const UpPullParams& p, int m, int6
     return a.result(1);
 }
 
-template <int METHOD, bool NANDEF, int VEC, bool STATUS>
+template <int METHOD, bool NANDEF, int VEC, int STATUS>
 __device__ __forceinline__ void up_pull_body(const UpPullParams& p, const PullMeasure& m, int mi, int64_t row, int64_t iv) {
     constexpr int U = 8;
     const int32_t k0 = p.row_start[row], k1 = p.row_start[row + 1];
@@ -86,11 +87,12 @@ __device__ __forceinline__ void up_pull_body(const UpPullParams& p, const PullMe
                 if (VEC == 4) {
                     const float4 t = ld_peer4(base_v[r] + off);
                     c[u].v[0] = t.x; c[u].v[1 % VEC] = t.y; c[u].v[2 % VEC] = t.z; c[u].v[3 % VEC] = t.w;
-                    if (STATUS) c[u].st = ld_peer_u32(base_s[r] + off);
+                    if (STATUS == ST_LOAD) c[u].st = ld_peer_u32(base_s[r] + off);
                 } else {
                     c[u].v[0] = *reinterpret_cast<const volatile float*>(base_v[r] + off);
-                    if (STATUS) c[u].st = *reinterpret_cast<const volatile uint8_t*>(base_s[r] + off);
+                    if (STATUS == ST_LOAD) c[u].st = *reinterpret_cast<const volatile uint8_t*>(base_s[r] + off);
                 }
+                if (STATUS == ST_DERIVE) c[u].st = derived_status<VEC, NANDEF>(c[u].v);
             }
         }
 #pragma unroll
@@ -109,7 +111,7 @@ __device__ __forceinline__ void up_pull_body(const UpPullParams& p, const PullMe
     if (STATUS) store_status<VEC>(m.st_out + out_off, k0 == k1 ? unset_status<VEC>() : st);  // no child: not set
 }
 
-template <bool NANDEF, int VEC, bool STATUS>
+template <bool NANDEF, int VEC, int STATUS>
 __device__ __forceinline__ void up_pull_dispatch(const UpPullParams& p, const PullMeasure& m, int mi, int64_t row, int64_t iv) {
     switch (m.method) {
         case OLAP_SUM: up_pull_body<OLAP_SUM, NANDEF, VEC, STATUS>(p, m, mi, row, iv); break;
@@ -132,13 +134,15 @@ __global__ void __launch_bounds__(256, 2) drillup_pull_kernel(const __grid_const
     if (row >= p.rows || iv >= p.IV) return;
     const int mi = blockIdx.z;
     const PullMeasure m = p.meas[mi];
-    const bool status = m.st_out != nullptr;
+    const int status = m.st_out ? (m.derive ? ST_DERIVE : ST_LOAD) : ST_NONE;
     if (m.nan_default) {
-        if (status) up_pull_dispatch<true, VEC, true>(p, m, mi, row, iv);
-        else up_pull_dispatch<true, VEC, false>(p, m, mi, row, iv);
+        if (status == ST_LOAD) up_pull_dispatch<true, VEC, ST_LOAD>(p, m, mi, row, iv);
+        else if (status == ST_DERIVE) up_pull_dispatch<true, VEC, ST_DERIVE>(p, m, mi, row, iv);
+        else up_pull_dispatch<true, VEC, ST_NONE>(p, m, mi, row, iv);
     } else {
-        if (status) up_pull_dispatch<false, VEC, true>(p, m, mi, row, iv);
-        else up_pull_dispatch<false, VEC, false>(p, m, mi, row, iv);
+        if (status == ST_LOAD) up_pull_dispatch<false, VEC, ST_LOAD>(p, m, mi, row, iv);
+        else if (status == ST_DERIVE) up_pull_dispatch<false, VEC, ST_DERIVE>(p, m, mi, row, iv);
+        else up_pull_dispatch<false, VEC, ST_NONE>(p, m, mi, row, iv);
     }
 }
 

@@ -156,10 +156,15 @@ int alloc_batch(int n, int64_t size, const int* types, const int* default_kinds,
         s->values = reinterpret_cast<float*>(base + vplane * k);
         s->status = with_status ? reinterpret_cast<uint8_t*>(base + vplane * n + splane * (shared_status ? 0 : k)) : nullptr;
         s->arena = arena;
+        s->shared_plane = with_status && shared_status && n > 1;
         out[k] = s;
     }
     return OLAP_OK;
 }
+
+// see olap_store::derived
+static bool is_derived(const olap_store* s) { return !s->status || (s->derived && !s->shared_plane); }
+static void set_derived(olap_store* s, bool yes) { s->derived = yes && !s->shared_plane; }
 
 // bytes of the guard (and of the alignment padding before it) that no longer hold 0xA5
 static void check_guards(const olap_store* s) {
@@ -642,6 +647,7 @@ int olap_store_create_batch(int n, int64_t size, const int* types, const int* de
         olap_store tmp = *out[k];
         tmp.status = st_out_of(out, k);
         OLAP_TRY(fill_default(&tmp));
+        set_derived(out[k], true);
     }
     return guard.done(finish_op());
 }
@@ -671,6 +677,7 @@ int olap_store_clone(const olap_store* s, olap_store** out) {
     OLAP_TRY(alloc_batch(1, s->size, &s->type, &s->default_kind, s->status != nullptr, false, out,
                          s->arena && s->arena->shareable));
     OutGuard guard(out, 1);
+    (*out)->derived = s->derived && !s->shared_plane;
     if (s->size) {
         OLAP_CUDA(cudaMemcpyAsync((*out)->values, s->values, (size_t)s->size * 4, cudaMemcpyDeviceToDevice, g.stream));
         if (s->status) OLAP_CUDA(cudaMemcpyAsync((*out)->status, s->status, (size_t)s->size, cudaMemcpyDeviceToDevice, g.stream));
@@ -682,6 +689,7 @@ int olap_store_copy_status(olap_store* dst, const olap_store* src) {
     if (!dst || !src) return fail(OLAP_E_INVALID, "olap_store_copy_status: null store");
     if (dst->size != src->size) return fail(OLAP_E_INVALID, "value length is invalid: %lld !== %lld", (long long)dst->size, (long long)src->size);
     OLAP_TRY(ensure_ctx());
+    dst->derived = false;
     if (dst->status && src->status && dst->size)
         OLAP_CUDA(cudaMemcpyAsync(dst->status, src->status, (size_t)dst->size, cudaMemcpyDeviceToDevice, g.stream));
     return finish_op();
@@ -695,8 +703,24 @@ int64_t olap_store_byte_length(const olap_store* s) {
 int olap_store_type(const olap_store* s) { return s ? s->type : -1; }
 int olap_store_default_kind(const olap_store* s) { return s ? s->default_kind : -1; }
 int olap_store_has_status(const olap_store* s) { return s && s->status ? 1 : 0; }
-void* olap_store_values_ptr(const olap_store* s) { return s ? s->values : nullptr; }
-void* olap_store_status_ptr(const olap_store* s) { return s ? s->status : nullptr; }
+// mutable access: whatever is written through these pointers, the library no longer knows that the status
+// plane follows from the values (olap_store_canonicalise re-establishes it)
+void* olap_store_values_ptr(olap_store* s) { if (s) s->derived = false; return s ? s->values : nullptr; }
+void* olap_store_status_ptr(olap_store* s) { if (s) s->derived = false; return s ? s->status : nullptr; }
+const void* olap_store_values_cptr(const olap_store* s) { return s ? s->values : nullptr; }
+const void* olap_store_status_cptr(const olap_store* s) { return s ? s->status : nullptr; }
+int olap_store_status_derived(const olap_store* s) { return s && is_derived(s) ? 1 : 0; }
+
+int olap_store_canonicalise(olap_store* s) {
+    if (!s) return fail(OLAP_E_INVALID, "olap_store_canonicalise: null store");
+    OLAP_TRY(ensure_ctx());
+    if (s->size) {
+        canon_f32_kernel<<<grid_for(ceil_div(s->size, 4), kStoreThreads), kStoreThreads, 0, g.stream>>>(s->values, s->status, s->size, s->default_kind);
+        LAUNCHED();
+    }
+    set_derived(s, true);
+    return finish_op();
+}
 
 // ---- data boundary ------------------------------------------------------------------
 static int check_len(const olap_store* s, int64_t n) {
@@ -726,6 +750,7 @@ int olap_store_upload_f32(olap_store* s, const float* host, int64_t n) {
     OLAP_CUDA(cudaMemcpyAsync(s->values, host, (size_t)n * 4, cudaMemcpyHostToDevice, g.stream));
     canon_f32_kernel<<<grid_for(ceil_div(n, 4), kStoreThreads), kStoreThreads, 0, g.stream>>>(s->values, s->status, n, s->default_kind);
     LAUNCHED();
+    set_derived(s, true);
     return finish_op();
 }
 
@@ -746,6 +771,7 @@ int olap_store_upload_f64(olap_store* s, const double* host, int64_t n) {
     OLAP_TRY(dev_free(tmp));
     // the host buffer is borrowed for the call only
     OLAP_CUDA(cudaStreamSynchronize(g.stream));
+    set_derived(s, true);
     if (first != ~0ull) return lossy_error(s, (int64_t)first - 1, host[first - 1]);
     return finish_op();
 }
@@ -820,6 +846,7 @@ int olap_store_fill(olap_store* s, double value) {
     fill_kernel<<<grid_for(s->size, kStoreThreads), kStoreThreads, 0, g.stream>>>(
         s->values, s->status, s->size, v, set ? OLAP_STATUS_SET : OLAP_STATUS_UNSET);
     LAUNCHED();
+    set_derived(s, true);
     return finish_op();
 }
 
@@ -927,6 +954,7 @@ int olap_store_import_sparse(olap_store* s, const int64_t* keys, const float* va
     if (!s || (count && (!keys || !values))) return fail(OLAP_E_INVALID, "olap_store_import_sparse: null argument");
     OLAP_TRY(ensure_ctx());
     OLAP_TRY(fill_default(s));
+    set_derived(s, true);
     if (count) {
         TablePack t;
         const size_t ok = t.add(keys, (size_t)count * 8);
@@ -1039,7 +1067,25 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
                 if (scratch) OLAP_TRY(dev_free(scratch));
             } else {
                 path = (I % 4 == 0) ? "drillup/mid-vec4" : (I % 2 == 0 ? "drillup/mid-vec2" : "drillup/mid-scalar");
-                OLAP_TRY(launch_up_mid(d_meas, meas.data(), n, csr, d_ps, d_ch, O, C, P, I));
+                // sources whose status plane follows from their values: the kernel recomputes the bytes from the
+                // cells it loads anyway and never reads the plane (4 instead of 5 bytes per input cell)
+                static const int derive_knob = [] { const char* e = getenv("OLAP_DERIVE_STATUS"); return e ? atoi(e) : 1; }();
+                bool changed_desc = false;
+                for (int k = 0; k < n; ++k)
+                    if (derive_knob && meas[k].st_in && src[k]->derived && !src[k]->shared_plane) {
+                        meas[k].st_in = nullptr;
+                        meas[k].derive = 1;
+                        changed_desc = true;
+                    }
+                const UpMeasure* d_meas_mid = d_meas;
+                TablePack t2;
+                if (changed_desc && !inline_meas) {  // descriptors travel through a device table: upload the edited ones
+                    const size_t o2 = t2.add(meas.data(), sizeof(UpMeasure) * n);
+                    OLAP_TRY(t2.upload());
+                    d_meas_mid = t2.ptr<UpMeasure>(o2);
+                }
+                OLAP_TRY(launch_up_mid(d_meas_mid, meas.data(), n, csr, d_ps, d_ch, O, C, P, I));
+                OLAP_TRY(t2.release());
             }
         } else {
             path = "drillup/generic";
@@ -1291,6 +1337,7 @@ int olap_dice(olap_store* const* src, int n, int ndim, const int64_t* old_len, c
     OutGuard guard(out, n);
     begin_op();
     const char* path = "dice/empty";
+    for (int k = 0; k < n; ++k) set_derived(out[k], is_derived(src[k]));  // a gather copies value and status together
     if (new_size) {
         auto meas = gather_measures(src, out, n);
         OLAP_TRY(run_gather(G_COPY, src, n, dims, new_size, old_size, meas, nullptr, &path));
@@ -1325,6 +1372,7 @@ int olap_reorder(olap_store* const* src, int n, int ndim, const int64_t* old_len
     OutGuard guard(out, n);
     begin_op();
     const char* path = "reorder/empty";
+    for (int k = 0; k < n; ++k) set_derived(out[k], is_derived(src[k]));
     if (size) {
         auto meas = gather_measures(src, out, n);
         TmaPlan tm = transpose_tma_plan(dims);
@@ -1525,6 +1573,7 @@ int olap_load(olap_store* dst, const olap_store* src, int ndim, const int64_t* m
     if (my_size != dst->size || his_size != src->size) return fail(OLAP_E_INVALID, "olap_load: dimensions do not match the stores");
     OLAP_TRY(ensure_ctx());
     begin_op();
+    dst->derived = dst->derived && is_derived(src);  // set cells take the other store's flags (README.md:704)
     bool fast = false;
     if (his_size && my_size && ndim >= 1 && his_size < ((int64_t)1 << 31)) {
         // innermost axis: his item j -> my item m0 + j ?  then runs stay contiguous
@@ -1769,7 +1818,7 @@ int olap_peer_unmap_all(void) {
 int olap_drill_up_pull(olap_store* const* like, int n, const int* methods, int64_t out_rows, int64_t inner,
                        const int32_t* row_start, const int32_t* child_rank, const int64_t* child_row, int n_ranks,
                        const int64_t* rank_rows, const void* const* base_values, const void* const* base_status,
-                       olap_store** out) {
+                       int derive_status, olap_store** out) {
     int64_t like_size = 0;
     OLAP_TRY(check_batch(like, n, "olap_drill_up_pull", &like_size));
     if (!methods || !row_start || !rank_rows || !base_values || !out) return fail(OLAP_E_INVALID, "olap_drill_up_pull: null argument");
@@ -1794,7 +1843,7 @@ int olap_drill_up_pull(olap_store* const* like, int n, const int* methods, int64
     }
     bool any_status = false;
     for (int k = 0; k < n; ++k) any_status |= like[k]->status != nullptr;
-    if (any_status && !base_status) return fail(OLAP_E_INVALID, "olap_drill_up_pull: stores carry a status plane but no status bases were given");
+    if (any_status && !base_status && !derive_status) return fail(OLAP_E_INVALID, "olap_drill_up_pull: stores carry a status plane but no status bases were given");
     for (int k = 0; k < n; ++k)
         for (int r = 0; r < n_ranks; ++r) {
             // a rank without rows is never dereferenced; every other base must be a real address
@@ -1810,8 +1859,9 @@ int olap_drill_up_pull(olap_store* const* like, int n, const int* methods, int64
         for (int k = 0; k < n; ++k) {
             // a status plane shared by several measures is read and written by the first of them only
             const bool own_status = out[k]->status && like[k]->status && st_out_of(out, k);
-            meas[k] = PullMeasure{out[k]->values, own_status ? out[k]->status : nullptr, methods[k], like[k]->default_kind};
-            if (own_status)
+            meas[k] = PullMeasure{out[k]->values, own_status ? out[k]->status : nullptr, methods[k], like[k]->default_kind,
+                                  derive_status ? 1 : 0};
+            if (own_status && !derive_status)
                 for (int r = 0; r < n_ranks; ++r) bs[(size_t)k * n_ranks + r] = base_status[(size_t)k * n_ranks + r];
         }
         TablePack t;
@@ -1884,6 +1934,7 @@ int olap_eval(const char* program, olap_store* const* inputs, int n_inputs, cons
                              inputs[0]->arena && inputs[0]->arena->shareable));
         out32 = result->values;
         st_out = result->status;
+        set_derived(result, true);  // the formula kernel writes SET / UNSET from the result it stores
     } else if (size) {
         void* tmp;
         OLAP_TRY(dev_alloc(&tmp, (size_t)size * 8));

@@ -617,8 +617,8 @@ class ShardedCube:
         for r, exported in enumerate(everyone):
             for k, (handle, v_off, s_off) in enumerate(exported):
                 if r == self.rank:
-                    base_v[k][r] = lib.olap_store_values_ptr(stores[k]._h)
-                    base_s[k][r] = lib.olap_store_status_ptr(stores[k]._h) or 0
+                    base_v[k][r] = lib.olap_store_values_cptr(stores[k]._h)
+                    base_s[k][r] = lib.olap_store_status_cptr(stores[k]._h) or 0
                     continue
                 if handle not in opened:
                     p = C.c_void_p()
@@ -672,23 +672,34 @@ class ShardedCube:
         row_start, child_rank, child_row = tables
         W, K = self.world, len(stores)
         lib = N.lib()
-        with_status = bool(lib.olap_store_status_ptr(stores[0]._h))
+        with_status = bool(lib.olap_store_has_status(stores[0]._h))
         flat_v = (C.c_void_p * (K * W))(*[base_v[k][r] or None for k in range(K) for r in range(W)])
         flat_s = (C.c_void_p * (K * W))(*[base_s[k][r] or None for k in range(K) for r in range(W)]) if with_status else None
         rank_rows = N.i64_array(rank_rows)
         results = (C.c_void_p * K)()
         # every rank's stores are complete (their producing kernels have finished) before anyone reads them
         N.check(lib.olap_sync())
-        self.comm.dist.barrier(group=self.comm.group)
+        # status planes that follow from the values are not read (4 instead of 5 bytes per cell over NVLink):
+        # only if that holds for every store of every rank; the all-reduce doubles as the barrier
+        derive = self._all_ranks(with_status and all(s.status_derived for s in stores))
         N.check(lib.olap_drill_up_pull(N.store_array([s._h for s in stores]), K, N.int_array([_method_code(m) for m in methods]),
                                        out_rows, self.inner, row_start.ctypes.data_as(N.p_i32),
                                        child_rank.ctypes.data_as(N.p_i32), child_row.ctypes.data_as(N.p_i64), W, rank_rows,
-                                       flat_v, flat_s, results))
+                                       flat_v, flat_s, int(derive), results))
+        self.last_pull_derived = bool(derive)
         # nobody frees or overwrites a store while a peer may still be reading it
         N.check(lib.olap_sync())
         self.last_pull_ms = lib.olap_last_op_ms()  # device time of the pull kernel on this rank (profiling aid)
         self.comm.dist.barrier(group=self.comm.group)
         return results
+
+    def _all_ranks(self, flag):
+        """Logical AND of a local flag over the ranks (a MIN all-reduce on the device: also a barrier)."""
+        import torch
+
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device="cuda")
+        self.comm.dist.all_reduce(t, op=self.comm.dist.ReduceOp.MIN, group=self.comm.group)
+        return bool(t.item())
 
     def _drill_up_pull2(self, out, full_map, touched, ids, methods, out_bounds):
         """Two-phase pull: (1) shard-local partial rollup of my rows into ONE compact partial row per
@@ -763,7 +774,7 @@ class ShardedCube:
         W, me, inner = self.world, self.rank, self.inner
         K = len(stores)
         rows_of = [out_bounds[r + 1] - out_bounds[r] for r in range(W)]
-        with_status = bool(N.lib().olap_store_status_ptr(stores[0]._h))
+        with_status = bool(N.lib().olap_store_has_status(stores[0]._h))
         r_max = max(rows_of)
         pad = lambda b: (b + 255) // 256 * 256  # every plane starts on a 256-byte boundary, like a store's own planes
         plane_v, plane_s = pad(W * r_max * inner * 4), pad(W * r_max * inner)

@@ -174,6 +174,17 @@ class GpuStore:
             store.import_sparse(keys, values)
         return store
 
+    @property
+    def status_derived(self):
+        """True when the status plane holds nothing the values do not say (include/olap_gpu.h,
+        olap_store_status_derived): rollups of such a store never read it."""
+        return bool(N.lib().olap_store_status_derived(self._h))
+
+    def canonicalise(self):
+        """After the planes were written through raw pointers (interop): canonicalise the values and
+        re-derive the status plane from them."""
+        N.check(N.lib().olap_store_canonicalise(self._h))
+
     def ipc_export(self):
         """(64-byte CUDA IPC handle, values offset, status offset or -1) of a shareable store."""
         handle = C.create_string_buffer(64)

@@ -435,3 +435,44 @@ def test_integer_stores_refuse_values_their_float32_cell_would_change():
     f = G(2, "float64", 0)  # float64 stores round by declared contract
     f.data = [0.1, 16777217.0]
     assert f.data == [float(np.float32(0.1)), 16777216.0]
+
+
+def test_derived_status_planes_are_tracked_and_not_needed():
+    """A store whose status plane follows from its values (after set data / fill / sparse import / eval, through
+    dice, reorder, clone) is rolled up WITHOUT reading that plane (4 instead of 5 bytes per input cell); the
+    flag must be lost exactly where the plane starts to carry information of its own."""
+    from olap_in_memory_b200 import _native as N
+    from olap_in_memory_b200 import interop
+
+    G = _gpu()
+    lib = N.lib()
+    rng = np.random.default_rng(3)
+    C_, I = 12, 64
+    data = rng.integers(1, 100, C_ * I).astype(np.float32)
+    data[rng.random(C_ * I) < 0.4] = 0.0
+    s = G(C_ * I, "float32", 0)
+    assert s.status_derived  # freshly created: every cell UNSET and default
+    s.set_data_f32(data)
+    assert s.status_derived
+    gmap = (np.arange(C_) // 4).astype(np.int32)
+    up = G.drillUp_lowered([s], [C_, I], [3, I], [gmap, None], ["sum"])[0]
+    assert lib.olap_last_op_path() == b"drillup/mid-vec4" and not up.status_derived  # OR-merged flags (0x3 = incomplete)
+    # the same rollup with the plane READ (a mutable raw pointer was handed out: the library forgets)
+    t = G(C_ * I, "float32", 0)
+    t.set_data_f32(data)
+    interop.status_tensor(t)
+    assert not t.status_derived
+    up2 = G.drillUp_lowered([t], [C_, I], [3, I], [gmap, None], ["sum"])[0]
+    assert np.array_equal(up.data_f32(), up2.data_f32()) and up.status == up2.status
+    assert set(up.status) <= {1, 2, 3} and 3 in up.status
+    t.canonicalise()
+    assert t.status_derived
+    # through dice / reorder / clone the flag survives; through drillDown it does not
+    d = G.dice_lowered([s], [C_, I], [np.arange(0, C_, 2, dtype=np.int32), np.arange(I, dtype=np.int32)])[0]
+    r = G.reorder_lowered([s], [C_, I], [1, 0])[0]
+    assert d.status_derived and r.status_derived and s.clone().status_derived
+    down = G.drillDown_lowered([up], [3, I], [C_, I], [gmap, np.arange(I, dtype=np.int32)], ["sum"])[0]
+    assert not down.status_derived
+    # an interpolated cube rolled up again keeps its 0x4 flags: the plane IS read there
+    again = G.drillUp_lowered([down], [C_, I], [3, I], [gmap, None], ["sum"])[0]
+    assert any(b & 4 for b in again.status)

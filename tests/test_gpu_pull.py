@@ -29,7 +29,7 @@ def _data(rng, n, default, kind):
     return v
 
 
-def _pull_all_ranks(lib, N, GpuStore, full, rows_in, inner, in_bounds, out_bounds, full_map, methods, default, with_status):
+def _pull_all_ranks(lib, N, GpuStore, full, rows_in, inner, in_bounds, out_bounds, full_map, methods, default, with_status, derive=False):
     from olap_in_memory_b200.sharded import _pull_tables
     from olap_in_memory_b200.store import _method_code
 
@@ -43,8 +43,10 @@ def _pull_all_ranks(lib, N, GpuStore, full, rows_in, inner, in_bounds, out_bound
             s.set_data_f32(full[k][lo:hi])
             per.append(s)
         shards.append(per)
-    base_v = (C.c_void_p * (K * W))(*[lib.olap_store_values_ptr(shards[r][k]._h) for k in range(K) for r in range(W)])
-    base_s = (C.c_void_p * (K * W))(*[lib.olap_store_status_ptr(shards[r][k]._h) for k in range(K) for r in range(W)]) if with_status else None
+    base_v = (C.c_void_p * (K * W))(*[lib.olap_store_values_cptr(shards[r][k]._h) for k in range(K) for r in range(W)])
+    base_s = (C.c_void_p * (K * W))(*[lib.olap_store_status_cptr(shards[r][k]._h) for k in range(K) for r in range(W)]) if with_status and not derive else None
+    if derive:  # stores filled by set_data_f32: their status planes follow from the values, the kernel must not need them
+        assert all(s.status_derived for per in shards for s in per)
     rank_rows = N.i64_array([in_bounds[r + 1] - in_bounds[r] for r in range(W)])
     values, status = [[] for _ in range(K)], [[] for _ in range(K)]
     for me in range(W):
@@ -53,7 +55,7 @@ def _pull_all_ranks(lib, N, GpuStore, full, rows_in, inner, in_bounds, out_bound
         out = (C.c_void_p * K)()
         N.check(lib.olap_drill_up_pull(N.store_array([s._h for s in shards[me]]), K, N.int_array([_method_code(m) for m in methods]),
                                        j1 - j0, inner, row_start.ctypes.data_as(N.p_i32), child_rank.ctypes.data_as(N.p_i32),
-                                       child_row.ctypes.data_as(N.p_i64), W, rank_rows, base_v, base_s, out))
+                                       child_row.ctypes.data_as(N.p_i64), W, rank_rows, base_v, base_s, int(derive), out))
         assert lib.olap_last_op_path() == b"drillup/pull-peers"
         for k in range(K):
             st = GpuStore._wrap(out[k])
@@ -85,6 +87,10 @@ def test_pull_equals_the_unsharded_rollup(default, with_status, inner):
         for in_bounds, out_bounds in (([0, 9, 18, 27, 35], [0, 4, 8, 12, 15]), ([0, 0, 20, 20, 35], [0, 15, 15, 15, 15]),
                                       ([0, 35], [0, 15]), ([0, 1, 2, 3, 4, 5, 6, 35], [0, 3, 3, 6, 9, 9, 12, 15])):
             got_v, got_s = _pull_all_ranks(lib, N, GpuStore, full, rows_in, inner, in_bounds, out_bounds, full_map, METHODS, default, with_status)
+            if with_status:  # the same without ever reading a status plane (derived from the values)
+                der_v, der_s = _pull_all_ranks(lib, N, GpuStore, full, rows_in, inner, in_bounds, out_bounds, full_map, METHODS, default, True, derive=True)
+                for k in range(len(METHODS)):
+                    assert np.array_equal(der_v[k].view(np.uint32), got_v[k].view(np.uint32)) and np.array_equal(der_s[k], got_s[k])
             whole = []
             for k in range(len(METHODS)):
                 s = GpuStore(rows_in * inner, "float32", default, with_status=with_status)
@@ -119,11 +125,12 @@ def test_pull_with_a_shared_status_plane_and_argument_errors():
     row_start = np.array([0, 3, 6], dtype=np.int32)
     child_rank = np.zeros(6, dtype=np.int32)
     child_row = np.array([0, 2, 4, 1, 3, 5], dtype=np.int64)
-    base_v = (C.c_void_p * 2)(lib.olap_store_values_ptr(a._h), lib.olap_store_values_ptr(b._h))
-    base_s = (C.c_void_p * 2)(lib.olap_store_status_ptr(a._h), lib.olap_store_status_ptr(b._h))
+    base_v = (C.c_void_p * 2)(lib.olap_store_values_cptr(a._h), lib.olap_store_values_cptr(b._h))
+    base_s = (C.c_void_p * 2)(lib.olap_store_status_cptr(a._h), lib.olap_store_status_cptr(b._h))
+    assert not a.status_derived  # a plane shared by several stores is never "derived"
     res = (C.c_void_p * 2)()
     args = lambda rows: (N.store_array([a._h, b._h]), 2, N.int_array([0, 5]), 2, inner, row_start.ctypes.data_as(N.p_i32),
-                         child_rank.ctypes.data_as(N.p_i32), rows.ctypes.data_as(N.p_i64), 1, N.i64_array([n]), base_v, base_s, res)
+                         child_rank.ctypes.data_as(N.p_i32), rows.ctypes.data_as(N.p_i64), 1, N.i64_array([n]), base_v, base_s, 0, res)
     N.check(lib.olap_drill_up_pull(*args(child_row)))
     ra, rb = GpuStore._wrap(res[0]), GpuStore._wrap(res[1])
     assert lib.olap_store_status_ptr(ra._h) == lib.olap_store_status_ptr(rb._h)  # the results share a plane too
