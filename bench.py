@@ -624,6 +624,7 @@ def run_sharded(args, rank, world, local_rank):
         res = op_outer()
         k_outer.append(getattr(res, "last_pull_ms", None) or lib.olap_last_op_ms())  # the pull kernel itself
         path_outer = "drillup/pull-peers" if getattr(res, "last_pull_ms", None) else lib.olap_last_op_path().decode()
+        pull_derived = bool(getattr(res, "last_pull_derived", False))  # status planes derived from the values: not read over NVLink
         del res
     k_inner_ms, k_outer_ms = max_over_ranks(np.mean(k_inner)), max_over_ranks(np.mean(k_outer))
 
@@ -648,7 +649,6 @@ def run_sharded(args, rank, world, local_rank):
     full_map = view._row_map(0, np.zeros(10, dtype=np.int32), [1] + [10] * (deep - 1), all_rows=True)
     direct_rows, partial_rows, _, _, _ = _exchange_costs(full_map, view.row_bounds, out_bounds)
     planes = measures + sum(1 for m in SHARDED_METHODS if m == "average")  # `average` partials travel as (sum, count)
-    pull_derived = bool(getattr(view, "last_pull_derived", False))  # status planes derived from the values: not read over NVLink
     cell_bytes = 4 if (exchange == "pull" and pull_derived) else 5
     nvlink_in = float(direct_rows * cell_bytes * measures * view.inner if exchange == "pull" else partial_rows * 5 * planes * view.inner)
     pulled = path_outer == "drillup/pull-peers" or exchange == "pull2"

@@ -107,6 +107,11 @@ def main():
             lambda: GpuStore.drillUp_lowered([s], [3652, I], [120, I], [month, ident(I)], [method]),
             (4 * 3652 + B * 120) * I, 3652 * I)
         del s
+    s = store(3652 * I, 0.0)
+    s.canonicalise()
+    run(f"drillup/derived-status time-inner day->month sum [{I},3652,1]",
+        lambda: GpuStore.drillUp_lowered([s], [I, 3652], [I, 120], [ident(I), month], ["sum"]), (4 * 3652 + B * 120) * I, 3652 * I)
+    del s
     s = store(3652 * I, 0.0, 0.25)
     run(f"drillup/time-outer day->month sum zero fill=0.25 [1,3652,{I}]",
         lambda: GpuStore.drillUp_lowered([s], [3652, I], [120, I], [month, ident(I)], ["sum"]), B * (3652 + 120) * I, 3652 * I)
@@ -176,6 +181,11 @@ def main():
     keep_r[3] = np.arange(2, 8, dtype=np.int32)
     run(f"dice/range t[2:8] {dims}", lambda: GpuStore.dice_lowered([s], dims, keep_r), B * 2 * (n * 6 // 10), n * 6 // 10)
     run(f"reorder/reverse axes {dims}", lambda: GpuStore.reorder_lowered([s], dims, [5, 4, 3, 2, 1, 0]), B * 2 * n, n)
+    if S:
+        s.canonicalise()  # status plane derived from the values: gathers and the pair transpose write it without reading it
+        run(f"dice/derived-status outer every-other a {dims}", lambda: GpuStore.dice_lowered([s], dims, keep), (4 + B) * (n // 2), n // 2)
+        run(f"reorder/derived-status reverse axes {dims}", lambda: GpuStore.reorder_lowered([s], dims, [5, 4, 3, 2, 1, 0]), (4 + B) * n, n)
+        interop.status_tensor(s)  # a mutable pointer was handed out: back to the loaded plane for the rows below
     run(f"reorder/swap outer two {dims}", lambda: GpuStore.reorder_lowered([s], dims, [1, 0, 2, 3, 4, 5]), B * 2 * n, n)
     run(f"reorder/swap inner two {dims}", lambda: GpuStore.reorder_lowered([s], dims, [0, 1, 2, 3, 5, 4]), B * 2 * n, n)
     run(f"reorder/rotate inner to front {dims}", lambda: GpuStore.reorder_lowered([s], dims, [5, 0, 1, 2, 3, 4]), B * 2 * n, n)

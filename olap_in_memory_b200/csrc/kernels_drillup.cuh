@@ -365,8 +365,13 @@ __device__ __forceinline__ Cells<VEC> load_cells(const float* src, const uint8_t
         c.v[0] = ld_stream1(src + off);
         c.st = STATUS == ST_LOAD ? (uint32_t)st_src[off] : 0u;
     }
-    if (STATUS == ST_DERIVE) c.st = derived_status<VEC, NANDEF>(c.v);
-    return c;
+    return c;  // ST_DERIVE: the bytes are computed where the cells are folded (cells_status), never next to the load
+}
+// status bytes of loaded cells at the point of use: keeps every load of a batch ahead of the first dependent instruction
+template <int VEC, int STATUS, bool NANDEF>
+__device__ __forceinline__ uint32_t cells_status(const Cells<VEC>& c) {
+    if (STATUS == ST_DERIVE) return derived_status<VEC, NANDEF>(c.v);
+    return c.st;
 }
 
 // VEC results (+ VEC status bytes packed in `st`) to consecutive cells
@@ -412,7 +417,7 @@ __device__ __forceinline__ void up_mid_body(const UpMidParams& p, const UpMeasur
         for (int u = 0; u < U; ++u) {
 #pragma unroll
             for (int e = 0; e < VEC; ++e) lane[e].step(c[u].v[e]);
-            st |= c[u].st;
+            st |= cells_status<VEC, STATUS, NANDEF>(c[u]);
         }
     }
     for (; k < k1; ++k) {
@@ -420,7 +425,7 @@ __device__ __forceinline__ void up_mid_body(const UpMidParams& p, const UpMeasur
         const Cells<VEC> c = load_cells<VEC, STATUS, NANDEF>(src, st_src, child * stride);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) lane[e].step(c.v[e]);
-        st |= c.st;
+        st |= cells_status<VEC, STATUS, NANDEF>(c);
     }
 
     const int64_t out_off = o * p.out_row + (int64_t)pi * p.I_total + inner;
@@ -517,7 +522,7 @@ __device__ __forceinline__ void up_split_body(const UpMidParams& p, const UpMeas
             for (int u = 0; u < U; ++u) {
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) lane[e].step(c[u].v[e]);
-                st |= c[u].st;
+                st |= cells_status<VEC, STATUS, NANDEF>(c[u]);
             }
         }
         for (; k < ke; ++k) {
@@ -525,7 +530,7 @@ __device__ __forceinline__ void up_split_body(const UpMidParams& p, const UpMeas
             const Cells<VEC> c = load_cells<VEC, STATUS, NANDEF>(src, st_src, child * p.I_total);
 #pragma unroll
             for (int e = 0; e < VEC; ++e) lane[e].step(c.v[e]);
-            st |= c.st;
+            st |= cells_status<VEC, STATUS, NANDEF>(c);
         }
     }
 #pragma unroll

@@ -22,6 +22,9 @@ struct GatherMeasure {
     int nan_default;
     int int_rounding;  // store type is int32/uint32 (in-memory.js:343)
     int method_is_sum;
+    // st_in == nullptr, st_out != nullptr: the source's status plane follows from its values (olap_store::derived);
+    // a COPY gather then writes  set ? SET : UNSET  from the cells it moves and never reads the plane
+    int derive = 0;
 };
 
 // drillDown bookkeeping of one new item: siblings under its parent, rank among them
@@ -205,6 +208,12 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
                 so |= (ok ? ((sb | OLAP_STATUS_INTERPOLATED) & 0xffu) : (uint32_t)OLAP_STATUS_UNSET) << (8 * e);
             }
             s[u] = so;
+        }
+        if (MODE == G_COPY && m.derive) {
+            s[u] = 0;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+                s[u] |= (present_f(v[u][e], m.nan_default) ? (uint32_t)OLAP_STATUS_SET : (uint32_t)OLAP_STATUS_UNSET) << (8 * e);
         }
         if (VEC == 4) {
             st_stream4(m.out + dst_off[u], make_float4(v[u][0], v[u][1 % VEC], v[u][2 % VEC], v[u][3 % VEC]));

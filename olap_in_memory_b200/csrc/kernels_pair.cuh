@@ -166,11 +166,14 @@ __host__ __device__ __forceinline__ void pair_stash(const PairParams& p, const P
 }
 
 // ---- phase 2: output runs, 4 cells per lane
+// STATUS: the status bytes travel through the shared tile.  nan_default >= 0 (and !STATUS): the source's status
+// plane is derived from its values — nothing is loaded or staged, the bytes are recomputed from the cells on
+// their way out (-1: no status plane at all).
 template <bool STATUS, class Mem>
 __host__ __device__ __forceinline__ void pair_phase2(const PairParams& p, uint32_t tid, float* dst, uint8_t* st_dst,
                                                      const float* s_val, const uint8_t* s_st,
                                                      const uint32_t* s_dst_row, uint32_t a_eff, uint32_t n_jq,
-                                                     uint32_t n_threads) {
+                                                     uint32_t n_threads, int nan_default = -1) {
     const uint32_t n_it = p.A * p.nJq;
     for (uint32_t it = tid; it < n_it; it += n_threads) {
         const uint32_t i = p.div_nJq.div(it), jq = it - i * p.nJq;
@@ -180,6 +183,12 @@ __host__ __device__ __forceinline__ void pair_phase2(const PairParams& p, uint32
             const size_t g = ((size_t)s_dst_row[i] + jq) << 2;
             Mem::st4(dst + g, v);
             if (STATUS) *reinterpret_cast<uint32_t*>(st_dst + g) = *reinterpret_cast<const uint32_t*>(s_st + sidx);
+            else if (nan_default >= 0) {
+                const bool nd = nan_default != 0;
+                const uint32_t b0 = (nd ? v.x == v.x : v.x != 0.0f) ? 2u : 1u, b1 = (nd ? v.y == v.y : v.y != 0.0f) ? 2u : 1u;
+                const uint32_t b2 = (nd ? v.z == v.z : v.z != 0.0f) ? 2u : 1u, b3 = (nd ? v.w == v.w : v.w != 0.0f) ? 2u : 1u;
+                *reinterpret_cast<uint32_t*>(st_dst + g) = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+            }
         }
     }
 }
@@ -259,7 +268,7 @@ __host__ __device__ __forceinline__ void pair2_phase2(const PairParams& p, uint3
 constexpr int kPairThreads = 640;  // >= micro-tiles of the largest tile (25 x 25)
 
 // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...; NM micro-tiles per thread.
-template <bool STATUS, int NM>
+template <bool STATUS, int NM, bool DERIVE = false>
 __device__ __forceinline__ void pair_body(const PairParams& p, const GatherMeasure& m, unsigned char* smem_p,
                                           uint32_t n_boxes) {
     float* s_val = reinterpret_cast<float*>(smem_p);
@@ -290,8 +299,8 @@ __device__ __forceinline__ void pair_body(const PairParams& p, const GatherMeasu
                 pair_load<STATUS, PairDevMem>(p, threadIdx.x + q * blockDim.x, m.in + sb,
                                               STATUS ? m.st_in + sb : nullptr, s_src_row, a_eff >> 2, b_eff >> 2, r[q]);
         }
-        pair_phase2<STATUS, PairDevMem>(p, threadIdx.x, m.out + db_cur, STATUS ? m.st_out + db_cur : nullptr, s_val,
-                                        s_st, s_dst_row, a_cur, nj_cur, blockDim.x);
+        pair_phase2<STATUS, PairDevMem>(p, threadIdx.x, m.out + db_cur, (STATUS || DERIVE) ? m.st_out + db_cur : nullptr, s_val,
+                                        s_st, s_dst_row, a_cur, nj_cur, blockDim.x, DERIVE ? m.nan_default : -1);
         if (!more) break;
         __syncthreads();  // everyone has drained the tile
     }
@@ -307,6 +316,7 @@ __global__ void __launch_bounds__(kPairThreads, NM == 1 ? 2 : 1) transpose_pair_
     for (uint32_t i = threadIdx.x; i < p.A; i += blockDim.x) s_dst_row[i] = __ldg(p.dst_row + i);
     __syncthreads();
     if (m.st_in) pair_body<true, NM>(p, m, smem_p, n_boxes);
+    else if (m.derive && m.st_out) pair_body<false, NM, true>(p, m, smem_p, n_boxes);
     else pair_body<false, NM>(p, m, smem_p, n_boxes);
 }
 

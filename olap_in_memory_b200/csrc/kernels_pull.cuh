@@ -92,14 +92,17 @@ __device__ __forceinline__ void up_pull_body(const UpPullParams& p, const PullMe
                     c[u].v[0] = *reinterpret_cast<const volatile float*>(base_v[r] + off);
                     if (STATUS == ST_LOAD) c[u].st = *reinterpret_cast<const volatile uint8_t*>(base_s[r] + off);
                 }
-                if (STATUS == ST_DERIVE) c[u].st = derived_status<VEC, NANDEF>(c[u].v);
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
 #pragma unroll
             for (int e = 0; e < VEC; ++e) lane[e].step(c[u].v[e]);
-            st |= c[u].st;
+            if (STATUS == ST_DERIVE) {
+                if (k + u < k1) st |= derived_status<VEC, NANDEF>(c[u].v);  // a slot past the last child contributes nothing
+            } else {
+                st |= c[u].st;
+            }
         }
     }
     const int64_t out_off = row * p.inner + cell;

@@ -119,7 +119,7 @@ inline TileDecision tile_plan(int64_t O, int64_t C, int64_t P, int64_t I, bool a
     return t;
 }
 
-template <int METHOD, bool NANDEF, bool RANGE, bool STATUS>
+template <int METHOD, bool NANDEF, bool RANGE, int STATUS>
 __device__ __forceinline__ void up_tile_reduce(const UpTileParams& p, const UpMeasure& m, const float* s_val,
                                                const uint8_t* s_st, int64_t o0, int rows, unsigned char* s_merge) {
     typedef Lane<METHOD, NANDEF> L;
@@ -150,8 +150,10 @@ __device__ __forceinline__ void up_tile_reduce(const UpTileParams& p, const UpMe
             for (int32_t k = ks; k < ke; ++k) {
                 const uint32_t c = RANGE ? (uint32_t)k : (uint32_t)p.children[k];
                 const uint32_t idx = base + c * (uint32_t)p.I;
-                lane.step(s_val[idx]);
-                if (STATUS) st |= s_st[idx];
+                const float v = s_val[idx];
+                lane.step(v);
+                if (STATUS == ST_LOAD) st |= s_st[idx];
+                if (STATUS == ST_DERIVE) st |= present_f(v, NANDEF) ? OLAP_STATUS_SET : OLAP_STATUS_UNSET;
             }
         }
         s_lane[threadIdx.x] = lane;
@@ -180,15 +182,17 @@ __device__ __forceinline__ void up_tile_reduce(const UpTileParams& p, const UpMe
         for (int32_t k = k0; k < k1; ++k) {
             const uint32_t c = RANGE ? (uint32_t)k : (uint32_t)p.children[k];
             const uint32_t idx = base + c * (uint32_t)p.I;
-            lane.step(s_val[idx]);
-            if (STATUS) st |= s_st[idx];
+            const float v = s_val[idx];
+            lane.step(v);
+            if (STATUS == ST_LOAD) st |= s_st[idx];
+            if (STATUS == ST_DERIVE) st |= present_f(v, NANDEF) ? OLAP_STATUS_SET : OLAP_STATUS_UNSET;
         }
         out[j] = lane_poisoned(lane) ? exact_redo<METHOD, RANGE>(s_val + base, p.I, p.children, k0, k1) : lane.result();
         if (STATUS) st_out[j] = (uint8_t)(k0 == k1 ? OLAP_STATUS_UNSET : st);
     }
 }
 
-template <bool NANDEF, bool RANGE, bool STATUS>
+template <bool NANDEF, bool RANGE, int STATUS>
 __device__ __forceinline__ void up_tile_dispatch(const UpTileParams& p, const UpMeasure& m, const float* s_val,
                                                  const uint8_t* s_st, int64_t o0, int rows, unsigned char* s_merge) {
     switch (m.method) {
@@ -204,13 +208,16 @@ __device__ __forceinline__ void up_tile_dispatch(const UpTileParams& p, const Up
 }
 
 template <bool RANGE>
-__global__ void __launch_bounds__(256) drillup_tile_kernel(const __grid_constant__ UpTileParams p) {
+__global__ void __launch_bounds__(256, 4) drillup_tile_kernel(const __grid_constant__ UpTileParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* s_val = reinterpret_cast<float*>(smem);
     uint8_t* s_st = smem + p.st_offset;
     const UpMeasure m = p.meas ? p.meas[blockIdx.y] : p.meas_inline[blockIdx.y];
-    const bool status = m.st_in != nullptr;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + p.st_offset + (status ? (((size_t)p.R * p.row_in + 15) & ~(size_t)15) : 0));
+    // ST_DERIVE: the source's status plane follows from its values (olap_store::derived): it is neither copied
+    // nor read, the bytes are recomputed from the staged cells
+    const int st_mode = m.st_in ? ST_LOAD : (m.derive ? ST_DERIVE : ST_NONE);
+    const bool status = st_mode == ST_LOAD;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + p.st_offset + (st_mode != ST_NONE ? (((size_t)p.R * p.row_in + 15) & ~(size_t)15) : 0));
     unsigned char* s_merge = smem + p.merge_offset;
 
     const int64_t o0 = (int64_t)blockIdx.x * p.R;
@@ -236,11 +243,13 @@ __global__ void __launch_bounds__(256) drillup_tile_kernel(const __grid_constant
     __syncthreads();
 
     if (m.nan_default) {
-        if (status) up_tile_dispatch<true, RANGE, true>(p, m, s_val, s_st, o0, rows, s_merge);
-        else up_tile_dispatch<true, RANGE, false>(p, m, s_val, s_st, o0, rows, s_merge);
+        if (st_mode == ST_LOAD) up_tile_dispatch<true, RANGE, ST_LOAD>(p, m, s_val, s_st, o0, rows, s_merge);
+        else if (st_mode == ST_DERIVE) up_tile_dispatch<true, RANGE, ST_DERIVE>(p, m, s_val, s_st, o0, rows, s_merge);
+        else up_tile_dispatch<true, RANGE, ST_NONE>(p, m, s_val, s_st, o0, rows, s_merge);
     } else {
-        if (status) up_tile_dispatch<false, RANGE, true>(p, m, s_val, s_st, o0, rows, s_merge);
-        else up_tile_dispatch<false, RANGE, false>(p, m, s_val, s_st, o0, rows, s_merge);
+        if (st_mode == ST_LOAD) up_tile_dispatch<false, RANGE, ST_LOAD>(p, m, s_val, s_st, o0, rows, s_merge);
+        else if (st_mode == ST_DERIVE) up_tile_dispatch<false, RANGE, ST_DERIVE>(p, m, s_val, s_st, o0, rows, s_merge);
+        else up_tile_dispatch<false, RANGE, ST_NONE>(p, m, s_val, s_st, o0, rows, s_merge);
     }
 }
 

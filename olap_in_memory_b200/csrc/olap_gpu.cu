@@ -1053,9 +1053,28 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
             const UpMeasure* d_meas = inline_meas ? nullptr : t.ptr<UpMeasure>(o_meas);
             const int32_t* d_ps = reinterpret_cast<const int32_t*>(d_stat + o_ps);
             const int32_t* d_ch = csr.contiguous ? nullptr : reinterpret_cast<const int32_t*>(d_stat + o_ch);
+            // sources whose status plane follows from their values: the mid / split / tile kernels recompute the
+            // bytes from the cells they load anyway and never read the plane (4 instead of 5 bytes per input cell)
+            static const int derive_knob = [] { const char* e = getenv("OLAP_DERIVE_STATUS"); return e ? atoi(e) : 1; }();
+            const UpMeasure* d_meas_drv = d_meas;
+            TablePack t2;
+            if (derive_knob && (tile.use || !lng.use)) {
+                bool changed_desc = false;
+                for (int k = 0; k < n; ++k)
+                    if (meas[k].st_in && src[k]->derived && !src[k]->shared_plane) {
+                        meas[k].st_in = nullptr;
+                        meas[k].derive = 1;
+                        changed_desc = true;
+                    }
+                if (changed_desc && !inline_meas) {  // descriptors travel through a device table: upload the edited ones
+                    const size_t o2 = t2.add(meas.data(), sizeof(UpMeasure) * n);
+                    OLAP_TRY(t2.upload());
+                    d_meas_drv = t2.ptr<UpMeasure>(o2);
+                }
+            }
             if (tile.use) {
                 path = "drillup/tile";
-                OLAP_TRY(launch_up_tile(d_meas, meas.data(), n, csr.contiguous, d_ps, d_ch, O, C, P, I, tile));
+                OLAP_TRY(launch_up_tile(d_meas_drv, meas.data(), n, csr.contiguous, d_ps, d_ch, O, C, P, I, tile));
             } else if (lng.use) {
                 path = "drillup/long";
                 void* scratch = nullptr;
@@ -1067,25 +1086,7 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
                 if (scratch) OLAP_TRY(dev_free(scratch));
             } else {
                 path = (I % 4 == 0) ? "drillup/mid-vec4" : (I % 2 == 0 ? "drillup/mid-vec2" : "drillup/mid-scalar");
-                // sources whose status plane follows from their values: the kernel recomputes the bytes from the
-                // cells it loads anyway and never reads the plane (4 instead of 5 bytes per input cell)
-                static const int derive_knob = [] { const char* e = getenv("OLAP_DERIVE_STATUS"); return e ? atoi(e) : 1; }();
-                bool changed_desc = false;
-                for (int k = 0; k < n; ++k)
-                    if (derive_knob && meas[k].st_in && src[k]->derived && !src[k]->shared_plane) {
-                        meas[k].st_in = nullptr;
-                        meas[k].derive = 1;
-                        changed_desc = true;
-                    }
-                const UpMeasure* d_meas_mid = d_meas;
-                TablePack t2;
-                if (changed_desc && !inline_meas) {  // descriptors travel through a device table: upload the edited ones
-                    const size_t o2 = t2.add(meas.data(), sizeof(UpMeasure) * n);
-                    OLAP_TRY(t2.upload());
-                    d_meas_mid = t2.ptr<UpMeasure>(o2);
-                }
-                OLAP_TRY(launch_up_mid(d_meas_mid, meas.data(), n, csr, d_ps, d_ch, O, C, P, I));
-                OLAP_TRY(t2.release());
+                OLAP_TRY(launch_up_mid(d_meas_drv, meas.data(), n, csr, d_ps, d_ch, O, C, P, I));
             }
         } else {
             path = "drillup/generic";
@@ -1124,6 +1125,18 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
 
 // ---- gather family ----------------------------------------------------------------------
 namespace {
+
+// COPY gathers of a store whose status plane follows from its values (olap_store::derived): the kernels that
+// support it (vector gather, pair transpose) write the bytes from the cells they move and never read the plane
+static void gather_derive(std::vector<GatherMeasure>& meas, olap_store* const* src, int n) {
+    static const int knob = [] { const char* e = getenv("OLAP_DERIVE_STATUS"); return e ? atoi(e) : 1; }();
+    if (!knob) return;
+    for (int k = 0; k < n; ++k)
+        if (meas[k].st_in && meas[k].st_out && src[k]->derived && !src[k]->shared_plane) {
+            meas[k].st_in = nullptr;
+            meas[k].derive = 1;
+        }
+}
 
 // Drop single-item dimensions (their constant offset goes to `const_off`) and merge
 // neighbours that stay adjacent and contiguous in the source.
@@ -1223,6 +1236,7 @@ static int run_gather(int mode, olap_store* const* src, int n, std::vector<GDim>
     GatherParams p{};
     TablePack t;
     std::vector<GatherMeasure> meas = meas_in;
+    if (mode == G_COPY) gather_derive(meas, src, n);
     for (auto& m : meas) { m.in += const_off; if (m.st_in) m.st_in += const_off; }
     const size_t o_meas = t.add(meas.data(), sizeof(GatherMeasure) * n);
     std::vector<size_t> o_tbl(dims.size(), 0), o_aux(dims.size(), 0);
@@ -1396,6 +1410,7 @@ int olap_reorder(olap_store* const* src, int n, int ndim, const int64_t* old_len
             OLAP_TRY(t.release());
         } else if (pp.use) {
             path = "reorder/pair-transpose";
+            gather_derive(meas, src, n);
             TablePack t;
             const size_t o_meas = t.add(meas.data(), sizeof(GatherMeasure) * n);
             const size_t o_src = t.add(pp.src_row.data(), pp.src_row.size() * sizeof(uint32_t));

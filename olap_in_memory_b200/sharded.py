@@ -656,7 +656,7 @@ class ShardedCube:
             self._pull_tables_cache = {key: tables}
         rank_rows = [self.row_bounds[r + 1] - self.row_bounds[r] for r in range(W)]
         results = self._pull_call(stores, methods, views, tables, rank_rows, j1 - j0)
-        out.last_pull_ms = self.last_pull_ms
+        out.last_pull_ms, out.last_pull_derived = self.last_pull_ms, self.last_pull_derived
         out.storedMeasures = {m: self._store_cls._wrap(results[k]) for k, m in enumerate(ids)}
         return out
 
@@ -729,7 +729,7 @@ class ShardedCube:
         tables = _pull2_tables(touched, j0, j1)
         results = self._pull_call(partials, [comb for _, _, comb in plan], views, tables, [int(t.size) for t in touched], j1 - j0)
         del partials
-        out.last_pull_ms = self.last_pull_ms
+        out.last_pull_ms, out.last_pull_derived = self.last_pull_ms, self.last_pull_derived
         combined = [self._store_cls._wrap(h) for h in results]
         k = 0
         for m, method in zip(ids, methods):
