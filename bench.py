@@ -694,7 +694,9 @@ def run_sharded(args, rank, world, local_rank):
         pass
     cells_per_step = 2 * measures * n_total
     value = cells_per_step / (ms_value * 1e-3)
-    inner_bytes = 5 * measures * (n_local + n_local // 10)
+    # the shard-local rollup reads 4 bytes per input cell when the status planes follow from the values, 5 otherwise
+    in_cell = 4 if all(cube.storedMeasures[name].status_derived for name in names) else 5
+    inner_bytes = measures * (in_cell * n_local + 5 * (n_local // 10))
     nv_gbs = nvlink_in / (k_outer_ms * 1e-3) / 1e9
     if rank == 0:
         line = {
@@ -716,7 +718,7 @@ def run_sharded(args, rank, world, local_rank):
                 "alternative_exchanges_ms": alternatives, "pulled_over_peer_memory": pulled, "prefix_after_rollup": deep,
                 "rows_per_rank_out": [out_bounds[r + 1] - out_bounds[r] for r in range(world)],
                 "inner_rollup": {"op": f"drillUp {last}->all (shard-local)", "ms": ms_inner, "kernel_ms": k_inner_ms, "kernel": path_inner,
-                                 "hbm_GBs_per_gpu": inner_bytes / (k_inner_ms * 1e-3) / 1e9,
+                                 "bytes_per_input_cell": in_cell, "hbm_GBs_per_gpu": inner_bytes / (k_inner_ms * 1e-3) / 1e9,
                                  "hbm_frac": inner_bytes / (k_inner_ms * 1e-3) / 1e9 / peak, "hbm_peak": peak, "peak_source": peak_src},
                 "sharded_rollup": {"op": "drillUp dim0->all (sharded dimension)", "ms": ms_outer, "kernel_ms": k_outer_ms, "kernel": path_outer,
                                    "nvlink_bytes_in_per_gpu": nvlink_in, "bytes_per_cell_over_nvlink": cell_bytes, "nvlink_GBs_per_gpu": nv_gbs, "nvlink_frac_of_770": nv_gbs / NVLINK_GBS,

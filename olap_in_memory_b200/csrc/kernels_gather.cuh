@@ -105,7 +105,7 @@ __device__ __forceinline__ float down_value(const GatherMeasure& m, const Gather
 }
 
 template <int MODE, int VEC, bool BIG>
-__global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ GatherParams p) {
+__global__ void __launch_bounds__(256, MODE == G_COPY ? 8 : 4) gather_kernel(const __grid_constant__ GatherParams p) {
     constexpr int U = 2;  // independent vectors per thread
     const GatherMeasure m = p.meas[blockIdx.y];
     const int64_t base = (int64_t)blockIdx.x * (256 * U) + threadIdx.x;
@@ -247,7 +247,7 @@ struct RowsTail {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(256, MODE == G_COPY ? 6 : 3) gather_rows_kernel(const __grid_constant__ GatherParams p,
+__global__ void __launch_bounds__(256) gather_rows_kernel(const __grid_constant__ GatherParams p,
                                                           const __grid_constant__ RowsTail tail) {
     __shared__ int64_t s_off[kRowsPerBlock];
     __shared__ uint32_t s_n[kRowsPerBlock], s_k[kRowsPerBlock];
@@ -282,27 +282,6 @@ __global__ void __launch_bounds__(256, MODE == G_COPY ? 6 : 3) gather_rows_kerne
     __syncthreads();
     const uint32_t cells = rows * tail.L;
     const int64_t base = row0 * tail.L;
-    // one cell: gathered through the two shared tables, transformed (drillDown modes), ready to store
-    auto cell = [&](uint32_t t, uint32_t r, uint32_t c, float v, uint32_t sb, uint32_t& so) {
-        so = sb;
-        if (MODE == G_COPY) return v;
-        const DownAux a = s_aux[c];
-        const uint32_t n = s_n[r] * (uint32_t)a.cnt;
-        const uint32_t k = s_k[r] * (uint32_t)a.cnt + (uint32_t)a.rank;
-        const double inv = s_n[r] == 1 ? a.inv : 1.0 / (double)n;
-        bool ok;
-        float out;
-        if (MODE == G_DOWN_FLOAT) {
-            const float q = canon_store((float)(n < (1u << 20) ? (double)v * inv : (double)v / (double)n), m.nan_default);
-            const bool truthy = v != 0.0f && v == v;
-            out = truthy ? q : default_of(m.nan_default);
-            ok = truthy && present_f(q, m.nan_default);
-        } else {
-            out = down_value(m, p, v, n, inv, k, base + t, ok);
-        }
-        so = ok ? ((sb | OLAP_STATUS_INTERPOLATED) & 0xffu) : (uint32_t)OLAP_STATUS_UNSET;
-        return out;
-    };
     constexpr int U = 4;
     for (uint32_t t0 = threadIdx.x; t0 < cells; t0 += 256 * U) {
         float v[U];
@@ -322,9 +301,26 @@ __global__ void __launch_bounds__(256, MODE == G_COPY ? 6 : 3) gather_rows_kerne
         for (int u = 0; u < U; ++u) {
             const uint32_t t = t0 + u * 256;
             if (t >= cells) continue;
-            uint32_t so;
-            const float o = cell(t, rr[u], cc[u], v[u], sb[u], so);
-            m.out[base + t] = o;
+            float r = v[u];
+            uint32_t so = sb[u];
+            if (MODE != G_COPY) {
+                const DownAux a = s_aux[cc[u]];
+                const uint32_t n = s_n[rr[u]] * (uint32_t)a.cnt;
+                const uint32_t k = s_k[rr[u]] * (uint32_t)a.cnt + (uint32_t)a.rank;
+                const double inv = s_n[rr[u]] == 1 ? a.inv : 1.0 / (double)n;
+                bool ok;
+                if (MODE == G_DOWN_FLOAT) {
+                    const float x = v[u];
+                    const float q = canon_store((float)(n < (1u << 20) ? (double)x * inv : (double)x / (double)n), m.nan_default);
+                    const bool truthy = x != 0.0f && x == x;
+                    r = truthy ? q : default_of(m.nan_default);
+                    ok = truthy && present_f(q, m.nan_default);
+                } else {
+                    r = down_value(m, p, v[u], n, inv, k, base + t, ok);
+                }
+                so = ok ? ((sb[u] | OLAP_STATUS_INTERPOLATED) & 0xffu) : (uint32_t)OLAP_STATUS_UNSET;
+            }
+            m.out[base + t] = r;
             if (m.st_out) m.st_out[base + t] = (uint8_t)so;
         }
     }

@@ -208,7 +208,7 @@ __device__ __forceinline__ void up_tile_dispatch(const UpTileParams& p, const Up
 }
 
 template <bool RANGE>
-__global__ void __launch_bounds__(256, 4) drillup_tile_kernel(const __grid_constant__ UpTileParams p) {
+__global__ void __launch_bounds__(256, 8) drillup_tile_kernel(const __grid_constant__ UpTileParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* s_val = reinterpret_cast<float*>(smem);
     uint8_t* s_st = smem + p.st_offset;

@@ -1410,7 +1410,7 @@ int olap_reorder(olap_store* const* src, int n, int ndim, const int64_t* old_len
             OLAP_TRY(t.release());
         } else if (pp.use) {
             path = "reorder/pair-transpose";
-            gather_derive(meas, src, n);
+            if (pp.p.split == 1) gather_derive(meas, src, n);  // the 2-CTA cluster variant always stages the status bytes
             TablePack t;
             const size_t o_meas = t.add(meas.data(), sizeof(GatherMeasure) * n);
             const size_t o_src = t.add(pp.src_row.data(), pp.src_row.size() * sizeof(uint32_t));
