@@ -1909,12 +1909,29 @@ int olap_drill_up_pull(olap_store* const* like, int n, const int* methods, int64
         const int64_t gx = ceil_div(p.IV, bx);
         if (gx > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "olap_drill_up_pull: inner run too long");
         const int64_t rows_per_launch = (int64_t)65535 * by;
+        // staged variant (cp.async into the thread's own shared-memory slots): all children of a row in flight at once
+        static const int staged_knob = [] { const char* e = getenv("OLAP_PULL_STAGED"); return e ? atoi(e) : 1; }();
+        int32_t max_children = 1;
+        for (int64_t j = 0; j < out_rows; ++j) max_children = std::max(max_children, row_start[j + 1] - row_start[j]);
+        const int chunk = std::min(16, (int)max_children);
+        const bool staged = staged_knob != 0 && vec4;
+        bool st_loaded = false;
+        for (int k = 0; k < n; ++k) st_loaded |= meas[k].st_out && !meas[k].derive;
+        const size_t staged_smem = (size_t)chunk * 256 * (16 + (st_loaded ? 4 : 0));
+        if (staged) {
+            static size_t attr = 0;
+            if (staged_smem > attr) {
+                OLAP_CUDA(cudaFuncSetAttribute(drillup_pull_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 256 * 20));
+                attr = 16 * 256 * 20;
+            }
+        }
         KERNELS_BEGIN();
         for (int64_t r0 = 0; r0 < out_rows; r0 += rows_per_launch) {
             p.row0 = r0;
             const int64_t gy = ceil_div(std::min(rows_per_launch, out_rows - r0), by);
             dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)n), block(bx, by);
-            if (vec4) drillup_pull_kernel<4><<<grid, block, 0, g.stream>>>(p);
+            if (vec4 && staged) drillup_pull_staged_kernel<<<grid, block, staged_smem, g.stream>>>(p, chunk);
+            else if (vec4) drillup_pull_kernel<4><<<grid, block, 0, g.stream>>>(p);
             else drillup_pull_kernel<1><<<grid, block, 0, g.stream>>>(p);
             LAUNCHED();
         }
