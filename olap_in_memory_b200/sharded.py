@@ -43,10 +43,6 @@ def _prod(xs):
     return p
 
 
-def _is_device_store(store):
-    return hasattr(store, "_h")
-
-
 # How a rollup of a sharded dimension moves its cells between GPUs (OLAP_SHARDED_EXCHANGE):
 #   "pull" (default on GPUs): the rank that owns an output row reads its child rows straight out of
 #          the peers' stores through CUDA-IPC-mapped pointers, inside ONE rollup kernel
@@ -196,7 +192,26 @@ class _PeerBuffers:
             N.check(N.lib().olap_peer_open(C.create_string_buffer(h, 64), C.byref(p)))
             ptrs.append(p.value)
         cls._cache[key] = ptrs
+        cls._owner[key] = (comm, mine.value)
         return ptrs
+
+    _owner = {}
+
+    @classmethod
+    def release(cls):
+        """Collective: every rank closes its mappings of the peers' receive buffers, then frees its own
+        (the push exchange keeps one buffer per size alive until this is called)."""
+        from . import _native as N
+
+        for key, ptrs in list(cls._cache.items()):
+            comm, mine = cls._owner.pop(key)
+            N.check(N.lib().olap_sync())
+            for r, p in enumerate(ptrs):
+                if r != comm.rank:
+                    N.check(N.lib().olap_peer_close(p))
+            comm.dist.barrier(group=comm.group)  # nobody maps my buffer any more
+            N.check(N.lib().olap_peer_free(mine))
+            del cls._cache[key]
 
 
 class _Comm:
@@ -395,27 +410,22 @@ class ShardedCube:
 
         local = torch.from_numpy(np.ascontiguousarray(self.getLocalData(measureId), dtype=np.float64))
         sizes = [(self.row_bounds[r + 1] - self.row_bounds[r]) * self.inner for r in range(self.world)]
-        if self.world > 1 and _is_device_store(next(iter(self.storedMeasures.values()))):
+        if self.world > 1 and self._store_cls.DEVICE == "cuda":
             local = local.cuda()
         return self.comm.all_gather(local, sizes).cpu().numpy()
 
     def getTotal(self, measureId):
         store = self.storedMeasures[measureId]
-        device = "cuda" if _is_device_store(store) and self.world > 1 else None
+        device = self._store_cls.DEVICE if self.world > 1 else None
         return self.comm.all_reduce_sum(store.total, device)
 
     @staticmethod
     def _set(store, values):
-        if hasattr(store, "set_data_f32"):
-            store.set_data_f32(np.asarray(values, dtype=np.float32))
-        else:
-            store.data = [float(v) for v in values]
+        store.set_data_f32(np.asarray(values, dtype=np.float32))
 
     @staticmethod
     def _get(store):
-        if hasattr(store, "data_f32"):
-            return store.data_f32().astype(np.float64)
-        return np.asarray(store.data, dtype=np.float64)
+        return store.data_f32().astype(np.float64)
 
     def _derive(self, dimensions, row_bounds=None):
         out = ShardedCube(dimensions, self.prefix, self._store_cls, self.comm.group, row_bounds)
@@ -425,14 +435,8 @@ class ShardedCube:
 
     # ----------------------------------------------------------- lowered store calls
     def _call(self, name, stores, *args):
-        fn = getattr(self._store_cls, name)
-        if _is_device_store(stores[0]):
-            return fn(stores, *args)  # batched static form of the device store
-        per_store = []
-        for k, s in enumerate(stores):
-            a = [x[k] if isinstance(x, _Per) else x for x in args]
-            per_store.append(fn(s, *a))
-        return per_store
+        """Batched static form of a lowered transform: one call for all measures."""
+        return getattr(self._store_cls, name)(stores, *[list(x) if isinstance(x, _Per) else x for x in args])
 
     def _local_lens(self):
         return [self.rows_local] + self.inner_lens
@@ -531,7 +535,7 @@ class ShardedCube:
             out.storedMeasures = dict(zip(ids, results))
             return out
         mode = EXCHANGE
-        if mode in ("auto", "pull", "pull2") and self.comm.on and all(_is_device_store(self.storedMeasures[m]) for m in ids):
+        if mode in ("auto", "pull", "pull2") and self.comm.on and self._store_cls.PEER_MEMORY:
             full_map = self._row_map(idx, group_map, new_prefix_lens, all_rows=True)
             touched = None
             if mode != "pull":
@@ -566,7 +570,7 @@ class ShardedCube:
             else:
                 plan.append((m, method, "plain"))
         stores = [self.storedMeasures[m] for m, _, _ in plan]
-        if mode != "nccl" and self.comm.on and _is_device_store(stores[0]):
+        if mode != "nccl" and self.comm.on and self._store_cls.PEER_MEMORY:
             received = self._partials_into_peers(stores, [meth for _, meth, _ in plan], row_map, out_bounds, new_rows_total)
             return self._combine(out, plan, ids, methods, received, my_out_rows)
         partials = self._partials(stores, old_len, new_len, maps, [meth for _, meth, _ in plan])
@@ -575,13 +579,8 @@ class ShardedCube:
         in_splits = [(out_bounds[r + 1] - out_bounds[r]) * inner for r in range(W)]
         out_splits = [my_out_rows * inner] * W
         received = []
-        for src_store in stores:
-            if _is_device_store(src_store):  # every cell is overwritten by the exchange: skip the default fill
-                recv = self._store_cls(W * my_out_rows * inner, src_store._type, src_store._defaultValue,
-                                       uninitialised=True)
-            else:
-                recv = self._store_cls(W * my_out_rows * inner, src_store._type, src_store._defaultValue)
-            received.append(recv)
+        for src_store in stores:  # every cell is overwritten by the exchange
+            received.append(self._store_cls.recv_like(src_store, W * my_out_rows * inner))
         self._exchange_all(partials, received, in_splits, out_splits)
         del partials
 
@@ -815,74 +814,29 @@ class ShardedCube:
         return received
 
     def _partials(self, stores, old_len, new_len, maps, methods):
-        if _is_device_store(stores[0]):
-            return self._store_cls.drillUp_lowered(stores, old_len, new_len, maps, methods)
-        out = []
-        for s, method in zip(stores, methods):
-            if method == "__count":  # CPU stand-in stores have no count method: roll up an indicator
-                ind = type(s)(s.size, s._type, s._defaultValue)
-                present = set(s._dataMap.keys())
-                ind.data = [1.0 if i in present else s._defaultValue for i in range(s.size)]
-                out.append(ind.drillUp_lowered(old_len, new_len, maps, "sum"))
-            else:
-                out.append(s.drillUp_lowered(old_len, new_len, maps, method))
-        return out
+        return self._store_cls.drillUp_lowered(stores, old_len, new_len, maps, methods)
 
     def _exchange_all(self, parts, recvs, in_splits, out_splits):
-        """All planes (values and status) of all partials in one grouped exchange."""
-        if not _is_device_store(parts[0]):
-            for part, recv in zip(parts, recvs):
-                self._exchange(part, recv, in_splits, out_splits)
-            return
-        import torch
+        """One all-to-all per plane (values, status) of every partial."""
+        cls = self._store_cls
+        sent = [cls.exchange_planes(part) for part in parts]
+        got = [cls.exchange_planes(recv) for recv in recvs]
+        if cls.DEVICE == "cuda":
+            import torch
 
-        from . import interop
+            from . import _native as N
 
-        pairs = []
-        for part, recv in zip(parts, recvs):
-            pairs.append((interop.values_tensor(recv), interop.values_tensor(part)))
-            st_in, st_out = interop.status_tensor(part), interop.status_tensor(recv)
-            if st_in is not None and st_out is not None:
-                pairs.append((st_out, st_in))
-        torch.cuda.current_stream().synchronize()
-        self.comm.all_to_all_many(pairs, out_splits, in_splits)
-        torch.cuda.synchronize()
-
-    def _exchange(self, part, recv, in_splits, out_splits):
-        import torch
-
-        if _is_device_store(part):
-            from . import interop
-
+            N.check(N.lib().olap_sync())
             torch.cuda.current_stream().synchronize()
-            self.comm.all_to_all(interop.values_tensor(recv), interop.values_tensor(part), out_splits, in_splits)
-            st_in, st_out = interop.status_tensor(part), interop.status_tensor(recv)
-            if st_in is not None and st_out is not None:
-                self.comm.all_to_all(st_out, st_in, out_splits, in_splits)
+        self.comm.all_to_all_many([(o, i) for outs, ins in zip(got, sent) for o, i in zip(outs, ins)], out_splits, in_splits)
+        if cls.DEVICE == "cuda":
             torch.cuda.synchronize()
-        else:
-            src = torch.tensor(part.data, dtype=torch.float64)
-            dst = torch.empty(sum(out_splits), dtype=torch.float64)
-            self.comm.all_to_all(dst, src, out_splits, in_splits)
-            recv.data = dst.tolist()
+        for recv, planes in zip(recvs, got):
+            cls.exchange_done(recv, planes)
 
     def _divide(self, sums, counts):
         """average = sum of sums / sum of counts; no contribution -> unset (in-memory.js:323-331)."""
-        if _is_device_store(sums):
-            # `c ? s / c : default` as the postfix program of olap_eval (one fused kernel)
-            default = "#nan" if sums._defaultValue != sums._defaultValue else "#0.0"
-            out = self._store_cls.eval_program(f"v1 v0 v1 / {default} ?:", [sums, counts], [], sums._type,
-                                               sums._defaultValue)
-            # the quotient keeps the merged status flags of the sums (the unsharded `average` ORs its
-            # children's flags exactly like `sum` does); the formula kernel alone would derive SET / UNSET
-            from . import _native as N
-
-            N.check(N.lib().olap_store_copy_status(out._h, sums._h))
-            return out
-        out = type(sums)(sums.size, sums._type, sums._defaultValue)
-        s, c = sums.data, counts.data
-        out.data = [sv / cv if (cv == cv and cv != 0) else sums._defaultValue for sv, cv in zip(s, c)]
-        return out
+        return self._store_cls.average_of(sums, counts)
 
     def dice(self, dimensionId, attribute, items, reorder=False):
         """Dice: a shard-local gather, whichever dimension is diced (no communication)."""
@@ -892,6 +846,11 @@ class ShardedCube:
     def diceRange(self, dimensionId, attribute, start, end):  # cube.js:809-832
         idx = self.getDimensionIndex(dimensionId)
         return self._dice_to(idx, self.dimensions[idx].diceRange(attribute, start, end))
+
+    @staticmethod
+    def release_peer_buffers():
+        """Free the receive buffers of the push exchange (collective; see _PeerBuffers.release)."""
+        _PeerBuffers.release()
 
     def removeDimension(self, dimensionId):
         """cube.js:950-964: roll the dimension up to 'all' with each measure's rule, then forget
@@ -1000,10 +959,7 @@ class ShardedCube:
         methods = [self.storedMeasuresRules[m].get(dimensionId) or "sum" for m in ids]
         if ids:
             stores = [self.storedMeasures[m] for m in ids]
-            if _is_device_store(stores[0]):
-                res = self._store_cls.drillDown_lowered(stores, old_len, new_len, maps, methods)
-            else:
-                res = [s.drillDown_lowered(old_len, new_len, maps, meth) for s, meth in zip(stores, methods)]
+            res = self._store_cls.drillDown_lowered(stores, old_len, new_len, maps, methods)
             out.storedMeasures = dict(zip(ids, res))
         return out
 

@@ -360,6 +360,40 @@ class GpuStore:
         del alive, dist_keep
         return GpuStore._finish(out, n)
 
+    # ---- what ShardedCube needs from a store class beyond the batched transforms -----------
+    DEVICE = "cuda"       # where the tensors of the collectives live
+    PEER_MEMORY = True    # stores can be mapped by the other processes of the box (pull / push exchange)
+
+    @classmethod
+    def recv_like(cls, store, size):
+        """A store about to be overwritten cell by cell by an exchange (no default fill)."""
+        return cls(size, store._type, store._defaultValue, uninitialised=True, shareable=True)
+
+    @staticmethod
+    def exchange_planes(store):
+        """The planes of a store as torch tensors an all-to-all can read or write in place."""
+        from . import interop
+
+        planes = [interop.values_tensor(store)]
+        st = interop.status_tensor(store)
+        if st is not None:
+            planes.append(st)
+        return planes
+
+    @staticmethod
+    def exchange_done(store, planes):
+        """The tensors of exchange_planes alias the store: nothing to copy back."""
+
+    @classmethod
+    def average_of(cls, sums, counts):
+        """sum of sums / sum of counts, no contribution -> unset (in-memory.js:323-331): one fused formula
+        kernel; the quotient keeps the merged status flags of the sums (the unsharded `average` ORs its
+        children's flags exactly like `sum` does; the formula kernel alone would derive SET / UNSET)."""
+        default = "#nan" if sums._defaultValue != sums._defaultValue else "#0.0"
+        out = cls.eval_program(f"v1 v0 v1 / {default} ?:", [sums, counts], [], sums._type, sums._defaultValue)
+        N.check(N.lib().olap_store_copy_status(out._h, sums._h))
+        return out
+
     # ---- computed measures (cube.js:331-363) ------------------------------------------
     @staticmethod
     def _program(expression, cell_names, total_names):

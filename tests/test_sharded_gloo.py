@@ -13,6 +13,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 METHODS = ["sum", "average", "highest", "lowest", "first", "last"]
 ROLLUPS = (("region", "country"), ("region", "all"), ("product", "family"), ("time", "quarter"))
 
@@ -82,9 +83,10 @@ def _worker(rank, world, port, prefix, default_is_nan, queue):
     try:
         from olap_in_memory_b200.sharded import ShardedCube
         from oracle.store_oracle import OracleStore
+        from shard_store import OracleShardStore
 
         default = math.nan if default_is_nan else 0.0
-        cube = ShardedCube(_dims(), prefix=prefix, store_cls=OracleStore)
+        cube = ShardedCube(_dims(), prefix=prefix, store_cls=OracleShardStore)
         _fill(cube, default)
         results = _collect(cube, list(cube.storedMeasures))
         if rank == 0:
@@ -97,6 +99,7 @@ def _worker(rank, world, port, prefix, default_is_nan, queue):
 def _expected(default_is_nan):
     from olap_in_memory_b200 import Cube
     from oracle.store_oracle import OracleStore
+    from shard_store import OracleShardStore
 
     cube = Cube(_dims(), OracleStore)
     _fill(cube, math.nan if default_is_nan else 0.0)
@@ -174,8 +177,9 @@ def _time_first_worker(rank, world, port, prefix, queue):
     try:
         from olap_in_memory_b200.sharded import ShardedCube
         from oracle.store_oracle import OracleStore
+        from shard_store import OracleShardStore
 
-        cube = ShardedCube(_time_first_dims(), prefix=prefix, store_cls=OracleStore)
+        cube = ShardedCube(_time_first_dims(), prefix=prefix, store_cls=OracleShardStore)
         ids = _time_first_fill(cube, 0.0)
         try:
             results = _time_first_collect(cube, ids)
@@ -205,6 +209,7 @@ def test_sharded_drilldown_of_the_sharded_dimension(world, prefix, supported):
         return
     from olap_in_memory_b200 import Cube
     from oracle.store_oracle import OracleStore
+    from shard_store import OracleShardStore
 
     single = Cube(_time_first_dims(), OracleStore)
     want = _time_first_collect(single, _time_first_fill(single, 0.0))
@@ -281,8 +286,9 @@ def _reorder_worker(rank, world, port, prefix, default_is_nan, queue):
     try:
         from olap_in_memory_b200.sharded import ShardedCube
         from oracle.store_oracle import OracleStore
+        from shard_store import OracleShardStore
 
-        cube = ShardedCube(_dims(), prefix=prefix, store_cls=OracleStore)
+        cube = ShardedCube(_dims(), prefix=prefix, store_cls=OracleShardStore)
         _fill(cube, math.nan if default_is_nan else 0.0)
         results = _reorder_collect(cube, prefix)
         if rank == 0:
@@ -306,6 +312,7 @@ def test_sharded_reorder_matches_single_cube(world, prefix, default_is_nan):
         assert p.exitcode == 0
     from olap_in_memory_b200 import Cube
     from oracle.store_oracle import OracleStore
+    from shard_store import OracleShardStore
 
     single = Cube(_dims(), OracleStore)
     _fill(single, math.nan if default_is_nan else 0.0)
@@ -330,13 +337,14 @@ def test_reorder_inside_the_shard_is_local():
     from olap_in_memory_b200 import Cube, GenericDimension
     from olap_in_memory_b200.sharded import ShardedCube
     from oracle.store_oracle import OracleStore
+    from shard_store import OracleShardStore
 
     def dims():
         return [GenericDimension(name, "root", [f"{name}{i}" for i in range(n)]) for name, n in (("a", 2), ("b", 3), ("c", 4), ("d", 5))]
 
     values = np.arange(1, 121, dtype=np.float64)
     values[::7] = 0
-    sharded, single = ShardedCube(dims(), prefix=2, store_cls=OracleStore), Cube(dims(), OracleStore)
+    sharded, single = ShardedCube(dims(), prefix=2, store_cls=OracleShardStore), Cube(dims(), OracleStore)
     for cube in (sharded, single):
         cube.createStoredMeasure("mm", {}, "float32", 0)
         cube.setData("mm", values.tolist())
@@ -399,6 +407,7 @@ def _fuzz_worker(rank, world, port, queue):
         from olap_in_memory_b200 import Cube
         from olap_in_memory_b200.sharded import ShardedCube
         from oracle.store_oracle import OracleStore
+        from shard_store import OracleShardStore
 
         log = []
         for seed in range(int(os.environ.get("OLAP_FUZZ_SEEDS", "24"))):
@@ -406,7 +415,7 @@ def _fuzz_worker(rank, world, port, queue):
             prefix = 1 + seed % 2
             default = math.nan if seed % 3 == 0 else 0.0
             dims = _fuzz_dims(rng)
-            sharded, single = ShardedCube(dims, prefix=prefix, store_cls=OracleStore), Cube(dims, OracleStore)
+            sharded, single = ShardedCube(dims, prefix=prefix, store_cls=OracleShardStore), Cube(dims, OracleStore)
             values = rng.integers(1, 100, 7 * 5 * 12).astype(np.float64)
             values[rng.random(values.size) < 0.3] = default
             for cube in (sharded, single):
