@@ -84,6 +84,7 @@ def main():
                 failures += 1
                 if rank == 0:
                     print("MISMATCH time-first", prefix, key, np.asarray(got[key]).ravel()[:8], np.asarray(want[key]).ravel()[:8])
+    ShardedCube.release_peer_buffers()  # collective: the push exchange's receive buffers go back
     t = torch.tensor([failures], device="cuda")
     dist.all_reduce(t)
     if rank == 0:

@@ -476,3 +476,46 @@ def test_derived_status_planes_are_tracked_and_not_needed():
     # an interpolated cube rolled up again keeps its 0x4 flags: the plane IS read there
     again = G.drillUp_lowered([down], [C_, I], [3, I], [gmap, None], ["sum"])[0]
     assert any(b & 4 for b in again.status)
+
+
+def test_readme_only_status_examples():
+    """README-ONLY (parity unpinned: this fork of the reference has no getStatus).  The examples of
+    /root/reference/README.md:698-732 and :755-771 transcribed as data: flags 0x1 not set / 0x2 set / 0x4
+    interpolated; `is_empty` = (s & 3) == 1, `is_incomplete` = (s & 3) == 3, `is_complete` = (s & 3) == 2,
+    `is_interpolated` = (s & 4) == 4; c === complete === !(status & 0x1), r === raw === !(status & 0x4)."""
+    from olap_in_memory_b200 import Cube, GenericDimension, TimeDimension
+
+    _gpu()
+
+    def flags(status):
+        return {"is_empty": (status & 0x3) == 0x1, "is_incomplete": (status & 0x3) == 0x3, "is_complete": (status & 0x3) == 0x2,
+                "is_interpolated": (status & 0x4) == 0x4}
+
+    # README.md:722-727: [NaN, empty], [1, incomplete], [2, complete] — a month cube rolled up to quarters:
+    # Q1 has no month set, Q2 has one of three, Q3 all three
+    cube = Cube([TimeDimension("time", "month", "2010-01", "2010-09")])
+    cube.createStoredMeasure("main_measure", {"time": "sum"}, "float32", math.nan)
+    nan = math.nan
+    cube.setData("main_measure", [nan, nan, nan, 1, nan, nan, 0.5, 0.5, 1])
+    q = cube.drillUp("time", "quarter")
+    data, status = q.getData("main_measure"), q.getStatus("main_measure")
+    assert math.isnan(data[0]) and data[1:] == [1.0, 2.0]
+    assert [flags(s) for s in status] == [
+        {"is_empty": True, "is_incomplete": False, "is_complete": False, "is_interpolated": False},
+        {"is_empty": False, "is_incomplete": True, "is_complete": False, "is_interpolated": False},
+        {"is_empty": False, "is_incomplete": False, "is_complete": True, "is_interpolated": False},
+    ]
+    # README.md:755-771: every cell set and raw -> { v, r: true, c: true }; after a drillDown r turns false
+    cube = Cube([GenericDimension("city", "root", ["paris", "madrid"]), TimeDimension("time", "quarter", "2010-Q1", "2010-Q2")])
+    cube.createStoredMeasure("main_measure", {"time": "sum"}, "float32", math.nan)
+    cube.setData("main_measure", [33, 7, 33, 7])
+    st = cube.getStatus("main_measure")
+    assert [(v, not (s & 0x4), not (s & 0x1)) for v, s in zip(cube.getData("main_measure"), st)] == [(33.0, True, True), (7.0, True, True)] * 2
+    months = cube.drillDown("time", "month")
+    assert all((s & 0x4) and not (s & 0x1) for s in months.getStatus("main_measure"))  # interpolated, still complete
+    assert months.getData("main_measure")[:3] == [11.0, 11.0, 11.0]
+    # "When the cube is filled with .hydrateFromCube(otherCube), the status flags are copied between cubes" (README.md:704)
+    target = Cube([GenericDimension("city", "root", ["paris", "madrid"]), TimeDimension("time", "month", "2010-01", "2010-06")])
+    target.createStoredMeasure("main_measure", {"time": "sum"}, "float32", math.nan)
+    target.hydrateFromCube(months)
+    assert all(s & 0x4 for s in target.getStatus("main_measure"))
