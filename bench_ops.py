@@ -185,6 +185,8 @@ def main():
         s.canonicalise()  # status plane derived from the values: gathers and the pair transpose write it without reading it
         run(f"dice/derived-status outer every-other a {dims}", lambda: GpuStore.dice_lowered([s], dims, keep), (4 + B) * (n // 2), n // 2)
         run(f"reorder/derived-status reverse axes {dims}", lambda: GpuStore.reorder_lowered([s], dims, [5, 4, 3, 2, 1, 0]), (4 + B) * n, n)
+        run(f"reorder/derived-status swap inner two {dims}", lambda: GpuStore.reorder_lowered([s], dims, [0, 1, 2, 3, 5, 4]), (4 + B) * n, n)
+        run(f"reorder/derived-status rotate inner to front {dims}", lambda: GpuStore.reorder_lowered([s], dims, [5, 0, 1, 2, 3, 4]), (4 + B) * n, n)
         interop.status_tensor(s)  # a mutable pointer was handed out: back to the loaded plane for the rows below
     run(f"reorder/swap outer two {dims}", lambda: GpuStore.reorder_lowered([s], dims, [1, 0, 2, 3, 4, 5]), B * 2 * n, n)
     run(f"reorder/swap inner two {dims}", lambda: GpuStore.reorder_lowered([s], dims, [0, 1, 2, 3, 5, 4]), B * 2 * n, n)

@@ -479,11 +479,17 @@ __device__ __forceinline__ uint32_t run_spos(const BoxDim& e0, uint32_t pos) {
     return hi * e0.s_outer + (pos - hi * e0.by) * e0.s_stride;
 }
 
-template <bool STATUS>
+// STATUS: ST_NONE, ST_LOAD (the bytes ride through the tile) or ST_DERIVE (the source plane follows from its values,
+// olap_store::derived: nothing is loaded or staged, the bytes are recomputed from the cells on their way out)
+__device__ __forceinline__ uint32_t box_status_of(float v, int nan_default) {
+    return present_f(v, nan_default) ? (uint32_t)OLAP_STATUS_SET : (uint32_t)OLAP_STATUS_UNSET;
+}
+
+template <int STATUS>
 __device__ __forceinline__ void transpose_full_box(const TransposeParams& p, const float* __restrict__ src,
                                                    const uint8_t* __restrict__ st_src, float* __restrict__ dst,
                                                    uint8_t* __restrict__ st_dst, float* s_val, uint8_t* s_st,
-                                                   const uint2* s_rd, const uint2* s_wr) {
+                                                   const uint2* s_rd, const uint2* s_wr, int nan_default) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (p.rd_vec4) {
         // 128-bit loads along the input run (4 cells per lane slot, 4 slots in flight)
@@ -501,7 +507,7 @@ __device__ __forceinline__ void transpose_full_box(const TransposeParams& p, con
                     const uint32_t g = t.x + pos * 4;
                     so[u] = t.y + pos * 4 * p.rd[0].s_stride;
                     v[u] = ld_stream4(src + g);
-                    if (STATUS) sb[u] = ld_stream_u32(st_src + g);
+                    if (STATUS == ST_LOAD) sb[u] = ld_stream_u32(st_src + g);
                 }
             }
 #pragma unroll
@@ -510,7 +516,7 @@ __device__ __forceinline__ void transpose_full_box(const TransposeParams& p, con
                     const uint32_t ss = p.rd[0].s_stride;
                     s_val[so[u]] = v[u].x; s_val[so[u] + ss] = v[u].y;
                     s_val[so[u] + 2 * ss] = v[u].z; s_val[so[u] + 3 * ss] = v[u].w;
-                    if (STATUS) {
+                    if (STATUS == ST_LOAD) {
                         s_st[so[u]] = (uint8_t)sb[u]; s_st[so[u] + ss] = (uint8_t)(sb[u] >> 8);
                         s_st[so[u] + 2 * ss] = (uint8_t)(sb[u] >> 16); s_st[so[u] + 3 * ss] = (uint8_t)(sb[u] >> 24);
                     }
@@ -533,14 +539,14 @@ __device__ __forceinline__ void transpose_full_box(const TransposeParams& p, con
                     const uint32_t g = t.x + pos * gs;
                     so[u] = t.y + run_spos(p.rd[0], pos);
                     v[u] = ld_stream1(src + g);
-                    if (STATUS) sb[u] = st_src[g];
+                    if (STATUS == ST_LOAD) sb[u] = st_src[g];
                 }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
                 if (ok[u]) {
                     s_val[so[u]] = v[u];
-                    if (STATUS) s_st[so[u]] = sb[u];
+                    if (STATUS == ST_LOAD) s_st[so[u]] = sb[u];
                 }
         }
     }
@@ -566,10 +572,14 @@ __device__ __forceinline__ void transpose_full_box(const TransposeParams& p, con
 #pragma unroll
                         for (int k = 0; k < 4; ++k) so[k] = t.y + run_spos(p.wr[0], pos * 4 + k);
                     }
-                    st_stream4(dst + g, make_float4(s_val[so[0]], s_val[so[1]], s_val[so[2]], s_val[so[3]]));
-                    if (STATUS)
+                    const float4 q = make_float4(s_val[so[0]], s_val[so[1]], s_val[so[2]], s_val[so[3]]);
+                    st_stream4(dst + g, q);
+                    if (STATUS == ST_LOAD)
                         *reinterpret_cast<uint32_t*>(st_dst + g) = (uint32_t)s_st[so[0]] | ((uint32_t)s_st[so[1]] << 8) |
                                                                    ((uint32_t)s_st[so[2]] << 16) | ((uint32_t)s_st[so[3]] << 24);
+                    if (STATUS == ST_DERIVE)
+                        *reinterpret_cast<uint32_t*>(st_dst + g) = box_status_of(q.x, nan_default) | (box_status_of(q.y, nan_default) << 8) |
+                                                                   (box_status_of(q.z, nan_default) << 16) | (box_status_of(q.w, nan_default) << 24);
                 }
             }
         }
@@ -583,20 +593,22 @@ __device__ __forceinline__ void transpose_full_box(const TransposeParams& p, con
                 if (slot_cell(r, p.runs_out, pass, u * 32 + lane, run, pos)) {
                     const uint2 t = s_wr[run];
                     const uint32_t g = t.x + pos * gs, so = t.y + run_spos(p.wr[0], pos);
-                    dst[g] = s_val[so];
-                    if (STATUS) st_dst[g] = s_st[so];
+                    const float q = s_val[so];
+                    dst[g] = q;
+                    if (STATUS == ST_LOAD) st_dst[g] = s_st[so];
+                    if (STATUS == ST_DERIVE) st_dst[g] = (uint8_t)box_status_of(q, nan_default);
                 }
             }
         }
     }
 }
 
-template <int NB, bool STATUS, bool CHECK>
+template <int NB, int STATUS, bool CHECK>
 __device__ __forceinline__ void transpose_phases(const TransposeParams& p, const float* __restrict__ src,
                                                  const uint8_t* __restrict__ st_src, float* __restrict__ dst,
                                                  uint8_t* __restrict__ st_dst, float* s_val, uint8_t* s_st,
                                                  const uint32_t (&ext_rd)[kMaxBoxDims],
-                                                 const uint32_t (&ext_wr)[kMaxBoxDims]) {
+                                                 const uint32_t (&ext_wr)[kMaxBoxDims], int nan_default) {
     // ---- phase 1: input runs -> shared memory (4 loads in flight per lane)
     {
         const RunWalker<NB, CHECK> w(p.rd, ext_rd, p.runs_in);
@@ -610,13 +622,13 @@ __device__ __forceinline__ void transpose_phases(const TransposeParams& p, const
             for (int u = 0; u < 4; ++u)
                 if (mask & (1u << u)) {
                     v[u] = __ldg(src + o.g[u]);
-                    if (STATUS) sb[u] = __ldg(st_src + o.g[u]);
+                    if (STATUS == ST_LOAD) sb[u] = __ldg(st_src + o.g[u]);
                 }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
                 if (mask & (1u << u)) {
                     s_val[o.s[u]] = v[u];
-                    if (STATUS) s_st[o.s[u]] = sb[u];
+                    if (STATUS == ST_LOAD) s_st[o.s[u]] = sb[u];
                 }
         }
     }
@@ -631,8 +643,10 @@ __device__ __forceinline__ void transpose_phases(const TransposeParams& p, const
 #pragma unroll
             for (int u = 0; u < 4; ++u)
                 if (mask & (1u << u)) {
-                    dst[o.g[u]] = s_val[o.s[u]];
-                    if (STATUS) st_dst[o.g[u]] = s_st[o.s[u]];
+                    const float q = s_val[o.s[u]];
+                    dst[o.g[u]] = q;
+                    if (STATUS == ST_LOAD) st_dst[o.g[u]] = s_st[o.s[u]];
+                    if (STATUS == ST_DERIVE) st_dst[o.g[u]] = (uint8_t)box_status_of(q, nan_default);
                 }
         }
     }
@@ -676,8 +690,9 @@ __global__ void __launch_bounds__(256, OLAP_TRANSPOSE_MIN_BLOCKS) transpose_kern
     }
     const float* src = m.in + s_base[0];
     float* dst = m.out + s_base[1];
+    const int st_mode = m.st_in ? ST_LOAD : (m.derive && m.st_out ? ST_DERIVE : ST_NONE);
     const uint8_t* st_src = m.st_in ? m.st_in + s_base[0] : nullptr;
-    uint8_t* st_dst = m.st_in ? m.st_out + s_base[1] : nullptr;
+    uint8_t* st_dst = st_mode != ST_NONE ? m.st_out + s_base[1] : nullptr;
     if (s_full) {
         // stage the (box independent) run tables next to the tile
         uint2* s_rd = reinterpret_cast<uint2*>(smem_t + p.tab_offset);
@@ -685,11 +700,13 @@ __global__ void __launch_bounds__(256, OLAP_TRANSPOSE_MIN_BLOCKS) transpose_kern
         for (uint32_t i = threadIdx.x; i < p.runs_in; i += 256) s_rd[i] = __ldg(p.rd_tab + i);
         for (uint32_t i = threadIdx.x; i < p.runs_out; i += 256) s_wr[i] = __ldg(p.wr_tab + i);
         __syncthreads();
-        if (m.st_in) transpose_full_box<true>(p, src, st_src, dst, st_dst, s_val, s_st, s_rd, s_wr);
-        else transpose_full_box<false>(p, src, st_src, dst, st_dst, s_val, s_st, s_rd, s_wr);
+        if (st_mode == ST_LOAD) transpose_full_box<ST_LOAD>(p, src, st_src, dst, st_dst, s_val, s_st, s_rd, s_wr, m.nan_default);
+        else if (st_mode == ST_DERIVE) transpose_full_box<ST_DERIVE>(p, src, st_src, dst, st_dst, s_val, s_st, s_rd, s_wr, m.nan_default);
+        else transpose_full_box<ST_NONE>(p, src, st_src, dst, st_dst, s_val, s_st, s_rd, s_wr, m.nan_default);
     } else {
-        if (m.st_in) transpose_phases<NB, true, true>(p, src, st_src, dst, st_dst, s_val, s_st, ext_rd, ext_wr);
-        else transpose_phases<NB, false, true>(p, src, st_src, dst, st_dst, s_val, s_st, ext_rd, ext_wr);
+        if (st_mode == ST_LOAD) transpose_phases<NB, ST_LOAD, true>(p, src, st_src, dst, st_dst, s_val, s_st, ext_rd, ext_wr, m.nan_default);
+        else if (st_mode == ST_DERIVE) transpose_phases<NB, ST_DERIVE, true>(p, src, st_src, dst, st_dst, s_val, s_st, ext_rd, ext_wr, m.nan_default);
+        else transpose_phases<NB, ST_NONE, true>(p, src, st_src, dst, st_dst, s_val, s_st, ext_rd, ext_wr, m.nan_default);
     }
 }
 

@@ -1420,6 +1420,7 @@ int olap_reorder(olap_store* const* src, int n, int ndim, const int64_t* old_len
             OLAP_TRY(t.release());
         } else if (tp.use) {
             path = "reorder/box-transpose";
+            gather_derive(meas, src, n);
             TablePack t;
             const size_t o_meas = t.add(meas.data(), sizeof(GatherMeasure) * n);
             const size_t o_rd = t.add(tp.rd_tab.data(), tp.rd_tab.size() * sizeof(uint2));

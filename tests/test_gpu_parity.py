@@ -367,7 +367,13 @@ def test_reorder_fuzz_against_numpy():
             s.set_data_f32(data)
             stores.append(s)
             datas.append(data)
+        # measure 0: status plane derived from the values (never read); measure 1: a mutable raw pointer was handed
+        # out, so its plane is loaded and moved — both flavours of every kernel in one call
+        from olap_in_memory_b200 import interop
+        interop.status_tensor(stores[1])
+        assert stores[0].status_derived and not stores[1].status_derived
         outs = G.reorder_lowered(stores, dims, perm)
+        assert outs[0].status_derived and not outs[1].status_derived
         path = N.lib().olap_last_op_path().decode()
         paths[path] = paths.get(path, 0) + 1
         for data, out in zip(datas, outs):
