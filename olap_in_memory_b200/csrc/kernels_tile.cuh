@@ -652,8 +652,10 @@ __device__ __forceinline__ void transpose_phases(const TransposeParams& p, const
     }
 }
 
-template <int NB>
-__global__ void __launch_bounds__(256, OLAP_TRANSPOSE_MIN_BLOCKS) transpose_kernel(const __grid_constant__ TransposeParams p) {
+// MINB: resident CTAs per SM the register budget is cut for.  Measured on the config-3 cube (r02): moving a loaded
+// status plane wants 5 (48 registers: swap inner 2.28 ms against 2.57 ms), deriving it wants 6 (2.24 against 2.35 ms).
+template <int NB, int MINB>
+__global__ void __launch_bounds__(256, MINB) transpose_kernel(const __grid_constant__ TransposeParams p) {
     extern __shared__ __align__(16) unsigned char smem_t[];
     __shared__ uint32_t s_ext[OLAP_MAX_DIMS];
     __shared__ int64_t s_base[2];
@@ -950,24 +952,24 @@ inline TransposePlan transpose_plan(const std::vector<GDim>& dims_in) {
     return plan;
 }
 
-inline int launch_transpose(const GatherMeasure* d_meas, const uint2* d_rd_tab, const uint2* d_wr_tab, int n,
+inline int launch_transpose(bool derive_all, const GatherMeasure* d_meas, const uint2* d_rd_tab, const uint2* d_wr_tab, int n,
                             TransposePlan& plan) {
     plan.p.meas = d_meas;
     plan.p.rd_tab = d_rd_tab;
     plan.p.wr_tab = d_wr_tab;
     static bool attr_set = false;
     if (!attr_set) {
-        OLAP_CUDA(cudaFuncSetAttribute(transpose_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        OLAP_CUDA(cudaFuncSetAttribute(transpose_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        OLAP_CUDA(cudaFuncSetAttribute(transpose_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+#define OLAP_T_ATTR(NB, MB) OLAP_CUDA(cudaFuncSetAttribute(transpose_kernel<NB, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))
+        OLAP_T_ATTR(2, 5); OLAP_T_ATTR(3, 5); OLAP_T_ATTR(4, 5); OLAP_T_ATTR(2, 6); OLAP_T_ATTR(3, 6); OLAP_T_ATTR(4, 6);
+#undef OLAP_T_ATTR
         attr_set = true;
     }
     const dim3 grid((unsigned)plan.n_boxes, (unsigned)n);
     mark_kernels_begin();
     switch (plan.p.nb) {
-        case 2: transpose_kernel<2><<<grid, 256, plan.smem, g.stream>>>(plan.p); break;
-        case 3: transpose_kernel<3><<<grid, 256, plan.smem, g.stream>>>(plan.p); break;
-        default: transpose_kernel<4><<<grid, 256, plan.smem, g.stream>>>(plan.p); break;
+        case 2: if (derive_all) transpose_kernel<2, 6><<<grid, 256, plan.smem, g.stream>>>(plan.p); else transpose_kernel<2, 5><<<grid, 256, plan.smem, g.stream>>>(plan.p); break;
+        case 3: if (derive_all) transpose_kernel<3, 6><<<grid, 256, plan.smem, g.stream>>>(plan.p); else transpose_kernel<3, 5><<<grid, 256, plan.smem, g.stream>>>(plan.p); break;
+        default: if (derive_all) transpose_kernel<4, 6><<<grid, 256, plan.smem, g.stream>>>(plan.p); else transpose_kernel<4, 5><<<grid, 256, plan.smem, g.stream>>>(plan.p); break;
     }
     ++g_launches;
     return OLAP_OK;

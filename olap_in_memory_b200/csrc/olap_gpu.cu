@@ -1426,7 +1426,9 @@ int olap_reorder(olap_store* const* src, int n, int ndim, const int64_t* old_len
             const size_t o_rd = t.add(tp.rd_tab.data(), tp.rd_tab.size() * sizeof(uint2));
             const size_t o_wr = t.add(tp.wr_tab.data(), tp.wr_tab.size() * sizeof(uint2));
             OLAP_TRY(t.upload());
-            OLAP_TRY(launch_transpose(t.ptr<GatherMeasure>(o_meas), t.ptr<uint2>(o_rd), t.ptr<uint2>(o_wr), n, tp));
+            bool derive_all = true;  // no measure moves a loaded status plane
+            for (int k = 0; k < n; ++k) derive_all &= meas[k].st_in == nullptr;
+            OLAP_TRY(launch_transpose(derive_all, t.ptr<GatherMeasure>(o_meas), t.ptr<uint2>(o_rd), t.ptr<uint2>(o_wr), n, tp));
             OLAP_TRY(t.release());
         } else {
             OLAP_TRY(run_gather(G_COPY, src, n, dims, size, size, meas, nullptr, &path));
