@@ -1592,16 +1592,45 @@ int olap_load(olap_store* dst, const olap_store* src, int ndim, const int64_t* m
     OLAP_TRY(ensure_ctx());
     begin_op();
     dst->derived = dst->derived && is_derived(src);  // set cells take the other store's flags (README.md:704)
+    // Trailing axes that both stores have in full and in the same order (his item j -> my item j) are ONE contiguous
+    // run on both sides: fold them into a single innermost axis (identity, no table) so that the vectorised scatter
+    // moves the run with 128-bit accesses (hydrateFromCube of cubes that differ in their outer dimensions only)
+    std::vector<int64_t> my_len_m(my_len, my_len + ndim), his_len_m(his_len, his_len + ndim);
+    std::vector<const int32_t*> maps_m(his_to_mine, his_to_mine + ndim);
+    int64_t id_run = 0;  // > 0: the (folded) innermost axis is the identity over id_run cells
+    if (his_size && my_size && his_size < ((int64_t)1 << 31)) {  // the vectorised scatter below takes these
+        int64_t run = 1;
+        int k = 0;
+        while (ndim - k >= 1) {
+            const int L = ndim - 1 - k;
+            bool identity = my_len_m[L] == his_len_m[L] && his_len_m[L] > 0 && run * his_len_m[L] < ((int64_t)1 << 31);
+            for (int64_t j = 0; j < his_len_m[L] && identity; ++j) identity = maps_m[L][j] == (int32_t)j;
+            if (!identity) break;
+            run *= his_len_m[L];
+            ++k;
+        }
+        if (k >= 2) {
+            ndim -= k - 1;
+            my_len_m[ndim - 1] = his_len_m[ndim - 1] = run;
+            maps_m[ndim - 1] = nullptr;
+            id_run = run;
+        }
+    }
+    my_len = my_len_m.data();
+    his_len = his_len_m.data();
+    his_to_mine = maps_m.data();
     bool fast = false;
     if (his_size && my_size && ndim >= 1 && his_size < ((int64_t)1 << 31)) {
         // innermost axis: his item j -> my item m0 + j ?  then runs stay contiguous
         const int L = ndim - 1;
         bool linear = his_len[L] > 0;
-        for (int64_t j = 0; j < his_len[L] && linear; ++j) linear = his_to_mine[L][j] >= 0 && his_to_mine[L][j] == his_to_mine[L][0] + (int32_t)j;
-        if (linear && his_to_mine[L][0] + his_len[L] > my_len[L]) return fail(OLAP_E_INVALID, "olap_load: item index outside [0, %lld)", (long long)my_len[L]);
+        const int32_t first = id_run ? 0 : (his_len[L] > 0 ? his_to_mine[L][0] : 0);
+        if (!id_run)
+            for (int64_t j = 0; j < his_len[L] && linear; ++j) linear = his_to_mine[L][j] >= 0 && his_to_mine[L][j] == first + (int32_t)j;
+        if (linear && first + his_len[L] > my_len[L]) return fail(OLAP_E_INVALID, "olap_load: item index outside [0, %lld)", (long long)my_len[L]);
         const int64_t I = linear ? his_len[L] : 1;
         const int nd = linear ? ndim - 1 : ndim;
-        const int VEC = (linear && I % 4 == 0 && his_to_mine[L][0] % 4 == 0 && my_len[L] % 4 == 0) ? 4 : 1;
+        const int VEC = (linear && I % 4 == 0 && first % 4 == 0 && my_len[L] % 4 == 0) ? 4 : 1;
         bool ok = true;
         for (int d = 0; d < nd; ++d) ok &= his_len[d] <= 0x7fffffffLL;
         if (ok) {
@@ -1629,7 +1658,7 @@ int olap_load(olap_store* dst, const olap_store* src, int ndim, const int64_t* m
             p.nd = nd;
             p.IV = (uint32_t)(I / VEC);
             p.div_iv = FastDiv(p.IV);
-            p.inner_off = linear ? his_to_mine[L][0] : 0;
+            p.inner_off = linear ? first : 0;
             p.n_vec = (uint32_t)(his_size / VEC);
             const int64_t gx = ceil_div((int64_t)p.n_vec, 256);
             KERNELS_BEGIN();
