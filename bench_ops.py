@@ -139,6 +139,14 @@ def main():
         lambda: GpuStore.drillUp_lowered([s], [Oc, Cc], [Oc, 8], [ident(Oc), seg8], ["sum"]), B * (Cc + 8) * Oc, Cc * Oc)
     run(f"drillup/long customers->segment average [{Oc},{Cc},1]",
         lambda: GpuStore.drillUp_lowered([s], [Oc, Cc], [Oc, 8], [ident(Oc), seg8], ["average"]), B * (Cc + 8) * Oc, Cc * Oc)
+    s.canonicalise()  # what setData leaves behind: the status plane follows from the values and is not read
+    run(f"drillup/derived-status customers->segment sum [{Oc},{Cc},1]",
+        lambda: GpuStore.drillUp_lowered([s], [Oc, Cc], [Oc, 8], [ident(Oc), seg8], ["sum"]), (4 * Cc + B * 8) * Oc, Cc * Oc)
+    run(f"drillup/derived-status customers->segment average [{Oc},{Cc},1]",
+        lambda: GpuStore.drillUp_lowered([s], [Oc, Cc], [Oc, 8], [ident(Oc), seg8], ["average"]), (4 * Cc + B * 8) * Oc, Cc * Oc)
+    seg8m = np.sort(seg8)
+    run(f"drillup/derived-status customers->segment (sorted map) first [{Oc},{Cc},1]",
+        lambda: GpuStore.drillUp_lowered([s], [Oc, Cc], [Oc, 8], [ident(Oc), seg8m], ["first"]), (4 * Cc + B * 8) * Oc, Cc * Oc)
     del s
     # univac-style: 10-item generic dims, 1e9 cells at scale 1 (identity axes are split so
     # that no map is longer than 1e4 entries)
@@ -235,7 +243,7 @@ def main():
     mine = GpuStore(nl * 2, "float32", 0.0)  # twice the items on the outer axis
     to_mine = [np.arange(0, 2 * dl[0], 2, dtype=np.int32)] + [ident(d) for d in dl[1:]]
 
-    def timed_host(name, fn, algo_bytes, cells):
+    def timed_host(name, fn, algo_bytes, cells, kernel_bracket=False):
         if only and not any(name.startswith(o) for o in only):
             return
         import time
@@ -251,11 +259,15 @@ def main():
         t = float(np.median(ts))
         row = {"op": name, "path": lib.olap_last_op_path().decode(), "ms": round(t, 4), "GBs": round(algo_bytes / (t * 1e-3) / 1e9, 1),
                "frac": round(algo_bytes / (t * 1e-3) / 1e9 / peak, 3), "cells_per_s": cells / (t * 1e-3), "timing": "host wall-clock, synchronous call"}
+        if kernel_bracket:  # the op's kernels alone (event bracket inside the library)
+            k = float(lib.olap_last_op_ms())
+            row["kernel_ms"] = round(k, 4)
+            row["kernel_frac"] = round(algo_bytes / (k * 1e-3) / 1e9 / peak, 3) if k > 0 else None
         results.append(row)
         print(json.dumps(row), flush=True)
 
     timed_host(f"load/scatter every-other outer item {dl} -> x2", lambda: mine.load_lowered(his, [2 * dl[0]] + dl[1:], dl, to_mine),
-               B * 2 * nl, nl)
+               B * 2 * nl, nl, kernel_bracket=True)
     timed_host(f"sparse/export fill 0.5 [{nl}] (12 B per set cell to the host)", lambda: his.export_sparse(), B * nl + 12 * (nl // 2), nl)
     del his, mine
     if not only or "total" in only:
@@ -266,10 +278,42 @@ def main():
         for _ in range(5):
             ins[0].total
         t = (time.perf_counter() - t0) / 5 * 1e3
+        k = float(lib.olap_last_op_ms())
         row = {"op": f"total [{nI}] (host-timed, includes sync + D2H of 16 B)", "ms": round(t, 4),
-               "GBs": round(4 * nI / t / 1e6, 1), "frac": round(4 * nI / t / 1e6 / peak, 3)}
+               "GBs": round(4 * nI / t / 1e6, 1), "frac": round(4 * nI / t / 1e6 / peak, 3),
+               "kernel_ms": round(k, 4), "kernel_frac": round(4 * nI / k / 1e6 / peak, 3) if k > 0 else None}
         results.append(row)
         print(json.dumps(row), flush=True)
+    if not only or "boundary" in only:
+        # the data boundary with PAGEABLE host arrays (what a typed array of the addon is): csrc/host_pipe.cuh
+        import time
+        import ctypes as C
+
+        nB = nI
+        host = np.random.default_rng(1).random(nB, dtype=np.float32) + 1.0
+        sB = GpuStore(nB, "float32", 0.0)
+        out_buf = np.zeros(nB, dtype=np.float32)  # touched once: no first-touch page faults in the timing
+
+        def wall(fn, reps=3):
+            fn()
+            ts = []
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                fn()
+                ts.append(time.perf_counter() - t0)
+            return float(np.median(ts))
+
+        t_up = wall(lambda: sB.set_data_f32(host))
+        t_down = wall(lambda: N.check(lib.olap_store_download_f32(sB._h, out_buf.ctypes.data, nB)))
+        t_fresh = wall(lambda: sB.data_f32())
+        assert np.array_equal(out_buf, host)
+        for name, t in (("boundary/upload pageable Float32Array", t_up), ("boundary/download into a touched pageable array", t_down),
+                        ("boundary/download into a fresh pageable array (first touch included)", t_fresh)):
+            row = {"op": f"{name} [{nB}]", "ms": round(t * 1e3, 3), "GBs": round(4 * nB / t / 1e9, 2),
+                   "copy_threads": os.environ.get("OLAP_COPY_THREADS", "default"), "host_pipe": os.environ.get("OLAP_HOST_PIPE", "1")}
+            results.append(row)
+            print(json.dumps(row), flush=True)
+        del sB
     if args.out:
         json.dump(results, open(args.out, "w"), indent=1)
 

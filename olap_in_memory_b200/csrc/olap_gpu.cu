@@ -20,6 +20,7 @@
 #include "kernels_long.cuh"
 #include "kernels_pull.cuh"
 #include "kernels_tma.cuh"
+#include "host_pipe.cuh"
 
 namespace olap {
 
@@ -747,7 +748,7 @@ int olap_store_upload_f32(olap_store* s, const float* host, int64_t n) {
     OLAP_TRY(check_len(s, n));
     OLAP_TRY(ensure_ctx());
     if (n == 0) return OLAP_OK;
-    OLAP_CUDA(cudaMemcpyAsync(s->values, host, (size_t)n * 4, cudaMemcpyHostToDevice, g.stream));
+    OLAP_TRY(copy_h2d(s->values, host, (size_t)n * 4));
     canon_f32_kernel<<<grid_for(ceil_div(n, 4), kStoreThreads), kStoreThreads, 0, g.stream>>>(s->values, s->status, n, s->default_kind);
     LAUNCHED();
     set_derived(s, true);
@@ -760,7 +761,7 @@ int olap_store_upload_f64(olap_store* s, const double* host, int64_t n) {
     if (n == 0) return OLAP_OK;
     void* tmp;
     OLAP_TRY(dev_alloc(&tmp, (size_t)n * 8 + 8));
-    OLAP_CUDA(cudaMemcpyAsync(tmp, host, (size_t)n * 8, cudaMemcpyHostToDevice, g.stream));
+    OLAP_TRY(copy_h2d(tmp, host, (size_t)n * 8));
     // integer stores hold exact integers in the reference (JS doubles): refuse what a Float32 cell would change
     unsigned long long* lossy = strict_ints(s) ? reinterpret_cast<unsigned long long*>(static_cast<char*>(tmp) + (size_t)n * 8) : nullptr;
     if (lossy) OLAP_CUDA(cudaMemsetAsync(lossy, 0xff, 8, g.stream));
@@ -780,9 +781,7 @@ int olap_store_download_f32(const olap_store* s, float* host, int64_t n) {
     OLAP_TRY(check_len(s, n));
     OLAP_TRY(ensure_ctx());
     if (n == 0) return OLAP_OK;
-    OLAP_CUDA(cudaMemcpyAsync(host, s->values, (size_t)n * 4, cudaMemcpyDeviceToHost, g.stream));
-    OLAP_CUDA(cudaStreamSynchronize(g.stream));
-    return OLAP_OK;
+    return copy_d2h(host, s->values, (size_t)n * 4);
 }
 
 int olap_store_download_f64(const olap_store* s, double* host, int64_t n) {
@@ -793,10 +792,8 @@ int olap_store_download_f64(const olap_store* s, double* host, int64_t n) {
     OLAP_TRY(dev_alloc(&tmp, (size_t)n * 8));
     to_f64_kernel<<<grid_for(n, kStoreThreads), kStoreThreads, 0, g.stream>>>(s->values, (double*)tmp, n);
     LAUNCHED();
-    OLAP_CUDA(cudaMemcpyAsync(host, tmp, (size_t)n * 8, cudaMemcpyDeviceToHost, g.stream));
-    OLAP_TRY(dev_free(tmp));
-    OLAP_CUDA(cudaStreamSynchronize(g.stream));
-    return OLAP_OK;
+    OLAP_TRY(copy_d2h(host, tmp, (size_t)n * 8));
+    return dev_free(tmp);
 }
 
 int olap_store_get_value(const olap_store* s, int64_t index, double* out) {
@@ -866,8 +863,11 @@ static int total_and_count(const olap_store* s, double* sum, int64_t* count) {
     unsigned long long* ocnt = (unsigned long long*)(b + (size_t)blocks * 16 + 8);
     unsigned int* ticket = (unsigned int*)(b + (size_t)blocks * 16 + 16);
     OLAP_CUDA(cudaMemsetAsync(ticket, 0, 4, g.stream));
+    begin_op();
+    KERNELS_BEGIN();
     total_kernel<<<blocks, kStoreThreads, 0, g.stream>>>(s->values, s->size, s->default_kind, psum, pcnt, ticket, osum, ocnt);
     LAUNCHED();
+    end_op("total");
     struct { double s; unsigned long long c; } host;
     OLAP_CUDA(cudaMemcpyAsync(&host, osum, 16, cudaMemcpyDeviceToHost, g.stream));
     OLAP_TRY(dev_free(scratch));
@@ -894,19 +894,15 @@ static int bytes_out(const olap_store* s, uint8_t* host, int64_t n, bool status)
     OLAP_TRY(ensure_ctx());
     if (n == 0) return OLAP_OK;
     if (status && s->status) {
-        OLAP_CUDA(cudaMemcpyAsync(host, s->status, (size_t)n, cudaMemcpyDeviceToHost, g.stream));
-        OLAP_CUDA(cudaStreamSynchronize(g.stream));
-        return OLAP_OK;
+        return copy_d2h(host, s->status, (size_t)n);
     }
     void* tmp;
     OLAP_TRY(dev_alloc(&tmp, (size_t)n));
     presence_kernel<<<grid_for(n, kStoreThreads), kStoreThreads, 0, g.stream>>>(
         s->values, (uint8_t*)tmp, n, s->default_kind, status ? OLAP_STATUS_SET : 1, status ? OLAP_STATUS_UNSET : 0);
     LAUNCHED();
-    OLAP_CUDA(cudaMemcpyAsync(host, tmp, (size_t)n, cudaMemcpyDeviceToHost, g.stream));
-    OLAP_TRY(dev_free(tmp));
-    OLAP_CUDA(cudaStreamSynchronize(g.stream));
-    return OLAP_OK;
+    OLAP_TRY(copy_d2h(host, tmp, (size_t)n));
+    return dev_free(tmp);
 }
 
 int olap_store_presence(const olap_store* s, uint8_t* host, int64_t n) { return bytes_out(s, host, n, false); }
@@ -939,11 +935,10 @@ int olap_store_export_sparse(const olap_store* s, int64_t capacity, int64_t* key
             OLAP_TRY(dev_alloc(&dv, (size_t)total * 4));
             compact_write_kernel<<<(unsigned)nb, 256, 0, g.stream>>>(s->values, s->size, s->default_kind, d_cnt, (int64_t*)dk, (float*)dv);
             LAUNCHED();
-            OLAP_CUDA(cudaMemcpyAsync(keys, dk, (size_t)total * 8, cudaMemcpyDeviceToHost, g.stream));
-            OLAP_CUDA(cudaMemcpyAsync(values, dv, (size_t)total * 4, cudaMemcpyDeviceToHost, g.stream));
+            OLAP_TRY(copy_d2h(keys, dk, (size_t)total * 8));
+            OLAP_TRY(copy_d2h(values, dv, (size_t)total * 4));
             OLAP_TRY(dev_free(dk));
             OLAP_TRY(dev_free(dv));
-            OLAP_CUDA(cudaStreamSynchronize(g.stream));
         }
     }
     OLAP_TRY(dev_free(cnt));
@@ -955,7 +950,19 @@ int olap_store_import_sparse(olap_store* s, const int64_t* keys, const float* va
     OLAP_TRY(ensure_ctx());
     OLAP_TRY(fill_default(s));
     set_derived(s, true);
-    if (count) {
+    if (count >= ((int64_t)1 << 20)) {  // large lists go straight to the device (pageable memory: through the pinned ring)
+        void *dk, *dv;
+        OLAP_TRY(dev_alloc(&dk, (size_t)count * 8));
+        OLAP_TRY(dev_alloc(&dv, (size_t)count * 4));
+        OLAP_TRY(copy_h2d(dk, keys, (size_t)count * 8));
+        OLAP_TRY(copy_h2d(dv, values, (size_t)count * 4));
+        import_sparse_kernel<<<(unsigned)ceil_div(count, kStoreThreads), kStoreThreads, 0, g.stream>>>(
+            s->values, s->status, (const int64_t*)dk, (const float*)dv, count, s->size, s->default_kind);
+        LAUNCHED();
+        OLAP_TRY(dev_free(dk));
+        OLAP_TRY(dev_free(dv));
+        OLAP_CUDA(cudaStreamSynchronize(g.stream));  // the host lists are borrowed for the call only
+    } else if (count) {
         TablePack t;
         const size_t ok = t.add(keys, (size_t)count * 8);
         const size_t ov = t.add(values, (size_t)count * 4);
@@ -1035,7 +1042,18 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
             for (int k = 0; k < n; ++k) any_status |= meas[k].st_in != nullptr;
             const TileDecision tile = tile_plan(O, C, P, I, any_status);
             LongDecision lng;
-            if (!tile.use) lng = long_plan(O, C, P, I, any_status, n, g.sm_count, csr.contiguous);
+            LanesDecision lanes;
+            static const int derive_knob = [] { const char* e = getenv("OLAP_DERIVE_STATUS"); return e ? atoi(e) : 1; }();
+            if (!tile.use) {
+                // planes that will really be read (the others follow from the values; read in words of 4 status bytes)
+                bool loaded = false, aligned = true;
+                for (int k = 0; k < n; ++k) {
+                    loaded |= meas[k].st_in && !(derive_knob && src[k]->derived && !src[k]->shared_plane);
+                    aligned &= (reinterpret_cast<uintptr_t>(meas[k].st_in) & 3) == 0;
+                }
+                if (aligned) lanes = lanes_plan(O, C, P, I, n, g.sm_count, loaded);
+            }
+            if (!tile.use && !lanes.use) lng = long_plan(O, C, P, I, any_status, n, g.sm_count, csr.contiguous);
             TablePack stat;
             const size_t o_ps = stat.add(csr.pstart.data(), csr.pstart.size() * 4);
             // a contiguous map needs no child list on the device (children[k] == k)
@@ -1046,6 +1064,11 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
                 o_seg = stat.add(lt.seg_ptr.data(), lt.seg_ptr.size() * 4);
                 if (!lt.perm16.empty()) o_perm = stat.add(lt.perm16.data(), lt.perm16.size() * 2);
             }
+            size_t o_map8 = 0;
+            if (lanes.use) {
+                const std::vector<uint8_t> lists = lanes_lists(maps[d], C, P);
+                o_map8 = stat.add(lists.data(), lists.size());
+            }
             const char* d_stat = nullptr;
             OLAP_TRY(cached_tables(stat, &d_stat));
             const bool inline_meas = n <= kInlineMeasures;
@@ -1055,10 +1078,9 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
             const int32_t* d_ch = csr.contiguous ? nullptr : reinterpret_cast<const int32_t*>(d_stat + o_ch);
             // sources whose status plane follows from their values: the mid / split / tile kernels recompute the
             // bytes from the cells they load anyway and never read the plane (4 instead of 5 bytes per input cell)
-            static const int derive_knob = [] { const char* e = getenv("OLAP_DERIVE_STATUS"); return e ? atoi(e) : 1; }();
             const UpMeasure* d_meas_drv = d_meas;
             TablePack t2;
-            if (derive_knob && (tile.use || !lng.use)) {
+            if (derive_knob && (tile.use || lanes.use || !lng.use)) {
                 bool changed_desc = false;
                 for (int k = 0; k < n; ++k)
                     if (meas[k].st_in && src[k]->derived && !src[k]->shared_plane) {
@@ -1075,6 +1097,14 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
             if (tile.use) {
                 path = "drillup/tile";
                 OLAP_TRY(launch_up_tile(d_meas_drv, meas.data(), n, csr.contiguous, d_ps, d_ch, O, C, P, I, tile));
+            } else if (lanes.use) {
+                path = "drillup/lanes";
+                void* scratch = nullptr;
+                if (lanes.SS > 1) OLAP_TRY(dev_alloc(&scratch, (size_t)lanes.scratch_stride * n));
+                OLAP_TRY(launch_up_lanes(d_meas_drv, meas.data(), n, csr.contiguous, d_ps, d_ch,
+                                         reinterpret_cast<const uint8_t*>(d_stat + o_map8), O, C, P, lanes,
+                                         static_cast<unsigned char*>(scratch)));
+                if (scratch) OLAP_TRY(dev_free(scratch));
             } else if (lng.use) {
                 path = "drillup/long";
                 void* scratch = nullptr;

@@ -525,3 +525,95 @@ def test_readme_only_status_examples():
     target.createStoredMeasure("main_measure", {"time": "sum"}, "float32", math.nan)
     target.hydrateFromCube(months)
     assert all(s & 0x4 for s in target.getStatus("main_measure"))
+
+
+@pytest.mark.parametrize("default", [0.0, math.nan])
+@pytest.mark.parametrize("monotone", [False, True])
+def test_lanes_rollup_of_many_long_rows(default, monotone, monkeypatch):
+    """drillup_lanes_kernel ([O >= 64, C >= 2048 and C % 4 == 0, 1] -> [O, P <= 8, 1], any map: customers -> segment):
+    the row sits on the lane, the warp-uniform parent selects the accumulator.  Against the C oracle: order-only rules
+    bit-exact (first / last follow child order through the ordered folds), sums within 1e-6 (tree-reduced regime),
+    status bytes exact, with a loaded and with a derived status plane, one and several segments per row, ragged row
+    groups and tiles, a parent without children.  Rows that do not start on 16 bytes stay with the long kernel."""
+    from olap_in_memory_b200 import _native as N
+    from olap_in_memory_b200 import interop
+    from oracle.c_oracle import COracleStore
+
+    G = _gpu()
+    rng = np.random.default_rng(9)
+    for O, C_, P, ss in ((70, 12304, 5, None), (129, 12048 + 76, 8, None), (64, 19000, 1, "1"), (200, 12600, 3, "1"),
+                         (65, 2052, 2, "1"), (70, 12301, 5, None)):
+        if ss is None:
+            monkeypatch.delenv("OLAP_LANES_SS", raising=False)
+        else:
+            monkeypatch.setenv("OLAP_LANES_SS", ss)
+        cmap = cases.random_map(rng, C_, P, monotone)
+        if P == 5:
+            cmap[cmap == 3] = 2  # parent 3 has no child at all: its cells stay unset
+        ident = np.arange(O, dtype=np.int32)
+        for kind in ("int", "small"):
+            data = cases.make_data(rng, O * C_, default, 0.6, kind)
+            methods = ["sum", "average", "highest", "lowest", "first", "last"] + (["product"] if kind == "small" else [])
+            ref = COracleStore(O * C_, "float32", default)
+            ref.set_data_f32(data)
+            for derived in (True, False):
+                stores = []
+                for _ in methods:
+                    s = G(O * C_, "float32", default)
+                    s.set_data_f32(data)
+                    if not derived:
+                        interop.status_tensor(s)
+                    stores.append(s)
+                outs = G.drillUp_lowered(stores, [O, C_], [O, P], [ident, cmap], methods)
+                assert N.lib().olap_last_op_path() == (b"drillup/lanes" if C_ % 4 == 0 else b"drillup/long"), (O, C_, P)
+                for method, out in zip(methods, outs):
+                    want = ref.drillUp_lowered([O, C_], [O, P], [ident, cmap], method).data_f64().astype(np.float32)
+                    got = out.data_f32()
+                    if method in ("sum", "average", "product"):
+                        assert np.allclose(got, want, rtol=1e-6, atol=0, equal_nan=True), (O, C_, P, kind, method, derived)
+                    else:
+                        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (O, C_, P, kind, method, derived)
+                # status: OR of the children's bytes, UNSET for a parent without children
+                set_ = (data == data) if default != default else (data != 0)
+                bits = np.where(set_, 2, 1).astype(np.uint8).reshape(O, C_)
+                want_st = np.ones((O, P), dtype=np.uint8)
+                for q in range(P):
+                    cols = np.flatnonzero(cmap == q)
+                    if cols.size:
+                        want_st[:, q] = np.bitwise_or.reduce(bits[:, cols], axis=1)
+                assert np.array_equal(np.asarray(outs[0].status, dtype=np.uint8).reshape(O, P), want_st), (O, C_, P, kind, derived)
+
+
+def test_pageable_host_buffers_travel_through_the_pinned_ring():
+    """Large transfers from / to plain (pageable) host memory are cut into chunks that go through a ring of pinned
+    buffers, the host-side copies on worker threads (csrc/host_pipe.cuh; in-memory.js:30-46 `get data` / `set data`).
+    Sizes that wrap the ring several times and end on a ragged chunk: every byte must arrive, in both directions, for
+    Float32 and Float64 arrays, status and presence bytes and the sparse lists."""
+    from olap_in_memory_b200 import _native as N
+
+    G = _gpu()
+    rng = np.random.default_rng(21)
+    n = 5 * (16 << 20) // 4 + 12345  # 5 chunks of 16 MiB and a tail
+    data = rng.integers(-5, 6, n).astype(np.float32)
+    data[rng.random(n) < 0.3] = 0.0
+    s = G(n, "float32", 0)
+    s.set_data_f32(data)
+    assert np.array_equal(s.data_f32().view(np.uint32), data.view(np.uint32))
+    st = np.empty(n, dtype=np.uint8)
+    N.check(N.lib().olap_store_status(s._h, st.ctypes.data, n))
+    assert np.array_equal(st, np.where(data != 0, 2, 1).astype(np.uint8))
+    assert np.array_equal(s.presence(), (data != 0).astype(np.uint8))
+    keys, values = s.export_sparse()
+    want_keys = np.flatnonzero(data != 0)
+    assert np.array_equal(keys, want_keys) and np.array_equal(values, data[want_keys])
+    t = G(n, "float32", 0)
+    t.import_sparse(keys, values)
+    assert np.array_equal(t.data_f32().view(np.uint32), data.view(np.uint32))
+    # Float64 in and out (upload_f64 / download_f64)
+    d64 = data.astype(np.float64)
+    u = G(n, "float64", math.nan)
+    N.check(N.lib().olap_store_upload_f64(u._h, d64.ctypes.data, n))
+    out64 = np.empty(n, dtype=np.float64)
+    N.check(N.lib().olap_store_download_f64(u._h, out64.ctypes.data, n))
+    assert np.array_equal(out64, d64)
+    assert s.total == float(d64.sum())
