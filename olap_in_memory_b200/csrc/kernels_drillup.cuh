@@ -644,7 +644,7 @@ __device__ void up_gen_body(const UpGenParams& p, const UpMeasure& m, int64_t j)
     if (m.st_out) m.st_out[j] = (uint8_t)st;
 }
 
-__global__ void __launch_bounds__(256) drillup_generic_kernel(const __grid_constant__ UpGenParams p) {
+static __global__ void __launch_bounds__(256) drillup_generic_kernel(const __grid_constant__ UpGenParams p) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= p.n_out) return;
     const UpMeasure m = p.meas[blockIdx.y];
@@ -912,7 +912,7 @@ __device__ __forceinline__ void down_inner_body(const DownInnerParams& p, const 
     }
 }
 
-__global__ void __launch_bounds__(256, 4) drilldown_inner_kernel(const __grid_constant__ DownInnerParams p) {
+static __global__ void __launch_bounds__(256, 4) drilldown_inner_kernel(const __grid_constant__ DownInnerParams p) {
     extern __shared__ __align__(16) unsigned char smem_di[];
     const DownMeasure m = p.meas[blockIdx.y];
     if (p.I == 1) {

@@ -342,7 +342,7 @@ struct ScatterParams {
     int64_t n;
 };
 
-__global__ void __launch_bounds__(256) load_scatter_kernel(const __grid_constant__ ScatterParams p) {
+static __global__ void __launch_bounds__(256) load_scatter_kernel(const __grid_constant__ ScatterParams p) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= p.n) return;
     int64_t rest = t, off = 0;

@@ -37,7 +37,7 @@ struct UpLongParams {
     int32_t G, logG;
     unsigned char* scratch;    // SS > 1: per measure [O*SS*row_out] 16-byte lane states, then as many status bytes
     int64_t scratch_stride;    // bytes per measure
-    const uint8_t* map8;       // drillup_lanes_kernel: per tile of 128 children, their positions grouped by parent + 16 list bounds
+    const uint8_t* map8;       // drillup_lanes_kernel (kernels_lanes.cuh): per-tile child lists
     int32_t lanes_cs;          // drillup_lanes_kernel: children per CTA segment
     uint32_t lanes_stage;      // drillup_lanes_kernel: bytes of one staging buffer of one warp
 };
@@ -379,310 +379,6 @@ __global__ void __launch_bounds__(kLongMergeThreads) drillup_long_merge_kernel(c
         default: OLAP_LONG_MERGE(OLAP_PRODUCT)
     }
 #undef OLAP_LONG_MERGE
-}
-
-// ---- drillup_lanes_kernel: MANY rows, long rows, few parents, ANY map ([O >= 64, C, 1] -> [O, P <= 8, 1]:
-// customers -> segment).  The map is the same for every row, so the kernel puts the ROW on the lane: all 32 lanes
-// of a warp (32 different rows) look at the same child at the same time, which makes the parent warp-uniform, and
-// the child lists per parent are walked by uniform loops that feed ONE register accumulator per parent — no
-// divergence, no random gather.  The long kernel reduces this shape through per-thread cell lists that hit random
-// shared-memory banks (0.33-0.41 of peak).
-//   * a CTA owns 32 rows x a segment of the children; each of its warps owns a contiguous chunk of the segment
-//     and runs its OWN cp.async pipeline over tiles of 32 rows x 128 children (512 contiguous bytes per row and
-//     tile): no CTA barrier in the loop, the next tile is in flight while this one is folded;
-//   * a tile sits row-major with an odd pitch (129 words; status bytes 33 words), copied 4 bytes at a time: the
-//     copies (lanes along a row) and the fold (lanes along rows, same column) are free of bank conflicts and the
-//     rows need no alignment;
-//   * the host lists, per tile, its children grouped by parent (positions inside the tile, one byte each, plus the
-//     P + 1 list bounds): they travel with the tile; a parent's list is folded as two chains (first half, second
-//     half, merged in order) so that two double adds are in flight per lane;
-//   * once per CTA the warps' lanes are folded IN ORDER (Lane::merge: first / last and the restart rule stay
-//     exact); with several segments per row the states go to the scratch array of the long kernel and its merge
-//     kernel folds them.
-constexpr int kLanesTile = 128, kLanesRows = 32, kLanesMaxP = 8, kLanesWarps = 2, kLanesStages = 2;
-constexpr uint32_t kLanesPitchV = (kLanesTile + 1) * 4;   // bytes between rows of a value tile
-constexpr uint32_t kLanesPitchS = kLanesTile + 4;         // ... of a status tile
-constexpr uint32_t kLanesValBytes = kLanesRows * kLanesPitchV, kLanesListBytes = kLanesTile + 16, kLanesStBytes = kLanesRows * kLanesPitchS;
-static_assert((kLanesValBytes + kLanesListBytes) % 16 == 0, "staging buffers keep 16-byte alignment");
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int METHOD, bool NANDEF, bool RANGE, int STATUS>
-__device__ __forceinline__ void up_lanes_body(const UpLongParams& p, const UpMeasure& m, unsigned char* smem, uint32_t rg,
-                                              int32_t ss) {
-    typedef Lane<METHOD, NANDEF> L;
-    static_assert(sizeof(L) <= kLongStateBytes, "lane state larger than its slot");
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row0 = (int64_t)rg * kLanesRows;
-    const int rows = (int)min((int64_t)kLanesRows, p.O - row0);
-    // my warp's chunk of the CTA's segment (both start on tile boundaries)
-    const int32_t chunk = p.lanes_cs / kLanesWarps;
-    const int32_t c_begin = min(p.C, ss * p.lanes_cs + warp * chunk), c_end = min(p.C, c_begin + chunk);
-    const int32_t n_tiles = (c_end - c_begin + kLanesTile - 1) / kLanesTile;
-    unsigned char* my = smem + (size_t)warp * kLanesStages * p.lanes_stage;
-    const float* g_row = m.in + row0 * (int64_t)p.C;
-    const uint8_t* g_st = STATUS == ST_LOAD ? m.st_in + row0 * (int64_t)p.C : nullptr;
-
-    auto issue = [&](int32_t t) {
-        const int32_t c0 = c_begin + t * kLanesTile;
-        const int32_t n = min(kLanesTile, c_end - c0);
-        const uint32_t sb = smem_u32(my + (size_t)(t % kLanesStages) * p.lanes_stage);
-#pragma unroll
-        for (int j = 0; j < kLanesTile / 32; ++j) {
-            const int cc = lane + 32 * j;
-            if (cc < n) {
-                const float* src = g_row + c0 + cc;
-                uint32_t dst = sb + 4u * cc;
-#pragma unroll 4
-                for (int r = 0; r < rows; ++r) {
-                    cp_async4(dst, src);
-                    dst += kLanesPitchV;
-                    src += p.C;
-                }
-            }
-        }
-        if (STATUS == ST_LOAD && 4 * lane < n) {  // C % 4 == 0: whole words of 4 status bytes
-            const uint8_t* s_src = g_st + c0 + 4 * lane;
-            uint32_t s_dst = sb + kLanesValBytes + kLanesListBytes + 4u * lane;
-#pragma unroll 4
-            for (int r = 0; r < rows; ++r) {
-                cp_async4(s_dst, s_src);
-                s_dst += kLanesPitchS;
-                s_src += p.C;
-            }
-        }
-        // the tile's lists: 128 positions + 16 bounds, 144 bytes per tile
-        if (lane < 9) cp_async16(sb + kLanesValBytes + 16u * lane, p.map8 + (size_t)(c0 / kLanesTile) * kLanesListBytes + 16 * lane);
-    };
-
-    L part[kLanesMaxP];
-    uint32_t pst[kLanesMaxP];
-#pragma unroll
-    for (int q = 0; q < kLanesMaxP; ++q) pst[q] = 0;
-
-#pragma unroll
-    for (int t = 0; t < kLanesStages; ++t) {
-        if (t < n_tiles) issue(t);
-        cp_async_commit();
-    }
-    for (int32_t t = 0; t < n_tiles; ++t) {
-        cp_async_wait<kLanesStages - 1>();
-        __syncwarp();
-        const unsigned char* sb = my + (size_t)(t % kLanesStages) * p.lanes_stage;
-        const float* sv = reinterpret_cast<const float*>(sb + (size_t)lane * kLanesPitchV);
-        const uint8_t* s_perm = sb + kLanesValBytes;
-        const uint8_t* sst = sb + kLanesValBytes + kLanesListBytes + (size_t)lane * kLanesPitchS;
-        const uint4 ow = *reinterpret_cast<const uint4*>(s_perm + kLanesTile);  // list bounds 0 .. 15
-        const uint32_t owords[4] = {ow.x, ow.y, ow.z, ow.w};
-#pragma unroll
-        for (int q = 0; q < kLanesMaxP; ++q) {
-            const int k0 = (int)((owords[q >> 2] >> (8 * (q & 3))) & 0xffu);
-            const int k1 = (int)((owords[(q + 1) >> 2] >> (8 * ((q + 1) & 3))) & 0xffu);
-            if (q < p.P && k0 < k1) {  // warp-uniform
-                const int kmid = k0 + ((k1 - k0 + 1) >> 1), n2 = k1 - kmid;
-                L a0, a1;
-                uint32_t st = 0;
-#pragma unroll 2
-                for (int i = 0; i < n2; ++i) {
-                    const uint32_t ca = s_perm[k0 + i], cb = s_perm[kmid + i];
-                    const float va = sv[ca], vb = sv[cb];
-                    if (STATUS == ST_LOAD) st |= (uint32_t)sst[ca] | (uint32_t)sst[cb];
-                    if (STATUS == ST_DERIVE)
-                        st |= (present_f(va, NANDEF) ? OLAP_STATUS_SET : OLAP_STATUS_UNSET) | (present_f(vb, NANDEF) ? OLAP_STATUS_SET : OLAP_STATUS_UNSET);
-                    a0.step(va);
-                    a1.step(vb);
-                }
-                if (kmid - k0 > n2) {  // odd list: the first chain is one longer
-                    const uint32_t ca = s_perm[kmid - 1];
-                    const float va = sv[ca];
-                    if (STATUS == ST_LOAD) st |= sst[ca];
-                    if (STATUS == ST_DERIVE) st |= present_f(va, NANDEF) ? OLAP_STATUS_SET : OLAP_STATUS_UNSET;
-                    a0.step(va);
-                }
-                a0.merge(a1);
-                part[q].merge(a0);
-                pst[q] |= st;
-            }
-        }
-        __syncwarp();  // every lane is done with this stage: refill it
-        if (t + kLanesStages < n_tiles) issue(t + kLanesStages);
-        cp_async_commit();
-    }
-    cp_async_wait<0>();
-    __syncthreads();  // all warps are out of their pipelines: the staging memory now holds the warps' lanes
-    uint8_t* s_pst = smem + (size_t)kLanesWarps * kLanesMaxP * 32 * kLongStateBytes;  // after the [warp][parent][row] states
-#pragma unroll
-    for (int q = 0; q < kLanesMaxP; ++q) {
-        *reinterpret_cast<L*>(smem + (size_t)((warp * kLanesMaxP + q) * 32 + lane) * kLongStateBytes) = part[q];
-        s_pst[(warp * kLanesMaxP + q) * 32 + lane] = (uint8_t)pst[q];
-    }
-    __syncthreads();
-    for (int q = warp; q < p.P; q += kLanesWarps) {
-        L acc;
-        uint32_t acc_st = 0;
-#pragma unroll
-        for (int w2 = 0; w2 < kLanesWarps; ++w2) {  // earlier children first
-            acc.merge(*reinterpret_cast<const L*>(smem + (size_t)((w2 * kLanesMaxP + q) * 32 + lane) * kLongStateBytes));
-            acc_st |= s_pst[(w2 * kLanesMaxP + q) * 32 + lane];
-        }
-        if (lane < rows) {
-            const int64_t o = row0 + lane;
-            if (p.SS == 1) {
-                up_long_finish<METHOD, NANDEF, RANGE>(p, m, o, q, acc, acc_st);
-            } else {
-                unsigned char* base = p.scratch + (size_t)blockIdx.y * p.scratch_stride;
-                const int64_t n_states = p.O * p.SS * p.row_out;
-                const int64_t slot = (o * p.SS + ss) * p.row_out + q;
-                *reinterpret_cast<L*>(base + slot * kLongStateBytes) = acc;
-                base[n_states * kLongStateBytes + slot] = (uint8_t)acc_st;
-            }
-        }
-    }
-}
-
-template <bool NANDEF, bool RANGE, int STATUS>
-__device__ __forceinline__ void up_lanes_dispatch(const UpLongParams& p, const UpMeasure& m, unsigned char* smem, uint32_t rg, int32_t ss) {
-    switch (m.method) {
-        case OLAP_SUM: up_lanes_body<OLAP_SUM, NANDEF, RANGE, STATUS>(p, m, smem, rg, ss); break;
-        case OLAP_AVERAGE: up_lanes_body<OLAP_AVERAGE, NANDEF, RANGE, STATUS>(p, m, smem, rg, ss); break;
-        case OLAP_HIGHEST: up_lanes_body<OLAP_HIGHEST, NANDEF, RANGE, STATUS>(p, m, smem, rg, ss); break;
-        case OLAP_LOWEST: up_lanes_body<OLAP_LOWEST, NANDEF, RANGE, STATUS>(p, m, smem, rg, ss); break;
-        case OLAP_FIRST: up_lanes_body<OLAP_FIRST, NANDEF, RANGE, STATUS>(p, m, smem, rg, ss); break;
-        case OLAP_LAST: up_lanes_body<OLAP_LAST, NANDEF, RANGE, STATUS>(p, m, smem, rg, ss); break;
-        case OLAP_COUNT: up_lanes_body<OLAP_COUNT, NANDEF, RANGE, STATUS>(p, m, smem, rg, ss); break;
-        default: up_lanes_body<OLAP_PRODUCT, NANDEF, RANGE, STATUS>(p, m, smem, rg, ss); break;
-    }
-}
-
-template <bool RANGE>
-__global__ void __launch_bounds__(kLanesWarps * 32, 3) drillup_lanes_kernel(const __grid_constant__ UpLongParams p) {
-    extern __shared__ __align__(128) unsigned char smem_lanes[];
-    const UpMeasure m = p.meas ? p.meas[blockIdx.y] : p.meas_inline[blockIdx.y];
-    const uint32_t rg = p.div_ss.div(blockIdx.x), ss = blockIdx.x - rg * (uint32_t)p.SS;
-    const int status = m.st_in ? ST_LOAD : (m.derive ? ST_DERIVE : ST_NONE);
-    if (m.nan_default) {
-        if (status == ST_LOAD) up_lanes_dispatch<true, RANGE, ST_LOAD>(p, m, smem_lanes, rg, (int32_t)ss);
-        else if (status == ST_DERIVE) up_lanes_dispatch<true, RANGE, ST_DERIVE>(p, m, smem_lanes, rg, (int32_t)ss);
-        else up_lanes_dispatch<true, RANGE, ST_NONE>(p, m, smem_lanes, rg, (int32_t)ss);
-    } else {
-        if (status == ST_LOAD) up_lanes_dispatch<false, RANGE, ST_LOAD>(p, m, smem_lanes, rg, (int32_t)ss);
-        else if (status == ST_DERIVE) up_lanes_dispatch<false, RANGE, ST_DERIVE>(p, m, smem_lanes, rg, (int32_t)ss);
-        else up_lanes_dispatch<false, RANGE, ST_NONE>(p, m, smem_lanes, rg, (int32_t)ss);
-    }
-}
-
-struct LanesDecision {
-    bool use = false;
-    int32_t Cs = 0, SS = 1;
-    int64_t scratch_stride = 0;
-};
-
-// Many long rows, few parents, innermost axis rolled up (see drillup_lanes_kernel).  `loaded_status`: some measure
-// brings a status plane that has to be read (one CTA less per SM).
-inline LanesDecision lanes_plan(int64_t O, int64_t C, int64_t P, int64_t I, int n_meas, int sm_count, bool loaded_status) {
-    // a status plane that has to be read is copied in words of 4 bytes: rows must start on them
-    LanesDecision d;
-    // OLAP_LANES=0 sends the shape back to the long kernel (read at every call so that a test can compare the two)
-    const char* knob_env = getenv("OLAP_LANES");
-    if (knob_env && atoi(knob_env) == 0) return d;
-    if (I != 1 || P > kLanesMaxP || P < 1 || O < 64 || C < 2048 || (loaded_status && (C & 3)) || C / P < 64 || C > 0x7fffffffLL || O > 0x3fffffffLL) return d;
-    const int64_t groups = ceil_div(O, kLanesRows);
-    const int64_t slots = (int64_t)sm_count * (loaded_status ? 2 : 3);
-    const int64_t unit = (int64_t)kLanesTile * kLanesWarps;
-    // segments per row: the fewest CTA waves of the shortest segments (+1 tile: the pipeline fills once per CTA)
-    int64_t best_cost = INT64_MAX, best_cs = 0, best_ss = 1;
-    int64_t max_ss = std::min<int64_t>(ceil_div(C, unit), 2048), min_ss = 1;
-    if (const char* e = getenv("OLAP_LANES_SS")) min_ss = max_ss = std::max<int64_t>(1, std::min<int64_t>(atoi(e), max_ss));  // tests, tuning
-    for (int64_t ss = min_ss; ss <= max_ss; ++ss) {
-        const int64_t cs = ceil_div(ceil_div(C, ss), unit) * unit;
-        const int64_t ss_eff = ceil_div(C, cs);
-        if (groups * ss_eff > 0x7fffffffLL) break;
-        const int64_t waves = ceil_div(groups * ss_eff * n_meas, slots);
-        const int64_t cost = waves * (cs / unit + 1);
-        if (cost < best_cost) { best_cost = cost; best_cs = cs; best_ss = ss_eff; }
-    }
-    if (!best_cs) return d;
-    d.Cs = (int32_t)best_cs;
-    d.SS = (int32_t)best_ss;
-    if (d.SS > 1) {
-        d.scratch_stride = (O * d.SS * P * (kLongStateBytes + 1) + 255) & ~(int64_t)255;
-        if (d.scratch_stride * n_meas > ((int64_t)1 << 30)) return d;
-    }
-    d.use = true;
-    return d;
-}
-
-// Per tile of 128 children: their positions inside the tile grouped by parent (parents ascending, children
-// ascending within a parent), then 16 bytes of list bounds (entry q = where parent q starts, entry P = the number
-// of children of the tile).  `map` == nullptr: every child rolls up to parent 0.
-inline std::vector<uint8_t> lanes_lists(const int32_t* map, int64_t C, int64_t P) {
-    const int64_t tiles = ceil_div(C, kLanesTile);
-    std::vector<uint8_t> t((size_t)tiles * kLanesListBytes, 0);
-    for (int64_t g0 = 0; g0 < tiles; ++g0) {
-        uint8_t* perm = t.data() + (size_t)g0 * kLanesListBytes;
-        uint8_t* bounds = perm + kLanesTile;
-        const int64_t c0 = g0 * kLanesTile;
-        const int n = (int)std::min<int64_t>(kLanesTile, C - c0);
-        int count[kLanesMaxP + 1] = {0};
-        for (int k = 0; k < n; ++k) ++count[(map ? map[c0 + k] : 0) + 1];
-        for (int q = 0; q < kLanesMaxP; ++q) count[q + 1] += count[q];
-        for (int q = 0; q <= kLanesMaxP; ++q) bounds[q] = (uint8_t)count[q];
-        for (int k = 0; k < n; ++k) perm[count[map ? map[c0 + k] : 0]++] = (uint8_t)k;
-    }
-    (void)P;
-    return t;
-}
-
-inline int launch_up_lanes(const UpMeasure* d_meas, const UpMeasure* h_meas, int n, bool contiguous, const int32_t* d_pstart,
-                           const int32_t* d_children, const uint8_t* d_map8, int64_t O, int64_t C, int64_t P,
-                           const LanesDecision& d, unsigned char* d_scratch) {
-    UpLongParams p{};
-    p.meas = d_meas;
-    if (!d_meas) for (int k = 0; k < n; ++k) p.meas_inline[k] = h_meas[k];
-    p.pstart = d_pstart;
-    p.children = d_children;
-    p.map8 = d_map8;
-    p.lanes_cs = d.Cs;
-    bool loaded = false;
-    for (int k = 0; k < n; ++k) loaded |= h_meas[k].st_in != nullptr;
-    p.lanes_stage = kLanesValBytes + kLanesListBytes + (loaded ? kLanesStBytes : 0u);
-    p.O = O; p.C = (int32_t)C; p.P = (int32_t)P; p.I = 1;
-    p.SS = d.SS;
-    p.row_out = (int32_t)P;
-    p.div_i = FastDiv(1u);
-    p.div_ss = FastDiv((uint32_t)d.SS);
-    p.scratch = d_scratch;
-    p.scratch_stride = d.scratch_stride;
-    const size_t smem = (size_t)kLanesWarps * kLanesStages * p.lanes_stage;
-    static_assert((size_t)kLanesWarps * kLanesStages * (kLanesValBytes + kLanesListBytes) >=
-                      (size_t)kLanesWarps * kLanesMaxP * 32 * (kLongStateBytes + 1),
-                  "the warps' lanes are folded through the staging memory");
-    static bool attr_set[2] = {false, false};
-    auto kern = contiguous ? drillup_lanes_kernel<true> : drillup_lanes_kernel<false>;
-    if (!attr_set[contiguous]) {
-        OLAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)((size_t)kLanesWarps * kLanesStages * (kLanesValBytes + kLanesListBytes + kLanesStBytes))));
-        attr_set[contiguous] = true;
-    }
-    mark_kernels_begin();
-    kern<<<dim3((unsigned)(ceil_div(O, kLanesRows) * d.SS), (unsigned)n), kLanesWarps * 32, smem, g.stream>>>(p);
-    ++g_launches;
-    if (d.SS > 1) {
-        const int64_t blocks = O * P;  // one CTA per output cell
-        if (blocks > 0x7fffffffLL) return fail(OLAP_E_UNSUPPORTED, "drillUp: grid too large");
-        if (contiguous) drillup_long_merge_kernel<true><<<dim3((unsigned)blocks, (unsigned)n), kLongMergeThreads, 0, g.stream>>>(p);
-        else drillup_long_merge_kernel<false><<<dim3((unsigned)blocks, (unsigned)n), kLongMergeThreads, 0, g.stream>>>(p);
-        ++g_launches;
-    }
-    return OLAP_OK;
 }
 
 // Contiguous map: seg_ptr[s * P + p] = first CSR position k of parent p with child >= s * Cs.

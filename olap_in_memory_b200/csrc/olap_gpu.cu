@@ -18,6 +18,7 @@
 #include "kernels_pair.cuh"
 #include "kernels_tile.cuh"
 #include "kernels_long.cuh"
+#include "kernels_lanes.cuh"
 #include "kernels_pull.cuh"
 #include "kernels_tma.cuh"
 #include "host_pipe.cuh"
@@ -1066,7 +1067,7 @@ int olap_drill_up(olap_store* const* src, int n, const int* methods, int ndim, c
             }
             size_t o_map8 = 0;
             if (lanes.use) {
-                const std::vector<uint8_t> lists = lanes_lists(maps[d], C, P);
+                const std::vector<uint8_t> lists = lanes_lists(maps[d], C, lanes.tile);
                 o_map8 = stat.add(lists.data(), lists.size());
             }
             const char* d_stat = nullptr;

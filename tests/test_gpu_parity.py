@@ -527,22 +527,27 @@ def test_readme_only_status_examples():
     assert all(s & 0x4 for s in target.getStatus("main_measure"))
 
 
+@pytest.mark.parametrize("geometry", ["0", "1"], ids=["tile64x2", "tile128x1"])
 @pytest.mark.parametrize("default", [0.0, math.nan])
 @pytest.mark.parametrize("monotone", [False, True])
-def test_lanes_rollup_of_many_long_rows(default, monotone, monkeypatch):
-    """drillup_lanes_kernel ([O >= 64, C >= 2048 and C % 4 == 0, 1] -> [O, P <= 8, 1], any map: customers -> segment):
+def test_lanes_rollup_of_many_long_rows(default, monotone, geometry, monkeypatch):
+    """drillup_lanes_kernel ([O >= 64, C, 1] -> [O, P <= 8, 1], rows too long for a tile, any map: customers -> segment):
     the row sits on the lane, the warp-uniform parent selects the accumulator.  Against the C oracle: order-only rules
     bit-exact (first / last follow child order through the ordered folds), sums within 1e-6 (tree-reduced regime),
     status bytes exact, with a loaded and with a derived status plane, one and several segments per row, ragged row
-    groups and tiles, a parent without children.  Rows that do not start on 16 bytes stay with the long kernel."""
+    groups and tiles, a parent without children.  A loaded plane whose rows do not start on 4 bytes stays with the long kernel."""
     from olap_in_memory_b200 import _native as N
     from olap_in_memory_b200 import interop
     from oracle.c_oracle import COracleStore
 
     G = _gpu()
+    # both pipeline geometries, and the loaded-plane path (by default such sources stay with the long kernel)
+    monkeypatch.setenv("OLAP_LANES_GEO", geometry)
+    monkeypatch.setenv("OLAP_LANES_LOADED", "1")
     rng = np.random.default_rng(9)
-    for O, C_, P, ss in ((70, 12304, 5, None), (129, 12048 + 76, 8, None), (64, 19000, 1, "1"), (200, 12600, 3, "1"),
-                         (65, 2052, 2, "1"), (70, 12301, 5, None)):
+    # rows of more than 200 KB: shorter ones fit a shared-memory tile and belong to the tile kernel
+    for O, C_, P, ss in ((70, 52304, 5, None), (129, 52048 + 76, 8, None), (64, 59000, 1, "1"), (97, 52600, 3, "1"),
+                         (65, 52052, 2, "2"), (70, 52301, 5, None)):
         if ss is None:
             monkeypatch.delenv("OLAP_LANES_SS", raising=False)
         else:
@@ -551,9 +556,15 @@ def test_lanes_rollup_of_many_long_rows(default, monotone, monkeypatch):
         if P == 5:
             cmap[cmap == 3] = 2  # parent 3 has no child at all: its cells stay unset
         ident = np.arange(O, dtype=np.int32)
-        for kind in ("int", "small"):
-            data = cases.make_data(rng, O * C_, default, 0.6, kind)
-            methods = ["sum", "average", "highest", "lowest", "first", "last"] + (["product"] if kind == "small" else [])
+        for kind in ("int", "pow2"):
+            if kind == "pow2":
+                # products of 0.5 / 1 / 2 stay far from underflow over 10^4 children (a product that lands on the
+                # default restarts in the reference, which no split reduction can follow) and are exact in any order
+                data = np.exp2(rng.integers(-1, 2, O * C_)).astype(np.float32)
+                data[rng.random(O * C_) >= 0.6] = default
+            else:
+                data = cases.make_data(rng, O * C_, default, 0.6, kind)
+            methods = ["sum", "average", "highest", "lowest", "first", "last"] + (["product"] if kind == "pow2" else [])
             ref = COracleStore(O * C_, "float32", default)
             ref.set_data_f32(data)
             for derived in (True, False):
@@ -565,7 +576,8 @@ def test_lanes_rollup_of_many_long_rows(default, monotone, monkeypatch):
                         interop.status_tensor(s)
                     stores.append(s)
                 outs = G.drillUp_lowered(stores, [O, C_], [O, P], [ident, cmap], methods)
-                assert N.lib().olap_last_op_path() == (b"drillup/lanes" if C_ % 4 == 0 else b"drillup/long"), (O, C_, P)
+                # a plane that has to be read travels in words of 4 status bytes: rows must start on them
+                assert N.lib().olap_last_op_path() == (b"drillup/lanes" if derived or C_ % 4 == 0 else b"drillup/long"), (O, C_, P)
                 for method, out in zip(methods, outs):
                     want = ref.drillUp_lowered([O, C_], [O, P], [ident, cmap], method).data_f64().astype(np.float32)
                     got = out.data_f32()
