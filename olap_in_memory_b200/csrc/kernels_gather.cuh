@@ -326,6 +326,90 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const __grid_constant_
     }
 }
 
+// ---- dice of the innermost axis alone: gather_inner_flat_kernel ------------------------
+// [R, D] -> [R, K] with every other axis untouched (dice / slice of the innermost dimension, in-memory.js:213-263):
+// the source rows are ONE contiguous span, so nothing has to be decoded per row, and a tile of RB rows looks the
+// same wherever it starts: output j of a tile always comes from cell (j / K) * D + keep[j % K] of the tile.
+// A persistent CTA computes that offset ONCE for each of the <= 32 outputs a thread owns per tile (consecutive
+// lanes, consecutive outputs), then for every tile: stages the RB rows with 16-byte cp.async copies, all in
+// flight at once (every sector of the span is touched anyway: kept and dropped cells share sectors) and per output issues one shared load and one
+// coalesced store (values: 128 bytes per warp, status: one full 32-byte sector per warp).
+// gather_rows_kernel spends a row decode (one division per outer axis) per row of K outputs and a division per
+// cell: 1.1e9 warp instructions on every-other of a 10-item axis of 1e9 cells (ncu: issue-bound, 0.48 of peak).
+constexpr int kFlatMaxK = 1024, kFlatCells = 8192;
+
+struct FlatParams {
+    const GatherMeasure* meas;
+    const int32_t* keep;   // [K] source offset of every kept item inside a row
+    int64_t rows;
+    uint32_t D, K, RB, n_tiles;
+    FastDiv div_k;
+};
+
+__device__ __forceinline__ void flat_cp_async16(void* smem_dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(src) : "memory");
+}
+
+// E: outputs per thread and tile (the smallest of 8 / 16 / 32 that covers RB * K / 256)
+template <int E>
+static __global__ void __launch_bounds__(256, 4) gather_inner_flat_kernel(const __grid_constant__ FlatParams p) {
+    extern __shared__ __align__(16) unsigned char smem_flat[];
+    float* s_val = reinterpret_cast<float*>(smem_flat);           // [RB * D]
+    uint8_t* s_st = smem_flat + (size_t)p.RB * p.D * 4;            // [RB * D]
+    const GatherMeasure m = p.meas[blockIdx.y];
+    // where my outputs of a tile come from (the same for every tile)
+    uint32_t off[E];
+    const uint32_t tile_out = p.RB * p.K;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const uint32_t j = threadIdx.x + 256u * e;
+        off[e] = 0;
+        if (j < tile_out) {
+            const uint32_t r = p.div_k.div(j), k = j - r * p.K;
+            off[e] = r * p.D + (uint32_t)p.keep[k];
+        }
+    }
+    const bool load_plane = m.st_in != nullptr, write_plane = m.st_out != nullptr, nan_default = m.nan_default != 0;
+    for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int64_t row0 = (int64_t)tile * p.RB;
+        const uint32_t rows = (uint32_t)min((int64_t)p.RB, p.rows - row0);
+        const uint32_t n_in = rows * p.D, n_out = rows * p.K;
+        const float* g_in = m.in + row0 * p.D;
+        const uint8_t* g_st = load_plane ? m.st_in + row0 * p.D : nullptr;
+        // the span starts on 16 bytes (RB * D is a multiple of 16 cells): asynchronous 16-byte copies, all in flight
+        for (uint32_t i = threadIdx.x * 4; i + 4 <= n_in; i += 1024) flat_cp_async16(s_val + i, g_in + i);
+        if (load_plane)
+            for (uint32_t i = threadIdx.x * 16; i + 16 <= n_in; i += 4096) flat_cp_async16(s_st + i, g_st + i);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (uint32_t i = (n_in & ~3u) + threadIdx.x; i < n_in; i += 256) s_val[i] = g_in[i];
+        if (load_plane)
+            for (uint32_t i = (n_in & ~15u) + threadIdx.x; i < n_in; i += 256) s_st[i] = g_st[i];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        float* g_out = m.out + row0 * p.K + threadIdx.x;
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (threadIdx.x + 256u * e < n_out) g_out[256 * e] = s_val[off[e]];
+        if (write_plane) {
+            uint8_t* g_so = m.st_out + row0 * p.K + threadIdx.x;
+            if (load_plane) {
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (threadIdx.x + 256u * e < n_out) g_so[256 * e] = s_st[off[e]];
+            } else if (nan_default) {  // derived plane
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (threadIdx.x + 256u * e < n_out) g_so[256 * e] = (uint8_t)(present_f(s_val[off[e]], 1) ? OLAP_STATUS_SET : OLAP_STATUS_UNSET);
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (threadIdx.x + 256u * e < n_out) g_so[256 * e] = (uint8_t)(present_f(s_val[off[e]], 0) ? OLAP_STATUS_SET : OLAP_STATUS_UNSET);
+            }
+        }
+        __syncthreads();  // the next tile overwrites the staged rows
+    }
+}
+
 // ---- load: input-driven scatter  dst[mine(his)] = src[his]  (in-memory.js:159-175).
 // Tables hold my offset contribution per his coordinate, or -1 when I lack the item
 // (then the cell is dropped).  His items are distinct, so the scatter is injective.

@@ -1209,6 +1209,54 @@ static int run_gather(int mode, olap_store* const* src, int n, std::vector<GDim>
         int64_t rows = 1;
         bool fits = last.len <= kRowsMaxL && last.len >= 1;
         for (auto& d : outer) { rows *= d.len; fits &= d.len <= 0x7fffffffLL; }
+        // the innermost axis alone is diced: the source rows are one contiguous span (gather_inner_flat_kernel)
+        static const int flat_knob = [] { const char* e = getenv("OLAP_FLAT"); return e ? atoi(e) : 1; }();
+        if (flat_knob && mode == G_COPY && outer.size() == 1 && outer[0].linear && last.aux.empty() && outer[0].aux.empty() &&
+            last.len <= kFlatMaxK && outer[0].stride >= last.len && outer[0].stride <= kFlatCells / 16 && const_off % 16 == 0 &&
+            rows >= 64 && rows < ((int64_t)1 << 31)) {
+            const int64_t D = outer[0].stride, K = last.len;
+            std::vector<int32_t> keep((size_t)K);
+            bool inside = true;
+            for (int64_t k = 0; k < K; ++k) {
+                const int64_t off = last.linear ? k * last.stride : last.tbl[(size_t)k];
+                inside &= off >= 0 && off < D;
+                keep[(size_t)k] = (int32_t)off;
+            }
+            for (int k = 0; k < n; ++k)  // wrapped memory may sit anywhere
+                inside &= (reinterpret_cast<uintptr_t>(meas_in[k].in) & 15) == 0 && (reinterpret_cast<uintptr_t>(meas_in[k].st_in) & 15) == 0 &&
+                          (reinterpret_cast<uintptr_t>(meas_in[k].st_out) & 3) == 0;
+            if (inside) {
+                FlatParams p{};
+                TablePack t;
+                std::vector<GatherMeasure> meas = meas_in;
+                gather_derive(meas, src, n);
+                bool any_plane = false;
+                for (auto& m : meas) { m.in += const_off; if (m.st_in) m.st_in += const_off; any_plane |= m.st_in != nullptr; }
+                const size_t o_meas = t.add(meas.data(), sizeof(GatherMeasure) * n);
+                const size_t o_keep = t.add(keep.data(), keep.size() * 4);
+                OLAP_TRY(t.upload());
+                p.meas = t.ptr<GatherMeasure>(o_meas);
+                p.keep = t.ptr<int32_t>(o_keep);
+                p.rows = rows;
+                p.D = (uint32_t)D; p.K = (uint32_t)K;
+                p.RB = (uint32_t)std::max<int64_t>(16, (kFlatCells / D) / 16 * 16);  // spans start on 16 cells: 128-bit loads of values and of status bytes
+                p.div_k = FastDiv((uint32_t)K);
+                const int64_t n_tiles = ceil_div(rows, p.RB);
+                p.n_tiles = (uint32_t)n_tiles;
+                const int64_t gx = std::min<int64_t>(n_tiles, std::max<int64_t>(1, (int64_t)g.sm_count * 4 / n));  // persistent CTAs
+                const size_t smem = (size_t)p.RB * D * (any_plane ? 5 : 4);
+                KERNELS_BEGIN();
+                const int64_t per_thread = ceil_div((int64_t)p.RB * K, 256);
+                const dim3 grid((unsigned)gx, (unsigned)n);
+                if (per_thread <= 8) gather_inner_flat_kernel<8><<<grid, 256, smem, g.stream>>>(p);
+                else if (per_thread <= 16) gather_inner_flat_kernel<16><<<grid, 256, smem, g.stream>>>(p);
+                else gather_inner_flat_kernel<32><<<grid, 256, smem, g.stream>>>(p);
+                LAUNCHED();
+                *path = "gather/inner-flat";
+                OLAP_TRY(t.release());
+                return OLAP_OK;
+            }
+        }
         if (fits && rows < ((int64_t)1 << 31)) {
             GatherParams p{};
             RowsTail tail{};

@@ -629,3 +629,40 @@ def test_pageable_host_buffers_travel_through_the_pinned_ring():
     N.check(N.lib().olap_store_download_f64(u._h, out64.ctypes.data, n))
     assert np.array_equal(out64, d64)
     assert s.total == float(d64.sum())
+
+
+@pytest.mark.parametrize("default", [0.0, math.nan])
+def test_dice_of_the_innermost_axis_alone(default):
+    """gather_inner_flat_kernel: [R, D] -> [R, K] with every other axis untouched (dice / slice of the innermost
+    dimension, in-memory.js:213-263): staged spans of whole rows, kept cells picked out of shared memory.  Bit-exact
+    against numpy fancy indexing for every-other, reordered, single-item and ragged lists, row counts that do not fill
+    the last CTA, outer axes that merge into the row count, loaded and derived status planes."""
+    from olap_in_memory_b200 import _native as N
+    from olap_in_memory_b200 import interop
+
+    G = _gpu()
+    rng = np.random.default_rng(33)
+    shapes = [([1000, 10], list(range(0, 10, 2))), ([77, 13, 10], [9, 0, 4]), ([4099, 7], [3]), ([300, 33], list(range(32, -1, -1))),
+              ([20, 50, 512], sorted(rng.choice(512, 100, replace=False).tolist())), ([6000, 4], [1, 2])]
+    for lens, keep in shapes:
+        n = int(np.prod(lens))
+        data = cases.make_data(rng, n, default, 0.6, "int")
+        keeps = [np.arange(d, dtype=np.int32) for d in lens[:-1]] + [np.asarray(keep, np.int32)]
+        want = data.reshape(-1, lens[-1])[:, keep].reshape(-1)
+        set_ = (data == data) if default != default else (data != 0)
+        want_st = np.where(set_, 2, 1).astype(np.uint8).reshape(-1, lens[-1])[:, keep].reshape(-1)
+        for derived in (True, False):
+            s = G(n, "float32", default)
+            s.set_data_f32(data)
+            if not derived:
+                st = interop.status_tensor(s)  # a plane of its own content: the kernel has to move it
+                st[::3] |= 4
+                want_st_l = np.where(set_, 2, 1).astype(np.uint8)
+                want_st_l[::3] |= 4
+                want_st_l = want_st_l.reshape(-1, lens[-1])[:, keep].reshape(-1)
+            out = G.dice_lowered([s], lens, keeps)[0]
+            if len(keep) > 1:  # a single kept item is a plain strided gather
+                assert N.lib().olap_last_op_path() == b"gather/inner-flat", (lens, keep)
+            assert np.array_equal(out.data_f32().view(np.uint32), want.view(np.uint32)), (lens, keep, derived)
+            assert np.array_equal(np.asarray(out.status, np.uint8), want_st if derived else want_st_l), (lens, keep, derived)
+            assert bool(out.status_derived) == derived
