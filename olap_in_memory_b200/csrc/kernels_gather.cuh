@@ -326,8 +326,9 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const __grid_constant_
     }
 }
 
-// ---- dice of the innermost axis alone: gather_inner_flat_kernel ------------------------
-// [R, D] -> [R, K] with every other axis untouched (dice / slice of the innermost dimension, in-memory.js:213-263):
+// ---- rearrangements inside short contiguous blocks: gather_inner_flat_kernel -------------
+// [R, D] -> [R, K] with the leading axes untouched: dice / slice of the innermost axes (in-memory.js:213-263) and
+// reorders that only swap trailing axes (in-memory.js:178-211; keep[] is then a permutation of the block):
 // the source rows are ONE contiguous span, so nothing has to be decoded per row, and a tile of RB rows looks the
 // same wherever it starts: output j of a tile always comes from cell (j / K) * D + keep[j % K] of the tile.
 // A persistent CTA computes that offset ONCE for each of the <= 32 outputs a thread owns per tile (consecutive
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const __grid_constant_
 // coalesced store (values: 128 bytes per warp, status: one full 32-byte sector per warp).
 // gather_rows_kernel spends a row decode (one division per outer axis) per row of K outputs and a division per
 // cell: 1.1e9 warp instructions on every-other of a 10-item axis of 1e9 cells (ncu: issue-bound, 0.48 of peak).
-constexpr int kFlatMaxK = 1024, kFlatCells = 8192;
+constexpr int kFlatCells = 8192;
 
 struct FlatParams {
     const GatherMeasure* meas;
@@ -350,9 +351,10 @@ __device__ __forceinline__ void flat_cp_async16(void* smem_dst, const void* src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(src) : "memory");
 }
 
-// E: outputs per thread and tile (the smallest of 8 / 16 / 32 that covers RB * K / 256)
-template <int E>
-static __global__ void __launch_bounds__(256, 4) gather_inner_flat_kernel(const __grid_constant__ FlatParams p) {
+// E: outputs per thread and tile (the smallest of 8 / 16 / 32 that covers RB * K / 256); MINB: CTAs per SM the
+// register allocation aims at (32 offsets per thread do not fit the 64 registers of 4 CTAs)
+template <int E, int MINB>
+static __global__ void __launch_bounds__(256, MINB) gather_inner_flat_kernel(const __grid_constant__ FlatParams p) {
     extern __shared__ __align__(16) unsigned char smem_flat[];
     float* s_val = reinterpret_cast<float*>(smem_flat);           // [RB * D]
     uint8_t* s_st = smem_flat + (size_t)p.RB * p.D * 4;            // [RB * D]

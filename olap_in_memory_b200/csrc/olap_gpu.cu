@@ -1188,8 +1188,100 @@ static void merge_dims(std::vector<GDim>& dims, int64_t* const_off) {
     dims.swap(out);
 }
 
+// COPY gathers that only rearrange cells INSIDE contiguous blocks of the source (gather_inner_flat_kernel): the
+// leading axes are untouched and merge into one linear "row" axis whose stride D is the block length, and every
+// source offset of the trailing axes stays inside the block — dice / slice of the innermost axes, reorders that
+// swap trailing axes (the 10 x 10 inner swap of config 3).  `dims` is in output order.  *done says whether the
+// kernel was launched.
+static int try_gather_flat(olap_store* const* src, int n, std::vector<GDim> dims, const std::vector<GatherMeasure>& meas_in,
+                           bool* done, const char** path) {
+    *done = false;
+    static const int flat_knob = [] { const char* e = getenv("OLAP_FLAT"); return e ? atoi(e) : 1; }();
+    if (!flat_knob) return OLAP_OK;
+    int64_t const_off = 0;
+    merge_dims(dims, &const_off);
+    if (dims.size() < 2 || !dims[0].linear || !dims[0].aux.empty() || const_off % 16) return OLAP_OK;
+    const int64_t rows = dims[0].len, D = dims[0].stride;
+    if (rows < 64 || rows >= ((int64_t)1 << 31) || D < 2 || D > kFlatCells || const_off + rows * D > src[0]->size) return OLAP_OK;  // whole blocks are staged
+    // long 128-bit inner runs are the vector gather's (0.87-0.94 of peak)
+    const GDim& inner = dims.back();
+    if (inner.linear && inner.stride == 1 && inner.len % 4 == 0 && inner.len >= 16) return OLAP_OK;
+    int64_t K = 1;
+    for (size_t d = 1; d < dims.size(); ++d) {
+        if (!dims[d].aux.empty()) return OLAP_OK;
+        K *= dims[d].len;
+        if (K > D || K < 1) return OLAP_OK;
+    }
+    std::vector<int32_t> keep((size_t)K);
+    for (int64_t k = 0; k < K; ++k) {  // row-major over the trailing output axes
+        int64_t rest = k, off = 0;
+        for (size_t d = dims.size() - 1; d >= 1; --d) {
+            const int64_t c = rest % dims[d].len;
+            rest /= dims[d].len;
+            off += dims[d].linear ? c * dims[d].stride : dims[d].tbl[(size_t)c];
+        }
+        if (off < 0 || off >= D) return OLAP_OK;
+        keep[(size_t)k] = (int32_t)off;
+    }
+    // rows per tile: spans start on 16 cells (16-byte copies of values and of status bytes)
+    const int64_t step = 16 / std::gcd<int64_t, int64_t>(D, 16);
+    const int64_t RB = (kFlatCells / D) / step * step;
+    if (RB < 1) return OLAP_OK;
+    // consecutive lanes read keep[j], keep[j + 1], ...: decline patterns that pile onto few shared-memory banks
+    {
+        const int64_t tile_out = RB * K;
+        int64_t conflicts = 0, warps = 0;
+        for (int64_t j0 = 0; j0 < tile_out; j0 += 32, ++warps) {
+            int bank[32] = {0};
+            int worst = 0;
+            for (int64_t j = j0; j < std::min(tile_out, j0 + 32); ++j) worst = std::max(worst, ++bank[((j / K) * D + keep[(size_t)(j % K)]) & 31]);
+            conflicts += worst;
+        }
+        if (conflicts > 4 * warps) return OLAP_OK;
+    }
+    for (int k = 0; k < n; ++k)  // wrapped memory may sit anywhere
+        if ((reinterpret_cast<uintptr_t>(meas_in[k].in) & 15) || (reinterpret_cast<uintptr_t>(meas_in[k].st_in) & 15) ||
+            (reinterpret_cast<uintptr_t>(meas_in[k].out) & 3) || (reinterpret_cast<uintptr_t>(meas_in[k].st_out) & 3))
+            return OLAP_OK;
+    FlatParams p{};
+    TablePack t;
+    std::vector<GatherMeasure> meas = meas_in;
+    gather_derive(meas, src, n);
+    bool any_plane = false;
+    for (auto& m : meas) { m.in += const_off; if (m.st_in) m.st_in += const_off; any_plane |= m.st_in != nullptr; }
+    const size_t o_meas = t.add(meas.data(), sizeof(GatherMeasure) * n);
+    const size_t o_keep = t.add(keep.data(), keep.size() * 4);
+    OLAP_TRY(t.upload());
+    p.meas = t.ptr<GatherMeasure>(o_meas);
+    p.keep = t.ptr<int32_t>(o_keep);
+    p.rows = rows;
+    p.D = (uint32_t)D; p.K = (uint32_t)K; p.RB = (uint32_t)RB;
+    p.div_k = FastDiv((uint32_t)K);
+    const int64_t n_tiles = ceil_div(rows, RB);
+    p.n_tiles = (uint32_t)n_tiles;
+    const int64_t per_thread = ceil_div(RB * K, 256);
+    const int per_sm = per_thread <= 16 ? 4 : 3;
+    const int64_t gx = std::min<int64_t>(n_tiles, std::max<int64_t>(1, (int64_t)g.sm_count * per_sm / n));  // persistent CTAs
+    const size_t smem = (size_t)RB * D * (any_plane ? 5 : 4);
+    const dim3 grid((unsigned)gx, (unsigned)n);
+    KERNELS_BEGIN();
+    if (per_thread <= 8) gather_inner_flat_kernel<8, 4><<<grid, 256, smem, g.stream>>>(p);
+    else if (per_thread <= 16) gather_inner_flat_kernel<16, 4><<<grid, 256, smem, g.stream>>>(p);
+    else gather_inner_flat_kernel<32, 3><<<grid, 256, smem, g.stream>>>(p);
+    LAUNCHED();
+    *path = "gather/inner-flat";
+    OLAP_TRY(t.release());
+    *done = true;
+    return OLAP_OK;
+}
+
 static int run_gather(int mode, olap_store* const* src, int n, std::vector<GDim>& dims, int64_t new_size, int64_t old_size,
                       const std::vector<GatherMeasure>& meas_in, int* d_error, const char** path) {
+    if (mode == G_COPY) {
+        bool done = false;
+        OLAP_TRY(try_gather_flat(src, n, dims, meas_in, &done, path));
+        if (done) return OLAP_OK;
+    }
     int64_t const_off = 0;
     merge_dims(dims, &const_off);
     int64_t I = 1;
@@ -1209,54 +1301,6 @@ static int run_gather(int mode, olap_store* const* src, int n, std::vector<GDim>
         int64_t rows = 1;
         bool fits = last.len <= kRowsMaxL && last.len >= 1;
         for (auto& d : outer) { rows *= d.len; fits &= d.len <= 0x7fffffffLL; }
-        // the innermost axis alone is diced: the source rows are one contiguous span (gather_inner_flat_kernel)
-        static const int flat_knob = [] { const char* e = getenv("OLAP_FLAT"); return e ? atoi(e) : 1; }();
-        if (flat_knob && mode == G_COPY && outer.size() == 1 && outer[0].linear && last.aux.empty() && outer[0].aux.empty() &&
-            last.len <= kFlatMaxK && outer[0].stride >= last.len && outer[0].stride <= kFlatCells / 16 && const_off % 16 == 0 &&
-            rows >= 64 && rows < ((int64_t)1 << 31)) {
-            const int64_t D = outer[0].stride, K = last.len;
-            std::vector<int32_t> keep((size_t)K);
-            bool inside = true;
-            for (int64_t k = 0; k < K; ++k) {
-                const int64_t off = last.linear ? k * last.stride : last.tbl[(size_t)k];
-                inside &= off >= 0 && off < D;
-                keep[(size_t)k] = (int32_t)off;
-            }
-            for (int k = 0; k < n; ++k)  // wrapped memory may sit anywhere
-                inside &= (reinterpret_cast<uintptr_t>(meas_in[k].in) & 15) == 0 && (reinterpret_cast<uintptr_t>(meas_in[k].st_in) & 15) == 0 &&
-                          (reinterpret_cast<uintptr_t>(meas_in[k].st_out) & 3) == 0;
-            if (inside) {
-                FlatParams p{};
-                TablePack t;
-                std::vector<GatherMeasure> meas = meas_in;
-                gather_derive(meas, src, n);
-                bool any_plane = false;
-                for (auto& m : meas) { m.in += const_off; if (m.st_in) m.st_in += const_off; any_plane |= m.st_in != nullptr; }
-                const size_t o_meas = t.add(meas.data(), sizeof(GatherMeasure) * n);
-                const size_t o_keep = t.add(keep.data(), keep.size() * 4);
-                OLAP_TRY(t.upload());
-                p.meas = t.ptr<GatherMeasure>(o_meas);
-                p.keep = t.ptr<int32_t>(o_keep);
-                p.rows = rows;
-                p.D = (uint32_t)D; p.K = (uint32_t)K;
-                p.RB = (uint32_t)std::max<int64_t>(16, (kFlatCells / D) / 16 * 16);  // spans start on 16 cells: 128-bit loads of values and of status bytes
-                p.div_k = FastDiv((uint32_t)K);
-                const int64_t n_tiles = ceil_div(rows, p.RB);
-                p.n_tiles = (uint32_t)n_tiles;
-                const int64_t gx = std::min<int64_t>(n_tiles, std::max<int64_t>(1, (int64_t)g.sm_count * 4 / n));  // persistent CTAs
-                const size_t smem = (size_t)p.RB * D * (any_plane ? 5 : 4);
-                KERNELS_BEGIN();
-                const int64_t per_thread = ceil_div((int64_t)p.RB * K, 256);
-                const dim3 grid((unsigned)gx, (unsigned)n);
-                if (per_thread <= 8) gather_inner_flat_kernel<8><<<grid, 256, smem, g.stream>>>(p);
-                else if (per_thread <= 16) gather_inner_flat_kernel<16><<<grid, 256, smem, g.stream>>>(p);
-                else gather_inner_flat_kernel<32><<<grid, 256, smem, g.stream>>>(p);
-                LAUNCHED();
-                *path = "gather/inner-flat";
-                OLAP_TRY(t.release());
-                return OLAP_OK;
-            }
-        }
         if (fits && rows < ((int64_t)1 << 31)) {
             GatherParams p{};
             RowsTail tail{};
@@ -1472,9 +1516,12 @@ int olap_reorder(olap_store* const* src, int n, int ndim, const int64_t* old_len
         if (tm.use && !tma_encode_fn()) tm.use = false;  // a driver without cuTensorMapEncodeTiled
         PairPlan pp;
         if (!tm.use) pp = transpose_pair_plan(dims);
+        bool flat_done = false;
+        if (!tm.use && !pp.use) OLAP_TRY(try_gather_flat(src, n, dims, meas, &flat_done, &path));  // trailing axes swapped inside short blocks
         TransposePlan tp;
-        if (!tm.use && !pp.use) tp = transpose_plan(dims);
-        if (tm.use) {
+        if (!tm.use && !pp.use && !flat_done) tp = transpose_plan(dims);
+        if (flat_done) {
+        } else if (tm.use) {
             path = "reorder/tma-transpose";
             std::vector<CUtensorMap> maps;
             OLAP_TRY(tma_encode_maps(tm, meas, maps));

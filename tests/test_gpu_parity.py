@@ -666,3 +666,45 @@ def test_dice_of_the_innermost_axis_alone(default):
             assert np.array_equal(out.data_f32().view(np.uint32), want.view(np.uint32)), (lens, keep, derived)
             assert np.array_equal(np.asarray(out.status, np.uint8), want_st if derived else want_st_l), (lens, keep, derived)
             assert bool(out.status_derived) == derived
+
+
+@pytest.mark.parametrize("default", [0.0, math.nan])
+def test_rearrangements_inside_short_blocks(default):
+    """gather_inner_flat_kernel beyond the single diced axis: reorders that swap trailing axes (the 10 x 10 inner swap
+    of config 3, a 3-axis rotation of a 6 x 5 x 4 block) and dices of two trailing axes at once, leading axes
+    untouched — against numpy transpose / fancy indexing, values and status bytes, loaded and derived planes."""
+    from olap_in_memory_b200 import _native as N
+    from olap_in_memory_b200 import interop
+
+    G = _gpu()
+    rng = np.random.default_rng(35)
+    for kind, lens, arg in (("reorder", [70, 9, 10, 10], [0, 1, 3, 2]), ("reorder", [1000, 6, 5, 4], [0, 3, 1, 2]),
+                            ("reorder", [333, 7, 3], [0, 2, 1]), ("dice", [500, 10, 12], [[1, 3, 8], [0, 5, 11, 2]]),
+                            ("dice", [90, 4, 10, 10], [None, [9, 0], list(range(10))])):
+        n = int(np.prod(lens))
+        data = cases.make_data(rng, n, default, 0.6, "int")
+        set_ = (data == data) if default != default else (data != 0)
+        st_derived = np.where(set_, 2, 1).astype(np.uint8)
+        st_loaded = st_derived.copy()
+        st_loaded[::3] |= 4
+
+        def move(x):
+            x = x.reshape(lens)
+            if kind == "reorder":
+                return np.ascontiguousarray(x.transpose(arg)).reshape(-1)
+            keeps = [np.arange(d) if k is None else np.asarray(k) for d, k in zip(lens, [None] * (len(lens) - len(arg)) + arg)]
+            return np.ascontiguousarray(x[np.ix_(*keeps)]).reshape(-1)
+
+        for derived in (True, False):
+            s = G(n, "float32", default)
+            s.set_data_f32(data)
+            if not derived:
+                interop.status_tensor(s)[::3] |= 4
+            if kind == "reorder":
+                out = G.reorder_lowered([s], lens, arg)[0]
+            else:
+                full = [None] * (len(lens) - len(arg)) + arg
+                out = G.dice_lowered([s], lens, [np.arange(d, dtype=np.int32) if k is None else np.asarray(k, np.int32) for d, k in zip(lens, full)])[0]
+            assert N.lib().olap_last_op_path() == b"gather/inner-flat", (kind, lens, arg)
+            assert np.array_equal(out.data_f32().view(np.uint32), move(data).view(np.uint32)), (kind, lens, arg, derived)
+            assert np.array_equal(np.asarray(out.status, np.uint8), move(st_derived if derived else st_loaded)), (kind, lens, arg, derived)
