@@ -16,6 +16,7 @@
 #include "kernels_gather.cuh"
 #include "kernels_store.cuh"
 #include "kernels_pair.cuh"
+#include "kernels_pair_async.cuh"
 #include "kernels_tile.cuh"
 #include "kernels_long.cuh"
 #include "kernels_lanes.cuh"
@@ -1537,12 +1538,17 @@ int olap_reorder(olap_store* const* src, int n, int ndim, const int64_t* old_len
         } else if (pp.use) {
             path = "reorder/pair-transpose";
             if (pp.p.split == 1) gather_derive(meas, src, n);  // the 2-CTA cluster variant always stages the status bytes
+            bool loaded = false;
+            for (int k = 0; k < n; ++k) loaded |= meas[k].st_in != nullptr;
+            const bool async = transpose_async_fits(pp, loaded);
+            if (async) path = "reorder/pair-async";
             TablePack t;
             const size_t o_meas = t.add(meas.data(), sizeof(GatherMeasure) * n);
             const size_t o_src = t.add(pp.src_row.data(), pp.src_row.size() * sizeof(uint32_t));
             const size_t o_dst = t.add(pp.dst_row.data(), pp.dst_row.size() * sizeof(uint32_t));
             OLAP_TRY(t.upload());
-            OLAP_TRY(launch_transpose_pair(t.ptr<GatherMeasure>(o_meas), t.ptr<uint32_t>(o_src), t.ptr<uint32_t>(o_dst), n, pp));
+            if (async) OLAP_TRY(launch_transpose_async(t.ptr<GatherMeasure>(o_meas), t.ptr<uint32_t>(o_src), t.ptr<uint32_t>(o_dst), n, pp, loaded));
+            else OLAP_TRY(launch_transpose_pair(t.ptr<GatherMeasure>(o_meas), t.ptr<uint32_t>(o_src), t.ptr<uint32_t>(o_dst), n, pp));
             OLAP_TRY(t.release());
         } else if (tp.use) {
             path = "reorder/box-transpose";

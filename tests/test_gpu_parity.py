@@ -224,7 +224,7 @@ def test_kernel_paths_are_the_intended_ones():
     G.reorder_lowered([s], [64, 40, 64], [1, 0, 2])
     assert path() == "gather/vec4"
     G.reorder_lowered([s], [64, 40, 64], [2, 1, 0])
-    assert path() == "reorder/pair-transpose"
+    assert path() in ("reorder/pair-async", "reorder/pair-transpose")
     G.reorder_lowered([G(63 * 40 * 65, "float32", 0)], [63, 40, 65], [2, 1, 0])
     assert path() == "reorder/box-transpose"
     G.dice_lowered([s], [64, 40, 64], [ident(64), np.arange(0, 40, 2, dtype=np.int32), ident(64)])
@@ -380,7 +380,7 @@ def test_reorder_fuzz_against_numpy():
             want = data.reshape(dims).transpose(perm).reshape(-1)
             assert np.array_equal(out.data_f32(), want), (dims, perm, path)
             assert np.array_equal(np.asarray(out.status), np.where(want != 0, 2, 1)), (dims, perm, path)
-    disjoint = paths.get("reorder/pair-transpose", 0) + paths.get("reorder/tma-transpose", 0)
+    disjoint = paths.get("reorder/pair-transpose", 0) + paths.get("reorder/pair-async", 0) + paths.get("reorder/tma-transpose", 0)
     assert disjoint >= 5 and paths.get("reorder/box-transpose", 0) >= 5, paths
 
 
@@ -708,3 +708,35 @@ def test_rearrangements_inside_short_blocks(default):
             assert N.lib().olap_last_op_path() == b"gather/inner-flat", (kind, lens, arg)
             assert np.array_equal(out.data_f32().view(np.uint32), move(data).view(np.uint32)), (kind, lens, arg, derived)
             assert np.array_equal(np.asarray(out.status, np.uint8), move(st_derived if derived else st_loaded)), (kind, lens, arg, derived)
+
+
+def test_async_pair_transpose(monkeypatch):
+    """OLAP_PAIR_ASYNC=1: the cp.async-staged variant of the disjoint-group transpose (kernels_pair_async.cuh;
+    opt-in, measured slower than the register-staged kernel): bit-exact against numpy.transpose, ragged tiles,
+    loaded and derived status planes in one call."""
+    from olap_in_memory_b200 import _native as N
+    from olap_in_memory_b200 import interop
+
+    G = _gpu()
+    monkeypatch.setenv("OLAP_PAIR_ASYNC", "1")
+    rng = np.random.default_rng(41)
+    taken = 0
+    for dims, perm in (([64, 40, 64], [2, 1, 0]), ([100, 12, 36, 10, 10], [4, 3, 2, 1, 0]), ([132, 3, 72], [2, 1, 0]), ([8, 200, 104], [0, 2, 1])):
+        n = int(np.prod(dims))
+        datas = [cases.make_data(rng, n, 0.0, 0.6, "int") for _ in range(2)]
+        stores = []
+        for data in datas:
+            s = G(n, "float32", 0)
+            s.set_data_f32(data)
+            stores.append(s)
+        interop.status_tensor(stores[1])[::5] |= 4  # a plane of its own content
+        outs = G.reorder_lowered(stores, dims, perm)
+        taken += N.lib().olap_last_op_path() == b"reorder/pair-async"  # shapes the pair planner declines take other kernels
+        for k, (data, out) in enumerate(zip(datas, outs)):
+            want = data.reshape(dims).transpose(perm).reshape(-1)
+            assert np.array_equal(out.data_f32().view(np.uint32), want.view(np.uint32)), (dims, perm, k)
+            st = np.where(data == data, np.where(data != 0, 2, 1), 2).astype(np.uint8)
+            if k == 1:
+                st[::5] |= 4
+            assert np.array_equal(np.asarray(out.status, np.uint8), st.reshape(dims).transpose(perm).reshape(-1)), (dims, perm, k)
+    assert taken >= 2
