@@ -345,6 +345,7 @@ struct FlatParams {
     int64_t rows;
     uint32_t D, K, RB, n_tiles;
     FastDiv div_k;
+    FastDiv div_rb;        // FRONT: the block's axes move to the FRONT of the output ([R, D] -> [K, R]); RB % 256 == 0
 };
 
 __device__ __forceinline__ void flat_cp_async16(void* smem_dst, const void* src) {
@@ -353,7 +354,10 @@ __device__ __forceinline__ void flat_cp_async16(void* smem_dst, const void* src)
 
 // E: outputs per thread and tile (the smallest of 8 / 16 / 32 that covers RB * K / 256); MINB: CTAs per SM the
 // register allocation aims at (32 offsets per thread do not fit the 64 registers of 4 CTAs)
-template <int E, int MINB>
+// FRONT: the rearranged block does not stay innermost but becomes the OUTERMOST part of the output ([R, D] -> [K, R]:
+// a short innermost axis rotated to the front): output k of row r goes to plane k, cell r — a tile writes K runs
+// of RB consecutive cells instead of one span.  Thread t owns rows t, t + 256, ... of every plane.
+template <int E, int MINB, bool FRONT>
 static __global__ void __launch_bounds__(256, MINB) gather_inner_flat_kernel(const __grid_constant__ FlatParams p) {
     extern __shared__ __align__(16) unsigned char smem_flat[];
     float* s_val = reinterpret_cast<float*>(smem_flat);           // [RB * D]
@@ -367,8 +371,13 @@ static __global__ void __launch_bounds__(256, MINB) gather_inner_flat_kernel(con
         const uint32_t j = threadIdx.x + 256u * e;
         off[e] = 0;
         if (j < tile_out) {
-            const uint32_t r = p.div_k.div(j), k = j - r * p.K;
-            off[e] = r * p.D + (uint32_t)p.keep[k];
+            if (FRONT) {
+                const uint32_t k = p.div_rb.div(j), r = j - k * p.RB;
+                off[e] = r * p.D + (uint32_t)p.keep[k];
+            } else {
+                const uint32_t r = p.div_k.div(j), k = j - r * p.K;
+                off[e] = r * p.D + (uint32_t)p.keep[k];
+            }
         }
     }
     const bool load_plane = m.st_in != nullptr, write_plane = m.st_out != nullptr, nan_default = m.nan_default != 0;
@@ -388,6 +397,22 @@ static __global__ void __launch_bounds__(256, MINB) gather_inner_flat_kernel(con
             for (uint32_t i = (n_in & ~15u) + threadIdx.x; i < n_in; i += 256) s_st[i] = g_st[i];
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
+        if (FRONT) {
+            float* g_out = m.out + row0;
+            uint8_t* g_so = write_plane ? m.st_out + row0 : nullptr;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const uint32_t j = threadIdx.x + 256u * e;
+                const uint32_t k = p.div_rb.div(j), r = j - k * p.RB;  // k is warp-uniform (RB % 256 == 0)
+                if (k < p.K && r < rows) {
+                    const int64_t g = (int64_t)k * p.rows + r;
+                    const float v = s_val[off[e]];
+                    g_out[g] = v;
+                    if (write_plane)
+                        g_so[g] = load_plane ? s_st[off[e]] : (uint8_t)(present_f(v, nan_default) ? OLAP_STATUS_SET : OLAP_STATUS_UNSET);
+                }
+            }
+        } else {
         float* g_out = m.out + row0 * p.K + threadIdx.x;
 #pragma unroll
         for (int e = 0; e < E; ++e)
@@ -407,6 +432,7 @@ static __global__ void __launch_bounds__(256, MINB) gather_inner_flat_kernel(con
                 for (int e = 0; e < E; ++e)
                     if (threadIdx.x + 256u * e < n_out) g_so[256 * e] = (uint8_t)(present_f(s_val[off[e]], 0) ? OLAP_STATUS_SET : OLAP_STATUS_UNSET);
             }
+        }
         }
         __syncthreads();  // the next tile overwrites the staged rows
     }

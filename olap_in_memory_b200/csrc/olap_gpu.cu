@@ -1201,41 +1201,64 @@ static int try_gather_flat(olap_store* const* src, int n, std::vector<GDim> dims
     if (!flat_knob) return OLAP_OK;
     int64_t const_off = 0;
     merge_dims(dims, &const_off);
-    if (dims.size() < 2 || !dims[0].linear || !dims[0].aux.empty() || const_off % 16) return OLAP_OK;
-    const int64_t rows = dims[0].len, D = dims[0].stride;
-    if (rows < 64 || rows >= ((int64_t)1 << 31) || D < 2 || D > kFlatCells || const_off + rows * D > src[0]->size) return OLAP_OK;  // whole blocks are staged
+    if (dims.size() < 2 || const_off % 16) return OLAP_OK;
+    // the untouched leading axes are either still the leading axes of the output (rows first: the block stays
+    // innermost) or its trailing axes (rows last: the block's axes moved to the FRONT)
+    const GDim& lead = dims[0];
+    const GDim& tail = dims.back();
+    bool front = false;
+    auto block_inside = [&](size_t first, size_t last, int64_t D) {  // every offset of axes [first, last] stays in [0, D)
+        int64_t hi = 0;
+        for (size_t d = first; d <= last; ++d) {
+            if (!dims[d].aux.empty()) return false;
+            int64_t lo_d = 0, hi_d = 0;
+            if (dims[d].linear) { hi_d = (dims[d].len - 1) * dims[d].stride; if (dims[d].stride < 0) return false; }
+            else for (int64_t v : dims[d].tbl) { lo_d = std::min(lo_d, v); hi_d = std::max(hi_d, v); }
+            if (lo_d < 0) return false;
+            hi += hi_d;
+        }
+        return hi < D;
+    };
+    if (lead.linear && lead.aux.empty() && lead.stride >= 2 && lead.stride <= kFlatCells && block_inside(1, dims.size() - 1, lead.stride)) front = false;
+    else if (tail.linear && tail.aux.empty() && tail.stride >= 2 && tail.stride <= 32 && block_inside(0, dims.size() - 2, tail.stride)) front = true;
+    else return OLAP_OK;
+    const GDim& row_axis = front ? tail : lead;
+    const size_t b0 = front ? 0 : 1, b1 = front ? dims.size() - 2 : dims.size() - 1;  // the block's axes, in output order
+    const int64_t rows = row_axis.len, D = row_axis.stride;
+    if (rows < 64 || rows >= ((int64_t)1 << 31) || const_off + rows * D > src[0]->size) return OLAP_OK;  // whole blocks are staged
     // long 128-bit inner runs are the vector gather's (0.87-0.94 of peak)
-    const GDim& inner = dims.back();
-    if (inner.linear && inner.stride == 1 && inner.len % 4 == 0 && inner.len >= 16) return OLAP_OK;
+    if (!front && tail.linear && tail.stride == 1 && tail.len % 4 == 0 && tail.len >= 16) return OLAP_OK;
     int64_t K = 1;
-    for (size_t d = 1; d < dims.size(); ++d) {
-        if (!dims[d].aux.empty()) return OLAP_OK;
+    for (size_t d = b0; d <= b1; ++d) {
         K *= dims[d].len;
         if (K > D || K < 1) return OLAP_OK;
     }
     std::vector<int32_t> keep((size_t)K);
-    for (int64_t k = 0; k < K; ++k) {  // row-major over the trailing output axes
+    for (int64_t k = 0; k < K; ++k) {  // row-major over the block's output axes
         int64_t rest = k, off = 0;
-        for (size_t d = dims.size() - 1; d >= 1; --d) {
+        for (size_t d = b1 + 1; d-- > b0;) {
             const int64_t c = rest % dims[d].len;
             rest /= dims[d].len;
             off += dims[d].linear ? c * dims[d].stride : dims[d].tbl[(size_t)c];
         }
-        if (off < 0 || off >= D) return OLAP_OK;
         keep[(size_t)k] = (int32_t)off;
     }
-    // rows per tile: spans start on 16 cells (16-byte copies of values and of status bytes)
-    const int64_t step = 16 / std::gcd<int64_t, int64_t>(D, 16);
+    // rows per tile: spans start on 16 cells (16-byte copies of values and of status bytes); FRONT: whole groups of
+    // 256 rows, so that the plane a thread writes to depends on the loop index only
+    const int64_t step = front ? 256 : 16 / std::gcd<int64_t, int64_t>(D, 16);
     const int64_t RB = (kFlatCells / D) / step * step;
     if (RB < 1) return OLAP_OK;
-    // consecutive lanes read keep[j], keep[j + 1], ...: decline patterns that pile onto few shared-memory banks
+    // consecutive lanes read neighbouring outputs: decline patterns that pile onto few shared-memory banks
     {
         const int64_t tile_out = RB * K;
         int64_t conflicts = 0, warps = 0;
         for (int64_t j0 = 0; j0 < tile_out; j0 += 32, ++warps) {
             int bank[32] = {0};
             int worst = 0;
-            for (int64_t j = j0; j < std::min(tile_out, j0 + 32); ++j) worst = std::max(worst, ++bank[((j / K) * D + keep[(size_t)(j % K)]) & 31]);
+            for (int64_t j = j0; j < std::min(tile_out, j0 + 32); ++j) {
+                const int64_t cell = front ? (j % RB) * D + keep[(size_t)(j / RB)] : (j / K) * D + keep[(size_t)(j % K)];
+                worst = std::max(worst, ++bank[cell & 31]);
+            }
             conflicts += worst;
         }
         if (conflicts > 4 * warps) return OLAP_OK;
@@ -1258,6 +1281,7 @@ static int try_gather_flat(olap_store* const* src, int n, std::vector<GDim> dims
     p.rows = rows;
     p.D = (uint32_t)D; p.K = (uint32_t)K; p.RB = (uint32_t)RB;
     p.div_k = FastDiv((uint32_t)K);
+    p.div_rb = FastDiv((uint32_t)RB);
     const int64_t n_tiles = ceil_div(rows, RB);
     p.n_tiles = (uint32_t)n_tiles;
     const int64_t per_thread = ceil_div(RB * K, 256);
@@ -1266,11 +1290,14 @@ static int try_gather_flat(olap_store* const* src, int n, std::vector<GDim> dims
     const size_t smem = (size_t)RB * D * (any_plane ? 5 : 4);
     const dim3 grid((unsigned)gx, (unsigned)n);
     KERNELS_BEGIN();
-    if (per_thread <= 8) gather_inner_flat_kernel<8, 4><<<grid, 256, smem, g.stream>>>(p);
-    else if (per_thread <= 16) gather_inner_flat_kernel<16, 4><<<grid, 256, smem, g.stream>>>(p);
-    else gather_inner_flat_kernel<32, 3><<<grid, 256, smem, g.stream>>>(p);
+    if (front) {
+        if (per_thread <= 16) gather_inner_flat_kernel<16, 4, true><<<grid, 256, smem, g.stream>>>(p);
+        else gather_inner_flat_kernel<32, 3, true><<<grid, 256, smem, g.stream>>>(p);
+    } else if (per_thread <= 8) gather_inner_flat_kernel<8, 4, false><<<grid, 256, smem, g.stream>>>(p);
+    else if (per_thread <= 16) gather_inner_flat_kernel<16, 4, false><<<grid, 256, smem, g.stream>>>(p);
+    else gather_inner_flat_kernel<32, 3, false><<<grid, 256, smem, g.stream>>>(p);
     LAUNCHED();
-    *path = "gather/inner-flat";
+    *path = front ? "gather/flat-to-front" : "gather/inner-flat";
     OLAP_TRY(t.release());
     *done = true;
     return OLAP_OK;
