@@ -127,7 +127,9 @@ int olap_host_free(void* p);
  * cube.  Results of transforms of a shareable store are shareable too. */
 #define OLAP_CREATE_SHAREABLE 4
 int olap_store_create(int64_t size, int type, int default_kind, int with_status, olap_store** out);
-/* n stores of equal size carved from one allocation (a cube's stored measures).
+/* n stores of equal size (a cube's stored measures), carved from one allocation while they are
+ * small (< 32 MiB each) or share a status plane; larger stores own their allocation, so that
+ * destroying some of them frees their memory.
  * shared_status != 0: one status plane shared by all n stores. */
 int olap_store_create_batch(int n, int64_t size, const int* types, const int* default_kinds,
                             int with_status, int shared_status, olap_store** out);

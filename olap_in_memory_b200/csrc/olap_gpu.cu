@@ -143,6 +143,21 @@ int alloc_batch(int n, int64_t size, const int* types, const int* default_kinds,
     const int n_status = with_status ? (shared_status ? 1 : n) : 0;
     const size_t bytes = vplane * n + splane * n_status;
     shareable |= g_share_all;
+    // Large stores with planes of their own get an allocation EACH: a cube that keeps 1 of 64 measures
+    // (dropMeasure, keepMeasures, dice by measures) must not pin the planes of the other 63.  Small ones share one
+    // block (one pool call per query); shared status planes and peer-mapped blocks need the single block.
+    const char* own_env = getenv("OLAP_OWN_ARENA_MB");  // read per call: a test lowers it
+    const size_t own_arena_bytes = (size_t)(own_env ? atoi(own_env) : 32) << 20;
+    if (n > 1 && !shareable && !(with_status && shared_status) && vplane + splane >= own_arena_bytes) {
+        for (int k = 0; k < n; ++k) {
+            const int rc = alloc_batch(1, size, types + k, default_kinds + k, with_status, false, out + k, false);
+            if (rc != OLAP_OK) {
+                for (int q = 0; q < k; ++q) { olap_store_destroy(out[q]); out[q] = nullptr; }
+                return rc;
+            }
+        }
+        return OLAP_OK;
+    }
     Arena* arena = new Arena();
     int rc = shareable ? share_alloc(&arena->base, bytes) : dev_alloc(&arena->base, bytes);
     if (rc != OLAP_OK) { delete arena; return rc; }

@@ -744,3 +744,37 @@ def test_async_pair_transpose(monkeypatch):
                 st[::5] |= 4
             assert np.array_equal(np.asarray(out.status, np.uint8), st.reshape(dims).transpose(perm).reshape(-1)), (dims, perm, k)
     assert taken >= 2
+
+
+def test_large_stores_own_their_allocation(monkeypatch):
+    """Stores of one batched call share one device allocation only while they are small: above the threshold
+    (32 MiB per store; lowered to 0 here) every result owns its block, so destroying some measures of a cube
+    returns their memory while the others live on.  The kept store must stay intact after its siblings are gone
+    and after their blocks were reused."""
+    import gc
+
+    from olap_in_memory_b200 import interop
+
+    G = _gpu()
+    monkeypatch.setenv("OLAP_OWN_ARENA_MB", "0")
+    rng = np.random.default_rng(51)
+    n = 64 * 40 * 64
+    datas = [cases.make_data(rng, n, 0.0, 0.7, "int") for _ in range(3)]
+    stores = []
+    for d in datas:
+        s = G(n, "float32", 0)
+        s.set_data_f32(d)
+        stores.append(s)
+    m = cases.random_map(rng, 40, 5, True)
+    ident = cases.identity
+    outs = G.drillUp_lowered(stores, [64, 40, 64], [64, 5, 64], [ident(64), m, ident(64)], ["sum", "highest", "first"])
+    ptrs = [interop.values_tensor(o).data_ptr() for o in outs]
+    plane = ((64 * 5 * 64 * 4 + 255) // 256) * 256
+    assert ptrs[1] - ptrs[0] != plane or ptrs[2] - ptrs[1] != plane  # not carved from one block
+    kept = outs[1].data_f32().copy()
+    del outs[2], outs[0]
+    gc.collect()
+    scratch = [G(64 * 5 * 64, "float32", 0) for _ in range(4)]  # reuses the freed blocks
+    for s in scratch:
+        s.set_data_f32(np.full(64 * 5 * 64, 7.0, np.float32))
+    assert np.array_equal(outs[0].data_f32().view(np.uint32), kept.view(np.uint32))

@@ -1,0 +1,6 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+(time timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4) > gpurun_out/tests_r02x.log 2>&1; cat gpurun_out/tests_r02x.log | tail -6
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
+timeout 600 python bench.py > gpurun_out/bench_r02x.json 2> gpurun_out/bench_r02x.err; cut -c1-300 gpurun_out/bench_r02x.json
