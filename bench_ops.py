@@ -199,6 +199,8 @@ def main():
     run(f"reorder/swap outer two {dims}", lambda: GpuStore.reorder_lowered([s], dims, [1, 0, 2, 3, 4, 5]), B * 2 * n, n)
     run(f"reorder/swap inner two {dims}", lambda: GpuStore.reorder_lowered([s], dims, [0, 1, 2, 3, 5, 4]), B * 2 * n, n)
     run(f"reorder/rotate inner to front {dims}", lambda: GpuStore.reorder_lowered([s], dims, [5, 0, 1, 2, 3, 4]), B * 2 * n, n)
+    rdims = dims[::-1]  # the mirror image: a short OUTER axis becomes the innermost one
+    run(f"reorder/rotate front to inner {rdims}", lambda: GpuStore.reorder_lowered([s], rdims, [1, 2, 3, 4, 5, 0]), B * 2 * n, n)
     del s
     # drillDown month -> day (10 months -> 304 days) with I = 100 and I = 1
     mdim = TimeDimension("time", "month", "2010-01", "2010-10")

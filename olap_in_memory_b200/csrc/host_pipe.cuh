@@ -8,6 +8,8 @@
 // taking a slice of the chunk.  Pinned (cudaHostAlloc / olap_host_alloc) and small buffers take the direct copy.
 #pragma once
 
+#include <unistd.h>
+
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -19,13 +21,14 @@ namespace olap {
 class CopyPool {
 public:
     static CopyPool& get() {
-        static CopyPool pool;
-        return pool;
+        static CopyPool* pool = new CopyPool();  // never destroyed: the workers end with the process (and a forked
+        return *pool;                            // child, which has none of them, must not try to join them)
     }
     int threads() const { return n_threads_; }
     // memcpy split into one slice per thread (the caller takes the first slice); returns when all are done
     void copy(void* dst, const void* src, size_t bytes) {
-        const int parts = (int)std::min<size_t>((size_t)n_threads_, std::max<size_t>(1, bytes >> 20));  // >= 1 MiB per slice
+        int parts = (int)std::min<size_t>((size_t)n_threads_, std::max<size_t>(1, bytes >> 20));  // >= 1 MiB per slice
+        if (getpid() != pid_) parts = 1;  // a forked child has no worker threads: copy on the calling thread
         if (parts <= 1) {
             memcpy(dst, src, bytes);
             return;
@@ -54,6 +57,7 @@ private:
         int n = e ? atoi(e) : 0;
         if (n <= 0) n = (int)std::min<unsigned>(8u, std::max<unsigned>(1u, std::thread::hardware_concurrency() / 2));  // 16 vCPUs: 4 threads 24-30 GB/s, 8 threads 26-39
         n_threads_ = std::max(1, std::min(n, 32));
+        pid_ = getpid();
         for (int t = 1; t < n_threads_; ++t) workers_.emplace_back([this] { run(); });
     }
     ~CopyPool() {
@@ -86,6 +90,7 @@ private:
         }
     }
     int n_threads_ = 1;
+    pid_t pid_ = 0;
     std::vector<std::thread> workers_;
     std::mutex m_;
     std::condition_variable cv_, done_;

@@ -438,6 +438,83 @@ static __global__ void __launch_bounds__(256, MINB) gather_inner_flat_kernel(con
     }
 }
 
+// ---- the mirror image of FRONT: gather_planes_flat_kernel --------------------------------
+// [K, R] -> [R, K]: short OUTER axes (K <= 32 planes of the source, anywhere in it) become the innermost axes of
+// the output.  A tile is RB consecutive rows: K runs of RB cells are staged (16-byte cp.async for the values,
+// 4-byte for the status bytes; plane pitch RB + 4: the fold reads at 4 k + r, conflict-free up to 8 planes, 2-way
+// beyond), then the RB * K outputs leave as ONE contiguous span, consecutive lanes consecutive cells.
+struct PlanesParams {
+    const GatherMeasure* meas;
+    const int64_t* plane_off;  // [K] source offset of plane k (cells, multiples of 4)
+    int64_t rows;
+    uint32_t K, RB, n_tiles;
+    FastDiv div_k, div_rb4;
+};
+
+template <int E, int MINB>
+static __global__ void __launch_bounds__(256, MINB) gather_planes_flat_kernel(const __grid_constant__ PlanesParams p) {
+    extern __shared__ __align__(16) unsigned char smem_planes[];
+    const uint32_t pitch = p.RB + 4;
+    float* s_val = reinterpret_cast<float*>(smem_planes);          // [K][pitch]
+    uint8_t* s_st = smem_planes + (size_t)p.K * pitch * 4;         // [K][pitch]
+    __shared__ int64_t s_off[32];
+    const GatherMeasure m = p.meas[blockIdx.y];
+    if (threadIdx.x < p.K) s_off[threadIdx.x] = p.plane_off[threadIdx.x];
+    uint32_t off[E];
+    const uint32_t tile_out = p.RB * p.K;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const uint32_t j = threadIdx.x + 256u * e;
+        off[e] = 0;
+        if (j < tile_out) {
+            const uint32_t r = p.div_k.div(j), k = j - r * p.K;
+            off[e] = k * pitch + r;
+        }
+    }
+    __syncthreads();
+    const bool load_plane = m.st_in != nullptr, write_plane = m.st_out != nullptr, nan_default = m.nan_default != 0;
+    const uint32_t rb4 = p.RB >> 2;
+    for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int64_t row0 = (int64_t)tile * p.RB;
+        const uint32_t rows = (uint32_t)min((int64_t)p.RB, p.rows - row0);
+        for (uint32_t c = threadIdx.x; c < p.K * rb4; c += 256) {
+            const uint32_t k = p.div_rb4.div(c), i = (c - k * rb4) << 2;
+            const int64_t g = s_off[k] + row0 + i;
+            if (i + 4 <= rows) {
+                flat_cp_async16(s_val + k * pitch + i, m.in + g);
+                if (load_plane) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(s_st + k * pitch + i)), "l"(m.st_in + g) : "memory");
+            } else {
+                for (uint32_t q = i; q < rows; ++q) {  // the ragged end of the last tile
+                    s_val[k * pitch + q] = m.in[g + (q - i)];
+                    if (load_plane) s_st[k * pitch + q] = m.st_in[g + (q - i)];
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const uint32_t n_out = rows * p.K;
+        float* g_out = m.out + row0 * p.K + threadIdx.x;
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (threadIdx.x + 256u * e < n_out) g_out[256 * e] = s_val[off[e]];
+        if (write_plane) {
+            uint8_t* g_so = m.st_out + row0 * p.K + threadIdx.x;
+            if (load_plane) {
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (threadIdx.x + 256u * e < n_out) g_so[256 * e] = s_st[off[e]];
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (threadIdx.x + 256u * e < n_out)
+                        g_so[256 * e] = (uint8_t)(present_f(s_val[off[e]], nan_default) ? OLAP_STATUS_SET : OLAP_STATUS_UNSET);  // derived plane
+            }
+        }
+        __syncthreads();  // the next tile overwrites the staged runs
+    }
+}
+
 // ---- load: input-driven scatter  dst[mine(his)] = src[his]  (in-memory.js:159-175).
 // Tables hold my offset contribution per his coordinate, or -1 when I lack the item
 // (then the cell is dropped).  His items are distinct, so the scatter is injective.

@@ -1318,6 +1318,74 @@ static int try_gather_flat(olap_store* const* src, int n, std::vector<GDim> dims
     return OLAP_OK;
 }
 
+// [K, R] -> [R, K]: short outer axes of the source become the innermost axes of the output (gather_planes_flat_kernel).
+// `dims` is in output order: the row axis comes first and is contiguous in the source.
+static int try_gather_planes(olap_store* const* src, int n, std::vector<GDim> dims, const std::vector<GatherMeasure>& meas_in,
+                             bool* done, const char** path) {
+    *done = false;
+    static const int knob = [] { const char* e = getenv("OLAP_FLAT"); return e ? atoi(e) : 1; }();
+    if (!knob) return OLAP_OK;
+    int64_t const_off = 0;
+    merge_dims(dims, &const_off);
+    if (dims.size() < 2 || const_off % 4 || !dims[0].linear || dims[0].stride != 1 || !dims[0].aux.empty()) return OLAP_OK;
+    const int64_t rows = dims[0].len;
+    if (rows < 4096 || rows >= ((int64_t)1 << 31)) return OLAP_OK;
+    int64_t K = 1;
+    for (size_t d = 1; d < dims.size(); ++d) {
+        if (!dims[d].aux.empty()) return OLAP_OK;
+        K *= dims[d].len;
+        if (K > 32 || K < 1) return OLAP_OK;
+    }
+    if (K < 2) return OLAP_OK;
+    std::vector<int64_t> plane((size_t)K);
+    for (int64_t k = 0; k < K; ++k) {  // row-major over the trailing output axes
+        int64_t rest = k, off = const_off;
+        for (size_t d = dims.size(); d-- > 1;) {
+            const int64_t c = rest % dims[d].len;
+            rest /= dims[d].len;
+            off += dims[d].linear ? c * dims[d].stride : dims[d].tbl[(size_t)c];
+        }
+        if (off < 0 || off % 4 || off + rows > src[0]->size) return OLAP_OK;
+        plane[(size_t)k] = off;
+    }
+    const int64_t RB = (kFlatCells / K) / 256 * 256;
+    if (RB < 256) return OLAP_OK;
+    for (int k = 0; k < n; ++k)  // wrapped memory may sit anywhere
+        if ((reinterpret_cast<uintptr_t>(meas_in[k].in) & 15) || (reinterpret_cast<uintptr_t>(meas_in[k].st_in) & 3) ||
+            (reinterpret_cast<uintptr_t>(meas_in[k].out) & 3))
+            return OLAP_OK;
+    PlanesParams p{};
+    TablePack t;
+    std::vector<GatherMeasure> meas = meas_in;
+    gather_derive(meas, src, n);
+    bool any_plane = false;
+    for (auto& m : meas) any_plane |= m.st_in != nullptr;
+    const size_t o_meas = t.add(meas.data(), sizeof(GatherMeasure) * n);
+    const size_t o_off = t.add(plane.data(), plane.size() * 8);
+    OLAP_TRY(t.upload());
+    p.meas = t.ptr<GatherMeasure>(o_meas);
+    p.plane_off = t.ptr<int64_t>(o_off);
+    p.rows = rows;
+    p.K = (uint32_t)K; p.RB = (uint32_t)RB;
+    p.div_k = FastDiv((uint32_t)K);
+    p.div_rb4 = FastDiv((uint32_t)(RB / 4));
+    const int64_t n_tiles = ceil_div(rows, RB);
+    p.n_tiles = (uint32_t)n_tiles;
+    const int64_t per_thread = RB * K / 256;
+    const int per_sm = per_thread <= 16 ? 4 : 3;
+    const int64_t gx = std::min<int64_t>(n_tiles, std::max<int64_t>(1, (int64_t)g.sm_count * per_sm / n));  // persistent CTAs
+    const size_t smem = (size_t)K * (RB + 4) * (any_plane ? 5 : 4);
+    const dim3 grid((unsigned)gx, (unsigned)n);
+    KERNELS_BEGIN();
+    if (per_thread <= 16) gather_planes_flat_kernel<16, 4><<<grid, 256, smem, g.stream>>>(p);
+    else gather_planes_flat_kernel<32, 3><<<grid, 256, smem, g.stream>>>(p);
+    LAUNCHED();
+    *path = "gather/planes-to-inner";
+    OLAP_TRY(t.release());
+    *done = true;
+    return OLAP_OK;
+}
+
 static int run_gather(int mode, olap_store* const* src, int n, std::vector<GDim>& dims, int64_t new_size, int64_t old_size,
                       const std::vector<GatherMeasure>& meas_in, int* d_error, const char** path) {
     if (mode == G_COPY) {
@@ -1561,6 +1629,7 @@ int olap_reorder(olap_store* const* src, int n, int ndim, const int64_t* old_len
         if (!tm.use) pp = transpose_pair_plan(dims);
         bool flat_done = false;
         if (!tm.use && !pp.use) OLAP_TRY(try_gather_flat(src, n, dims, meas, &flat_done, &path));  // trailing axes swapped inside short blocks
+        if (!tm.use && !pp.use && !flat_done) OLAP_TRY(try_gather_planes(src, n, dims, meas, &flat_done, &path));  // short outer axes rotated to innermost
         TransposePlan tp;
         if (!tm.use && !pp.use && !flat_done) tp = transpose_plan(dims);
         if (flat_done) {

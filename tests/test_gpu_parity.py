@@ -678,12 +678,16 @@ def test_rearrangements_inside_short_blocks(default):
 
     G = _gpu()
     rng = np.random.default_rng(35)
-    # the last three: a short innermost axis (or block) rotated to the FRONT of the output — the same staging, the
-    # outputs of a tile leave as one run per plane (path gather/flat-to-front)
-    for kind, lens, arg in (("reorder", [70, 9, 10, 10], [0, 1, 3, 2]), ("reorder", [1000, 6, 5, 4], [0, 3, 1, 2]),
-                            ("reorder", [333, 7, 3], [0, 2, 1]), ("dice", [500, 10, 12], [[1, 3, 8], [0, 5, 11, 2]]),
-                            ("dice", [90, 4, 10, 10], [None, [9, 0], list(range(10))]),
-                            ("reorder", [300, 7, 10], [2, 0, 1]), ("reorder", [2001, 4, 3], [1, 2, 0]), ("reorder", [40, 50, 3, 2], [3, 2, 0, 1])):
+    # inner-flat: the block stays innermost; flat-to-front: a short innermost axis (or block) becomes the OUTERMOST part
+    # of the output (one run per plane leaves a tile); planes-to-inner: the mirror image, short outer axes become the
+    # innermost ones
+    flat, front, planes = b"gather/inner-flat", b"gather/flat-to-front", b"gather/planes-to-inner"
+    for kind, lens, arg, want_path in (
+            ("reorder", [70, 9, 10, 10], [0, 1, 3, 2], flat), ("reorder", [1000, 6, 5, 4], [0, 3, 1, 2], flat),
+            ("reorder", [333, 7, 3], [0, 2, 1], flat), ("dice", [500, 10, 12], [[1, 3, 8], [0, 5, 11, 2]], flat),
+            ("dice", [90, 4, 10, 10], [None, [9, 0], list(range(10))], flat),
+            ("reorder", [300, 7, 10], [2, 0, 1], front), ("reorder", [2001, 4, 3], [1, 2, 0], front), ("reorder", [40, 50, 3, 2], [3, 2, 0, 1], front),
+            ("reorder", [10, 5004], [1, 0], planes), ("reorder", [3, 4, 5000], [2, 0, 1], planes), ("reorder", [2, 70, 100], [1, 2, 0], planes)):
         n = int(np.prod(lens))
         data = cases.make_data(rng, n, default, 0.6, "int")
         set_ = (data == data) if default != default else (data != 0)
@@ -708,8 +712,7 @@ def test_rearrangements_inside_short_blocks(default):
             else:
                 full = [None] * (len(lens) - len(arg)) + arg
                 out = G.dice_lowered([s], lens, [np.arange(d, dtype=np.int32) if k is None else np.asarray(k, np.int32) for d, k in zip(lens, full)])[0]
-            to_front = kind == "reorder" and arg[0] != 0
-            assert N.lib().olap_last_op_path() == (b"gather/flat-to-front" if to_front else b"gather/inner-flat"), (kind, lens, arg)
+            assert N.lib().olap_last_op_path() == want_path, (kind, lens, arg)
             assert np.array_equal(out.data_f32().view(np.uint32), move(data).view(np.uint32)), (kind, lens, arg, derived)
             assert np.array_equal(np.asarray(out.status, np.uint8), move(st_derived if derived else st_loaded)), (kind, lens, arg, derived)
 
