@@ -8,6 +8,7 @@
 
 #include "../../olap_in_memory_b200/csrc/kernels_pair.cuh"
 #include "../../olap_in_memory_b200/csrc/kernels_tile.cuh"
+#include "../../olap_in_memory_b200/csrc/kernels_lanes.cuh"
 
 namespace olap {
 thread_local std::string g_error;
@@ -130,8 +131,69 @@ static int emulate_pair(const std::vector<int64_t>& len, const std::vector<int>&
     return 0;
 }
 
+// drillup_lanes_kernel's host side: the segment plan covers every child exactly once in whole tiles, and the per-tile
+// lists are a grouping of the tile's children by parent (a permutation, ascending inside a parent) with its inverse in
+// the copy loop's layout.
+static int check_lanes(int64_t O, int64_t C, int64_t P, int n_meas, bool loaded, unsigned seed) {
+    const LanesDecision d = lanes_plan(O, C, P, 1, n_meas, 148, loaded);
+    if (!d.use) return 0;
+    const int64_t unit = (int64_t)d.tile * kLanesWarps;
+    if (d.tile != 64 && d.tile != 128) { printf("lanes: tile\n"); return 1; }
+    if (d.Cs < unit || d.Cs % unit || (int64_t)d.SS * d.Cs < C || (int64_t)(d.SS - 1) * d.Cs >= C) { printf("lanes: segments %d x %d over %lld\n", d.SS, d.Cs, (long long)C); return 1; }
+    if (d.SS > 1 && d.scratch_stride < O * d.SS * P * 17) { printf("lanes: scratch\n"); return 1; }
+    std::vector<int32_t> map((size_t)C);
+    unsigned x = seed * 2654435761u + 12345u;
+    for (auto& m : map) { x = x * 1664525u + 1013904223u; m = (int32_t)((x >> 16) % (unsigned)P); }
+    if (seed & 1) std::sort(map.begin(), map.end());
+    const std::vector<uint8_t> t = lanes_lists(map.data(), C, d.tile);
+    const size_t table = 2 * (size_t)d.tile + 16;
+    const int per_lane = d.tile / 32;
+    if (t.size() != (size_t)ceil_div(C, d.tile) * table || table % 16) { printf("lanes: table size\n"); return 1; }
+    for (int64_t g0 = 0; g0 * d.tile < C; ++g0) {
+        const uint8_t* perm = t.data() + (size_t)g0 * table;
+        const uint8_t* bounds = perm + d.tile;
+        const uint8_t* rank = bounds + 16;
+        const int n = (int)std::min<int64_t>(d.tile, C - g0 * d.tile);
+        if (bounds[0] != 0 || bounds[P] != n) { printf("lanes: bounds\n"); return 1; }
+        for (int q = 0; q < 8; ++q) if (bounds[q] > bounds[q + 1] || (q >= P && bounds[q] != n)) { printf("lanes: bounds order\n"); return 1; }
+        std::vector<int> seen((size_t)n, 0);
+        for (int q = 0; q < P; ++q)
+            for (int k = bounds[q]; k < bounds[q + 1]; ++k) {
+                const int c = perm[k];
+                if (c >= n || seen[(size_t)c]++ || map[(size_t)(g0 * d.tile + c)] != q) { printf("lanes: list of parent %d\n", q); return 1; }
+                if (k > bounds[q] && perm[k - 1] >= c) { printf("lanes: children not ascending\n"); return 1; }
+                if (rank[(c & 31) * per_lane + (c >> 5)] != k) { printf("lanes: rank is not the inverse\n"); return 1; }
+            }
+    }
+    return 0;
+}
+
 int main() {
     int bad = 0, n = 0, n_pair = 0;
+    {
+        int taken = 0;
+        unsigned seed = 0;
+        for (int64_t O : {64, 70, 1196, 100000})
+            for (int64_t C : {2048, 2052, 40961, 100000, 333333})
+                for (int64_t P : {1, 2, 5, 8})
+                    for (int n_meas : {1, 3})
+                        for (int loaded = 0; loaded < 2; ++loaded) {
+                            setenv("OLAP_LANES_LOADED", "1", 1);
+                            setenv("OLAP_LANES_GEO", (seed & 2) ? "1" : "0", 1);
+                            const LanesDecision d = lanes_plan(O, C, P, 1, n_meas, 148, loaded != 0);
+                            taken += d.use;
+                            bad += check_lanes(O, C, P, n_meas, loaded != 0, seed++);
+                            ++n;
+                        }
+        unsetenv("OLAP_LANES_LOADED");
+        unsetenv("OLAP_LANES_GEO");
+        // a status plane that has to be read travels in 4-byte words: odd row lengths are declined; so are short rows,
+        // many parents, inner runs
+        if (lanes_plan(1000, 100001, 4, 1, 1, 148, true).use || lanes_plan(10, 100000, 4, 1, 1, 148, false).use ||
+            lanes_plan(1000, 100000, 9, 1, 1, 148, false).use || lanes_plan(1000, 100000, 4, 2, 1, 148, false).use) { printf("lanes: should decline\n"); ++bad; }
+        printf("lanes plans taken: %d\n", taken);
+        if (taken < 100) { printf("lanes planner declined almost everything\n"); ++bad; }
+    }
     {
         const std::vector<std::vector<int64_t>> pshapes = {
             {20, 20, 20, 10, 10, 10}, {100, 100, 100, 10, 10, 10}, {64, 64}, {128, 36}, {36, 128}, {100, 104}, {3652, 32, 32},
