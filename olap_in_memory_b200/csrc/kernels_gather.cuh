@@ -8,6 +8,9 @@
 // dimensions that are untouched and contiguous on both sides are merged into an inner
 // run of length I that is moved with 128-bit accesses.
 #pragma once
+#include <algorithm>
+#include <numeric>
+
 #include "common.cuh"
 
 namespace olap {
@@ -326,6 +329,25 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const __grid_constant_
     }
 }
 
+// Drop single-item dimensions (their constant offset goes to `const_off`) and merge
+// neighbours that stay adjacent and contiguous in the source.
+inline void merge_dims(std::vector<GDim>& dims, int64_t* const_off) {
+    std::vector<GDim> out;
+    for (auto& d : dims) {
+        if (d.len == 1) {
+            if (!d.linear) *const_off += d.tbl[0];
+            continue;  // aux of a single item is {1 sibling, rank 0}: neutral
+        }
+        if (!out.empty() && out.back().linear && d.linear && out.back().stride == d.len * d.stride) {
+            out.back().len *= d.len;
+            out.back().stride = d.stride;
+        } else {
+            out.push_back(std::move(d));
+        }
+    }
+    dims.swap(out);
+}
+
 // ---- rearrangements inside short contiguous blocks: gather_inner_flat_kernel -------------
 // [R, D] -> [R, K] with the leading axes untouched: dice / slice of the innermost axes (in-memory.js:213-263) and
 // reorders that only swap trailing axes (in-memory.js:178-211; keep[] is then a permutation of the block):
@@ -347,6 +369,96 @@ struct FlatParams {
     FastDiv div_k;
     FastDiv div_rb;        // FRONT: the block's axes move to the FRONT of the output ([R, D] -> [K, R]); RB % 256 == 0
 };
+
+// Output j of a tile (consecutive lanes, consecutive j) is row r of the tile and position k of the block; it comes
+// from cell r * D + keep[k] of the staged span.  Shared by the kernel and the CPU emulation (tests/host/plan_check.cu).
+struct FlatIdx { uint32_t r, k; };
+__host__ __device__ __forceinline__ FlatIdx flat_split(const FlatParams& p, bool front, uint32_t j) {
+    FlatIdx ix;
+    if (front) { ix.k = p.div_rb.div(j); ix.r = j - ix.k * p.RB; }
+    else { ix.r = p.div_k.div(j); ix.k = j - ix.r * p.K; }
+    return ix;
+}
+
+// Host side of gather_inner_flat_kernel.  `dims` is the gather in output order (GDim: length and source stride or
+// offset table per output axis).  The untouched leading axes of the source merge into one linear "row" axis whose
+// stride D is the block length; they are either still the leading axes of the output (rows first: the block stays
+// innermost) or its trailing axes (rows last: the block's axes moved to the FRONT).
+struct FlatPlan {
+    bool use = false, front = false;
+    int64_t rows = 0, D = 0, K = 0, RB = 0, const_off = 0;
+    std::vector<int32_t> keep;  // [K] source offset inside a block of every output position of the block (row-major)
+};
+
+inline FlatPlan flat_plan(std::vector<GDim> dims, int64_t src_size) {
+    FlatPlan plan;
+    int64_t const_off = 0;
+    merge_dims(dims, &const_off);
+    if (dims.size() < 2 || const_off % 16) return plan;
+    const GDim& lead = dims[0];
+    const GDim& tail = dims.back();
+    bool front = false;
+    auto block_inside = [&](size_t first, size_t last, int64_t D) {  // every offset of axes [first, last] stays in [0, D)
+        int64_t hi = 0;
+        for (size_t d = first; d <= last; ++d) {
+            if (!dims[d].aux.empty()) return false;
+            int64_t lo_d = 0, hi_d = 0;
+            if (dims[d].linear) { hi_d = (dims[d].len - 1) * dims[d].stride; if (dims[d].stride < 0) return false; }
+            else for (int64_t v : dims[d].tbl) { lo_d = std::min(lo_d, v); hi_d = std::max(hi_d, v); }
+            if (lo_d < 0) return false;
+            hi += hi_d;
+        }
+        return hi < D;
+    };
+    if (lead.linear && lead.aux.empty() && lead.stride >= 2 && lead.stride <= kFlatCells && block_inside(1, dims.size() - 1, lead.stride)) front = false;
+    else if (tail.linear && tail.aux.empty() && tail.stride >= 2 && tail.stride <= 32 && block_inside(0, dims.size() - 2, tail.stride)) front = true;
+    else return plan;
+    const GDim& row_axis = front ? tail : lead;
+    const size_t b0 = front ? 0 : 1, b1 = front ? dims.size() - 2 : dims.size() - 1;  // the block's axes, in output order
+    const int64_t rows = row_axis.len, D = row_axis.stride;
+    if (rows < 64 || rows >= ((int64_t)1 << 31) || const_off + rows * D > src_size) return plan;  // whole blocks are staged
+    // long 128-bit inner runs are the vector gather's (0.87-0.94 of peak)
+    if (!front && tail.linear && tail.stride == 1 && tail.len % 4 == 0 && tail.len >= 16) return plan;
+    int64_t K = 1;
+    for (size_t d = b0; d <= b1; ++d) {
+        K *= dims[d].len;
+        if (K > D || K < 1) return plan;
+    }
+    plan.keep.resize((size_t)K);
+    for (int64_t k = 0; k < K; ++k) {  // row-major over the block's output axes
+        int64_t rest = k, off = 0;
+        for (size_t d = b1 + 1; d-- > b0;) {
+            const int64_t c = rest % dims[d].len;
+            rest /= dims[d].len;
+            off += dims[d].linear ? c * dims[d].stride : dims[d].tbl[(size_t)c];
+        }
+        plan.keep[(size_t)k] = (int32_t)off;
+    }
+    // rows per tile: spans start on 16 cells (16-byte copies of values and of status bytes); FRONT: whole groups of
+    // 256 rows, so that the plane a thread writes to depends on the loop index only
+    const int64_t step = front ? 256 : 16 / std::gcd<int64_t, int64_t>(D, 16);
+    const int64_t RB = (kFlatCells / D) / step * step;
+    if (RB < 1) return plan;
+    // consecutive lanes read neighbouring outputs: decline patterns that pile onto few shared-memory banks
+    {
+        const int64_t tile_out = RB * K;
+        int64_t conflicts = 0, warps = 0;
+        for (int64_t j0 = 0; j0 < tile_out; j0 += 32, ++warps) {
+            int bank[32] = {0};
+            int worst = 0;
+            for (int64_t j = j0; j < std::min(tile_out, j0 + 32); ++j) {
+                const int64_t cell = front ? (j % RB) * D + plan.keep[(size_t)(j / RB)] : (j / K) * D + plan.keep[(size_t)(j % K)];
+                worst = std::max(worst, ++bank[cell & 31]);
+            }
+            conflicts += worst;
+        }
+        if (conflicts > 4 * warps) return plan;
+    }
+    plan.use = true;
+    plan.front = front;
+    plan.rows = rows; plan.D = D; plan.K = K; plan.RB = RB; plan.const_off = const_off;
+    return plan;
+}
 
 __device__ __forceinline__ void flat_cp_async16(void* smem_dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(src) : "memory");
@@ -371,13 +483,8 @@ static __global__ void __launch_bounds__(256, MINB) gather_inner_flat_kernel(con
         const uint32_t j = threadIdx.x + 256u * e;
         off[e] = 0;
         if (j < tile_out) {
-            if (FRONT) {
-                const uint32_t k = p.div_rb.div(j), r = j - k * p.RB;
-                off[e] = r * p.D + (uint32_t)p.keep[k];
-            } else {
-                const uint32_t r = p.div_k.div(j), k = j - r * p.K;
-                off[e] = r * p.D + (uint32_t)p.keep[k];
-            }
+            const FlatIdx ix = flat_split(p, FRONT, j);
+            off[e] = ix.r * p.D + (uint32_t)p.keep[ix.k];
         }
     }
     const bool load_plane = m.st_in != nullptr, write_plane = m.st_out != nullptr, nan_default = m.nan_default != 0;
@@ -403,7 +510,8 @@ static __global__ void __launch_bounds__(256, MINB) gather_inner_flat_kernel(con
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const uint32_t j = threadIdx.x + 256u * e;
-                const uint32_t k = p.div_rb.div(j), r = j - k * p.RB;  // k is warp-uniform (RB % 256 == 0)
+                const FlatIdx ix = flat_split(p, true, j);  // the plane k is warp-uniform (RB % 256 == 0)
+                const uint32_t k = ix.k, r = ix.r;
                 if (k < p.K && r < rows) {
                     const int64_t g = (int64_t)k * p.rows + r;
                     const float v = s_val[off[e]];
@@ -450,6 +558,46 @@ struct PlanesParams {
     uint32_t K, RB, n_tiles;
     FastDiv div_k, div_rb4;
 };
+
+// Host side: `dims` in output order — the row axis comes first and is contiguous in the source, the trailing
+// output axes select one of K <= 32 planes (any offsets that are multiples of 4 cells).
+struct PlanesPlan {
+    bool use = false;
+    int64_t rows = 0, K = 0, RB = 0;
+    std::vector<int64_t> plane;  // [K] source offset of every plane (row-major over the trailing output axes)
+};
+
+inline PlanesPlan planes_plan(std::vector<GDim> dims, int64_t src_size) {
+    PlanesPlan plan;
+    int64_t const_off = 0;
+    merge_dims(dims, &const_off);
+    if (dims.size() < 2 || const_off % 4 || !dims[0].linear || dims[0].stride != 1 || !dims[0].aux.empty()) return plan;
+    const int64_t rows = dims[0].len;
+    if (rows < 4096 || rows >= ((int64_t)1 << 31)) return plan;
+    int64_t K = 1;
+    for (size_t d = 1; d < dims.size(); ++d) {
+        if (!dims[d].aux.empty()) return plan;
+        K *= dims[d].len;
+        if (K > 32 || K < 1) return plan;
+    }
+    if (K < 2) return plan;
+    plan.plane.resize((size_t)K);
+    for (int64_t k = 0; k < K; ++k) {  // row-major over the trailing output axes
+        int64_t rest = k, off = const_off;
+        for (size_t d = dims.size(); d-- > 1;) {
+            const int64_t c = rest % dims[d].len;
+            rest /= dims[d].len;
+            off += dims[d].linear ? c * dims[d].stride : dims[d].tbl[(size_t)c];
+        }
+        if (off < 0 || off % 4 || off + rows > src_size) return plan;
+        plan.plane[(size_t)k] = off;
+    }
+    const int64_t RB = (kFlatCells / K) / 256 * 256;
+    if (RB < 256) return plan;
+    plan.use = true;
+    plan.rows = rows; plan.K = K; plan.RB = RB;
+    return plan;
+}
 
 template <int E, int MINB>
 static __global__ void __launch_bounds__(256, MINB) gather_planes_flat_kernel(const __grid_constant__ PlanesParams p) {

@@ -1185,25 +1185,6 @@ static void gather_derive(std::vector<GatherMeasure>& meas, olap_store* const* s
         }
 }
 
-// Drop single-item dimensions (their constant offset goes to `const_off`) and merge
-// neighbours that stay adjacent and contiguous in the source.
-static void merge_dims(std::vector<GDim>& dims, int64_t* const_off) {
-    std::vector<GDim> out;
-    for (auto& d : dims) {
-        if (d.len == 1) {
-            if (!d.linear) *const_off += d.tbl[0];
-            continue;  // aux of a single item is {1 sibling, rank 0}: neutral
-        }
-        if (!out.empty() && out.back().linear && d.linear && out.back().stride == d.len * d.stride) {
-            out.back().len *= d.len;
-            out.back().stride = d.stride;
-        } else {
-            out.push_back(std::move(d));
-        }
-    }
-    dims.swap(out);
-}
-
 // COPY gathers that only rearrange cells INSIDE contiguous blocks of the source (gather_inner_flat_kernel): the
 // leading axes are untouched and merge into one linear "row" axis whose stride D is the block length, and every
 // source offset of the trailing axes stays inside the block — dice / slice of the innermost axes, reorders that
@@ -1214,70 +1195,11 @@ static int try_gather_flat(olap_store* const* src, int n, std::vector<GDim> dims
     *done = false;
     static const int flat_knob = [] { const char* e = getenv("OLAP_FLAT"); return e ? atoi(e) : 1; }();
     if (!flat_knob) return OLAP_OK;
-    int64_t const_off = 0;
-    merge_dims(dims, &const_off);
-    if (dims.size() < 2 || const_off % 16) return OLAP_OK;
-    // the untouched leading axes are either still the leading axes of the output (rows first: the block stays
-    // innermost) or its trailing axes (rows last: the block's axes moved to the FRONT)
-    const GDim& lead = dims[0];
-    const GDim& tail = dims.back();
-    bool front = false;
-    auto block_inside = [&](size_t first, size_t last, int64_t D) {  // every offset of axes [first, last] stays in [0, D)
-        int64_t hi = 0;
-        for (size_t d = first; d <= last; ++d) {
-            if (!dims[d].aux.empty()) return false;
-            int64_t lo_d = 0, hi_d = 0;
-            if (dims[d].linear) { hi_d = (dims[d].len - 1) * dims[d].stride; if (dims[d].stride < 0) return false; }
-            else for (int64_t v : dims[d].tbl) { lo_d = std::min(lo_d, v); hi_d = std::max(hi_d, v); }
-            if (lo_d < 0) return false;
-            hi += hi_d;
-        }
-        return hi < D;
-    };
-    if (lead.linear && lead.aux.empty() && lead.stride >= 2 && lead.stride <= kFlatCells && block_inside(1, dims.size() - 1, lead.stride)) front = false;
-    else if (tail.linear && tail.aux.empty() && tail.stride >= 2 && tail.stride <= 32 && block_inside(0, dims.size() - 2, tail.stride)) front = true;
-    else return OLAP_OK;
-    const GDim& row_axis = front ? tail : lead;
-    const size_t b0 = front ? 0 : 1, b1 = front ? dims.size() - 2 : dims.size() - 1;  // the block's axes, in output order
-    const int64_t rows = row_axis.len, D = row_axis.stride;
-    if (rows < 64 || rows >= ((int64_t)1 << 31) || const_off + rows * D > src[0]->size) return OLAP_OK;  // whole blocks are staged
-    // long 128-bit inner runs are the vector gather's (0.87-0.94 of peak)
-    if (!front && tail.linear && tail.stride == 1 && tail.len % 4 == 0 && tail.len >= 16) return OLAP_OK;
-    int64_t K = 1;
-    for (size_t d = b0; d <= b1; ++d) {
-        K *= dims[d].len;
-        if (K > D || K < 1) return OLAP_OK;
-    }
-    std::vector<int32_t> keep((size_t)K);
-    for (int64_t k = 0; k < K; ++k) {  // row-major over the block's output axes
-        int64_t rest = k, off = 0;
-        for (size_t d = b1 + 1; d-- > b0;) {
-            const int64_t c = rest % dims[d].len;
-            rest /= dims[d].len;
-            off += dims[d].linear ? c * dims[d].stride : dims[d].tbl[(size_t)c];
-        }
-        keep[(size_t)k] = (int32_t)off;
-    }
-    // rows per tile: spans start on 16 cells (16-byte copies of values and of status bytes); FRONT: whole groups of
-    // 256 rows, so that the plane a thread writes to depends on the loop index only
-    const int64_t step = front ? 256 : 16 / std::gcd<int64_t, int64_t>(D, 16);
-    const int64_t RB = (kFlatCells / D) / step * step;
-    if (RB < 1) return OLAP_OK;
-    // consecutive lanes read neighbouring outputs: decline patterns that pile onto few shared-memory banks
-    {
-        const int64_t tile_out = RB * K;
-        int64_t conflicts = 0, warps = 0;
-        for (int64_t j0 = 0; j0 < tile_out; j0 += 32, ++warps) {
-            int bank[32] = {0};
-            int worst = 0;
-            for (int64_t j = j0; j < std::min(tile_out, j0 + 32); ++j) {
-                const int64_t cell = front ? (j % RB) * D + keep[(size_t)(j / RB)] : (j / K) * D + keep[(size_t)(j % K)];
-                worst = std::max(worst, ++bank[cell & 31]);
-            }
-            conflicts += worst;
-        }
-        if (conflicts > 4 * warps) return OLAP_OK;
-    }
+    const FlatPlan fp = flat_plan(std::move(dims), src[0]->size);
+    if (!fp.use) return OLAP_OK;
+    const bool front = fp.front;
+    const int64_t const_off = fp.const_off, rows = fp.rows, D = fp.D, K = fp.K, RB = fp.RB;
+    const std::vector<int32_t>& keep = fp.keep;
     for (int k = 0; k < n; ++k)  // wrapped memory may sit anywhere
         if ((reinterpret_cast<uintptr_t>(meas_in[k].in) & 15) || (reinterpret_cast<uintptr_t>(meas_in[k].st_in) & 15) ||
             (reinterpret_cast<uintptr_t>(meas_in[k].out) & 3) || (reinterpret_cast<uintptr_t>(meas_in[k].st_out) & 3))
@@ -1325,31 +1247,10 @@ static int try_gather_planes(olap_store* const* src, int n, std::vector<GDim> di
     *done = false;
     static const int knob = [] { const char* e = getenv("OLAP_FLAT"); return e ? atoi(e) : 1; }();
     if (!knob) return OLAP_OK;
-    int64_t const_off = 0;
-    merge_dims(dims, &const_off);
-    if (dims.size() < 2 || const_off % 4 || !dims[0].linear || dims[0].stride != 1 || !dims[0].aux.empty()) return OLAP_OK;
-    const int64_t rows = dims[0].len;
-    if (rows < 4096 || rows >= ((int64_t)1 << 31)) return OLAP_OK;
-    int64_t K = 1;
-    for (size_t d = 1; d < dims.size(); ++d) {
-        if (!dims[d].aux.empty()) return OLAP_OK;
-        K *= dims[d].len;
-        if (K > 32 || K < 1) return OLAP_OK;
-    }
-    if (K < 2) return OLAP_OK;
-    std::vector<int64_t> plane((size_t)K);
-    for (int64_t k = 0; k < K; ++k) {  // row-major over the trailing output axes
-        int64_t rest = k, off = const_off;
-        for (size_t d = dims.size(); d-- > 1;) {
-            const int64_t c = rest % dims[d].len;
-            rest /= dims[d].len;
-            off += dims[d].linear ? c * dims[d].stride : dims[d].tbl[(size_t)c];
-        }
-        if (off < 0 || off % 4 || off + rows > src[0]->size) return OLAP_OK;
-        plane[(size_t)k] = off;
-    }
-    const int64_t RB = (kFlatCells / K) / 256 * 256;
-    if (RB < 256) return OLAP_OK;
+    const PlanesPlan pl = planes_plan(std::move(dims), src[0]->size);
+    if (!pl.use) return OLAP_OK;
+    const int64_t rows = pl.rows, K = pl.K, RB = pl.RB;
+    const std::vector<int64_t>& plane = pl.plane;
     for (int k = 0; k < n; ++k)  // wrapped memory may sit anywhere
         if ((reinterpret_cast<uintptr_t>(meas_in[k].in) & 15) || (reinterpret_cast<uintptr_t>(meas_in[k].st_in) & 3) ||
             (reinterpret_cast<uintptr_t>(meas_in[k].out) & 3))

@@ -168,8 +168,100 @@ static int check_lanes(int64_t O, int64_t C, int64_t P, int n_meas, bool loaded,
     return 0;
 }
 
+// gather_inner_flat_kernel / gather_planes_flat_kernel: the host planners (orientation, block offsets, plane offsets,
+// rows per tile) and the tile index math the kernels share with this file (flat_split), replayed on the CPU against
+// the plain gather.  `dims` is the gather in output order.  Returns -1 when both planners decline.
+static int n_flat = 0, n_front = 0, n_planes = 0;
+static int emulate_flat(const std::vector<GDim>& dims, int64_t src_size) {
+    int64_t n_out = 1;
+    for (const GDim& d : dims) n_out *= d.len;
+    std::vector<int64_t> want((size_t)n_out), got((size_t)n_out, -1);
+    {
+        std::vector<int64_t> c(dims.size(), 0);
+        for (int64_t o = 0; o < n_out; ++o) {
+            int64_t srci = 0;
+            for (size_t i = 0; i < dims.size(); ++i) srci += dims[i].linear ? c[i] * dims[i].stride : dims[i].tbl[(size_t)c[i]];
+            want[(size_t)o] = srci;
+            for (int i = (int)dims.size() - 1; i >= 0; --i) { if (++c[i] < dims[i].len) break; c[i] = 0; }
+        }
+    }
+    const FlatPlan fp = flat_plan(dims, src_size);
+    if (fp.use) {
+        ++(fp.front ? n_front : n_flat);
+        if (fp.RB < 1 || fp.RB * fp.D > kFlatCells || (fp.RB * fp.D) % 16 || ceil_div(fp.RB * fp.K, 256) > 32 || (fp.front && fp.RB % 256)) { printf("flat: tile %lld x %lld\n", (long long)fp.RB, (long long)fp.D); return 1; }
+        FlatParams p{};
+        p.rows = fp.rows; p.D = (uint32_t)fp.D; p.K = (uint32_t)fp.K; p.RB = (uint32_t)fp.RB;
+        p.div_k = FastDiv(p.K); p.div_rb = FastDiv(p.RB);
+        if (fp.rows * fp.K != n_out) { printf("flat: output size\n"); return 1; }
+        for (int64_t row0 = 0; row0 < fp.rows; row0 += fp.RB) {
+            const int64_t rows_t = std::min<int64_t>(fp.RB, fp.rows - row0);
+            for (uint32_t j = 0; j < p.RB * p.K; ++j) {
+                const FlatIdx ix = flat_split(p, fp.front, j);
+                int64_t dst;
+                if (fp.front) { if (ix.k >= p.K || ix.r >= rows_t) continue; dst = (int64_t)ix.k * fp.rows + row0 + ix.r; }
+                else { if (j >= rows_t * fp.K) continue; dst = row0 * fp.K + j; }
+                if (ix.r >= rows_t || ix.k >= p.K || got[(size_t)dst] != -1) { printf("flat: output %lld written twice / out of tile\n", (long long)dst); return 1; }
+                got[(size_t)dst] = fp.const_off + (row0 + ix.r) * fp.D + fp.keep[ix.k];
+            }
+        }
+    } else {
+        const PlanesPlan pl = planes_plan(dims, src_size);
+        if (!pl.use) return -1;
+        ++n_planes;
+        if (pl.RB % 256 || pl.RB * pl.K > kFlatCells || pl.K > 32 || pl.rows * pl.K != n_out) { printf("planes: tile\n"); return 1; }
+        for (int64_t row0 = 0; row0 < pl.rows; row0 += pl.RB) {
+            const int64_t rows_t = std::min<int64_t>(pl.RB, pl.rows - row0);
+            for (int64_t j = 0; j < rows_t * pl.K; ++j) {
+                const int64_t r = j / pl.K, k = j % pl.K, dst = row0 * pl.K + j;
+                if (pl.plane[(size_t)k] % 4 || got[(size_t)dst] != -1) { printf("planes: output %lld\n", (long long)dst); return 1; }
+                got[(size_t)dst] = pl.plane[(size_t)k] + row0 + r;
+            }
+        }
+    }
+    for (int64_t o = 0; o < n_out; ++o)
+        if (got[(size_t)o] != want[(size_t)o]) { printf("flat: output %lld comes from %lld, want %lld\n", (long long)o, (long long)got[(size_t)o], (long long)want[(size_t)o]); return 1; }
+    return 0;
+}
+
+static std::vector<GDim> perm_dims(const std::vector<int64_t>& len, const std::vector<int>& perm) {
+    const int k = (int)len.size();
+    std::vector<int64_t> stride(k);
+    int64_t acc = 1;
+    for (int i = k - 1; i >= 0; --i) { stride[i] = acc; acc *= len[i]; }
+    std::vector<GDim> dims(k);
+    for (int i = 0; i < k; ++i) { dims[i].len = len[perm[i]]; dims[i].linear = true; dims[i].stride = stride[perm[i]]; }
+    return dims;
+}
+
 int main() {
     int bad = 0, n = 0, n_pair = 0;
+    {
+        // reorders: every permutation of a few shapes whose trailing / leading axes are short
+        const std::vector<std::vector<int64_t>> fshapes = {{70, 9, 10, 10}, {1000, 6, 5, 4}, {333, 7, 3}, {300, 7, 10}, {2001, 4, 3}, {40, 50, 3, 2},
+                                                           {10, 5004}, {3, 4, 5000}, {2, 70, 100}, {5, 8200, 2}, {4100, 32}, {32, 4100}, {9000, 33}};
+        for (const auto& len : fshapes) {
+            std::vector<int> perm(len.size());
+            std::iota(perm.begin(), perm.end(), 0);
+            int64_t size = 1;
+            for (int64_t l : len) size *= l;
+            do {
+                const int r = emulate_flat(perm_dims(len, perm), size);
+                if (r > 0) { printf("  shape of %zu axes, first %lld\n", len.size(), (long long)len[0]); ++bad; }
+                ++n;
+            } while (std::next_permutation(perm.begin(), perm.end()));
+        }
+        // dices: tables on the trailing axes, leading axes untouched; a table on a leading axis must be declined
+        auto table_dim = [](std::vector<int64_t> items, int64_t stride) { GDim d; d.len = (int64_t)items.size(); d.linear = false; for (int64_t i : items) d.tbl.push_back(i * stride); return d; };
+        auto lin_dim = [](int64_t len, int64_t stride) { GDim d; d.len = len; d.linear = true; d.stride = stride; return d; };
+        bad += emulate_flat({lin_dim(1000, 10), table_dim({0, 2, 4, 6, 8}, 1)}, 10000) != 0;
+        bad += emulate_flat({lin_dim(77, 130), lin_dim(13, 10), table_dim({9, 0, 4}, 1)}, 77 * 130) != 0;
+        bad += emulate_flat({lin_dim(500, 120), table_dim({1, 3, 8}, 12), table_dim({0, 5, 11, 2}, 1)}, 500 * 120) != 0;
+        bad += emulate_flat({lin_dim(90, 400), lin_dim(4, 100), table_dim({9, 0}, 10), lin_dim(10, 1)}, 90 * 400) != 0;
+        bad += emulate_flat({table_dim({0, 2, 4}, 1000), lin_dim(100, 10), table_dim({1, 2}, 1)}, 5000) != -1;
+        n += 5;
+        printf("flat gathers emulated: %d block-local, %d to the front, %d planes to innermost\n", n_flat, n_front, n_planes);
+        if (n_flat < 10 || n_front < 5 || n_planes < 5) { printf("flat planners declined almost everything\n"); ++bad; }
+    }
     {
         int taken = 0;
         unsigned seed = 0;
