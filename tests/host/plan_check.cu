@@ -9,6 +9,9 @@
 #include "../../olap_in_memory_b200/csrc/kernels_pair.cuh"
 #include "../../olap_in_memory_b200/csrc/kernels_tile.cuh"
 #include "../../olap_in_memory_b200/csrc/kernels_lanes.cuh"
+#include "../../olap_in_memory_b200/csrc/host_pipe.cuh"
+
+#include <sys/wait.h>
 
 namespace olap {
 thread_local std::string g_error;
@@ -223,6 +226,33 @@ static int emulate_flat(const std::vector<GDim>& dims, int64_t src_size) {
     return 0;
 }
 
+// host_pipe.cuh: the worker-thread copy behind the pinned ring.  Every byte arrives for sizes around the slicing
+// thresholds and odd alignments, and a forked child (which has none of the workers) still copies.
+static int check_copy_pool() {
+    setenv("OLAP_COPY_THREADS", "4", 1);
+    CopyPool& pool = CopyPool::get();
+    if (pool.threads() != 4) { printf("copy pool: %d threads\n", pool.threads()); return 1; }
+    const size_t cap = ((size_t)34 << 20) + 64;
+    std::vector<unsigned char> src(cap), dst(cap);
+    unsigned x = 7;
+    for (auto& b : src) { x = x * 1664525u + 1013904223u; b = (unsigned char)(x >> 24); }
+    for (size_t bytes : {(size_t)0, (size_t)1, (size_t)4095, (size_t)1 << 20, ((size_t)1 << 20) + 1, ((size_t)2 << 20) - 1, ((size_t)5 << 20) + 123, (size_t)16 << 20, ((size_t)33 << 20) + 7})
+        for (size_t shift : {(size_t)0, (size_t)3}) {
+            std::fill(dst.begin(), dst.end(), 0);
+            pool.copy(dst.data() + shift, src.data() + 1 + shift, bytes);
+            if (memcmp(dst.data() + shift, src.data() + 1 + shift, bytes) || dst[shift + bytes] != 0 || (shift && dst[shift - 1] != 0)) { printf("copy pool: %zu bytes\n", bytes); return 1; }
+        }
+    const pid_t child = fork();
+    if (child == 0) {
+        std::fill(dst.begin(), dst.end(), 0);
+        pool.copy(dst.data(), src.data(), (size_t)10 << 20);
+        _exit(memcmp(dst.data(), src.data(), (size_t)10 << 20) ? 1 : 0);
+    }
+    int status = 1;
+    if (child < 0 || waitpid(child, &status, 0) != child || !WIFEXITED(status) || WEXITSTATUS(status) != 0) { printf("copy pool: forked child\n"); return 1; }
+    return 0;
+}
+
 static std::vector<GDim> perm_dims(const std::vector<int64_t>& len, const std::vector<int>& perm) {
     const int k = (int)len.size();
     std::vector<int64_t> stride(k);
@@ -235,6 +265,8 @@ static std::vector<GDim> perm_dims(const std::vector<int64_t>& len, const std::v
 
 int main() {
     int bad = 0, n = 0, n_pair = 0;
+    bad += check_copy_pool();
+    ++n;
     {
         // reorders: every permutation of a few shapes whose trailing / leading axes are short
         const std::vector<std::vector<int64_t>> fshapes = {{70, 9, 10, 10}, {1000, 6, 5, 4}, {333, 7, 3}, {300, 7, 10}, {2001, 4, 3}, {40, 50, 3, 2},
