@@ -917,6 +917,34 @@ class ShardedCube:
             out.storedMeasures = dict(zip(ids, res))
         return out
 
+    def rebalance(self):
+        """After a dice of a sharded dimension the surviving rows stay where they lived: the shards become uneven,
+        some may be empty (SURVEY.md §8e "drop/reassign whole rows; rebalance optional").  Rebalancing gives every
+        rank an even share again.  The old and the new partition are both contiguous in global row order, so rank r
+        sends ONE contiguous run of its rows to every rank whose new range overlaps its old one and receives its new
+        rows in ascending order of the sending rank: one all-to-all per plane, nothing is reordered on either side.
+        Returns self when the rows are already spread evenly."""
+        new_bounds = split_rows(self.rows_total, self.world)
+        if list(new_bounds) == list(self.row_bounds):
+            return self
+        out = self._derive(self.dimensions, new_bounds)
+        ids = list(self.storedMeasures)
+        if not ids:
+            return out
+        stores = [self.storedMeasures[m] for m in ids]
+
+        def overlap(a0, a1, b0, b1):
+            return max(0, min(a1, b1) - max(a0, b0))
+
+        W = self.world
+        n0, n1 = new_bounds[self.rank], new_bounds[self.rank + 1]
+        in_splits = [overlap(self.row0, self.row1, new_bounds[r], new_bounds[r + 1]) * self.inner for r in range(W)]
+        out_splits = [overlap(self.row_bounds[s], self.row_bounds[s + 1], n0, n1) * self.inner for s in range(W)]
+        received = [self._empty_like(s, (n1 - n0) * self.inner) for s in stores]
+        self._exchange_all(stores, received, in_splits, out_splits)
+        out.storedMeasures = dict(zip(ids, received))
+        return out
+
     def drillDown(self, dimensionId, attribute):
         """drillDown: shard-local whichever dimension is drilled (every child row is produced by
         the rank that holds its parent row; no communication)."""

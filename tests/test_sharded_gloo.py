@@ -68,6 +68,21 @@ def _collect(cube, ids):
     results["dice_region_total"] = diced.getTotal("m_sum")
     for m in ids:
         results[("dice_region", "country", m)] = np.asarray(diced.drillUp("region", "country").getData(m), dtype=np.float64)
+    # ... and after the rows were spread evenly again (ShardedCube.rebalance: one all-to-all per plane)
+    even = diced
+    if hasattr(diced, "rebalance"):
+        from olap_in_memory_b200.sharded import split_rows
+
+        even = diced.rebalance()
+        assert list(even.row_bounds) == list(split_rows(even.rows_total, even.world)), (even.row_bounds, diced.row_bounds)
+        assert even.rebalance() is even
+    results["rebalanced"] = np.asarray(even.getData("m_first"), dtype=np.float64)
+    for m in ids:
+        results[("rebalanced", "country", m)] = np.asarray(even.drillUp("region", "country").getData(m), dtype=np.float64)
+        results[("rebalanced", "quarter", m)] = np.asarray(even.drillUp("time", "quarter").getData(m), dtype=np.float64)
+    one = cube.dice("region", "city", ["c6"])  # every surviving row on the last rank
+    one = one.rebalance() if hasattr(one, "rebalance") else one
+    results["rebalanced_one_row"] = np.asarray(one.drillUp("product", "family").getData("m_average"), dtype=np.float64)
     diced = cube.dice("product", "sku", ["p0", "p3"]).dice("region", "country", ["odd"])
     for m in ids:
         results[("dice_product_region", "all", m)] = np.asarray(diced.drillUp("product", "all").getData(m), dtype=np.float64)
@@ -430,6 +445,9 @@ def _fuzz_worker(rank, world, port, queue):
                     log.append((seed, step, name, "refused"))
                     continue
                 sharded, single = moved, getattr(single, name)(*args)
+                if name in ("dice", "diceRange") and (seed + step) % 2 == 0:
+                    sharded = sharded.rebalance()  # rows spread evenly again; the cube must stay the same cube
+                    name = name + "+rebalance"
                 assert sharded.dimensionIds == single.dimensionIds, (seed, step, name, args)
                 for m in ("m_sum", "m_high"):
                     got, want = np.asarray(sharded.getData(m), np.float64), np.asarray(single.getData(m), np.float64)
@@ -457,4 +475,4 @@ def test_random_operation_sequences_on_three_ranks():
     print(f"fuzz: {len(log)} checks, {sum(1 for e in log if e[3] == 'refused')} refused, ops {sorted({e[2] for e in log})}")
     assert not bad, bad[:5]
     assert sum(1 for entry in log if entry[3] == "ok") >= 60, len(log)
-    assert {entry[2] for entry in log if entry[3] == "ok"} >= {"drillUp", "dice", "diceRange", "reorderDimensions", "removeDimension"}
+    assert {entry[2] for entry in log if entry[3] == "ok"} >= {"drillUp", "dice", "diceRange", "reorderDimensions", "removeDimension", "dice+rebalance"}
