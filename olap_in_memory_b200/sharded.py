@@ -920,18 +920,32 @@ class ShardedCube:
     def rebalance(self):
         """After a dice of a sharded dimension the surviving rows stay where they lived: the shards become uneven,
         some may be empty (SURVEY.md §8e "drop/reassign whole rows; rebalance optional").  Rebalancing gives every
-        rank an even share again.  The old and the new partition are both contiguous in global row order, so rank r
-        sends ONE contiguous run of its rows to every rank whose new range overlaps its old one and receives its new
-        rows in ascending order of the sending rank: one all-to-all per plane, nothing is reordered on either side.
-        Returns self when the rows are already spread evenly."""
-        new_bounds = split_rows(self.rows_total, self.world)
-        if list(new_bounds) == list(self.row_bounds):
+        rank an even share again.  Returns self when the rows are already spread evenly."""
+        return self._repartition(split_rows(self.rows_total, self.world))
+
+    def _repartition(self, new_bounds, prefix=None):
+        """Move whole rows so that rank r holds rows [new_bounds[r], new_bounds[r + 1]).  The old and the new partition
+        are both contiguous in global row order, so rank r sends ONE contiguous run of its rows to every rank whose
+        new range overlaps its old one and receives its new rows in ascending order of the sending rank: one
+        all-to-all per plane, nothing is reordered on either side.  `prefix`: how many leading dimensions the new
+        cube counts as sharded (rows are then rows of THAT prefix; the cells do not move for it)."""
+        new_bounds = [int(b) for b in new_bounds]
+        prefix = self.prefix if prefix is None else int(prefix)
+        if new_bounds == list(self.row_bounds) and prefix == self.prefix:
             return self
-        out = self._derive(self.dimensions, new_bounds)
+        below = _prod(d.numItems for d in self.dimensions[prefix:self.prefix])  # old rows per new row (prefix <= self.prefix)
+        if any(b % below for b in new_bounds):
+            raise ValueError("new shard bounds must fall on rows of the new prefix")
+        out = ShardedCube(self.dimensions, prefix, self._store_cls, self.comm.group, [b // below for b in new_bounds])
+        out.storedMeasuresRules = dict(self.storedMeasuresRules)
+        out.computedMeasures = dict(self.computedMeasures)
         ids = list(self.storedMeasures)
         if not ids:
             return out
         stores = [self.storedMeasures[m] for m in ids]
+        if new_bounds == list(self.row_bounds):  # same cells on every rank, only the bookkeeping changes
+            out.storedMeasures = dict(zip(ids, stores))
+            return out
 
         def overlap(a0, a1, b0, b1):
             return max(0, min(a1, b1) - max(a0, b0))
@@ -1015,8 +1029,11 @@ class ShardedCube:
                 out.storedMeasures = dict(zip(ids, self._reorder(stores, self._local_lens(), order)))
             return out
         if self.prefix != 1:
-            raise NotImplementedError("reorder that moves a sharded dimension needs the cube sharded on its "
-                                      "outermost dimension alone (prefix=1)")
+            # shard on the outermost dimension alone first (whole rows of it move between neighbouring ranks: one
+            # all-to-all per plane, _repartition), then re-partition on the dimension that comes to the front
+            below = _prod(d.numItems for d in self.dimensions[1:self.prefix])
+            outer_bounds = [b * below for b in split_rows(lens[0], self.world)]
+            return self._repartition(outer_bounds, prefix=1).reorderDimensions(dimensionIds)
         W, k = self.world, perm[0]
         new_bounds = split_rows(lens[k], W)
         out = self._derive(new_dims, new_bounds)
