@@ -984,8 +984,13 @@ class ShardedCube:
             old_row = (outer * old_prefix_lens[idx] + child_to_parent[coord]) * below + low
             owner = np.searchsorted(np.asarray(self.row_bounds[1:]), old_row, side="right")
             if owner.size > 1 and np.any(np.diff(owner) < 0):
-                raise NotImplementedError("drillDown of a sharded dimension whose shard bounds cut through it "
-                                          "re-partitions rows; shard on that dimension alone (prefix=1) or align the bounds")
+                # the shard bounds cut through an item of the drilled dimension: move whole rows between
+                # neighbouring ranks first, so that every rank holds whole items of it (_repartition), then expand
+                aligned = [b * below for b in split_rows(_prod(old_prefix_lens[: idx + 1]), self.world)]
+                if aligned == list(self.row_bounds):
+                    raise NotImplementedError("drillDown of a sharded dimension whose shard bounds cut through it "
+                                              "re-partitions rows; shard on that dimension alone (prefix=1) or align the bounds")
+                return self._repartition(aligned).drillDown(dimensionId, attribute)
             new_bounds = [int(b) for b in np.searchsorted(owner, np.arange(self.world + 1), side="left")]
             out = self._derive(new_dims, new_bounds)
             mine = old_row[new_bounds[self.rank]:new_bounds[self.rank + 1]] - self.row0
