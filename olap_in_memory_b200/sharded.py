@@ -899,7 +899,23 @@ class ShardedCube:
             # ascending order, so every rank's survivors are one contiguous range of the new row
             # numbering; the shard sizes may become uneven.
             if kept.size > 1 and np.any(np.diff(kept) <= 0):
-                raise NotImplementedError("dice(reorder=True) that permutes a sharded dimension moves rows between ranks")
+                # dice(reorder=True) that permutes a sharded dimension: drop the rows in place first (ascending
+                # items, nothing moves), then shuffle whole rows into the requested order (_shuffle_rows)
+                order = np.argsort(kept, kind="stable")
+                if np.any(np.diff(kept[order]) == 0):
+                    raise ValueError("dice: an item is listed twice")
+                items = old_dim.getItems()
+                ascending = self._dice_to(idx, old_dim.dice(old_dim.rootAttribute, [items[i] for i in kept[order]], False))
+                # position of every requested item in the ascending cube
+                rank_of = np.empty(kept.size, dtype=np.int64)
+                rank_of[order] = np.arange(kept.size)
+                new_prefix_lens = [d.numItems for d in new_dims[: self.prefix]]
+                below = _prod(new_prefix_lens[idx + 1:])
+                new_rows = np.arange(_prod(new_prefix_lens), dtype=np.int64)
+                outer, rest = np.divmod(new_rows, new_prefix_lens[idx] * below)
+                coord, low = np.divmod(rest, below)
+                old_of_new = (outer * new_prefix_lens[idx] + rank_of[coord]) * below + low
+                return ascending._shuffle_rows(old_of_new, new_dims)
             old_prefix_lens = [d.numItems for d in self.dimensions[: self.prefix]]
             survives = np.zeros(old_prefix_lens[idx], dtype=bool)
             survives[kept] = True
@@ -915,6 +931,47 @@ class ShardedCube:
         if ids:
             res = self._call("dice_lowered", [self.storedMeasures[m] for m in ids], self._local_lens(), keep)
             out.storedMeasures = dict(zip(ids, res))
+        return out
+
+    def _shuffle_rows(self, old_of_new, new_dims):
+        """Whole rows into a new global order: new row j is old row old_of_new[j] (a permutation of the rows, or an
+        injective selection).  Every rank gathers the rows it has to send in ascending new-row order (so that the
+        runs for rank 0, 1, ... follow each other), one all-to-all per plane moves them, and the receiver — whose
+        blocks arrive grouped by sending rank — gathers them into ascending new-row order."""
+        old_of_new = np.asarray(old_of_new, dtype=np.int64)
+        total = int(old_of_new.size)
+        W = self.world
+        new_bounds = split_rows(total, W)
+        out = ShardedCube(new_dims, self.prefix, self._store_cls, self.comm.group, new_bounds)
+        out.storedMeasuresRules = dict(self.storedMeasuresRules)
+        out.computedMeasures = dict(self.computedMeasures)
+        ids = list(self.storedMeasures)
+        if not ids:
+            return out
+        stores = [self.storedMeasures[m] for m in ids]
+        src = np.searchsorted(np.asarray(self.row_bounds[1:]), old_of_new, side="right")   # who holds the row now
+        dst = np.searchsorted(np.asarray(new_bounds[1:]), np.arange(total), side="right")    # who gets it
+        inner_idx = np.arange(self.inner, dtype=np.int32)
+        mine = np.flatnonzero(src == self.rank)  # new rows I hold, ascending: grouped by destination rank
+        in_splits = [int(np.count_nonzero(dst[mine] == r)) * self.inner for r in range(W)]
+        n0, n1 = new_bounds[self.rank], new_bounds[self.rank + 1]
+        src_mine = src[n0:n1]
+        out_splits = [int(np.count_nonzero(src_mine == s)) * self.inner for s in range(W)]
+        if mine.size and self.inner:
+            sent = self._call("dice_lowered", stores, [self.rows_local, self.inner],
+                              [(old_of_new[mine] - self.row0).astype(np.int32), inner_idx])
+        else:
+            sent = [self._empty_like(s, 0) for s in stores]
+        received = [self._empty_like(s, (n1 - n0) * self.inner) for s in stores]
+        self._exchange_all(sent, received, in_splits, out_splits)
+        del sent
+        # received: block of rank 0's rows (ascending new row), block of rank 1's rows, ...
+        arrival = np.argsort(src_mine, kind="stable")          # arrival position -> local new row
+        if (n1 - n0) and self.inner and np.any(arrival != np.arange(n1 - n0)):
+            position = np.empty(n1 - n0, dtype=np.int32)
+            position[arrival] = np.arange(n1 - n0, dtype=np.int32)  # local new row -> arrival position
+            received = self._call("dice_lowered", received, [n1 - n0, self.inner], [position, inner_idx])
+        out.storedMeasures = dict(zip(ids, received))
         return out
 
     def rebalance(self):

@@ -80,6 +80,17 @@ def _collect(cube, ids):
     for m in ids:
         results[("rebalanced", "country", m)] = np.asarray(even.drillUp("region", "country").getData(m), dtype=np.float64)
         results[("rebalanced", "quarter", m)] = np.asarray(even.drillUp("time", "quarter").getData(m), dtype=np.float64)
+    # dice(reorder=True) that permutes the (possibly) sharded dimension: rows dropped in place, then shuffled between ranks
+    for items in (["c5", "c1", "c6", "c2"], ["c6", "c5", "c4", "c3", "c2", "c1", "c0"], ["c3", "c0"]):
+        shuffled = cube.dice("region", "city", items, True)
+        assert shuffled.getDimension("region").getItems() == items if hasattr(shuffled, "getDimension") else True
+        results[("dice_permuted", tuple(items))] = np.asarray(shuffled.getData("m_last"), dtype=np.float64)
+        # (first / last of a rollup AFTER a permuting dice follow the Map's insertion order in the reference, SURVEY.md
+        # A13 / A14: a declared divergence, not compared here)
+        results[("dice_permuted_up", tuple(items))] = np.asarray(shuffled.drillUp("region", "country").getData("m_highest"), dtype=np.float64)
+        results[("dice_permuted_sum", tuple(items))] = np.asarray(shuffled.drillUp("region", "all").getData("m_sum"), dtype=np.float64)
+    permuted_product = cube.dice("product", "sku", ["p4", "p0", "p2"], True)
+    results["dice_permuted_product"] = np.asarray(permuted_product.getData("m_sum"), dtype=np.float64)
     one = cube.dice("region", "city", ["c6"])  # every surviving row on the last rank
     one = one.rebalance() if hasattr(one, "rebalance") else one
     results["rebalanced_one_row"] = np.asarray(one.drillUp("product", "family").getData("m_average"), dtype=np.float64)
