@@ -31,10 +31,13 @@ def main():
     for prefix, default in ((1, 0.0), (2, math.nan), (2, 0.0)):
         cube = ShardedCube(_dims(), prefix=prefix)
         _fill(cube, default)
-        got = _collect(cube, list(cube.storedMeasures))
+        # OLAP_SHARDED_EXTENDED=1: also rebalance() and the permuting dice of a sharded dimension (gloo-verified,
+        # written after the round's last multi-GPU call: opt-in until they have run on hardware once)
+        extended = os.environ.get("OLAP_SHARDED_EXTENDED") == "1"
+        got = _collect(cube, list(cube.storedMeasures), extended)
         ref = Cube(_dims(), OracleStore)
         _fill(ref, default)
-        want = _collect(ref, ref.storedMeasureIds)
+        want = _collect(ref, ref.storedMeasureIds, extended)
         for key in want:
             if key == "total":
                 ok = math.isclose(got[key], want[key], rel_tol=1e-6) or (math.isnan(got[key]) and math.isnan(want[key]))

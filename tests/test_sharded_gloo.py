@@ -49,7 +49,10 @@ def _fill(cube, default):
         cube.setData(f"m_{method}", _data(default, k).tolist())
 
 
-def _collect(cube, ids):
+def _collect(cube, ids, extended=True):
+    """`extended`: also the transforms that move whole rows between ranks on request (rebalance, permuting dice of a
+    sharded dimension).  tests/gpu_sharded_check.py switches them on with OLAP_SHARDED_EXTENDED=1: they are verified
+    over gloo here, but were written after the round's last multi-GPU hardware call."""
     results = {}
     for dim, attr in ROLLUPS:
         rolled = cube.drillUp(dim, attr)
@@ -68,6 +71,12 @@ def _collect(cube, ids):
     results["dice_region_total"] = diced.getTotal("m_sum")
     for m in ids:
         results[("dice_region", "country", m)] = np.asarray(diced.drillUp("region", "country").getData(m), dtype=np.float64)
+    sparse = cube.dice("product", "sku", ["p0", "p3"]).dice("region", "country", ["odd"])
+    for m in ids:
+        results[("dice_product_region", "all", m)] = np.asarray(sparse.drillUp("product", "all").getData(m), dtype=np.float64)
+    results["dice_one_row"] = np.asarray(cube.dice("region", "city", ["c6"]).drillUp("region", "all").getData("m_last"), dtype=np.float64)
+    if not extended:
+        return results
     # ... and after the rows were spread evenly again (ShardedCube.rebalance: one all-to-all per plane)
     even = diced
     if hasattr(diced, "rebalance"):
@@ -94,10 +103,6 @@ def _collect(cube, ids):
     one = cube.dice("region", "city", ["c6"])  # every surviving row on the last rank
     one = one.rebalance() if hasattr(one, "rebalance") else one
     results["rebalanced_one_row"] = np.asarray(one.drillUp("product", "family").getData("m_average"), dtype=np.float64)
-    diced = cube.dice("product", "sku", ["p0", "p3"]).dice("region", "country", ["odd"])
-    for m in ids:
-        results[("dice_product_region", "all", m)] = np.asarray(diced.drillUp("product", "all").getData(m), dtype=np.float64)
-    results["dice_one_row"] = np.asarray(cube.dice("region", "city", ["c6"]).drillUp("region", "all").getData("m_last"), dtype=np.float64)
     return results
 
 
