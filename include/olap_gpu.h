@@ -203,7 +203,11 @@ int olap_store_status_derived(const olap_store* s);
 
 /* ---- data boundary -------------------------------------------------------- */
 /* `set data` in-memory.js:39-46.  n != size fails with
- * "value length is invalid: <size> !== <n>".  Values equal to the default are unset. */
+ * "value length is invalid: <size> !== <n>".  Values equal to the default are unset.
+ * Host buffers of every call of this section are borrowed for the call.  They may be pinned
+ * (olap_host_alloc: one copy at PCIe speed) or plain pageable memory (a typed array of the Node
+ * addon): transfers of 8 MiB and more then travel in chunks through the library's ring of pinned
+ * buffers, the host-side copies on worker threads (csrc/host_pipe.cuh). */
 int olap_store_upload_f32(olap_store* s, const float* host, int64_t n);
 int olap_store_upload_f64(olap_store* s, const double* host, int64_t n);
 /* `get data` in-memory.js:30-37 (unset cells read as the default) */
