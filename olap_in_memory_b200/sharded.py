@@ -951,15 +951,15 @@ class ShardedCube:
         stores = [self.storedMeasures[m] for m in ids]
         src = np.searchsorted(np.asarray(self.row_bounds[1:]), old_of_new, side="right")   # who holds the row now
         dst = np.searchsorted(np.asarray(new_bounds[1:]), np.arange(total), side="right")    # who gets it
-        inner_idx = np.arange(self.inner, dtype=np.int32)
+        inner_keep = [np.arange(n, dtype=np.int32) for n in self.inner_lens]  # per inner dimension: no table of inner cells
         mine = np.flatnonzero(src == self.rank)  # new rows I hold, ascending: grouped by destination rank
         in_splits = [int(np.count_nonzero(dst[mine] == r)) * self.inner for r in range(W)]
         n0, n1 = new_bounds[self.rank], new_bounds[self.rank + 1]
         src_mine = src[n0:n1]
         out_splits = [int(np.count_nonzero(src_mine == s)) * self.inner for s in range(W)]
         if mine.size and self.inner:
-            sent = self._call("dice_lowered", stores, [self.rows_local, self.inner],
-                              [(old_of_new[mine] - self.row0).astype(np.int32), inner_idx])
+            sent = self._call("dice_lowered", stores, [self.rows_local] + self.inner_lens,
+                              [(old_of_new[mine] - self.row0).astype(np.int32)] + inner_keep)
         else:
             sent = [self._empty_like(s, 0) for s in stores]
         received = [self._empty_like(s, (n1 - n0) * self.inner) for s in stores]
@@ -970,7 +970,7 @@ class ShardedCube:
         if (n1 - n0) and self.inner and np.any(arrival != np.arange(n1 - n0)):
             position = np.empty(n1 - n0, dtype=np.int32)
             position[arrival] = np.arange(n1 - n0, dtype=np.int32)  # local new row -> arrival position
-            received = self._call("dice_lowered", received, [n1 - n0, self.inner], [position, inner_idx])
+            received = self._call("dice_lowered", received, [n1 - n0] + self.inner_lens, [position] + inner_keep)
         out.storedMeasures = dict(zip(ids, received))
         return out
 
