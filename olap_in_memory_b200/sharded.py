@@ -1127,7 +1127,9 @@ class ShardedCube:
         if my_k * d0_total * O == 0:
             out.storedMeasures = {m: self._empty_like(s, 0) for m, s in zip(ids, stores)}
             return out
-        gathered = self._call("dice_lowered", received, [my_k * d0_total, O], [rows, np.arange(O, dtype=np.int32)])
+        # (identity lists per remaining dimension, not one list over all O cells of a row: O is 1e8 for a 1e10-cell cube)
+        gathered = self._call("dice_lowered", received, [my_k * d0_total] + other_lens,
+                              [rows] + [np.arange(n, dtype=np.int32) for n in other_lens])
         del received
         # 4. local transpose to the requested order
         final = [0] + [1 if j == 0 else 2 + others.index(j) for j in perm[1:]]
